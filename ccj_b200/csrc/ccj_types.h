@@ -1,0 +1,135 @@
+// ccj_b200 -- shared host/device plain-data types, constants and table layouts.
+//
+// Everything here is POD so it can sit in device global memory and be filled by the host
+// loader (energy_model.cpp).  Names follow the reference's domain vocabulary:
+//   reference src/matrices.hh      (TriangleMatrix / Matrix4D semantics)
+//   reference src/h_globals.hh:7-25 (pseudoknot penalties)
+//   reference src/ViennaRNA/params/basic.h:57-118 (vrna_param_t fields we need)
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define CCJ_HD __host__ __device__ __forceinline__
+#else
+#define CCJ_HD inline
+#endif
+
+#define CCJ_INF 10000000        /* reference src/matrices.hh:10 */
+#define CCJ_INTERN_INF 32767    /* Matrix4D::INTERN_INF, src/matrices.hh:150 */
+#define CCJ_V_UNSET 10000       /* free_energy_node default, src/h_struct.hh:100 */
+#define CCJ_TURN 3
+#define CCJ_MAXLOOP 30
+
+// ---- 4D gap tables (order = the reference's in-cell evaluation order is NOT this order; this is
+//      the export order shared with oracle/ref_dump.cc) -------------------------------------------
+enum ccj_table4 {
+    T_PK = 0, T_PL, T_PR, T_PM, T_PO, T_PfromL, T_PfromR, T_PfromM, T_PfromMprime, T_PfromO,
+    T_PLmloop00, T_PLmloop01, T_PLmloop10, T_PRmloop00, T_PRmloop01, T_PRmloop10,
+    T_PMmloop00, T_PMmloop01, T_PMmloop10, T_POmloop00, T_POmloop01, T_POmloop10,
+    CCJ_NT4 = 22
+};
+
+// ---- 2D tables ----------------------------------------------------------------------------------
+enum ccj_table2 {
+    T2_V = 0,   // free_energy_node::energy   (init 10000)
+    T2_VTYPE,   // free_energy_node::type     (init 'N')
+    T2_WM, T2_WMv, T2_WMp,  // init INF+1
+    T2_P, T2_WBP, T2_WPP,   // init INF+1
+    T2_WB, T2_WP,           // derived: get_WB/get_WP for 1<=i<=j<=n (src/pseudo_loop.cc:647-661)
+    CCJ_NT2 = 10,
+    CCJ_NT2_EXPORT = 8
+};
+
+// ---- energy model as the device sees it ------------------------------------------------------------
+// Pair types 0..7 (0 = no pair), bases 0..4 (0 unused for ACGU input), exactly the index space of
+// vrna_param_t so that every reference lookup has a 1:1 counterpart.
+#define CCJ_MAX_SPECIAL 40
+#define CCJ_LOOP_TAB 64      /* bulge / interior sizes 0..63 (PK interior windows reach u=56) */
+#define CCJ_HAIRPIN_TAB 4096 /* hairpin sizes 0..4095, >30 extrapolated with the host libm */
+
+struct ccj_model {
+    int32_t stack[8][8];
+    int32_t hairpin[CCJ_HAIRPIN_TAB];    // hairpin[size], incl. lxc*log extrapolation (hairpin.h:158-161)
+    int32_t bulge[CCJ_LOOP_TAB];         // bulge[nl]      (internal.h:505-507)
+    int32_t internal_loop[CCJ_LOOP_TAB]; // internal_loop[u] (internal.h:556-560)
+    int32_t mismatchExt[8][5][5];
+    int32_t mismatchI[8][5][5];
+    int32_t mismatch1nI[8][5][5];
+    int32_t mismatch23I[8][5][5];
+    int32_t mismatchH[8][5][5];
+    int32_t mismatchM[8][5][5];
+    int32_t dangle5[8][5];
+    int32_t dangle3[8][5];
+    int32_t int11[8][8][5][5];
+    int32_t int21[8][8][5][5][5];
+    int32_t int22[8][8][5][5][5][5];
+    int32_t ninio2;      // P->ninio[2]
+    int32_t max_ninio;   // MAX_NINIO
+    int32_t MLbase, MLclosing, TerminalAU;
+    int32_t MLintern[8];
+    // special hairpins, ASCII, matched against the ASCII sequence exactly like the reference's strstr
+    // on P->Tetraloops etc. (hairpin.h:166-193).  Entries are blank separated with a fixed pitch, so a
+    // blank-free probe of the entry length can only match at an entry start.
+    int32_t n_tetra, n_tri, n_hexa;
+    char tetra[CCJ_MAX_SPECIAL][8];
+    char tri[CCJ_MAX_SPECIAL][8];
+    char hexa[CCJ_MAX_SPECIAL][8];
+    int32_t tetra_E[CCJ_MAX_SPECIAL], tri_E[CCJ_MAX_SPECIAL], hexa_E[CCJ_MAX_SPECIAL];
+    int32_t special_hp;
+    int32_t dangles;     // model_details.dangles (set AFTER scaling, src/W_final.cc:25)
+    // pair[][] and rtype[] (src/ViennaRNA/pair_mat.h:20-38,80-155); noGU already applied
+    int32_t pair[5][5];
+    int32_t rtype[8];
+    // pseudoknot penalties (src/h_globals.hh:7-25)
+    int32_t PS_penalty, PSM_penalty, PSP_penalty, PB_penalty, PUP_penalty, PPS_penalty;
+    int32_t a_penalty, b_penalty, c_penalty, ap_penalty, bp_penalty, cp_penalty;
+    double e_stP_penalty, e_intP_penalty;
+};
+
+// ---- per-sequence view ----------------------------------------------------------------------------
+struct ccj_seq {
+    int32_t n;
+    int32_t pad_;
+    const int8_t *S;     // S[0..n+1]; S[i] base code of nucleotide i (1-based), S[n+1]=S[1], S[0]=S[n]
+    const char *seq;     // ASCII, 0-based, n chars (upper case)
+    int16_t *t4;         // CCJ_NT4 tables, each `stride4` int16
+    int64_t stride4;
+    int32_t *t2;         // CCJ_NT2 tables, each `stride2` int32, diagonal-major
+    int64_t stride2;
+    int32_t *W;          // W[0..n]
+    // traceback outputs
+    int32_t *pair_out;   // f[1..n].pair  (index 0 unused), -1 = unpaired
+    int8_t *ftype_out;   // f[1..n].type
+    int32_t *status;     // [0]=status code, [1]=number of "Should not be here!" lines, [2]=aux
+};
+
+// ---- 4D layout ---------------------------------------------------------------------------------------
+// A cell is (i,j,k,l) with 1<=i<=j, j<k-1, k<=l<=n  (Matrix4D::get validity, src/matrices.hh:177-182).
+// We address it by arm lengths a=j-i, b=l-k and the anchors (i,k):  nesting [b][i][a][k], k fastest.
+// All cells of one DP level t=a+b (the wavefront step) with equal (a,b,i) are contiguous in k, so a
+// warp whose lanes walk k reads and writes whole 64-byte runs.
+//   block(b,i) : rows a=0..q-1, row a holds k=i+a+2 .. n-b  (length q-a),  q = n-b-i-1
+CCJ_HD int64_t ccj_pent(int64_t q) { return q * (q + 1) * (q + 2) * (q + 3) / 24; }
+CCJ_HD int64_t ccj_tet(int64_t q) { return q * (q + 1) * (q + 2) / 6; }
+CCJ_HD int64_t ccj_cells4(int n) { return n >= 3 ? ccj_pent(n - 2) : 0; } /* == C(n+1,4) */
+
+CCJ_HD int64_t ccj_idx4(int n, int i, int j, int k, int l) {
+    const int a = j - i, b = l - k;
+    const int q = n - b - i - 1;
+    return (ccj_pent(n - 2) - ccj_pent(n - b - 2)) + (ccj_tet(n - b - 2) - ccj_tet(q)) +
+           (int64_t)a * q - (int64_t)a * (a - 1) / 2 + (k - i - a - 2);
+}
+
+CCJ_HD bool ccj_valid4(int i, int j, int k, int l) { return i <= j && j < k - 1 && k <= l; }
+
+// ---- 2D layout: diagonal-major, idx = (j-i)*(n+1) + i, 1<=i<=j<=n ----------------------------------
+CCJ_HD int64_t ccj_stride2(int n) { return (int64_t)n * (n + 1) + (n + 1); }
+CCJ_HD int32_t ccj_idx2(int n, int i, int j) { return (j - i) * (n + 1) + i; }
+
+// status codes written by the traceback (host maps them back to the reference's messages / exit codes)
+enum ccj_status {
+    CCJ_OK = 0,
+    CCJ_EXIT_FAILURE = 1,       // reference printed a message to stderr and exit(EXIT_FAILURE)
+    CCJ_EXIT_ZERO_NOT_GOOD = 2, // "NOT GOOD RESTR INTER" then exit(0) (src/W_final.cc:232-235)
+    CCJ_STACK_OVERFLOW = 3      // our traceback stack was too small (never the reference's behaviour)
+};

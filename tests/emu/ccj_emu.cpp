@@ -1,0 +1,138 @@
+// TEST TOOL (not part of the product): compiles the product's host/device cell functions
+// (ccj_b200/csrc/ccj_cells*.cuh) for the CPU and sweeps them single-threaded in the SAME wavefront
+// order the CUDA kernels use (2D span s, then 4D level t=s).  It exists so that the recurrences, the
+// table layout and the level schedule can be debugged against oracle/_ref without a GPU.
+// The shipped library never contains this loop: without CUDA the product fails loudly.
+//
+//   ccj_emu hash <parfile> <dangles> <seq>   -> same text as `ccj_ref_dump hash`
+//   ccj_emu fold <parfile> <dangles> <seq>   -> same stdout/stderr/exit code as the CCJ binary
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../ccj_b200/csrc/energy_model.hpp"
+#include "../../ccj_b200/csrc/ccj_cells4.cuh"
+#ifndef CCJ_EMU_NO_TB
+#include "../../ccj_b200/csrc/ccj_traceback.cuh"
+#include "../../ccj_b200/csrc/ccj_render.hpp"
+#endif
+
+struct Fnv {
+    uint64_t h = 1469598103934665603ULL;
+    void add(uint64_t v) { h ^= v; h *= 1099511628211ULL; }
+};
+
+static const char *k4dNames[22] = {
+    "PK", "PL", "PR", "PM", "PO", "PfromL", "PfromR", "PfromM", "PfromMprime", "PfromO",
+    "PLmloop00", "PLmloop01", "PLmloop10", "PRmloop00", "PRmloop01", "PRmloop10",
+    "PMmloop00", "PMmloop01", "PMmloop10", "POmloop00", "POmloop01", "POmloop10"};
+static const char *k2dNames[8] = {"V", "Vtype", "WM", "WMv", "WMp", "P", "WBP", "WPP"};
+
+int main(int argc, char **argv) {
+    if (argc < 5) {
+        fprintf(stderr, "usage: ccj_emu hash|fold <parfile> <dangles> <seq> [noGU]\n");
+        return 2;
+    }
+    std::string mode = argv[1], seq = argv[4], err;
+    int dangles = atoi(argv[3]);
+    int noGU = argc > 5 ? atoi(argv[5]) : 0;
+    ccj::RawParams rp;
+    if (!ccj::load_par_file(argv[2], rp, err)) {
+        fprintf(stderr, "%s\n", err.c_str());
+        return 1;
+    }
+    static ccj_model M;
+    ccj::build_model(rp, dangles, noGU, M);
+
+    const int n = (int)seq.size();
+    std::vector<int8_t> S(n + 2);
+    for (int i = 1; i <= n; ++i) S[i] = (int8_t)ccj::encode_base(seq[i - 1]);
+    S[n + 1] = S[1];
+    S[0] = S[n];
+    const int64_t cells = ccj_cells4(n), s2 = ccj_stride2(n);
+    std::vector<int16_t> t4((size_t)(cells * CCJ_NT4 + 8), (int16_t)0x5555);  // poison: every valid cell must be written
+    std::vector<int32_t> t2((size_t)(s2 * CCJ_NT2));
+    std::vector<int32_t> W(n + 1, 0), pairv(n + 2, -1), st(4, 0);
+    std::vector<int8_t> ftype(n + 2, 'N');
+    for (int64_t x = 0; x < s2; ++x) {
+        t2[T2_V * s2 + x] = CCJ_V_UNSET;
+        t2[T2_VTYPE * s2 + x] = 'N';
+        for (int t = T2_WM; t < CCJ_NT2; ++t) t2[t * s2 + x] = CCJ_INF + 1;
+    }
+    ccj_cx c;
+    c.M = &M;
+    c.q.n = n;
+    c.q.S = S.data();
+    c.q.seq = seq.c_str();
+    c.q.t4 = t4.data();
+    c.q.stride4 = cells;
+    c.q.t2 = t2.data();
+    c.q.stride2 = s2;
+    c.q.W = W.data();
+    c.q.pair_out = pairv.data();
+    c.q.ftype_out = ftype.data();
+    c.q.status = st.data();
+
+    ccj_serial par;
+    for (int s = 0; s < n; ++s) {
+        // K_P + K_2D of span s
+        for (int i = 1; i + s <= n; ++i) {
+            const int l = i + s;
+            int mn = CCJ_INF;
+            for (int j = i; j < l; ++j)
+                for (int d = j + 1; d < l; ++d)
+                    for (int k = d + 1; k < l; ++k) mn = ccj_min(mn, ccj_P_term(c, i, l, j, d, k));
+            if (mn < CCJ_INF / 2) t2[T2_P * s2 + ccj_idx2(n, i, l)] = mn;
+            ccj_cell2d(c, i, l, par);
+        }
+        // K_4D of level t = s
+        const int t = s;
+        if (t <= n - 3)
+            for (int a = 0; a <= t; ++a) {
+                const int b = t - a;
+                for (int i = 1; i <= n - t - 2; ++i)
+                    for (int k = i + a + 2; k <= n - b; ++k) ccj_cell4d(c, i, i + a, k, k + b);
+            }
+    }
+    for (int j = CCJ_TURN + 1; j <= n; ++j) W[j] = ccj_W_at(c, j, par);
+
+    if (mode == "hash") {
+        printf("n %d\n", n);
+        for (int t = 0; t < 22; ++t) {
+            Fnv f;
+            long finite = 0;
+            int mn = 1 << 30;
+            for (int i = 1; i <= n; ++i)
+                for (int j = i; j <= n; ++j)
+                    for (int k = j + 2; k <= n; ++k)
+                        for (int l = k; l <= n; ++l) {
+                            int v = ccj_get4(c, t, i, j, k, l);
+                            f.add((uint16_t)(int16_t)v);
+                            if (v < 32767) { ++finite; if (v < mn) mn = v; }
+                        }
+            printf("%s %ld %d %016llx\n", k4dNames[t], finite, finite ? mn : 0, (unsigned long long)f.h);
+        }
+        for (int t = 0; t < 8; ++t) {
+            Fnv f;
+            long finite = 0;
+            long long sum = 0;
+            for (int i = 1; i <= n; ++i)
+                for (int j = i; j <= n; ++j) {
+                    int32_t v = ccj_raw2(c, t, i, j);
+                    f.add((uint32_t)v);
+                    if (v < CCJ_INF / 2) { ++finite; sum += v; }
+                }
+            printf("%s %ld %lld %016llx\n", k2dNames[t], finite, sum, (unsigned long long)f.h);
+        }
+        return 0;
+    }
+#ifndef CCJ_EMU_NO_TB
+    if (mode == "fold") {
+        ccj_traceback(c, par);
+        return ccj::emit_result(seq, n, W[n], pairv.data(), st.data(), stdout, stderr);
+    }
+#endif
+    return 2;
+}
