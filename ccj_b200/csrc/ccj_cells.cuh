@@ -182,11 +182,24 @@ CCJ_HD int ccj_Vint_term(const ccj_cx &c, int i, int j, int k, int l) {
 // `Par` spreads independent candidates of one cell over cooperating lanes:  lane in [0,nlanes),
 // red(v) returns the minimum over the lanes (identity when nlanes==1, e.g. on the host), sync() makes
 // the lanes' earlier stores visible to each other.
+// (value, position-in-reference-order) of the best candidate so far; lexicographic minimum == the
+// reference's "first strictly smaller wins"
+struct ccj_best {
+    int val, ord;
+};
+CCJ_HD void ccj_cand(ccj_best &b, int val, int ord) {
+    if (val < b.val || (val == b.val && ord < b.ord)) {
+        b.val = val;
+        b.ord = ord;
+    }
+}
+
 struct ccj_serial {
     static constexpr int nlanes = 1;
     CCJ_HD int lane() const { return 0; }
     CCJ_HD int red(int v) const { return v; }
     CCJ_HD void sync() const {}
+    CCJ_HD ccj_best argmin(ccj_best b) const { return b; }
 };
 
 // All nested/2D tables of one (i,j):  V -> (P given) -> WBP, WPP, WB, WP -> WMv, WMp -> WM, i.e. the order

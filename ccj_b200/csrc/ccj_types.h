@@ -100,8 +100,13 @@ struct ccj_seq {
     // traceback outputs
     int32_t *pair_out;   // f[1..n].pair  (index 0 unused), -1 = unpaired
     int8_t *ftype_out;   // f[1..n].type
-    int32_t *status;     // [0]=status code, [1]=number of "Should not be here!" lines, [2]=aux
+    int32_t *status;     // [0]=status code, [1]=number of "Should not be here!" lines, [2]=message id,
+                         // [3],[4]=i,j of a "NOT GOOD RESTR INTER" exit; CCJ_STATUS_INTS ints
+    int32_t *tb_stack;   // traceback stack, 5 ints per node
+    int32_t tb_cap;      // capacity in nodes
+    int32_t pad2_;
 };
+#define CCJ_STATUS_INTS 8
 
 // ---- 4D layout ---------------------------------------------------------------------------------------
 // A cell is (i,j,k,l) with 1<=i<=j, j<k-1, k<=l<=n  (Matrix4D::get validity, src/matrices.hh:177-182).

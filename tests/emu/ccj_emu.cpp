@@ -54,7 +54,7 @@ int main(int argc, char **argv) {
     const int64_t cells = ccj_cells4(n), s2 = ccj_stride2(n);
     std::vector<int16_t> t4((size_t)(cells * CCJ_NT4 + 8), (int16_t)0x5555);  // poison: every valid cell must be written
     std::vector<int32_t> t2((size_t)(s2 * CCJ_NT2));
-    std::vector<int32_t> W(n + 1, 0), pairv(n + 2, -1), st(4, 0);
+    std::vector<int32_t> W(n + 1, 0), pairv(n + 2, -1), st(CCJ_STATUS_INTS, 0), tbs(5 * (16 * n + 64));
     std::vector<int8_t> ftype(n + 2, 'N');
     for (int64_t x = 0; x < s2; ++x) {
         t2[T2_V * s2 + x] = CCJ_V_UNSET;
@@ -74,6 +74,8 @@ int main(int argc, char **argv) {
     c.q.pair_out = pairv.data();
     c.q.ftype_out = ftype.data();
     c.q.status = st.data();
+    c.q.tb_stack = tbs.data();
+    c.q.tb_cap = 16 * n + 64;
 
     ccj_serial par;
     for (int s = 0; s < n; ++s) {
