@@ -1,0 +1,589 @@
+// extern "C" layer of libccj_b200.so: contexts, waves, launch schedule, result read-back.
+// See include/ccj_b200.h for the contract and the reference code each entry point replaces.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/ccj_b200.h"
+#include "ccj_kernels.cuh"
+#include "ccj_render.hpp"
+#include "energy_model.hpp"
+
+namespace {
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct SeqPlan {
+    int n;
+    size_t in_off, out_off, tab_off;  // offsets into the three regions
+    size_t in_bytes, out_bytes, tab_bytes;
+};
+
+// per-sequence byte needs
+void plan_seq(int n, SeqPlan &p) {
+    p.n = n;
+    // inputs: S (n+2 int8), seq (n chars)
+    p.in_bytes = align_up((size_t)(n + 2) + (size_t)n + 2, 16);
+    // outputs: status | W[0..n] | pair[0..n+1]
+    p.out_bytes = align_up(sizeof(int32_t) * (CCJ_STATUS_INTS + (size_t)(n + 1) + (size_t)(n + 2)), 16);
+    // tables: t4, t2, ftype, traceback stack
+    size_t t4 = align_up((size_t)ccj_cells4(n) * CCJ_NT4 * sizeof(int16_t) + 16, 256);
+    size_t t2 = align_up((size_t)ccj_stride2(n) * CCJ_NT2 * sizeof(int32_t), 256);
+    size_t ft = align_up((size_t)n + 2, 16);
+    size_t tb = align_up(sizeof(int32_t) * 5 * (size_t)(16 * n + 64), 256);
+    p.tab_bytes = t4 + t2 + ft + tb;
+}
+
+}  // namespace
+
+struct ccj_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    bool model_ok = false;
+    ccj_model *h_model = nullptr;  // heap (large)
+    ccj_model *d_model = nullptr;
+
+    // arena
+    char *d_arena = nullptr;
+    size_t arena_bytes = 0;
+    ccj_seq *d_seqs = nullptr;
+    size_t d_seqs_cap = 0;
+    char *h_stage = nullptr;  // pinned staging for inputs/outputs
+    size_t h_stage_bytes = 0;
+
+    // current wave
+    std::vector<SeqPlan> plan;
+    std::vector<std::string> wave_seqs;
+    size_t in_total = 0, out_total = 0, tab_total = 0;
+    int nmax = 0;
+    bool prepared = false, filled = false, traced = false;
+    float fill_ms = 0.f, tb_ms = 0.f;
+    int fill_launches = 0;
+
+    // CUDA graphs of the fill, keyed by (nmax, nseq)
+    std::map<std::pair<int, int>, cudaGraphExec_t> graphs;
+};
+
+namespace {
+
+int fail(ccj_ctx *ctx, int code, const std::string &msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(ctx, CCJ_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+void drop_graphs(ccj_ctx *ctx) {
+    for (auto &g : ctx->graphs) cudaGraphExecDestroy(g.second);
+    ctx->graphs.clear();
+}
+
+int ensure_arena(ccj_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->arena_bytes) return 0;
+    if (ctx->d_arena) {
+        CU(cudaFree(ctx->d_arena));
+        ctx->d_arena = nullptr;
+        ctx->arena_bytes = 0;
+    }
+    CU(cudaMalloc((void **)&ctx->d_arena, bytes));
+    ctx->arena_bytes = bytes;
+    return 0;
+}
+
+int ensure_stage(ccj_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->h_stage_bytes) return 0;
+    if (ctx->h_stage) CU(cudaFreeHost(ctx->h_stage));
+    ctx->h_stage = nullptr;
+    ctx->h_stage_bytes = 0;
+    CU(cudaMallocHost((void **)&ctx->h_stage, bytes));
+    ctx->h_stage_bytes = bytes;
+    return 0;
+}
+
+int ensure_seqs(ccj_ctx *ctx, size_t count) {
+    if (count <= ctx->d_seqs_cap) return 0;
+    drop_graphs(ctx);  // graphs bake the descriptor pointer
+    if (ctx->d_seqs) CU(cudaFree(ctx->d_seqs));
+    ctx->d_seqs = nullptr;
+    size_t cap = std::max<size_t>(count, 1024);
+    CU(cudaMalloc((void **)&ctx->d_seqs, cap * sizeof(ccj_seq)));
+    ctx->d_seqs_cap = cap;
+    return 0;
+}
+
+size_t budget_bytes(ccj_ctx *ctx) {
+    size_t fr = 0, tot = 0;
+    if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return 0;
+    fr += ctx->arena_bytes;  // our own arena can be recycled
+    const size_t reserve = (size_t)1 << 30;
+    return fr > reserve ? fr - reserve : 0;
+}
+
+int validate(ccj_ctx *ctx, const char *s, int64_t len) {
+    if (len <= 0) return fail(ctx, CCJ_ERR_SEQUENCE, "sequence is missing");
+    if (len > CCJ_HAIRPIN_TAB - 2) return fail(ctx, CCJ_ERR_TOO_LARGE, "sequence longer than supported");
+    for (int64_t x = 0; x < len; ++x) {
+        const char ch = s[x];
+        if (!(ch == 'G' || ch == 'C' || ch == 'A' || ch == 'U' || ch == 'T')) {
+            char buf[128];
+            snprintf(buf, sizeof buf, "Sequence contains character %c that is not G,C,A,U, or T.", ch);
+            return fail(ctx, CCJ_ERR_SEQUENCE, buf);
+        }
+    }
+    return 0;
+}
+
+// the fill's launch sequence: per span s  K_P(s) -> K_2D(s) -> K_4D(level s)   (DESIGN.md "schedule")
+void enqueue_fill(ccj_ctx *ctx, ccj::LaunchDims d) {
+    ccj::launch_init(ctx->d_model, ctx->d_seqs, d, ctx->stream);
+    for (int s = 0; s < d.nmax; ++s) {
+        ccj::launch_P(ctx->d_model, ctx->d_seqs, d, s, ctx->stream);
+        ccj::launch_2d(ctx->d_model, ctx->d_seqs, d, s, ctx->stream);
+        ccj::launch_4d(ctx->d_model, ctx->d_seqs, d, s, ctx->stream);
+    }
+    ccj::launch_W(ctx->d_model, ctx->d_seqs, d, ctx->stream);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *ccj_version(void) { return "ccj_b200 0.1 (sm_100a)"; }
+
+int ccj_ctx_create(int device, ccj_ctx **out) {
+    if (!out) return CCJ_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) return CCJ_ERR_CUDA;
+    ccj_ctx *ctx = new ccj_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+        cudaMalloc((void **)&ctx->d_model, sizeof(ccj_model)) != cudaSuccess) {
+        delete ctx;
+        return CCJ_ERR_CUDA;
+    }
+    ctx->h_model = new ccj_model();
+    *out = ctx;
+    return 0;
+}
+
+void ccj_ctx_destroy(ccj_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    drop_graphs(ctx);
+    if (ctx->d_arena) cudaFree(ctx->d_arena);
+    if (ctx->d_seqs) cudaFree(ctx->d_seqs);
+    if (ctx->d_model) cudaFree(ctx->d_model);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx->h_model;
+    delete ctx;
+}
+
+const char *ccj_last_error(const ccj_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+
+int ccj_model_load(ccj_ctx *ctx, const char *par_file, int dangles, int no_gu) {
+    if (!ctx || !par_file) return CCJ_ERR_ARG;
+    ccj::RawParams *rp = new ccj::RawParams();
+    std::string err;
+    if (!ccj::load_par_file(par_file, *rp, err)) {
+        delete rp;
+        return fail(ctx, CCJ_ERR_PARAMS, err);
+    }
+    ccj::build_model(*rp, dangles, no_gu, *ctx->h_model);
+    delete rp;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(ctx->d_model, ctx->h_model, sizeof(ccj_model), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->model_ok = true;
+    return 0;
+}
+
+int64_t ccj_wave_capacity(ccj_ctx *ctx, int n) {
+    if (!ctx || n < 1) return 0;
+    cudaSetDevice(ctx->device);
+    SeqPlan p;
+    plan_seq(n, p);
+    const size_t per = p.in_bytes + p.out_bytes + p.tab_bytes + 512;
+    return (int64_t)(budget_bytes(ctx) / per);
+}
+
+void *ccj_stream(ccj_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int ccj_batch_prepare(ccj_ctx *ctx, const char *seqs, const int64_t *offsets, int nseq) {
+    if (!ctx || !seqs || !offsets || nseq < 1) return CCJ_ERR_ARG;
+    if (!ctx->model_ok) return fail(ctx, CCJ_ERR_STATE, "no energy model loaded");
+    CU(cudaSetDevice(ctx->device));
+    ctx->prepared = ctx->filled = ctx->traced = false;
+    ctx->plan.assign(nseq, SeqPlan());
+    ctx->wave_seqs.assign(nseq, std::string());
+    size_t in_total = 0, out_total = 0, tab_total = 0;
+    int nmax = 0;
+    for (int s = 0; s < nseq; ++s) {
+        const int64_t len = offsets[s + 1] - offsets[s];
+        int rc = validate(ctx, seqs + offsets[s], len);
+        if (rc) return rc;
+        SeqPlan &p = ctx->plan[s];
+        plan_seq((int)len, p);
+        p.in_off = in_total;
+        p.out_off = out_total;
+        p.tab_off = tab_total;
+        in_total += p.in_bytes;
+        out_total += p.out_bytes;
+        tab_total += p.tab_bytes;
+        nmax = std::max(nmax, (int)len);
+        ctx->wave_seqs[s].assign(seqs + offsets[s], (size_t)len);
+    }
+    in_total = align_up(in_total, 256);
+    out_total = align_up(out_total, 256);
+    const size_t need = in_total + out_total + tab_total;
+    if (need > budget_bytes(ctx)) return fail(ctx, CCJ_ERR_TOO_LARGE, "batch does not fit GPU memory; use ccj_fold_batch");
+    int rc = ensure_arena(ctx, need);
+    if (rc) return rc;
+    rc = ensure_stage(ctx, std::max(in_total, out_total) + (size_t)nseq * sizeof(ccj_seq));
+    if (rc) return rc;
+    rc = ensure_seqs(ctx, nseq);
+    if (rc) return rc;
+
+    // stage inputs + descriptors
+    char *d_in = ctx->d_arena, *d_out = ctx->d_arena + in_total, *d_tab = ctx->d_arena + in_total + out_total;
+    memset(ctx->h_stage, 0, in_total);
+    ccj_seq *hd = reinterpret_cast<ccj_seq *>(ctx->h_stage + std::max(in_total, out_total));
+    for (int s = 0; s < nseq; ++s) {
+        const SeqPlan &p = ctx->plan[s];
+        const int n = p.n;
+        int8_t *S = reinterpret_cast<int8_t *>(ctx->h_stage + p.in_off);
+        char *sq = ctx->h_stage + p.in_off + (n + 2);
+        const std::string &str = ctx->wave_seqs[s];
+        for (int x = 1; x <= n; ++x) S[x] = (int8_t)ccj::encode_base(str[x - 1]);
+        S[n + 1] = S[1];
+        S[0] = S[n];
+        memcpy(sq, str.data(), n);
+        ccj_seq &q = hd[s];
+        memset(&q, 0, sizeof q);
+        q.n = n;
+        q.S = reinterpret_cast<const int8_t *>(d_in + p.in_off);
+        q.seq = d_in + p.in_off + (n + 2);
+        char *o = d_out + p.out_off;
+        q.status = reinterpret_cast<int32_t *>(o);
+        q.W = q.status + CCJ_STATUS_INTS;
+        q.pair_out = q.W + (n + 1);
+        char *t = d_tab + p.tab_off;
+        q.t4 = reinterpret_cast<int16_t *>(t);
+        q.stride4 = ccj_cells4(n);
+        t += align_up((size_t)ccj_cells4(n) * CCJ_NT4 * sizeof(int16_t) + 16, 256);
+        q.t2 = reinterpret_cast<int32_t *>(t);
+        q.stride2 = ccj_stride2(n);
+        t += align_up((size_t)ccj_stride2(n) * CCJ_NT2 * sizeof(int32_t), 256);
+        q.ftype_out = reinterpret_cast<int8_t *>(t);
+        t += align_up((size_t)n + 2, 16);
+        q.tb_stack = reinterpret_cast<int32_t *>(t);
+        q.tb_cap = 16 * n + 64;
+    }
+    CU(cudaMemcpyAsync(d_in, ctx->h_stage, in_total, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_seqs, hd, (size_t)nseq * sizeof(ccj_seq), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->in_total = in_total;
+    ctx->out_total = out_total;
+    ctx->tab_total = tab_total;
+    ctx->nmax = nmax;
+    ctx->prepared = true;
+    return 0;
+}
+
+int ccj_batch_fill(ccj_ctx *ctx) {
+    if (!ctx) return CCJ_ERR_ARG;
+    if (!ctx->prepared) return fail(ctx, CCJ_ERR_STATE, "ccj_batch_prepare was not called");
+    CU(cudaSetDevice(ctx->device));
+    ccj::LaunchDims d;
+    d.nseq = (int)ctx->plan.size();
+    d.nmax = ctx->nmax;
+    const std::pair<int, int> key(d.nmax, d.nseq);
+    auto it = ctx->graphs.find(key);
+    if (it == ctx->graphs.end()) {
+        // capture the per-level launch sequence once per wave shape
+        cudaGraph_t g = nullptr;
+        CU(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        enqueue_fill(ctx, d);
+        CU(cudaStreamEndCapture(ctx->stream, &g));
+        cudaGraphExec_t ge = nullptr;
+        CU(cudaGraphInstantiate(&ge, g, 0));
+        CU(cudaGraphDestroy(g));
+        if (ctx->graphs.size() > 32) drop_graphs(ctx);
+        it = ctx->graphs.emplace(key, ge).first;
+    }
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    CU(cudaGraphLaunch(it->second, ctx->stream));
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    CU(cudaEventElapsedTime(&ctx->fill_ms, ctx->ev0, ctx->ev1));
+    ctx->fill_launches = ccj::fill_launch_count(d.nmax);
+    ctx->filled = true;
+    ctx->traced = false;
+    return 0;
+}
+
+int ccj_batch_traceback(ccj_ctx *ctx) {
+    if (!ctx) return CCJ_ERR_ARG;
+    if (!ctx->filled) return fail(ctx, CCJ_ERR_STATE, "ccj_batch_fill was not called");
+    CU(cudaSetDevice(ctx->device));
+    ccj::LaunchDims d;
+    d.nseq = (int)ctx->plan.size();
+    d.nmax = ctx->nmax;
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    ccj::launch_traceback(ctx->d_model, ctx->d_seqs, d, ctx->stream);
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    CU(cudaEventElapsedTime(&ctx->tb_ms, ctx->ev0, ctx->ev1));
+    ctx->traced = true;
+    return 0;
+}
+
+int ccj_batch_fetch(ccj_ctx *ctx, ccj_result *results, int32_t *pairs, char *structs) {
+    if (!ctx || !results) return CCJ_ERR_ARG;
+    if (!ctx->traced) return fail(ctx, CCJ_ERR_STATE, "ccj_batch_traceback was not called");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(ctx->h_stage, ctx->d_arena + ctx->in_total, ctx->out_total, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    size_t off = 0;
+    for (size_t s = 0; s < ctx->plan.size(); ++s) {
+        const SeqPlan &p = ctx->plan[s];
+        const int n = p.n;
+        const int32_t *st = reinterpret_cast<const int32_t *>(ctx->h_stage + p.out_off);
+        const int32_t *W = st + CCJ_STATUS_INTS;
+        const int32_t *pr = W + (n + 1);
+        ccj_result &r = results[s];
+        r.energy_dcal = W[n];
+        r.status = st[0];
+        r.n_should_not_be_here = st[1];
+        r.msg_id = st[2];
+        r.aux_i = st[3];
+        r.aux_j = st[4];
+        if (pairs)
+            for (int x = 0; x < n; ++x) pairs[off + x] = pr[x + 1];
+        if (structs) {
+            const std::string sstr = ccj::fill_structure(n, pr);
+            memcpy(structs + off, sstr.data(), n);
+        }
+        off += n;
+    }
+    return 0;
+}
+
+float ccj_last_fill_ms(const ccj_ctx *ctx) { return ctx ? ctx->fill_ms : 0.f; }
+float ccj_last_traceback_ms(const ccj_ctx *ctx) { return ctx ? ctx->tb_ms : 0.f; }
+int ccj_last_fill_launches(const ccj_ctx *ctx) { return ctx ? ctx->fill_launches : 0; }
+
+int ccj_fold_batch(ccj_ctx *ctx, const char *seqs, const int64_t *offsets, int nseq, ccj_result *results,
+                   int32_t *pairs, char *structs) {
+    if (!ctx || !seqs || !offsets || nseq < 1 || !results) return CCJ_ERR_ARG;
+    if (!ctx->model_ok) return fail(ctx, CCJ_ERR_STATE, "no energy model loaded");
+    CU(cudaSetDevice(ctx->device));
+    const size_t budget = budget_bytes(ctx);
+    int s0 = 0;
+    float fill_ms = 0.f, tb_ms = 0.f;
+    int launches = 0;
+    while (s0 < nseq) {
+        // greedy wave: consecutive sequences while they fit
+        size_t bytes = 1024;
+        int s1 = s0;
+        while (s1 < nseq) {
+            const int64_t len = offsets[s1 + 1] - offsets[s1];
+            int rc = validate(ctx, seqs + offsets[s1], len);
+            if (rc) return rc;
+            SeqPlan p;
+            plan_seq((int)len, p);
+            const size_t add = p.in_bytes + p.out_bytes + p.tab_bytes;
+            if (bytes + add > budget) break;
+            bytes += add;
+            ++s1;
+        }
+        if (s1 == s0) return fail(ctx, CCJ_ERR_TOO_LARGE, "a sequence does not fit this GPU's memory");
+        const int64_t base = offsets[s0];
+        std::vector<int64_t> off(s1 - s0 + 1);
+        for (int s = s0; s <= s1; ++s) off[s - s0] = offsets[s] - base;
+        int rc = ccj_batch_prepare(ctx, seqs + base, off.data(), s1 - s0);
+        if (!rc) rc = ccj_batch_fill(ctx);
+        if (!rc) rc = ccj_batch_traceback(ctx);
+        if (!rc) rc = ccj_batch_fetch(ctx, results + s0, pairs ? pairs + base : nullptr, structs ? structs + base : nullptr);
+        if (rc) return rc;
+        fill_ms += ctx->fill_ms;
+        tb_ms += ctx->tb_ms;
+        launches += ctx->fill_launches;
+        s0 = s1;
+    }
+    ctx->fill_ms = fill_ms;
+    ctx->tb_ms = tb_ms;
+    ctx->fill_launches = launches;
+    return 0;
+}
+
+int64_t ccj_table4_len(int n) { return ccj_cells4(n); }
+int64_t ccj_table2_len(int n) { return (int64_t)n * (n + 1) / 2; }
+
+int ccj_export_table4(ccj_ctx *ctx, int seq_index, int table, int16_t *out, int64_t out_len) {
+    if (!ctx || !out || table < 0 || table >= CCJ_NT4) return CCJ_ERR_ARG;
+    if (!ctx->filled || seq_index < 0 || seq_index >= (int)ctx->plan.size())
+        return fail(ctx, CCJ_ERR_STATE, "no filled wave / bad sequence index");
+    const SeqPlan &p = ctx->plan[seq_index];
+    const int n = p.n;
+    const int64_t cells = ccj_cells4(n);
+    if (out_len < cells) return fail(ctx, CCJ_ERR_ARG, "output buffer too small");
+    CU(cudaSetDevice(ctx->device));
+    std::vector<int16_t> raw((size_t)cells);
+    const char *d_tab = ctx->d_arena + ctx->in_total + ctx->out_total + p.tab_off;
+    CU(cudaMemcpy(raw.data(), d_tab + (size_t)table * cells * sizeof(int16_t), (size_t)cells * sizeof(int16_t),
+                  cudaMemcpyDeviceToHost));
+    int64_t x = 0;
+    for (int i = 1; i <= n; ++i)
+        for (int j = i; j <= n; ++j)
+            for (int k = j + 2; k <= n; ++k)
+                for (int l = k; l <= n; ++l) out[x++] = raw[(size_t)ccj_idx4(n, i, j, k, l)];
+    return 0;
+}
+
+int ccj_export_table2(ccj_ctx *ctx, int seq_index, int table, int32_t *out, int64_t out_len) {
+    if (!ctx || !out || table < 0 || table >= CCJ_NT2) return CCJ_ERR_ARG;
+    if (!ctx->filled || seq_index < 0 || seq_index >= (int)ctx->plan.size())
+        return fail(ctx, CCJ_ERR_STATE, "no filled wave / bad sequence index");
+    const SeqPlan &p = ctx->plan[seq_index];
+    const int n = p.n;
+    if (out_len < (int64_t)n * (n + 1) / 2) return fail(ctx, CCJ_ERR_ARG, "output buffer too small");
+    CU(cudaSetDevice(ctx->device));
+    const int64_t s2 = ccj_stride2(n);
+    std::vector<int32_t> raw((size_t)s2);
+    const char *d_tab = ctx->d_arena + ctx->in_total + ctx->out_total + p.tab_off;
+    const size_t t4b = align_up((size_t)ccj_cells4(n) * CCJ_NT4 * sizeof(int16_t) + 16, 256);
+    CU(cudaMemcpy(raw.data(), d_tab + t4b + (size_t)table * s2 * sizeof(int32_t), (size_t)s2 * sizeof(int32_t),
+                  cudaMemcpyDeviceToHost));
+    int64_t x = 0;
+    for (int i = 1; i <= n; ++i)
+        for (int j = i; j <= n; ++j) out[x++] = raw[(size_t)ccj_idx2(n, i, j)];
+    return 0;
+}
+
+static void fnv_add(uint64_t &h, uint64_t v) {
+    h ^= v;
+    h *= 1099511628211ULL;
+}
+
+int ccj_table4_hash(ccj_ctx *ctx, int seq_index, int table, uint64_t *hash, int64_t *finite, int32_t *min_value) {
+    if (!ctx || !hash) return CCJ_ERR_ARG;
+    if (!ctx->filled || seq_index < 0 || seq_index >= (int)ctx->plan.size())
+        return fail(ctx, CCJ_ERR_STATE, "no filled wave / bad sequence index");
+    const int64_t len = ccj_cells4(ctx->plan[seq_index].n);
+    std::vector<int16_t> buf((size_t)len + 1);
+    int rc = ccj_export_table4(ctx, seq_index, table, buf.data(), len);
+    if (rc) return rc;
+    uint64_t h = 1469598103934665603ULL;
+    int64_t fin = 0;
+    int32_t mn = 1 << 30;
+    for (int64_t x = 0; x < len; ++x) {
+        fnv_add(h, (uint16_t)buf[x]);
+        if (buf[x] < 32767) {
+            ++fin;
+            if (buf[x] < mn) mn = buf[x];
+        }
+    }
+    *hash = h;
+    if (finite) *finite = fin;
+    if (min_value) *min_value = fin ? mn : 0;
+    return 0;
+}
+
+int ccj_table2_hash(ccj_ctx *ctx, int seq_index, int table, uint64_t *hash, int64_t *finite, int64_t *sum) {
+    if (!ctx || !hash) return CCJ_ERR_ARG;
+    if (!ctx->filled || seq_index < 0 || seq_index >= (int)ctx->plan.size())
+        return fail(ctx, CCJ_ERR_STATE, "no filled wave / bad sequence index");
+    const int n = ctx->plan[seq_index].n;
+    const int64_t len = (int64_t)n * (n + 1) / 2;
+    std::vector<int32_t> buf((size_t)len + 1);
+    int rc = ccj_export_table2(ctx, seq_index, table, buf.data(), len);
+    if (rc) return rc;
+    uint64_t h = 1469598103934665603ULL;
+    int64_t fin = 0, sm = 0;
+    for (int64_t x = 0; x < len; ++x) {
+        fnv_add(h, (uint32_t)buf[x]);
+        if (buf[x] < CCJ_INF / 2) {
+            ++fin;
+            sm += buf[x];
+        }
+    }
+    *hash = h;
+    if (finite) *finite = fin;
+    if (sum) *sum = sm;
+    return 0;
+}
+
+int64_t ccj_layout_index(int n, int i, int j, int k, int l) {
+    if (n < 1 || i < 1 || l > n || !ccj_valid4(i, j, k, l)) return -1;
+    return ccj_idx4(n, i, j, k, l);
+}
+
+int ccj_model_text(const char *par_file, int dangles, int no_gu, const char *out_path, char *err, size_t err_len) {
+    if (!par_file || !out_path) return CCJ_ERR_ARG;
+    ccj::RawParams *rp = new ccj::RawParams();
+    std::string e;
+    if (!ccj::load_par_file(par_file, *rp, e)) {
+        if (err && err_len) snprintf(err, err_len, "%s", e.c_str());
+        delete rp;
+        return CCJ_ERR_PARAMS;
+    }
+    ccj_model *m = new ccj_model();
+    ccj::build_model(*rp, dangles, no_gu, *m);
+    FILE *f = fopen(out_path, "w");
+    if (!f) {
+        delete rp;
+        delete m;
+        return CCJ_ERR_ARG;
+    }
+#define D2(name, l0, l1) for (int a = 0; a < l0; ++a) for (int b = 0; b < l1; ++b) fprintf(f, #name " %d %d %d\n", a, b, m->name[a][b]);
+#define D3(name, l0, l1, l2) for (int a = 0; a < l0; ++a) for (int b = 0; b < l1; ++b) for (int c = 0; c < l2; ++c) fprintf(f, #name " %d %d %d %d\n", a, b, c, m->name[a][b][c]);
+    D2(stack, 8, 8)
+    for (int a = 0; a < 31; ++a) fprintf(f, "hairpin %d %d\n", a, m->hairpin[a]);
+    for (int a = 0; a < 31; ++a) fprintf(f, "bulge %d %d\n", a, m->bulge[a]);
+    for (int a = 0; a < 31; ++a) fprintf(f, "internal_loop %d %d\n", a, m->internal_loop[a]);
+    D3(mismatchExt, 8, 5, 5) D3(mismatchI, 8, 5, 5) D3(mismatch1nI, 8, 5, 5) D3(mismatch23I, 8, 5, 5)
+    D3(mismatchH, 8, 5, 5) D3(mismatchM, 8, 5, 5) D2(dangle5, 8, 5) D2(dangle3, 8, 5)
+    for (int a = 0; a < 8; ++a) for (int b = 0; b < 8; ++b) for (int c = 0; c < 5; ++c) for (int d = 0; d < 5; ++d)
+        fprintf(f, "int11 %d %d %d %d %d\n", a, b, c, d, m->int11[a][b][c][d]);
+    for (int a = 0; a < 8; ++a) for (int b = 0; b < 8; ++b) for (int c = 0; c < 5; ++c) for (int d = 0; d < 5; ++d)
+        for (int g = 0; g < 5; ++g) fprintf(f, "int21 %d %d %d %d %d %d\n", a, b, c, d, g, m->int21[a][b][c][d][g]);
+    for (int a = 0; a < 8; ++a) for (int b = 0; b < 8; ++b) for (int c = 0; c < 5; ++c) for (int d = 0; d < 5; ++d)
+        for (int g = 0; g < 5; ++g) for (int h = 0; h < 5; ++h)
+            fprintf(f, "int22 %d %d %d %d %d %d %d\n", a, b, c, d, g, h, m->int22[a][b][c][d][g][h]);
+#undef D2
+#undef D3
+    fprintf(f, "ninio 2 %d\n", m->ninio2);
+    fprintf(f, "MLbase %d\n", m->MLbase);
+    for (int a = 0; a < 8; ++a) fprintf(f, "MLintern %d %d\n", a, m->MLintern[a]);
+    fprintf(f, "MLclosing %d\nTerminalAU %d\n", m->MLclosing, m->TerminalAU);
+    for (int a = 0; a < m->n_tetra; ++a) if (m->tetra[a][0]) fprintf(f, "Tetraloop_E %.6s %d\n", m->tetra[a], m->tetra_E[a]);
+    for (int a = 0; a < m->n_tri; ++a) if (m->tri[a][0]) fprintf(f, "Triloop_E %.5s %d\n", m->tri[a], m->tri_E[a]);
+    for (int a = 0; a < m->n_hexa; ++a) if (m->hexa[a][0]) fprintf(f, "Hexaloop_E %.8s %d\n", m->hexa[a], m->hexa_E[a]);
+    fprintf(f, "special_hp %d\ndangles %d\n", m->special_hp, m->dangles);
+    fclose(f);
+    delete rp;
+    delete m;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,161 @@
+// sm_100a kernels: v1 "generic index" version.  Every kernel is a thin scheduling shell around the
+// cell functions of ccj_cells*.cuh / ccj_traceback.cuh (which carry the reference citations).
+#include "ccj_kernels.cuh"
+#include "ccj_traceback.cuh"
+
+namespace ccj {
+
+// warp-cooperative candidate spreading (Par concept of ccj_cells.cuh)
+struct WarpPar {
+    static constexpr int nlanes = 32;
+    __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
+    __device__ __forceinline__ int red(int v) const { return __reduce_min_sync(0xffffffffu, v); }
+    __device__ __forceinline__ void sync() const { __syncwarp(); }
+    __device__ __forceinline__ ccj_best argmin(ccj_best b) const {
+        const int m = __reduce_min_sync(0xffffffffu, b.val);
+        const int o = __reduce_min_sync(0xffffffffu, b.val == m ? b.ord : 0x7fffffff);
+        ccj_best r;
+        r.val = m;
+        r.ord = o;
+        return r;
+    }
+};
+
+__global__ void k_init(const ccj_model *M, const ccj_seq *seqs) {
+    const ccj_seq q = seqs[blockIdx.y];
+    const int64_t s2 = q.stride2;
+    for (int64_t x = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; x < s2; x += (int64_t)gridDim.x * blockDim.x) {
+        q.t2[T2_V * s2 + x] = CCJ_V_UNSET;
+        q.t2[T2_VTYPE * s2 + x] = 'N';
+#pragma unroll
+        for (int t = T2_WM; t < CCJ_NT2; ++t) q.t2[t * s2 + x] = CCJ_INF + 1;
+        if (x <= q.n) {
+            q.W[x] = 0;
+            q.pair_out[x] = -1;
+            q.ftype_out[x] = 'N';
+        }
+        if (x < CCJ_STATUS_INTS) q.status[x] = 0;
+    }
+}
+
+// P(i,l), l=i+s: blockIdx.x -> i, blockIdx.y -> j (first split point), threads -> (d,k)
+__global__ void __launch_bounds__(256) k_P(const ccj_model *M, const ccj_seq *seqs, int s) {
+    ccj_cx c;
+    c.M = M;
+    c.q = seqs[blockIdx.z];
+    const int n = c.q.n;
+    const int i = 1 + blockIdx.x, l = i + s;
+    if (l > n) return;
+    const int j = i + blockIdx.y;
+    if (j >= l) return;
+    const int w = l - j - 1;  // d in [j+1, l-1], k in [d+1, l-1]
+    int mn = CCJ_INF;
+    for (int p = threadIdx.x; p < w * w; p += blockDim.x) {
+        const int d = j + 1 + p / w, k = j + 1 + p % w;
+        if (k > d) mn = ccj_min(mn, ccj_P_term(c, i, l, j, d, k));
+    }
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    __shared__ int sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mn;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int x = 1; x < (int)(blockDim.x >> 5); ++x) mn = ccj_min(mn, sm[x]);
+        // "if (min_energy < INF/2) P.set(i,l) = min_energy", table pre-set to INF+1
+        if (mn < CCJ_INF / 2) atomicMin(&c.q.t2[T2_P * c.q.stride2 + ccj_idx2(n, i, l)], mn);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_2d(const ccj_model *M, const ccj_seq *seqs, int s) {
+    ccj_cx c;
+    c.M = M;
+    c.q = seqs[blockIdx.y];
+    const int i = 1 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int j = i + s;
+    if (j > c.q.n) return;
+    WarpPar par;
+    ccj_cell2d(c, i, j, par);
+}
+
+// level t: blockIdx.y -> a (b=t-a), blockIdx.z -> sequence, blockIdx.x -> (i-tile, k-tile), lanes walk k
+#define K4_TI 4
+__global__ void __launch_bounds__(32 * K4_TI) k_4d(const ccj_model *M, const ccj_seq *seqs, int t, int ktiles) {
+    ccj_cx c;
+    c.M = M;
+    c.q = seqs[blockIdx.z];
+    const int n = c.q.n;
+    const int m = n - t - 2;  // rows i = 1..m, row i has m+1-i cells
+    if (m < 1) return;
+    const int a = blockIdx.y, b = t - a;
+    const int ti = blockIdx.x / ktiles, tk = blockIdx.x % ktiles;
+    const int i = 1 + ti * K4_TI + threadIdx.y;
+    const int kk = tk * 32 + threadIdx.x;
+    if (i > m || kk > m - i) return;
+    const int k = i + a + 2 + kk;
+    ccj_cell4d(c, i, i + a, k, k + b);
+}
+
+__global__ void k_W(const ccj_model *M, const ccj_seq *seqs) {
+    ccj_cx c;
+    c.M = M;
+    c.q = seqs[blockIdx.x];
+    WarpPar par;
+    for (int j = CCJ_TURN + 1; j <= c.q.n; ++j) {
+        const int w = ccj_W_at(c, j, par);
+        if (par.lane() == 0) c.q.W[j] = w;
+        __syncwarp();
+    }
+}
+
+__global__ void k_traceback(const ccj_model *M, const ccj_seq *seqs) {
+    ccj_cx c;
+    c.M = M;
+    c.q = seqs[blockIdx.x];
+    WarpPar par;
+    ccj_traceback(c, par);
+}
+
+// ---------------------------------------------------------------------------------------------
+void launch_init(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cudaStream_t st) {
+    const int64_t s2 = ccj_stride2(d.nmax);
+    int bx = (int)((s2 + 255) / 256);
+    if (bx > 1024) bx = 1024;
+    k_init<<<dim3(bx, d.nseq), 256, 0, st>>>(M, seqs);
+}
+
+void launch_P(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int s, cudaStream_t st) {
+    if (s < 3 || s > d.nmax - 1) return;  // needs i<=j<d<k<l
+    k_P<<<dim3(d.nmax - s, s, d.nseq), 256, 0, st>>>(M, seqs, s);
+}
+
+void launch_2d(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int s, cudaStream_t st) {
+    const int rows = d.nmax - s;
+    if (rows < 1) return;
+    k_2d<<<dim3((rows + 3) / 4, d.nseq), 128, 0, st>>>(M, seqs, s);
+}
+
+void launch_4d(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st) {
+    const int m = d.nmax - t - 2;
+    if (m < 1) return;
+    const int itiles = (m + K4_TI - 1) / K4_TI, ktiles = (m + 31) / 32;
+    k_4d<<<dim3(itiles * ktiles, t + 1, d.nseq), dim3(32, K4_TI), 0, st>>>(M, seqs, t, ktiles);
+}
+
+void launch_W(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cudaStream_t st) {
+    k_W<<<d.nseq, 32, 0, st>>>(M, seqs);
+}
+
+void launch_traceback(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cudaStream_t st) {
+    k_traceback<<<d.nseq, 32, 0, st>>>(M, seqs);
+}
+
+int fill_launch_count(int nmax) {
+    int c = 2;  // init + W
+    for (int s = 0; s < nmax; ++s) {
+        if (s >= 3 && s <= nmax - 1) ++c;
+        ++c;
+        if (nmax - s - 2 >= 1) ++c;
+    }
+    return c;
+}
+
+}  // namespace ccj

@@ -1,0 +1,31 @@
+// sm_100a kernels of the CCJ fill + traceback (declarations of the host-side launchers).
+// One DP "level" t = (j-i)+(l-k) of the 4D tables is one launch; see DESIGN.md for the schedule.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "ccj_types.h"
+
+namespace ccj {
+
+struct LaunchDims {
+    int nseq;   // sequences in the wave (blockIdx.z / .y)
+    int nmax;   // longest sequence of the wave
+};
+
+// sets the 2D tables to their "unset" values, W=0, pair=-1, status=0
+void launch_init(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cudaStream_t st);
+// P(i,i+s) for all i, all sequences (src/pseudo_loop.cc:166-179)
+void launch_P(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int s, cudaStream_t st);
+// V, WBP, WPP, WB, WP, WMv, WMp, WM at span s
+void launch_2d(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int s, cudaStream_t st);
+// all 22 gap tables of level t
+void launch_4d(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st);
+// exterior W (src/W_final.cc:68-77)
+void launch_W(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cudaStream_t st);
+// traceback, one warp per sequence
+void launch_traceback(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cudaStream_t st);
+
+// number of kernel launches the fill of a wave with longest sequence nmax issues (for gpu_launches)
+int fill_launch_count(int nmax);
+
+}  // namespace ccj

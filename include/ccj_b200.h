@@ -1,0 +1,110 @@
+/* ccj_b200 -- C ABI of the B200-native CCJ MFE fill + traceback.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ or torch types.  The reference
+ * (mateog4712/CCJ) has no FFI; its "interface" for this path is the C++ class surface of
+ * src/W_final.hh:18-71 (W_final(seq,dangle), double ccj(), std::string structure, params_),
+ * src/pseudo_loop.hh:13-56 and src/s_energy_matrix.hh:16-68, driven by src/CCJ.cc:44-49,58-115.
+ * Each entry point below names the reference code it replaces.  The C++ shells in
+ * ccj_b200/csrc/{W_final,pseudo_loop,s_energy_matrix}.hh and the CCJ command line are written on
+ * top of exactly these functions.
+ *
+ * Error convention: every function returns 0 on success, a negative ccj_error on failure (message
+ * via ccj_last_error).  Nothing here calls exit(); the reference's exit()/message behaviour of a
+ * fold is reported per sequence in ccj_result and re-created by the caller (ccj_render.hpp).
+ * There is no CPU fallback: without a CUDA device ccj_ctx_create fails.
+ */
+#ifndef CCJ_B200_H
+#define CCJ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ccj_ctx ccj_ctx;
+
+enum ccj_error {
+    CCJ_ERR_CUDA = -1,      /* CUDA runtime failure (no device, out of memory, launch error) */
+    CCJ_ERR_ARG = -2,       /* bad argument */
+    CCJ_ERR_PARAMS = -3,    /* parameter file unreadable / malformed; reference: "Not a valid parameter file!" */
+    CCJ_ERR_SEQUENCE = -4,  /* character outside GCAUT (src/CCJ.cc:23-36) or empty sequence */
+    CCJ_ERR_TOO_LARGE = -5, /* a single sequence does not fit this GPU's memory */
+    CCJ_ERR_STATE = -6      /* call order (no model loaded, no batch prepared, ...) */
+};
+
+/* Per-sequence outcome.  status: 0 = the reference would print "SEQ\nSTRUCT (E)" and return 0;
+ * 1 = the reference would print `msg_id`'s message on stderr and exit(1); 2 = "NOT GOOD RESTR INTER"
+ * and exit(0).  n_should_not_be_here = number of "Should not be here!" lines the reference prints
+ * on stdout before anything else (src/W_final.cc:714-715). */
+typedef struct ccj_result {
+    int32_t energy_dcal; /* W[n]; energy = energy_dcal / 100.0 (src/W_final.cc:79) */
+    int32_t status;
+    int32_t n_should_not_be_here;
+    int32_t msg_id;      /* prefix*256 + node type character, see ccj_render.hpp */
+    int32_t aux_i, aux_j;
+} ccj_result;
+
+/* One context = one GPU, one stream, one energy model.  Replaces the process-global state of the
+ * reference (ViennaRNA parameter globals, noGU, pair[][], PK penalty globals). */
+int ccj_ctx_create(int device, ccj_ctx **out);
+void ccj_ctx_destroy(ccj_ctx *ctx);
+const char *ccj_last_error(const ccj_ctx *ctx);
+
+/* vrna_params_load(file) + scale_parameters() + model_details.dangles = dangles + make_pair_matrix()
+ * (src/CCJ.cc:80-99, src/W_final.cc:20-25).  noGU as src/CCJ.cc:77. */
+int ccj_model_load(ccj_ctx *ctx, const char *par_file, int dangles, int no_gu);
+
+/* W_final::W_final + W_final::ccj for `nseq` independent sequences (src/CCJ.cc:44-49).
+ *   seqs     : concatenated upper-case sequences over GCAU(T), no separators
+ *   offsets  : nseq+1 offsets into seqs (sequence s is seqs[offsets[s] .. offsets[s+1]))
+ *   results  : nseq entries
+ *   pairs    : optional (may be NULL), same offsets: 1-based partner of each nucleotide, -1 = unpaired
+ *              (minimum_fold::pair, src/h_struct.hh:9-18)
+ *   structs  : optional (may be NULL), same offsets: dot-bracket characters (W_final::structure)
+ * Sequences are processed in waves sized to the GPU's free memory. */
+int ccj_fold_batch(ccj_ctx *ctx, const char *seqs, const int64_t *offsets, int nseq, ccj_result *results,
+                   int32_t *pairs, char *structs);
+
+/* The same work split for measurement: prepare (H2D + table allocation, one wave only), fill
+ * (W_final::ccj's loops, src/W_final.cc:60-77), traceback (:84-103), fetch (D2H). */
+int ccj_batch_prepare(ccj_ctx *ctx, const char *seqs, const int64_t *offsets, int nseq);
+int ccj_batch_fill(ccj_ctx *ctx);
+int ccj_batch_traceback(ccj_ctx *ctx);
+int ccj_batch_fetch(ccj_ctx *ctx, ccj_result *results, int32_t *pairs, char *structs);
+/* device time of the last ccj_batch_fill / ccj_batch_traceback (CUDA events on the context's stream) */
+float ccj_last_fill_ms(const ccj_ctx *ctx);
+float ccj_last_traceback_ms(const ccj_ctx *ctx);
+/* kernels launched by the last ccj_batch_fill */
+int ccj_last_fill_launches(const ccj_ctx *ctx);
+/* how many sequences of length n fit one wave on this context's GPU right now */
+int64_t ccj_wave_capacity(ccj_ctx *ctx, int n);
+/* the CUDA stream the context launches on (cudaStream_t), for callers that time with their own events */
+void *ccj_stream(ccj_ctx *ctx);
+
+/* Table access for parity tests (Matrix4D::get / TriangleMatrix raw values of the prepared wave).
+ * Export order: 4D: i=1..n, j=i..n, k=j+2..n, l=k..n (C(n+1,4) int16); 2D: i=1..n, j=i..n (int32).
+ * table ids: enum ccj_table4 / ccj_table2 in ccj_b200/csrc/ccj_types.h (same order as oracle/ref_dump.cc). */
+int ccj_export_table4(ccj_ctx *ctx, int seq_index, int table, int16_t *out, int64_t out_len);
+int ccj_export_table2(ccj_ctx *ctx, int seq_index, int table, int32_t *out, int64_t out_len);
+int64_t ccj_table4_len(int n);
+int64_t ccj_table2_len(int n);
+/* FNV-1a 64 over the exported values (uint16 / uint32 each), the hash oracle/ref_dump.cc prints */
+int ccj_table4_hash(ccj_ctx *ctx, int seq_index, int table, uint64_t *hash, int64_t *finite, int32_t *min_value);
+int ccj_table2_hash(ccj_ctx *ctx, int seq_index, int table, uint64_t *hash, int64_t *finite, int64_t *sum);
+
+/* Host-only helpers (no GPU needed), used by the CPU test-suite:
+ * ccj_model_text writes the scaled model in the "name idx... value" text form of
+ * `oracle/_ref/ccj_ref_dump params` to `out_path`; ccj_layout_index is the storage offset of cell
+ * (i,j,k,l) inside one 4D table (-1 for an invalid index). */
+int ccj_model_text(const char *par_file, int dangles, int no_gu, const char *out_path, char *err, size_t err_len);
+int64_t ccj_layout_index(int n, int i, int j, int k, int l);
+
+/* library / build identification */
+const char *ccj_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CCJ_B200_H */

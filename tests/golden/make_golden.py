@@ -1,0 +1,123 @@
+"""Generates the golden fixtures of tests/golden/ by running the UNMODIFIED reference built by
+oracle/Makefile (oracle/_ref/CCJ, oracle/_ref/ccj_ref_dump).  Run in the build container only:
+
+    python tests/golden/make_golden.py folds      # (rc, stdout, stderr) per sequence  -> folds.json
+    python tests/golden/make_golden.py hashes     # per-table FNV hashes               -> table_hashes.json
+    python tests/golden/make_golden.py long       # n=100/150/200 benchmark inputs     -> folds_long.json
+    python tests/golden/make_golden.py params     # scaled vrna_param_t dump           -> params_*.txt.gz
+
+Sequence generators are the ones BASELINE.json / SURVEY.md 8d name for each config.
+"""
+import gzip
+import json
+import random
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parent.parent
+REF = ROOT / "oracle" / "_ref" / "CCJ"
+DUMP = ROOT / "oracle" / "_ref" / "ccj_ref_dump"
+PARAMS = ROOT / "params"
+
+H60 = "AAUAGGCGCAGCAUACACGGUCGAGCUGCGCCAAUAACAAUACGACCGUGAUAAAUAAAA"
+K60 = "AUAGGACGCAAGGCUCGAAGCGUCCAAUAAUCCGUGCAACGAGCCAAGCACGGAUAAAAA"
+
+
+def designed(n):
+    unit = H60 + "AAUAAUAAUA" + K60 + "AAUAAUAAUA"
+    return (unit * (n // len(unit) + 1))[:n]
+
+
+def rand_seq(seed, n):
+    rng = random.Random(seed)
+    return "".join(rng.choice("ACGU") for _ in range(n))
+
+
+def seed200():
+    random.seed(200)
+    return "".join(random.choice("ACGU") for _ in range(200))
+
+
+def run_ref(seq, par="rna_Turner04.par", dangles=2, extra=()):
+    p = subprocess.run([str(REF), "-P", str(PARAMS / par), "-d", str(dangles), *extra, seq],
+                       capture_output=True, text=True, cwd=str(ROOT))
+    return {"seq": seq, "par": par, "dangles": dangles, "extra": list(extra), "rc": p.returncode,
+            "stdout": p.stdout, "stderr": p.stderr}
+
+
+def run_hash(seq, par="rna_Turner04.par", dangles=2):
+    p = subprocess.run([str(DUMP), "hash", str(PARAMS / par), str(dangles), seq], capture_output=True, text=True,
+                       cwd=str(ROOT))
+    assert p.returncode == 0, p.stderr
+    tabs = {}
+    for line in p.stdout.splitlines()[1:]:
+        name, cnt, agg, h = line.split()
+        tabs[name] = [int(cnt), int(agg), h]
+    return {"seq": seq, "par": par, "dangles": dangles, "tables": tabs}
+
+
+def fold_jobs():
+    jobs = []
+    fixed = ["GCAACGAUGACAUACAUCGCUAGUCGACGC", H60, K60, "UUAGUUGUGCCGCAGCGAAGUAGUGCUUGAAAUAUGCGAC",
+             "CCCUAAGUAGGAGCGUAUGCGCCCAGUAACCAAUGCCUGUUGAGAUGCCAGACGCGUAAC", "UAACGGUAGUACUAUCCAGCUCACGAGC",
+             "ACGU", "A", "AC", "ACG", "GGGGAAAACCCC", "GGGAAACCC",
+             "CAAAACAUAGAAACCAUCAAUAGACAGGUCAUAAUCGGUCCACCGGAUCAUUGGUGCAUAGAGCCUGGGCGUUAACGCCC"]
+    for s in fixed:
+        jobs.append((s, "rna_Turner04.par", 2, ()))
+    for s in fixed[:6]:
+        jobs.append((s, "rna_DirksPierce09.par", 2, ()))
+        jobs.append((s, "rna_Turner04.par", 1, ()))
+        jobs.append((s, "rna_Turner04.par", 0, ()))
+        jobs.append((s, "rna_Turner04.par", 2, ("--noGU",)))
+    for seed in range(240):
+        rng = random.Random(7000 + seed)
+        n = rng.randint(1, 56)
+        par = rng.choice(["rna_Turner04.par"] * 5 + ["rna_DirksPierce09.par"])
+        d = rng.choice([2, 2, 2, 2, 1, 0])
+        jobs.append((rand_seq(90000 + seed, n), par, d, ()))
+    return jobs
+
+
+def main():
+    what = sys.argv[1]
+    if what == "folds":
+        with ThreadPoolExecutor(8) as ex:
+            out = list(ex.map(lambda j: run_ref(j[0], j[1], j[2], j[3]), fold_jobs()))
+        (HERE / "folds.json").write_text(json.dumps(out, indent=0))
+        print(len(out), "folds;", sum(r["rc"] != 0 for r in out), "with rc!=0;",
+              sum("Should not" in r["stdout"] for r in out), "with 'Should not be here!'")
+    elif what == "hashes":
+        seqs = [("GCAACGAUGACAUACAUCGCUAGUCGACGC", "rna_Turner04.par", 2), (H60, "rna_Turner04.par", 2),
+                (K60, "rna_Turner04.par", 2), (H60, "rna_DirksPierce09.par", 2), (K60, "rna_Turner04.par", 1),
+                (K60, "rna_Turner04.par", 0)]
+        seqs += [(rand_seq(500 + x, 20 + 3 * x), "rna_Turner04.par", 2) for x in range(12)]
+        seqs += [(rand_seq(1000, 100)[:80], "rna_Turner04.par", 2)]
+        with ThreadPoolExecutor(8) as ex:
+            out = list(ex.map(lambda j: run_hash(*j), seqs))
+        (HERE / "table_hashes.json").write_text(json.dumps(out, indent=0))
+        print(len(out), "hash sets")
+    elif what == "long":
+        jobs = [(rand_seq(1000 + x, 100), "rna_Turner04.par", 2, ()) for x in range(14)]
+        jobs += [(designed(100), "rna_Turner04.par", 2, ())]
+        jobs += [(rand_seq(20000 + x, 150), "rna_Turner04.par", 2, ()) for x in range(4)]
+        jobs += [(designed(150), "rna_Turner04.par", 2, ())]
+        jobs += [(seed200(), "rna_Turner04.par", 2, ()), (designed(200), "rna_Turner04.par", 2, ())]
+        jobs = jobs[::-1]  # longest first
+        with ThreadPoolExecutor(8) as ex:
+            out = list(ex.map(lambda j: run_ref(j[0], j[1], j[2], j[3]), jobs))
+        (HERE / "folds_long.json").write_text(json.dumps(out[::-1], indent=0))
+        print(len(out), "long folds")
+    elif what == "params":
+        for par in ["rna_Turner04.par", "rna_DirksPierce09.par"]:
+            p = subprocess.run([str(DUMP), "params", str(PARAMS / par), "2"], capture_output=True, text=True)
+            assert p.returncode == 0
+            with gzip.open(HERE / f"params_{par[:-4]}.txt.gz", "wt") as f:
+                f.write(p.stdout)
+        print("params dumped")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,55 @@
+"""CPU: the product's cell functions (ccj_cells*.cuh, ccj_traceback.cuh -- the same code the CUDA
+kernels call) compiled for the host and swept in the kernels' wavefront order, checked against the
+golden vectors the reference produced (tests/golden/*.json).  Sized to stay within a few minutes."""
+import subprocess
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def emu(emu_bin, mode, rec):
+    args = [str(emu_bin), mode, str(ROOT / "params" / rec["par"]), str(rec["dangles"]), rec["seq"]]
+    if "--noGU" in rec.get("extra", []):
+        args.append("1")
+    return subprocess.run(args, capture_output=True, text=True)
+
+
+def test_golden_folds_small(emu_bin, golden_folds):
+    recs = [r for r in golden_folds if len(r["seq"]) <= 36]
+    assert len(recs) > 100
+    n_err = 0
+    for r in recs:
+        p = emu(emu_bin, "fold", r)
+        assert (p.returncode, p.stdout, p.stderr) == (r["rc"], r["stdout"], r["stderr"]), r["seq"]
+        n_err += r["rc"] != 0
+    assert n_err >= 1  # the corpus exercises the reference's exit(1) path
+
+
+def test_golden_table_hashes_small(emu_bin, golden_hashes):
+    recs = [r for r in golden_hashes if len(r["seq"]) <= 41]
+    assert len(recs) >= 6
+    for r in recs:
+        p = emu(emu_bin, "hash", r)
+        assert p.returncode == 0
+        got = {}
+        for line in p.stdout.splitlines()[1:]:
+            name, cnt, agg, h = line.split()
+            got[name] = [int(cnt), int(agg), h]
+        assert got == r["tables"], r["seq"]
+
+
+def test_emu_matches_reference_binary_when_present(emu_bin):
+    """Extra randomised check, only where oracle/_ref was built (the build container)."""
+    import random
+    ref = ROOT / "oracle" / "_ref" / "CCJ"
+    if not ref.exists():
+        pytest.skip("oracle/_ref not built")
+    for seed in range(12):
+        rng = random.Random(4242 + seed)
+        seq = "".join(rng.choice("ACGU") for _ in range(rng.randint(8, 34)))
+        par = str(ROOT / "params" / "rna_Turner04.par")
+        a = subprocess.run([str(ref), "-P", par, seq], capture_output=True, text=True)
+        b = subprocess.run([str(emu_bin), "fold", par, "2", seq], capture_output=True, text=True)
+        assert (a.returncode, a.stdout, a.stderr) == (b.returncode, b.stdout, b.stderr), seq

@@ -1,0 +1,131 @@
+"""GPU: the CUDA path through the C ABI against (1) the committed golden vectors of the reference,
+(2) the reference binary itself where oracle/_ref travelled to the box, (3) size-independent
+properties at the benchmark sizes.  Bar: bit-exact (integer dcal/mol, dot-bracket, exit behaviour)."""
+import random
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import ccj_b200
+
+ROOT = Path(__file__).resolve().parent.parent
+REF = ROOT / "oracle" / "_ref" / "CCJ"
+DUMP = ROOT / "oracle" / "_ref" / "ccj_ref_dump"
+pytestmark = pytest.mark.gpu
+
+
+def group(recs):
+    g = {}
+    for r in recs:
+        g.setdefault((r["par"], r["dangles"], "--noGU" in r.get("extra", [])), []).append(r)
+    return g
+
+
+def check(folds, recs):
+    for f, r in zip(folds, recs):
+        assert (f.returncode, f.stdout, f.stderr) == (r["rc"], r["stdout"], r["stderr"]), r["seq"]
+
+
+def test_golden_folds(ctx_factory, golden_folds):
+    """277 sequences (1..80 nt; Turner04/DP09; d0/d1/d2; noGU) incl. the reference's exit(1) cases."""
+    for (par, d, nogu), recs in group(golden_folds).items():
+        ctx = ctx_factory(par, d, nogu)
+        check(ctx.fold_batch([r["seq"] for r in recs]), recs)
+
+
+def test_golden_table_hashes(ctx_factory, golden_hashes):
+    """All 22 gap tables + V/WM/WMv/WMp/P/WBP/WPP, FNV-1a hashes of the reference's tables."""
+    for r in golden_hashes:
+        ctx = ctx_factory(r["par"], r["dangles"], False)
+        ctx.prepare([r["seq"]])
+        ctx.fill()
+        for name, want in r["tables"].items():
+            got = ctx.table4_hash(0, name) if name in ccj_b200.TABLE4 else ctx.table2_hash(0, name)
+            assert got == want, (r["seq"], name)
+
+
+def test_golden_long(ctx_factory, golden_long):
+    """BASELINE configs: 100-nt random (config 2 seeds), 150-nt (config 4 seeds), 200-nt (config 3)."""
+    if not golden_long:
+        pytest.skip("folds_long.json not generated")
+    ctx = ctx_factory()
+    check(ctx.fold_batch([r["seq"] for r in golden_long]), golden_long)
+    assert any("Should not be here!" in r["stdout"] for r in golden_long)
+
+
+def test_against_reference_binary_on_the_box(ctx_factory):
+    if not REF.exists():
+        pytest.skip("oracle/_ref did not travel")
+    rng = random.Random(31337)
+    seqs = ["".join(rng.choice("ACGU") for _ in range(rng.randint(1, 62))) for _ in range(40)]
+    ctx = ctx_factory()
+    folds = ctx.fold_batch(seqs)
+    par = str(ROOT / "params" / "rna_Turner04.par")
+    for s, f in zip(seqs, folds):
+        p = subprocess.run([str(REF), "-P", par, s], capture_output=True, text=True)
+        assert (p.returncode, p.stdout, p.stderr) == (f.returncode, f.stdout, f.stderr), s
+
+
+def test_full_tables_against_reference_dump(ctx_factory, tmp_path):
+    """Every int16 of every table, not only hashes (n=48 random)."""
+    if not DUMP.exists():
+        pytest.skip("oracle/_ref did not travel")
+    rng = random.Random(99)
+    seq = "".join(rng.choice("ACGU") for _ in range(48))
+    out = tmp_path / "t.bin"
+    subprocess.run([str(DUMP), "bin", str(ROOT / "params" / "rna_Turner04.par"), "2", seq, str(out)], check=True)
+    raw = out.read_bytes()
+    hdr = np.frombuffer(raw[:16], dtype=np.int32)
+    n = int(hdr[1])
+    assert n == 48
+    cells = ccj_b200.cells(n)
+    t4 = np.frombuffer(raw[16:16 + 22 * cells * 2], dtype=np.int16).reshape(22, cells)
+    t2 = np.frombuffer(raw[16 + 22 * cells * 2:], dtype=np.int32).reshape(8, n * (n + 1) // 2)
+    ctx = ctx_factory()
+    ctx.prepare([seq])
+    ctx.fill()
+    for t, name in enumerate(ccj_b200.TABLE4):
+        np.testing.assert_array_equal(ctx.table4(0, name), t4[t], err_msg=name)
+    for t, name in enumerate(ccj_b200.TABLE2[:8]):
+        np.testing.assert_array_equal(ctx.table2(0, name), t2[t], err_msg=name)
+
+
+def test_batch_invariance_and_ragged_batches(ctx_factory):
+    """A fold must not depend on its neighbours in the batch, their lengths, or the wave split."""
+    rng = random.Random(5)
+    seqs = ["".join(rng.choice("ACGU") for _ in range(n)) for n in [1, 2, 3, 4, 5, 9, 33, 17, 60, 41, 7, 52, 28]]
+    ctx = ctx_factory()
+    together = ctx.fold_batch(seqs)
+    alone = [ctx.fold(s) for s in seqs]
+    assert together == alone
+    assert ctx.fold_batch(seqs[::-1]) == together[::-1]
+
+
+def test_edge_inputs(ctx_factory):
+    ctx = ctx_factory()
+    assert ctx.fold("A").stdout == "A\n. (0)\n"
+    assert ctx.fold("ACGU").stdout == "ACGU\n.... (0)\n"
+    assert ctx.fold_batch([]) == []
+    with pytest.raises(ccj_b200.CCJError):
+        ctx.fold("ACGN")
+    with pytest.raises(ccj_b200.CCJError):
+        ctx.fold("")
+
+
+def test_structure_is_consistent_with_pairs_at_benchmark_size(ctx_factory):
+    """Size-independent properties at n=100: balanced brackets per family, energy <= 0, identical reruns."""
+    rng = random.Random(1000)
+    seq = "".join(rng.choice("ACGU") for _ in range(100))
+    ctx = ctx_factory()
+    a, b = ctx.fold(seq), ctx.fold(seq)
+    assert a == b
+    assert a.energy_dcal <= 0
+    if a.status == 0:
+        for o, c in ("()", "[]", "{}", "<>"):
+            depth = 0
+            for ch in a.structure:
+                depth += (ch == o) - (ch == c)
+                assert depth >= 0
+            assert depth == 0
