@@ -91,6 +91,8 @@ def load_library(path: Optional[os.PathLike] = None) -> C.CDLL:
     lib.ccj_table4_len.restype = C.c_int64
     lib.ccj_table2_len.argtypes = [i32]
     lib.ccj_table2_len.restype = C.c_int64
+    lib.ccj_batch_fill_profiled.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.ccj_count_terms.argtypes = [C.c_char_p, i32, i32, i64p]
     u64p = C.POINTER(C.c_uint64)
     lib.ccj_table4_hash.argtypes = [vp, i32, i32, u64p, i64p, C.POINTER(C.c_int32)]
     lib.ccj_table2_hash.argtypes = [vp, i32, i32, u64p, i64p, i64p]
@@ -245,6 +247,13 @@ class Context:
         self._check(self._lib.ccj_batch_fill(self._h))
         return float(self._lib.ccj_last_fill_ms(self._h))
 
+    def fill_profiled(self):
+        """Fill launched kernel by kernel; returns summed device ms of (K_4D, K_P, K_2D, other)."""
+        ms = (C.c_float * 4)()
+        self._check(self._lib.ccj_batch_fill_profiled(self._h, ms))
+        return {"k4d_ms": ms[0], "kP_ms": ms[1], "k2d_ms": ms[2], "other_ms": ms[3],
+                "total_ms": float(self._lib.ccj_last_fill_ms(self._h))}
+
     def traceback(self) -> float:
         self._check(self._lib.ccj_batch_traceback(self._h))
         return float(self._lib.ccj_last_traceback_ms(self._h))
@@ -309,6 +318,20 @@ def model_text(par_file: str, dangles: int = 2, no_gu: bool = False) -> str:
         if rc != 0:
             raise CCJError(rc, err.value.decode())
         return f.read()
+
+
+def count_terms(seq: str, no_gu: bool = False) -> dict:
+    """Algorithmic work of one fold: cells, split terms, P terms, evaluated window terms,
+    and the derived algorithmic bytes: 2*(split + 2*P + iloop) + 44*cells."""
+    out = (C.c_int64 * 4)()
+    rc = load_library().ccj_count_terms(seq.encode(), len(seq), int(no_gu), out)
+    if rc != 0:
+        raise CCJError(rc, "ccj_count_terms")
+    d = {"cells": out[0], "split": out[1], "pterms": out[2], "iloop": out[3]}
+    d["bytes_4d"] = 2 * (d["split"] + d["iloop"]) + 44 * d["cells"]
+    d["bytes_P"] = 2 * 2 * d["pterms"]
+    d["bytes"] = d["bytes_4d"] + d["bytes_P"]
+    return d
 
 
 def layout_index(n: int, i: int, j: int, k: int, l: int) -> int:

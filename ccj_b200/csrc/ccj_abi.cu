@@ -24,6 +24,31 @@ struct SeqPlan {
     size_t in_bytes, out_bytes, tab_bytes;
 };
 
+// the per-sequence device buffers behind ccj_seq, in arena order
+enum { TAB_T4 = 0, TAB_T2, TAB_W3, TAB_ESTP, TAB_INLIST, TAB_OUTLIST, TAB_INCNT, TAB_OUTCNT, TAB_FTYPE, TAB_TBSTACK,
+       TAB_COUNT };
+size_t tab_bytes(int n, int which) {
+    const size_t tri = (size_t)n * (n - 1) / 2 + 1;
+    switch (which) {
+        case TAB_T4: return align_up((size_t)ccj_cells4(n) * CCJ_NT4_STORE * sizeof(int16_t) + 16, 256);
+        case TAB_T2: return align_up((size_t)ccj_stride2(n) * CCJ_NT2 * sizeof(int32_t), 256);
+        case TAB_W3: return align_up((size_t)ccj_stride2(n) * 4 * sizeof(int32_t), 256);
+        case TAB_ESTP: return align_up((size_t)ccj_stride2(n) * sizeof(int32_t), 256);
+        case TAB_INLIST:
+        case TAB_OUTLIST: return align_up(tri * CCJ_WIN * sizeof(uint32_t), 256);
+        case TAB_INCNT:
+        case TAB_OUTCNT: return align_up(tri * sizeof(int32_t), 256);
+        case TAB_FTYPE: return align_up((size_t)n + 2, 256);
+        case TAB_TBSTACK: return align_up(sizeof(int32_t) * 5 * (size_t)(16 * n + 64), 256);
+    }
+    return 0;
+}
+size_t tab_offset(int n, int which) {
+    size_t o = 0;
+    for (int x = 0; x < which; ++x) o += tab_bytes(n, x);
+    return o;
+}
+
 // per-sequence byte needs
 void plan_seq(int n, SeqPlan &p) {
     p.n = n;
@@ -32,11 +57,8 @@ void plan_seq(int n, SeqPlan &p) {
     // outputs: status | W[0..n] | pair[0..n+1]
     p.out_bytes = align_up(sizeof(int32_t) * (CCJ_STATUS_INTS + (size_t)(n + 1) + (size_t)(n + 2)), 16);
     // tables: t4, t2, ftype, traceback stack
-    size_t t4 = align_up((size_t)ccj_cells4(n) * CCJ_NT4 * sizeof(int16_t) + 16, 256);
-    size_t t2 = align_up((size_t)ccj_stride2(n) * CCJ_NT2 * sizeof(int32_t), 256);
-    size_t ft = align_up((size_t)n + 2, 16);
-    size_t tb = align_up(sizeof(int32_t) * 5 * (size_t)(16 * n + 64), 256);
-    p.tab_bytes = t4 + t2 + ft + tb;
+    p.tab_bytes = 0;
+    for (int x = 0; x < TAB_COUNT; ++x) p.tab_bytes += tab_bytes(n, x);
 }
 
 }  // namespace
@@ -146,12 +168,20 @@ int validate(ccj_ctx *ctx, const char *s, int64_t len) {
 }
 
 // the fill's launch sequence: per span s  K_P(s) -> K_2D(s) -> K_4D(level s)   (DESIGN.md "schedule")
+bool use_tuned(int nmax) {
+    const char *g = getenv("CCJ_FILL_GENERIC");  // debugging aid: force the generic-index level kernel
+    return !(g && g[0] == '1') && ccj::fill4_tuned_supported(nmax);
+}
+
 void enqueue_fill(ccj_ctx *ctx, ccj::LaunchDims d) {
+    const bool tuned = use_tuned(d.nmax);
     ccj::launch_init(ctx->d_model, ctx->d_seqs, d, ctx->stream);
+    if (tuned) ccj::launch_prep(ctx->d_model, ctx->d_seqs, d, ctx->stream);
     for (int s = 0; s < d.nmax; ++s) {
         ccj::launch_P(ctx->d_model, ctx->d_seqs, d, s, ctx->stream);
         ccj::launch_2d(ctx->d_model, ctx->d_seqs, d, s, ctx->stream);
-        ccj::launch_4d(ctx->d_model, ctx->d_seqs, d, s, ctx->stream);
+        if (tuned) ccj::launch_4d_tuned(ctx->d_model, ctx->d_seqs, d, s, ctx->stream);
+        else ccj::launch_4d(ctx->d_model, ctx->d_seqs, d, s, ctx->stream);
     }
     ccj::launch_W(ctx->d_model, ctx->d_seqs, d, ctx->stream);
 }
@@ -285,15 +315,18 @@ int ccj_batch_prepare(ccj_ctx *ctx, const char *seqs, const int64_t *offsets, in
         q.W = q.status + CCJ_STATUS_INTS;
         q.pair_out = q.W + (n + 1);
         char *t = d_tab + p.tab_off;
-        q.t4 = reinterpret_cast<int16_t *>(t);
+        q.t4 = reinterpret_cast<int16_t *>(t + tab_offset(n, TAB_T4));
         q.stride4 = ccj_cells4(n);
-        t += align_up((size_t)ccj_cells4(n) * CCJ_NT4 * sizeof(int16_t) + 16, 256);
-        q.t2 = reinterpret_cast<int32_t *>(t);
+        q.t2 = reinterpret_cast<int32_t *>(t + tab_offset(n, TAB_T2));
         q.stride2 = ccj_stride2(n);
-        t += align_up((size_t)ccj_stride2(n) * CCJ_NT2 * sizeof(int32_t), 256);
-        q.ftype_out = reinterpret_cast<int8_t *>(t);
-        t += align_up((size_t)n + 2, 16);
-        q.tb_stack = reinterpret_cast<int32_t *>(t);
+        q.w3 = reinterpret_cast<int32_t *>(t + tab_offset(n, TAB_W3));
+        q.estP = reinterpret_cast<int32_t *>(t + tab_offset(n, TAB_ESTP));
+        q.inlist = reinterpret_cast<uint32_t *>(t + tab_offset(n, TAB_INLIST));
+        q.outlist = reinterpret_cast<uint32_t *>(t + tab_offset(n, TAB_OUTLIST));
+        q.incnt = reinterpret_cast<int32_t *>(t + tab_offset(n, TAB_INCNT));
+        q.outcnt = reinterpret_cast<int32_t *>(t + tab_offset(n, TAB_OUTCNT));
+        q.ftype_out = reinterpret_cast<int8_t *>(t + tab_offset(n, TAB_FTYPE));
+        q.tb_stack = reinterpret_cast<int32_t *>(t + tab_offset(n, TAB_TBSTACK));
         q.tb_cap = 16 * n + 64;
     }
     CU(cudaMemcpyAsync(d_in, ctx->h_stage, in_total, cudaMemcpyHostToDevice, ctx->stream));
@@ -335,6 +368,50 @@ int ccj_batch_fill(ccj_ctx *ctx) {
     CU(cudaGetLastError());
     CU(cudaEventElapsedTime(&ctx->fill_ms, ctx->ev0, ctx->ev1));
     ctx->fill_launches = ccj::fill_launch_count(d.nmax);
+    ctx->filled = true;
+    ctx->traced = false;
+    return 0;
+}
+
+int ccj_batch_fill_profiled(ccj_ctx *ctx, float *kernel_ms) {
+    if (!ctx || !kernel_ms) return CCJ_ERR_ARG;
+    if (!ctx->prepared) return fail(ctx, CCJ_ERR_STATE, "ccj_batch_prepare was not called");
+    CU(cudaSetDevice(ctx->device));
+    ccj::LaunchDims d;
+    d.nseq = (int)ctx->plan.size();
+    d.nmax = ctx->nmax;
+    const int nlaunch = ccj::fill_launch_count(d.nmax) + 1;
+    std::vector<cudaEvent_t> ev((size_t)nlaunch + 1);
+    std::vector<int> kind;
+    for (auto &e : ev) CU(cudaEventCreate(&e));
+    size_t x = 0;
+    cudaStream_t st = ctx->stream;
+    CU(cudaEventRecord(ev[x++], st));
+    auto mark = [&](int k) { cudaEventRecord(ev[x++], st); kind.push_back(k); };
+    const bool tuned = use_tuned(d.nmax);
+    ccj::launch_init(ctx->d_model, ctx->d_seqs, d, st); mark(3);
+    if (tuned) { ccj::launch_prep(ctx->d_model, ctx->d_seqs, d, st); mark(3); }
+    for (int s = 0; s < d.nmax; ++s) {
+        if (s >= 3 && s <= d.nmax - 1) { ccj::launch_P(ctx->d_model, ctx->d_seqs, d, s, st); mark(1); }
+        ccj::launch_2d(ctx->d_model, ctx->d_seqs, d, s, st); mark(2);
+        if (d.nmax - s - 2 >= 1) {
+            if (tuned) ccj::launch_4d_tuned(ctx->d_model, ctx->d_seqs, d, s, st);
+            else ccj::launch_4d(ctx->d_model, ctx->d_seqs, d, s, st);
+            mark(0);
+        }
+    }
+    ccj::launch_W(ctx->d_model, ctx->d_seqs, d, st); mark(3);
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    for (int k = 0; k < 4; ++k) kernel_ms[k] = 0.f;
+    for (size_t y = 0; y < kind.size(); ++y) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, ev[y], ev[y + 1]));
+        kernel_ms[kind[y]] += ms;
+    }
+    CU(cudaEventElapsedTime(&ctx->fill_ms, ev[0], ev[x - 1]));
+    for (auto &e : ev) cudaEventDestroy(e);
+    ctx->fill_launches = nlaunch;
     ctx->filled = true;
     ctx->traced = false;
     return 0;
@@ -471,7 +548,7 @@ int ccj_export_table2(ccj_ctx *ctx, int seq_index, int table, int32_t *out, int6
     const int64_t s2 = ccj_stride2(n);
     std::vector<int32_t> raw((size_t)s2);
     const char *d_tab = ctx->d_arena + ctx->in_total + ctx->out_total + p.tab_off;
-    const size_t t4b = align_up((size_t)ccj_cells4(n) * CCJ_NT4 * sizeof(int16_t) + 16, 256);
+    const size_t t4b = tab_offset(n, TAB_T2);
     CU(cudaMemcpy(raw.data(), d_tab + t4b + (size_t)table * s2 * sizeof(int32_t), (size_t)s2 * sizeof(int32_t),
                   cudaMemcpyDeviceToHost));
     int64_t x = 0;
@@ -530,6 +607,73 @@ int ccj_table2_hash(ccj_ctx *ctx, int seq_index, int table, uint64_t *hash, int6
     *hash = h;
     if (finite) *finite = fin;
     if (sum) *sum = sm;
+    return 0;
+}
+
+// SURVEY.md App. D term model + exact can_pair-gated window counts (rows a9-a23 of 8a)
+int ccj_count_terms(const char *seq, int n, int no_gu, int64_t *out) {
+    if (!seq || n < 1 || !out) return CCJ_ERR_ARG;
+    auto m0 = [](int64_t x) { return x > 0 ? x : (int64_t)0; };
+    std::vector<int> S(n + 2);
+    for (int i = 1; i <= n; ++i) S[i] = ccj::encode_base(seq[i - 1]);
+    static const int bp[5][5] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 5}, {0, 0, 0, 1, 0}, {0, 0, 2, 0, 3}, {0, 6, 0, 4, 0}};
+    auto pt = [&](int i, int j) {
+        int t = bp[S[i]][S[j]];
+        if (no_gu && (t == 3 || t == 4)) t = 0;
+        return t;
+    };
+    auto cp = [&](int i, int j) { return j - i > 3 && pt(i, j) > 0; };
+    int64_t cells = 0, split = 0, pterms = 0, iloop = 0;
+    // weights: number of (i,gap) placements of arms (a,b): w = sum_{g=2}^{n-1-a-b} (n-a-g-b)
+    for (int a = 0; a <= n - 3; ++a)
+        for (int b = 0; a + b <= n - 3; ++b) {
+            const int64_t m = n - a - b - 2, w = m * (m + 1) / 2;
+            const int64_t a1 = m0(a - 1), b1 = m0(b - 1);
+            const int64_t sp = (1 + 2 * a) + a + (a + a1) + (1 + 2 * b) + (1 + b) + (1 + b) + (1 + a + b) + (1 + b) +
+                               (1 + a + b1) + (1 + a + b) + b + (a + b1) + (2 * a1 + 3) + (2 * b1 + 2) + a1 + b1 +
+                               (a1 + b1 + 2) + (a1 + b1 + 4) + 12;
+            cells += w;
+            split += w * sp;
+        }
+    for (int s = 3; s <= n - 1; ++s) pterms += (int64_t)(n - s) * ((int64_t)s * (s - 1) * (s - 2) / 6);
+    // PL windows depend on (i,j) only; PR on (k,l) only
+    for (int i = 1; i <= n; ++i)
+        for (int j = i; j <= n; ++j) {
+            if (!(pt(i, j) > 0 && cp(i, j))) continue;
+            int64_t cnt = 0;
+            const int max_d = std::min(j, i + 30);
+            for (int d = i + 1; d < max_d; ++d)
+                for (int dp = j - 1; dp > std::max(d + 3, j - 30); --dp) cnt += cp(d, dp);
+            const int64_t right = (int64_t)(n - j - 1) * (n - j) / 2;  // (k,l) with k>=j+2, k<=l<=n
+            const int64_t left = (int64_t)(i - 2) * (i - 1) / 2;       // (i',j') with i'<=j'<=i-2
+            iloop += cnt * (m0(right) + m0(left));
+        }
+    // PM windows: pair (j,k), d in (max(i,j-30), j), dp in (k, min(l,k+30))
+    for (int j = 1; j <= n; ++j)
+        for (int k = j + 2; k <= n; ++k) {
+            if (!(pt(j, k) > 0 && cp(j, k))) continue;
+            // cnt[x][y] = pairs with d >= j-x, dp <= k+y
+            int64_t pre[31][31];
+            for (int x = 0; x <= 30; ++x)
+                for (int y = 0; y <= 30; ++y) {
+                    int64_t v = 0;
+                    if (x > 0 && y > 0) {
+                        const int d = j - x, dp = k + y;
+                        v = pre[x - 1][y] + pre[x][y - 1] - pre[x - 1][y - 1];
+                        if (d >= 1 && dp <= n && x <= 29 && y <= 29) v += cp(d, dp);
+                    }
+                    pre[x][y] = v;
+                }
+            for (int i = 1; i <= j; ++i)
+                for (int l = k; l <= n; ++l) {
+                    const int x = std::min(j - i, 29), y = std::min(l - k, 29);
+                    iloop += pre[x][y];
+                }
+        }
+    out[0] = cells;
+    out[1] = split;
+    out[2] = pterms;
+    out[3] = iloop;
     return 0;
 }
 

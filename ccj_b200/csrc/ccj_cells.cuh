@@ -265,8 +265,14 @@ CCJ_HD void ccj_cell2d(const ccj_cx &c, int i, int j, const Par &par) {
             if (wpp < CCJ_INF / 2) wpp_s = wpp;
             t2[T2_WBP * s2 + ij] = wbp_s;
             t2[T2_WPP * s2 + ij] = wpp_s;
-            t2[T2_WB * s2 + ij] = ccj_min(M->cp_penalty * (j - i + 1), wbp_s);
-            t2[T2_WP * s2 + ij] = ccj_min(M->PUP_penalty * (j - i + 1), wpp_s);
+            const int wb = ccj_min(M->cp_penalty * (j - i + 1), wbp_s);
+            const int wp = ccj_min(M->PUP_penalty * (j - i + 1), wpp_s);
+            t2[T2_WB * s2 + ij] = wb;
+            t2[T2_WP * s2 + ij] = wp;
+            if (c.q.w3) {  // packed {WB,WP,WBP,-} for the tuned 4D kernel
+                int32_t *w = c.q.w3 + 4 * (int64_t)ij;
+                w[0] = wb; w[1] = wp; w[2] = wbp_s; w[3] = 0;
+            }
         }
     }
 

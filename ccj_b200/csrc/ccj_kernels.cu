@@ -24,18 +24,19 @@ struct WarpPar {
 __global__ void k_init(const ccj_model *M, const ccj_seq *seqs) {
     const ccj_seq q = seqs[blockIdx.y];
     const int64_t s2 = q.stride2;
-    for (int64_t x = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; x < s2; x += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t x = tid; x < s2; x += nth) {
         q.t2[T2_V * s2 + x] = CCJ_V_UNSET;
         q.t2[T2_VTYPE * s2 + x] = 'N';
 #pragma unroll
         for (int t = T2_WM; t < CCJ_NT2; ++t) q.t2[t * s2 + x] = CCJ_INF + 1;
-        if (x <= q.n) {
-            q.W[x] = 0;
-            q.pair_out[x] = -1;
-            q.ftype_out[x] = 'N';
-        }
-        if (x < CCJ_STATUS_INTS) q.status[x] = 0;
     }
+    for (int64_t x = tid; x <= q.n + 1; x += nth) {
+        if (x <= q.n) q.W[x] = 0;
+        q.pair_out[x] = -1;
+        q.ftype_out[x] = 'N';
+    }
+    for (int64_t x = tid; x < CCJ_STATUS_INTS; x += nth) q.status[x] = 0;
 }
 
 // P(i,l), l=i+s: blockIdx.x -> i, blockIdx.y -> j (first split point), threads -> (d,k)

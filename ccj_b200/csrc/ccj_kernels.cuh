@@ -20,6 +20,10 @@ void launch_P(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int s, cuda
 void launch_2d(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int s, cudaStream_t st);
 // all 22 gap tables of level t
 void launch_4d(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st);
+// tuned level kernel (ccj_fill4.cu) + its per-sequence precomputation (e_stP table, window partner lists)
+void launch_prep(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cudaStream_t st);
+void launch_4d_tuned(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st);
+bool fill4_tuned_supported(int nmax);
 // exterior W (src/W_final.cc:68-77)
 void launch_W(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cudaStream_t st);
 // traceback, one warp per sequence

@@ -26,7 +26,9 @@ enum ccj_table4 {
     T_PK = 0, T_PL, T_PR, T_PM, T_PO, T_PfromL, T_PfromR, T_PfromM, T_PfromMprime, T_PfromO,
     T_PLmloop00, T_PLmloop01, T_PLmloop10, T_PRmloop00, T_PRmloop01, T_PRmloop10,
     T_PMmloop00, T_PMmloop01, T_PMmloop10, T_POmloop00, T_POmloop01, T_POmloop10,
-    CCJ_NT4 = 22
+    CCJ_NT4 = 22,
+    T_MPP = 22,       /* internal: min(PL,PR) of the cell = get_PfromMdoubleprime without PB (pseudo_loop.cc:675-678) */
+    CCJ_NT4_STORE = 23
 };
 
 // ---- 2D tables ----------------------------------------------------------------------------------
@@ -102,27 +104,37 @@ struct ccj_seq {
     int8_t *ftype_out;   // f[1..n].type
     int32_t *status;     // [0]=status code, [1]=number of "Should not be here!" lines, [2]=message id,
                          // [3],[4]=i,j of a "NOT GOOD RESTR INTER" exit; CCJ_STATUS_INTS ints
+    // per-sequence precomputation for the tuned 4D kernel (ccj_fill4.cu)
+    int32_t *w3;         // int4 {WB,WP,WBP,0} per 2D index (diagonal-major), written with the 2D tables
+    int32_t *estP;       // get_e_stP(i,j) per 2D index
+    uint32_t *inlist;    // interior-loop partners INSIDE closing pair (i,j): slot tri(i,j)*CCJ_WIN, see ccj_fill4.cu
+    uint32_t *outlist;   // interior-loop partners OUTSIDE inner pair (j,k)
+    int32_t *incnt, *outcnt;  // entries per slot
     int32_t *tb_stack;   // traceback stack, 5 ints per node
     int32_t tb_cap;      // capacity in nodes
     int32_t pad2_;
 };
 #define CCJ_STATUS_INTS 8
+#define CCJ_WIN 841      /* 29*29 window slots of get_P{L,R,M}iloop (src/pseudo_loop.cc:694-700) */
+CCJ_HD int ccj_tri(int i, int j) { return (j - 1) * (j - 2) / 2 + (i - 1); } /* 1<=i<j<=n -> [0, n(n-1)/2) */
 
 // ---- 4D layout ---------------------------------------------------------------------------------------
 // A cell is (i,j,k,l) with 1<=i<=j, j<k-1, k<=l<=n  (Matrix4D::get validity, src/matrices.hh:177-182).
-// We address it by arm lengths a=j-i, b=l-k and the anchors (i,k):  nesting [b][i][a][k], k fastest.
-// All cells of one DP level t=a+b (the wavefront step) with equal (a,b,i) are contiguous in k, so a
-// warp whose lanes walk k reads and writes whole 64-byte runs.
-//   block(b,i) : rows a=0..q-1, row a holds k=i+a+2 .. n-b  (length q-a),  q = n-b-i-1
+// We address it by arm lengths a=j-i, b=l-k and the anchors (i,k):  nesting [b][a][i][k], k fastest.
+// One (a,b) "slab" holds the packed triangle {i=1..m, k=i+a+2..n-b}, m=n-a-b-2, row i of length m+1-i.
+// All cells of one DP level t=a+b (the wavefront step) with equal (a,b) are therefore ONE contiguous
+// run of m(m+1)/2 int16: a warp whose lanes walk that run writes whole 64-byte lines, and the split-point
+// reads X(i,d,k,l) / X(d,j,k,l) / X(i,j,d,l) / X(i,j,k,d) of neighbouring lanes are neighbours too.
+//   offset = Cb(b) - Tet(m) + (i-1)(2m+2-i)/2 + (k-j-2),   Cb(b) = Pent(n-2) - Pent(n-b-3)
 CCJ_HD int64_t ccj_pent(int64_t q) { return q * (q + 1) * (q + 2) * (q + 3) / 24; }
 CCJ_HD int64_t ccj_tet(int64_t q) { return q * (q + 1) * (q + 2) / 6; }
 CCJ_HD int64_t ccj_cells4(int n) { return n >= 3 ? ccj_pent(n - 2) : 0; } /* == C(n+1,4) */
+CCJ_HD int64_t ccj_cb(int n, int b) { return ccj_pent(n - 2) - ccj_pent(n - b - 3); }
 
 CCJ_HD int64_t ccj_idx4(int n, int i, int j, int k, int l) {
     const int a = j - i, b = l - k;
-    const int q = n - b - i - 1;
-    return (ccj_pent(n - 2) - ccj_pent(n - b - 2)) + (ccj_tet(n - b - 2) - ccj_tet(q)) +
-           (int64_t)a * q - (int64_t)a * (a - 1) / 2 + (k - i - a - 2);
+    const int64_t m = n - a - b - 2;
+    return ccj_cb(n, b) - ccj_tet(m) + (int64_t)(i - 1) * (2 * m + 2 - i) / 2 + (k - j - 2);
 }
 
 CCJ_HD bool ccj_valid4(int i, int j, int k, int l) { return i <= j && j < k - 1 && k <= l; }

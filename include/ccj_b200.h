@@ -101,6 +101,15 @@ int ccj_table2_hash(ccj_ctx *ctx, int seq_index, int table, uint64_t *hash, int6
 int ccj_model_text(const char *par_file, int dangles, int no_gu, const char *out_path, char *err, size_t err_len);
 int64_t ccj_layout_index(int n, int i, int j, int k, int l);
 
+/* Measurement helpers.
+ * ccj_batch_fill_profiled: same work as ccj_batch_fill but launched kernel by kernel (no graph) with a
+ * CUDA event pair around every launch; kernel_ms[0..3] = summed device time of K_4D, K_P, K_2D, other.
+ * ccj_count_terms (host only): the algorithmic work of one fold as SURVEY.md 8d defines it:
+ * out[0]=cells C(n+1,4), out[1]=split terms, out[2]=P terms, out[3]=interior-window terms this
+ * sequence evaluates (can_pair-gated), all exact. */
+int ccj_batch_fill_profiled(ccj_ctx *ctx, float *kernel_ms);
+int ccj_count_terms(const char *seq, int n, int no_gu, int64_t *out);
+
 /* library / build identification */
 const char *ccj_version(void);
 

@@ -62,6 +62,7 @@ int main(int argc, char **argv) {
         for (int t = T2_WM; t < CCJ_NT2; ++t) t2[t * s2 + x] = CCJ_INF + 1;
     }
     ccj_cx c;
+    memset(&c.q, 0, sizeof c.q);
     c.M = &M;
     c.q.n = n;
     c.q.S = S.data();
