@@ -25,7 +25,7 @@ struct SeqPlan {
 };
 
 // the per-sequence device buffers behind ccj_seq, in arena order
-enum { TAB_T4 = 0, TAB_T2, TAB_W3, TAB_ESTP, TAB_INLIST, TAB_OUTLIST, TAB_INCNT, TAB_OUTCNT, TAB_FTYPE, TAB_TBSTACK,
+enum { TAB_T4 = 0, TAB_T2, TAB_W3, TAB_ESTP, TAB_INLIST, TAB_OUTLIST, TAB_INCNT, TAB_OUTCNT, TAB_SCRATCH, TAB_FTYPE, TAB_TBSTACK,
        TAB_COUNT };
 size_t tab_bytes(int n, int which) {
     const size_t tri = (size_t)n * (n - 1) / 2 + 1;
@@ -38,6 +38,7 @@ size_t tab_bytes(int n, int which) {
         case TAB_OUTLIST: return align_up(tri * CCJ_WIN * sizeof(uint32_t), 256);
         case TAB_INCNT:
         case TAB_OUTCNT: return align_up(tri * sizeof(int32_t), 256);
+        case TAB_SCRATCH: return align_up((size_t)ccj_level_max(n) * ccj::fill4_partials() * sizeof(int16_t) + 64, 256);
         case TAB_FTYPE: return align_up((size_t)n + 2, 256);
         case TAB_TBSTACK: return align_up(sizeof(int32_t) * 5 * (size_t)(16 * n + 64), 256);
     }
@@ -325,6 +326,8 @@ int ccj_batch_prepare(ccj_ctx *ctx, const char *seqs, const int64_t *offsets, in
         q.outlist = reinterpret_cast<uint32_t *>(t + tab_offset(n, TAB_OUTLIST));
         q.incnt = reinterpret_cast<int32_t *>(t + tab_offset(n, TAB_INCNT));
         q.outcnt = reinterpret_cast<int32_t *>(t + tab_offset(n, TAB_OUTCNT));
+        q.scratch = reinterpret_cast<int16_t *>(t + tab_offset(n, TAB_SCRATCH));
+        q.scratch_stride = ccj_level_max(n);
         q.ftype_out = reinterpret_cast<int8_t *>(t + tab_offset(n, TAB_FTYPE));
         q.tb_stack = reinterpret_cast<int32_t *>(t + tab_offset(n, TAB_TBSTACK));
         q.tb_cap = 16 * n + 64;

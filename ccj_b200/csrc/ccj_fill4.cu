@@ -84,180 +84,401 @@ __global__ void __launch_bounds__(128) k_prep(const ccj_model *M, const ccj_seq 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Level kernels.  A cell's work is split over 7 independent "roles" (4 split-point groups, 3 interior
+// windows) that run as separate thread blocks of ONE launch and leave int16-saturated partial minima in a
+// per-level scratch; a second launch assembles the 22 tables in the reference's in-cell order.
+// Splitting keeps every role at <= 9 accumulators, so 4 split points can be in flight per thread (28-40
+// independent loads) at twice the occupancy of a monolithic cell kernel -- the monolithic version was
+// latency-bound (84 % long-scoreboard stalls, profiles/r1_notes.md).
+// Saturating a partial at 32767 is exact: every later operation is +non-negative constant / min, and the
+// final store clamps at 32767 anyway (Matrix4D::set, src/matrices.hh:188-191).
+// ---------------------------------------------------------------------------------------------
 #define K4_THREADS 128
 #define K4_MAXN 448  // int32 offsets and the shared tables below
 
-struct T4 {
-    const int16_t *__restrict__ p[CCJ_NT4_STORE];
+enum {  // partial ids in the scratch
+    Q_PK1 = 0, Q_PfL2, Q_PfM, Q_PLm00a, Q_PLm01, Q_PLm10a, Q_PMm00a,              // role L1
+    Q_PfL1, Q_PfO1, Q_PLm00b, Q_PLm10b, Q_PMm10a, Q_POm00a, Q_POm10a,               // role L2
+    Q_PK3, Q_PfR1, Q_PfMp, Q_PRm00a, Q_PRm10, Q_PMm00b,                              // role R3
+    Q_PfR2, Q_PfO2, Q_PRm00b, Q_PRm01, Q_PMm01, Q_PMm10b, Q_POm00b, Q_POm01, Q_POm10b,  // role R4
+    Q_PLw, Q_PRw, Q_PMw,                                                              // windows
+    Q_COUNT
 };
+enum { ROLE_L1 = 0, ROLE_L2, ROLE_R3, ROLE_R4, ROLE_WL, ROLE_WR, ROLE_WM, ROLE_COUNT };
 
 __device__ __forceinline__ int ld16(const int16_t *__restrict__ p, int off) { return (int)__ldg(p + off); }
-__device__ __forceinline__ int amin(int acc, int x, int w) { return min(acc, x + w); }
+__device__ __forceinline__ int16_t sat16(int x) { return (int16_t)max(min(x, 32767), -32768); }
 
-__global__ void __launch_bounds__(K4_THREADS) k_4d_v2(const ccj_model *__restrict__ M, const ccj_seq *__restrict__ seqs, int t) {
-    __shared__ int s_tet[K4_MAXN + 4];  // Tet(x)
-    __shared__ int s_cb[K4_MAXN + 4];   // Cb(b)
-    const ccj_seq q = seqs[blockIdx.z];
+struct Cell {
+    int n, m, a, b, i, j, k, l, p, c;  // p: index inside slab (a,b); c: index inside the level
+};
+
+// shared tables + decode of the thread's cell; returns false for threads past the slab
+__device__ __forceinline__ bool cell_setup(const ccj_seq &q, int t, int a, int blk, int *s_tet, int *s_cb, Cell &C) {
     const int n = q.n;
     const int m = n - t - 2;
-    if (m < 1) return;
-    const int ncell = m * (m + 1) / 2;
-    if ((int)(blockIdx.x * K4_THREADS) >= ncell) return;
     for (int x = threadIdx.x; x <= n; x += K4_THREADS) {
         s_tet[x] = (int)ccj_tet(x);
         s_cb[x] = x <= n - 3 ? (int)ccj_cb(n, x) : 0;
     }
     __syncthreads();
-    const int p = blockIdx.x * K4_THREADS + threadIdx.x;
-    if (p >= ncell) return;
-
-    const int a = blockIdx.y, b = t - a;
+    const int ncell = m * (m + 1) / 2;
+    const int p = blk * K4_THREADS + threadIdx.x;
+    if (p >= ncell) return false;
     // invert p = (i-1)(2m+2-i)/2 + kk  (rows i=1..m of length m+1-i)
     int r = (int)(((2 * m + 1) - sqrtf((float)((2 * m + 1) * (2 * m + 1) - 8 * p))) * 0.5f);
     if (r < 0) r = 0;
     if (r > m - 1) r = m - 1;
     while (r > 0 && r * (2 * m + 1 - r) / 2 > p) --r;
     while ((r + 1) * (2 * m - r) / 2 <= p) ++r;
-    const int i = r + 1;
+    C.n = n; C.m = m; C.a = a; C.b = t - a;
+    C.i = r + 1;
     const int kk = p - r * (2 * m + 1 - r) / 2;
-    const int j = i + a, k = j + 2 + kk, l = k + b;
+    C.j = C.i + a; C.k = C.j + 2 + kk; C.l = C.k + C.b;
+    C.p = p;
+    C.c = a * ncell + p;
+    return true;
+}
 
+#define TB(tbl) (t4 + (int64_t)(tbl) * st4)
+#define OFF(aa, bb, ii, kx) (s_cb[bb] - s_tet[n - (aa) - (bb)-2] + ((((ii)-1) * (2 * (n - (aa) - (bb)-2) + 2 - (ii))) >> 1) + ((kx) - (ii) - (aa)-2))
+#define U4 4
+
+__global__ void __launch_bounds__(K4_THREADS) k_roles(const ccj_model *__restrict__ M, const ccj_seq *__restrict__ seqs, int t) {
+    __shared__ int s_tet[K4_MAXN + 4];
+    __shared__ int s_cb[K4_MAXN + 4];
+    const int role = blockIdx.z % ROLE_COUNT;
+    const ccj_seq q = seqs[blockIdx.z / ROLE_COUNT];
+    const int n = q.n;
+    if (n - t - 2 < 1) return;
+    {
+        const int m0 = n - t - 2;
+        if ((int)(blockIdx.x * K4_THREADS) >= m0 * (m0 + 1) / 2) return;
+    }
+    Cell C;
+    if (!cell_setup(q, t, blockIdx.y, blockIdx.x, s_tet, s_cb, C)) return;
+    const int a = C.a, b = C.b, i = C.i, j = C.j, k = C.k, l = C.l, m = C.m;
     const int16_t *__restrict__ t4 = q.t4;
     const int64_t st4 = q.stride4;
-#define TB(tbl) (t4 + (int64_t)(tbl) * st4)
     const int4 *__restrict__ W3 = reinterpret_cast<const int4 *>(q.w3);
     const int n1 = n + 1;
-    // generic offset of cell (ii, ii+aa, kx, kx+bb)
-#define OFF(aa, bb, ii, kx) (s_cb[bb] - s_tet[n - (aa) - (bb)-2] + ((((ii)-1) * (2 * (n - (aa) - (bb)-2) + 2 - (ii))) >> 1) + ((kx) - (ii) - (aa)-2))
-    const int off0 = OFF(a, b, i, k);
     const int INF = CCJ_INF;
+    int16_t *__restrict__ sc = q.scratch + C.c;
+    const int64_t ss = q.scratch_stride;
+#define SAVE(id, v) sc[(int64_t)(id) * ss] = sat16(v)
+
+    if (role == ROLE_L1) {
+        // X(i,d,k,l), d=i+ap, with the 2D record of (d+1, j)   [src/pseudo_loop.cc:184-187,357-361,399-402,
+        // 449-458,468-471,481-487,548-551]
+        int aPK = INF, aPfL = INF, aPfM = INF, aPLm00 = INF, aPLm01 = INF, aPLm10 = INF, aPMm00 = INF;
+        if (a >= 1) {
+            const int16_t *__restrict__ pPK = TB(T_PK), *__restrict__ pPfL = TB(T_PfromL), *__restrict__ pPfMp = TB(T_PfromMprime),
+                          *__restrict__ pPLm00 = TB(T_PLmloop00), *__restrict__ pPLm10 = TB(T_PLmloop10),
+                          *__restrict__ pPMm00 = TB(T_PMmloop00);
+            {  // d=i
+                const int o = OFF(0, b, i, k);
+                const int4 w = __ldg(&W3[(a - 1) * n1 + i + 1]);
+                const int x = ld16(pPLm00, o);
+                aPLm00 = min(aPLm00, x + w.x);
+                aPLm01 = min(aPLm01, x + w.z);
+                aPMm00 = min(aPMm00, ld16(pPMm00, o) + w.x);
+            }
+            const int ub = n - b - 2, cbb = s_cb[b], ri = i - 1, kc = k - i - 2;
+            int ap = 1;
+            for (; ap + U4 <= a; ap += U4) {
+                int o[U4];
+                int4 w[U4];
+                int v0[U4], v1[U4], v2[U4], v3[U4], v4[U4], v5[U4];
+#pragma unroll
+                for (int u = 0; u < U4; ++u) {
+                    const int m1 = ub - ap - u;
+                    o[u] = cbb - s_tet[m1] + ((ri * (2 * m1 + 2 - i)) >> 1) + (kc - ap - u);
+                    w[u] = __ldg(&W3[(a - ap - u - 1) * n1 + i + ap + u + 1]);
+                }
+#pragma unroll
+                for (int u = 0; u < U4; ++u) {
+                    v0[u] = ld16(pPK, o[u]); v1[u] = ld16(pPfL, o[u]); v2[u] = ld16(pPfMp, o[u]);
+                    v3[u] = ld16(pPLm00, o[u]); v4[u] = ld16(pPLm10, o[u]); v5[u] = ld16(pPMm00, o[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < U4; ++u) {
+                    aPK = min(aPK, v0[u] + w[u].y); aPfL = min(aPfL, v1[u] + w[u].y); aPfM = min(aPfM, v2[u] + w[u].y);
+                    aPLm00 = min(aPLm00, v3[u] + w[u].x); aPLm01 = min(aPLm01, v3[u] + w[u].z);
+                    aPLm10 = min(aPLm10, v4[u] + w[u].x); aPMm00 = min(aPMm00, v5[u] + w[u].x);
+                }
+            }
+            for (; ap < a; ++ap) {
+                const int m1 = ub - ap;
+                const int o1 = cbb - s_tet[m1] + ((ri * (2 * m1 + 2 - i)) >> 1) + (kc - ap);
+                const int4 w1 = __ldg(&W3[(a - ap - 1) * n1 + i + ap + 1]);
+                aPK = min(aPK, ld16(pPK, o1) + w1.y); aPfL = min(aPfL, ld16(pPfL, o1) + w1.y);
+                aPfM = min(aPfM, ld16(pPfMp, o1) + w1.y);
+                const int x1 = ld16(pPLm00, o1);
+                aPLm00 = min(aPLm00, x1 + w1.x); aPLm01 = min(aPLm01, x1 + w1.z);
+                aPLm10 = min(aPLm10, ld16(pPLm10, o1) + w1.x); aPMm00 = min(aPMm00, ld16(pPMm00, o1) + w1.x);
+            }
+        }
+        SAVE(Q_PK1, aPK); SAVE(Q_PfL2, aPfL); SAVE(Q_PfM, aPfM); SAVE(Q_PLm00a, aPLm00); SAVE(Q_PLm01, aPLm01);
+        SAVE(Q_PLm10a, aPLm10); SAVE(Q_PMm00a, aPMm00);
+    } else if (role == ROLE_L2) {
+        // X(d,j,k,l), d=i+ap, with the 2D record of (i, d-1)   [:357-359,425-428,450-453,481-483,581-584,599-602,632-635]
+        int aPfL = INF, aPfO = INF, aPLm00 = INF, aPLm10 = INF, aPMm10 = INF, aPOm00 = INF, aPOm10 = INF;
+        if (a >= 1) {
+            const int16_t *__restrict__ pPfL = TB(T_PfromL), *__restrict__ pPfO = TB(T_PfromO), *__restrict__ pPLm00 = TB(T_PLmloop00),
+                          *__restrict__ pPMm00 = TB(T_PMmloop00), *__restrict__ pPOm00 = TB(T_POmloop00);
+            {  // d=j
+                const int o = OFF(0, b, j, k);
+                const int4 w = __ldg(&W3[(a - 1) * n1 + i]);
+                const int x = ld16(pPLm00, o);
+                aPLm00 = min(aPLm00, x + w.x);
+                aPLm10 = min(aPLm10, x + w.z);
+                aPMm10 = min(aPMm10, ld16(pPMm00, o) + w.z);
+                const int y = ld16(pPOm00, o);
+                aPOm00 = min(aPOm00, y + w.x);
+                aPOm10 = min(aPOm10, y + w.z);
+            }
+            const int ub = n - b - 2, cbb = s_cb[b], kc = k - j - 2;
+            int ap = 1;
+            for (; ap + U4 <= a; ap += U4) {
+                int o[U4];
+                int4 w[U4];
+                int v0[U4], v1[U4], v2[U4], v3[U4], v4[U4];
+#pragma unroll
+                for (int u = 0; u < U4; ++u) {
+                    const int d = i + ap + u, m2 = ub - (a - ap - u);
+                    o[u] = cbb - s_tet[m2] + (((d - 1) * (2 * m2 + 2 - d)) >> 1) + kc;
+                    w[u] = __ldg(&W3[(ap + u - 1) * n1 + i]);
+                }
+#pragma unroll
+                for (int u = 0; u < U4; ++u) {
+                    v0[u] = ld16(pPfL, o[u]); v1[u] = ld16(pPfO, o[u]); v2[u] = ld16(pPLm00, o[u]);
+                    v3[u] = ld16(pPMm00, o[u]); v4[u] = ld16(pPOm00, o[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < U4; ++u) {
+                    aPfL = min(aPfL, v0[u] + w[u].y); aPfO = min(aPfO, v1[u] + w[u].y);
+                    aPLm00 = min(aPLm00, v2[u] + w[u].x); aPLm10 = min(aPLm10, v2[u] + w[u].z);
+                    aPMm10 = min(aPMm10, v3[u] + w[u].z);
+                    aPOm00 = min(aPOm00, v4[u] + w[u].x); aPOm10 = min(aPOm10, v4[u] + w[u].z);
+                }
+            }
+            for (; ap < a; ++ap) {
+                const int d = i + ap, m2 = ub - (a - ap);
+                const int o2 = cbb - s_tet[m2] + (((d - 1) * (2 * m2 + 2 - d)) >> 1) + kc;
+                const int4 w2 = __ldg(&W3[(ap - 1) * n1 + i]);
+                aPfL = min(aPfL, ld16(pPfL, o2) + w2.y); aPfO = min(aPfO, ld16(pPfO, o2) + w2.y);
+                const int x2 = ld16(pPLm00, o2);
+                aPLm00 = min(aPLm00, x2 + w2.x); aPLm10 = min(aPLm10, x2 + w2.z);
+                aPMm10 = min(aPMm10, ld16(pPMm00, o2) + w2.z);
+                const int y2 = ld16(pPOm00, o2);
+                aPOm00 = min(aPOm00, y2 + w2.x); aPOm10 = min(aPOm10, y2 + w2.z);
+            }
+        }
+        SAVE(Q_PfL1, aPfL); SAVE(Q_PfO1, aPfO); SAVE(Q_PLm00b, aPLm00); SAVE(Q_PLm10b, aPLm10); SAVE(Q_PMm10a, aPMm10);
+        SAVE(Q_POm00a, aPOm00); SAVE(Q_POm10a, aPOm10);
+    } else if (role == ROLE_R3) {
+        // X(i,j,d,l), d=k+bq, with the 2D record of (k, d-1)   [:189-192,379-381,412-415,499-503,534-537,552-555]
+        int aPK = INF, aPfR = INF, aPfMp = INF, aPRm00 = INF, aPRm10 = INF, aPMm00 = INF;
+        if (b >= 1) {
+            const int16_t *__restrict__ pPK = TB(T_PK), *__restrict__ pPfR = TB(T_PfromR), *__restrict__ pMpp = TB(T_MPP),
+                          *__restrict__ pPRm00 = TB(T_PRmloop00), *__restrict__ pPMm00 = TB(T_PMmloop00);
+            {  // d=l
+                const int o = OFF(a, 0, i, l);
+                const int4 w = __ldg(&W3[(b - 1) * n1 + k]);
+                const int x = ld16(pPRm00, o);
+                aPRm00 = min(aPRm00, x + w.x);
+                aPRm10 = min(aPRm10, x + w.z);
+                aPMm00 = min(aPMm00, ld16(pPMm00, o) + w.x);
+            }
+            const int ua = n - a - 2, ri = i - 1, kc = k - j - 2;
+            int bq = 1;
+            for (; bq + U4 <= b; bq += U4) {
+                int o[U4];
+                int4 w[U4];
+                int v0[U4], v1[U4], v2[U4], v3[U4], v4[U4];
+#pragma unroll
+                for (int u = 0; u < U4; ++u) {
+                    const int b3 = b - bq - u, m3 = ua - b3;
+                    o[u] = s_cb[b3] - s_tet[m3] + ((ri * (2 * m3 + 2 - i)) >> 1) + (kc + bq + u);
+                    w[u] = __ldg(&W3[(bq + u - 1) * n1 + k]);
+                }
+#pragma unroll
+                for (int u = 0; u < U4; ++u) {
+                    v0[u] = ld16(pPK, o[u]); v1[u] = ld16(pPfR, o[u]); v2[u] = ld16(pMpp, o[u]);
+                    v3[u] = ld16(pPRm00, o[u]); v4[u] = ld16(pPMm00, o[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < U4; ++u) {
+                    aPK = min(aPK, v0[u] + w[u].y); aPfR = min(aPfR, v1[u] + w[u].y); aPfMp = min(aPfMp, v2[u] + w[u].y);
+                    aPRm00 = min(aPRm00, v3[u] + w[u].x); aPRm10 = min(aPRm10, v3[u] + w[u].z);
+                    aPMm00 = min(aPMm00, v4[u] + w[u].x);
+                }
+            }
+            for (; bq < b; ++bq) {
+                const int b3 = b - bq, m3 = ua - b3;
+                const int o3 = s_cb[b3] - s_tet[m3] + ((ri * (2 * m3 + 2 - i)) >> 1) + (kc + bq);
+                const int4 w3 = __ldg(&W3[(bq - 1) * n1 + k]);
+                aPK = min(aPK, ld16(pPK, o3) + w3.y); aPfR = min(aPfR, ld16(pPfR, o3) + w3.y);
+                aPfMp = min(aPfMp, ld16(pMpp, o3) + w3.y);
+                const int x3 = ld16(pPRm00, o3);
+                aPRm00 = min(aPRm00, x3 + w3.x); aPRm10 = min(aPRm10, x3 + w3.z);
+                aPMm00 = min(aPMm00, ld16(pPMm00, o3) + w3.x);
+            }
+        }
+        SAVE(Q_PK3, aPK); SAVE(Q_PfR1, aPfR); SAVE(Q_PfMp, aPfMp); SAVE(Q_PRm00a, aPRm00); SAVE(Q_PRm10, aPRm10);
+        SAVE(Q_PMm00b, aPMm00);
+    } else if (role == ROLE_R4) {
+        // X(i,j,k,d), d=k+bq, with the 2D record of (d+1, l)   [:382-383,429-432,504-507,520-523,567-570,585-588,
+        // 603-606,618-621,636-639]
+        int aPfR = INF, aPfO = INF, aPRm00 = INF, aPRm01 = INF, aPMm01 = INF, aPMm10 = INF, aPOm00 = INF, aPOm01 = INF,
+            aPOm10 = INF;
+        if (b >= 1) {
+            const int16_t *__restrict__ pPfR = TB(T_PfromR), *__restrict__ pPfO = TB(T_PfromO), *__restrict__ pPRm00 = TB(T_PRmloop00),
+                          *__restrict__ pPMm00 = TB(T_PMmloop00), *__restrict__ pPMm10 = TB(T_PMmloop10),
+                          *__restrict__ pPOm00 = TB(T_POmloop00), *__restrict__ pPOm10 = TB(T_POmloop10);
+            {  // d=k
+                const int o = OFF(a, 0, i, k);
+                const int4 w = __ldg(&W3[(b - 1) * n1 + k + 1]);
+                const int x = ld16(pPRm00, o);
+                aPRm00 = min(aPRm00, x + w.x);
+                aPRm01 = min(aPRm01, x + w.z);
+                aPMm01 = min(aPMm01, ld16(pPMm00, o) + w.z);
+                const int y = ld16(pPOm00, o);
+                aPOm00 = min(aPOm00, y + w.x);
+                aPOm01 = min(aPOm01, y + w.z);
+            }
+            const int ua = n - a - 2, ri = i - 1, kc = k - j - 2;
+            int bq = 1;
+            for (; bq + U4 <= b; bq += U4) {
+                int o[U4];
+                int4 w[U4];
+                int v0[U4], v1[U4], v2[U4], v3[U4], v4[U4], v5[U4], v6[U4];
+#pragma unroll
+                for (int u = 0; u < U4; ++u) {
+                    const int b4 = bq + u, m4 = ua - b4;
+                    o[u] = s_cb[b4] - s_tet[m4] + ((ri * (2 * m4 + 2 - i)) >> 1) + kc;
+                    w[u] = __ldg(&W3[(b - b4 - 1) * n1 + k + b4 + 1]);
+                }
+#pragma unroll
+                for (int u = 0; u < U4; ++u) {
+                    v0[u] = ld16(pPfR, o[u]); v1[u] = ld16(pPfO, o[u]); v2[u] = ld16(pPRm00, o[u]); v3[u] = ld16(pPMm00, o[u]);
+                    v4[u] = ld16(pPMm10, o[u]); v5[u] = ld16(pPOm00, o[u]); v6[u] = ld16(pPOm10, o[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < U4; ++u) {
+                    aPfR = min(aPfR, v0[u] + w[u].y); aPfO = min(aPfO, v1[u] + w[u].y);
+                    aPRm00 = min(aPRm00, v2[u] + w[u].x); aPRm01 = min(aPRm01, v2[u] + w[u].z);
+                    aPMm01 = min(aPMm01, v3[u] + w[u].z); aPMm10 = min(aPMm10, v4[u] + w[u].x);
+                    aPOm00 = min(aPOm00, v5[u] + w[u].x); aPOm01 = min(aPOm01, v5[u] + w[u].z);
+                    aPOm10 = min(aPOm10, v6[u] + w[u].x);
+                }
+            }
+            for (; bq < b; ++bq) {
+                const int m4 = ua - bq;
+                const int o4 = s_cb[bq] - s_tet[m4] + ((ri * (2 * m4 + 2 - i)) >> 1) + kc;
+                const int4 w4 = __ldg(&W3[(b - bq - 1) * n1 + k + bq + 1]);
+                aPfR = min(aPfR, ld16(pPfR, o4) + w4.y); aPfO = min(aPfO, ld16(pPfO, o4) + w4.y);
+                const int x4 = ld16(pPRm00, o4);
+                aPRm00 = min(aPRm00, x4 + w4.x); aPRm01 = min(aPRm01, x4 + w4.z);
+                aPMm01 = min(aPMm01, ld16(pPMm00, o4) + w4.z); aPMm10 = min(aPMm10, ld16(pPMm10, o4) + w4.x);
+                const int y4 = ld16(pPOm00, o4);
+                aPOm00 = min(aPOm00, y4 + w4.x); aPOm01 = min(aPOm01, y4 + w4.z);
+                aPOm10 = min(aPOm10, ld16(pPOm10, o4) + w4.x);
+            }
+        }
+        SAVE(Q_PfR2, aPfR); SAVE(Q_PfO2, aPfO); SAVE(Q_PRm00b, aPRm00); SAVE(Q_PRm01, aPRm01); SAVE(Q_PMm01, aPMm01);
+        SAVE(Q_PMm10b, aPMm10); SAVE(Q_POm00b, aPOm00); SAVE(Q_POm01, aPOm01); SAVE(Q_POm10b, aPOm10);
+    } else if (role == ROLE_WL) {
+        // get_PLiloop (src/pseudo_loop.cc:682-703); the closing-pair test of compute_PL is applied by k_final
+        int mn = INF;
+        if (a > CCJ_TURN && __ldg(&M->pair[q.S[i]][q.S[j]]) > 0) {
+            const int16_t *__restrict__ pPL = TB(T_PL);
+            if (a > CCJ_TURN + 2) mn = ld16(pPL, OFF(a - 2, b, i + 1, k)) + __ldg(&q.estP[a * n1 + i]);
+            const int slot = ccj_tri(i, j);
+            const uint32_t *__restrict__ lst = q.inlist + (int64_t)slot * CCJ_WIN;
+            const int cnt = __ldg(&q.incnt[slot]);
+            const int cbb = s_cb[b], kc = k - j - 2;
+#pragma unroll 4
+            for (int e = 0; e < cnt; ++e) {
+                const uint32_t en = __ldg(&lst[e]);
+                const int x = (en >> 16) & 0xff, y = en >> 24;
+                const int mm = m + x + y, ii = i + x;
+                const int o2 = cbb - s_tet[mm] + (((ii - 1) * (2 * mm + 2 - ii)) >> 1) + (kc + y);
+                mn = min(mn, (int)(int16_t)(en & 0xffff) + ld16(pPL, o2));
+            }
+        }
+        SAVE(Q_PLw, mn);
+    } else if (role == ROLE_WR) {
+        // get_PRiloop (src/pseudo_loop.cc:717-738)
+        int mn = INF;
+        if (b > CCJ_TURN && __ldg(&M->pair[q.S[k]][q.S[l]]) > 0) {
+            const int16_t *__restrict__ pPR = TB(T_PR);
+            if (b > CCJ_TURN + 2) mn = ld16(pPR, OFF(a, b - 2, i, k + 1)) + __ldg(&q.estP[b * n1 + k]);
+            const int slot = ccj_tri(k, l);
+            const uint32_t *__restrict__ lst = q.inlist + (int64_t)slot * CCJ_WIN;
+            const int cnt = __ldg(&q.incnt[slot]);
+            const int rr = i - 1, kc = k - j - 2;
+#pragma unroll 4
+            for (int e = 0; e < cnt; ++e) {
+                const uint32_t en = __ldg(&lst[e]);
+                const int x = (en >> 16) & 0xff, y = en >> 24;
+                const int mm = m + x + y;
+                const int o2 = s_cb[b - x - y] - s_tet[mm] + ((rr * (2 * mm + 2 - i)) >> 1) + (kc + x);
+                mn = min(mn, (int)(int16_t)(en & 0xffff) + ld16(pPR, o2));
+            }
+        }
+        SAVE(Q_PRw, mn);
+    } else {
+        // get_PMiloop (src/pseudo_loop.cc:752-773)
+        int mn = INF;
+        if (k - j > CCJ_TURN && a >= 1 && b >= 1 && __ldg(&M->pair[q.S[j]][q.S[k]]) > 0) {
+            const int16_t *__restrict__ pPM = TB(T_PM);
+            mn = ld16(pPM, OFF(a - 1, b - 1, i, k + 1)) + __ldg(&q.estP[(k - j + 2) * n1 + (j - 1)]);
+            const int slot = ccj_tri(j, k);
+            const uint32_t *__restrict__ lst = q.outlist + (int64_t)slot * CCJ_WIN;
+            const int cnt = __ldg(&q.outcnt[slot]);
+            const int rr = i - 1, kc = k - j - 2;
+#pragma unroll 4
+            for (int e = 0; e < cnt; ++e) {
+                const uint32_t en = __ldg(&lst[e]);
+                const int x = (en >> 16) & 0xff, y = en >> 24;
+                if (x < a && y < b) {
+                    const int mm = m + x + y;
+                    const int o2 = s_cb[b - y] - s_tet[mm] + ((rr * (2 * mm + 2 - i)) >> 1) + (kc + y + x);
+                    mn = min(mn, (int)(int16_t)(en & 0xffff) + ld16(pPM, o2));
+                }
+            }
+        }
+        SAVE(Q_PMw, mn);
+    }
+#undef SAVE
+}
+
+// same-cell assembly in the reference's order (src/pseudo_loop.cc:85-127) from the partial minima
+__global__ void __launch_bounds__(K4_THREADS) k_final(const ccj_model *__restrict__ M, const ccj_seq *__restrict__ seqs, int t) {
+    __shared__ int s_tet[K4_MAXN + 4];
+    __shared__ int s_cb[K4_MAXN + 4];
+    const ccj_seq q = seqs[blockIdx.z];
+    const int n = q.n;
+    if (n - t - 2 < 1) return;
+    {
+        const int m0 = n - t - 2;
+        if ((int)(blockIdx.x * K4_THREADS) >= m0 * (m0 + 1) / 2) return;
+    }
+    Cell C;
+    if (!cell_setup(q, t, blockIdx.y, blockIdx.x, s_tet, s_cb, C)) return;
+    const int a = C.a, b = C.b, i = C.i, j = C.j, k = C.k, l = C.l;
+    const int16_t *__restrict__ t4 = q.t4;
+    const int64_t st4 = q.stride4;
+    const int n1 = n + 1;
+    const int INF = CCJ_INF, II = CCJ_INTERN_INF;
     const int bp = M->bp_penalty, cp = M->cp_penalty, PB = M->PB_penalty, apbp = M->ap_penalty + M->bp_penalty;
-
-    // ---------------- left-arm split points: d = i+ap, ap = 0..a ----------------
-    int aPK1 = INF, aPfL2 = INF, aPfM = INF, aPLm00 = INF, aPLm01 = INF, aPLm10 = INF, aPMm00 = INF;
-    int aPfL1 = INF, aPfO1 = INF, aPMm10 = INF, aPOm00 = INF, aPOm10 = INF;
-    if (a >= 1) {
-        const int16_t *__restrict__ pPLm00 = TB(T_PLmloop00), *__restrict__ pPMm00 = TB(T_PMmloop00),
-                                    *__restrict__ pPOm00 = TB(T_POmloop00);
-        {  // L1 boundary d=i: X(i,i,k,l) with W(i+1,j)
-            const int o = OFF(0, b, i, k);
-            const int4 w = __ldg(&W3[(a - 1) * n1 + i + 1]);
-            const int x = ld16(pPLm00, o);
-            aPLm00 = amin(aPLm00, x, w.x);
-            aPLm01 = amin(aPLm01, x, w.z);
-            aPMm00 = amin(aPMm00, ld16(pPMm00, o), w.x);
-        }
-        {  // L2 boundary d=j: X(j,j,k,l) with W(i,j-1)
-            const int o = OFF(0, b, j, k);
-            const int4 w = __ldg(&W3[(a - 1) * n1 + i]);
-            const int x = ld16(pPLm00, o);
-            aPLm00 = amin(aPLm00, x, w.x);
-            aPLm10 = amin(aPLm10, x, w.z);
-            aPMm10 = amin(aPMm10, ld16(pPMm00, o), w.z);
-            const int y = ld16(pPOm00, o);
-            aPOm00 = amin(aPOm00, y, w.x);
-            aPOm10 = amin(aPOm10, y, w.z);
-        }
-        const int16_t *__restrict__ pPK = TB(T_PK), *__restrict__ pPfL = TB(T_PfromL), *__restrict__ pPfMp = TB(T_PfromMprime),
-                                    *__restrict__ pPLm10 = TB(T_PLmloop10), *__restrict__ pPfO = TB(T_PfromO);
-        const int ub = n - b - 2;
-#pragma unroll 2
-        for (int ap = 1; ap < a; ++ap) {
-            // L1: cell (i, i+ap, k, l), 2D term at (i+ap+1, j)
-            const int m1 = ub - ap;
-            const int o1 = s_cb[b] - s_tet[m1] + (((i - 1) * (2 * m1 + 2 - i)) >> 1) + (k - i - ap - 2);
-            const int4 w1 = __ldg(&W3[(a - ap - 1) * n1 + i + ap + 1]);
-            // L2: cell (d, j, k, l) with d=i+ap (arm length a-ap), 2D term at (i, d-1)
-            const int d = i + ap;
-            const int m2 = ub - (a - ap);
-            const int o2 = s_cb[b] - s_tet[m2] + (((d - 1) * (2 * m2 + 2 - d)) >> 1) + (k - j - 2);
-            const int4 w2 = __ldg(&W3[(ap - 1) * n1 + i]);
-            aPK1 = amin(aPK1, ld16(pPK, o1), w1.y);
-            aPfL2 = amin(aPfL2, ld16(pPfL, o1), w1.y);
-            aPfM = amin(aPfM, ld16(pPfMp, o1), w1.y);
-            const int x1 = ld16(pPLm00, o1);
-            aPLm00 = amin(aPLm00, x1, w1.x);
-            aPLm01 = amin(aPLm01, x1, w1.z);
-            aPLm10 = amin(aPLm10, ld16(pPLm10, o1), w1.x);
-            aPMm00 = amin(aPMm00, ld16(pPMm00, o1), w1.x);
-            aPfL1 = amin(aPfL1, ld16(pPfL, o2), w2.y);
-            aPfO1 = amin(aPfO1, ld16(pPfO, o2), w2.y);
-            const int x2 = ld16(pPLm00, o2);
-            aPLm00 = amin(aPLm00, x2, w2.x);
-            aPLm10 = amin(aPLm10, x2, w2.z);
-            aPMm10 = amin(aPMm10, ld16(pPMm00, o2), w2.z);
-            const int y2 = ld16(pPOm00, o2);
-            aPOm00 = amin(aPOm00, y2, w2.x);
-            aPOm10 = amin(aPOm10, y2, w2.z);
-        }
-    }
-
-    // ---------------- right-arm split points: d = k+bq, bq = 0..b ----------------
-    int aPK3 = INF, aPfR1 = INF, aPfMp = INF, aPRm00 = INF, aPRm10 = INF;
-    int aPfR2 = INF, aPfO2 = INF, aPRm01 = INF, aPMm01 = INF, aPOm01 = INF;
-    if (b >= 1) {
-        const int16_t *__restrict__ pPRm00 = TB(T_PRmloop00), *__restrict__ pPMm00 = TB(T_PMmloop00),
-                                    *__restrict__ pPOm00 = TB(T_POmloop00);
-        {  // R3 boundary d=l: X(i,j,l,l) with W(k,l-1)
-            const int o = OFF(a, 0, i, l);
-            const int4 w = __ldg(&W3[(b - 1) * n1 + k]);
-            const int x = ld16(pPRm00, o);
-            aPRm00 = amin(aPRm00, x, w.x);
-            aPRm10 = amin(aPRm10, x, w.z);
-            aPMm00 = amin(aPMm00, ld16(pPMm00, o), w.x);
-        }
-        {  // R4 boundary d=k: X(i,j,k,k) with W(k+1,l)
-            const int o = OFF(a, 0, i, k);
-            const int4 w = __ldg(&W3[(b - 1) * n1 + k + 1]);
-            const int x = ld16(pPRm00, o);
-            aPRm00 = amin(aPRm00, x, w.x);
-            aPRm01 = amin(aPRm01, x, w.z);
-            aPMm01 = amin(aPMm01, ld16(pPMm00, o), w.z);
-            const int y = ld16(pPOm00, o);
-            aPOm00 = amin(aPOm00, y, w.x);
-            aPOm01 = amin(aPOm01, y, w.z);
-        }
-        const int16_t *__restrict__ pPK = TB(T_PK), *__restrict__ pPfR = TB(T_PfromR), *__restrict__ pMpp = TB(T_MPP),
-                                    *__restrict__ pPfO = TB(T_PfromO), *__restrict__ pPMm10 = TB(T_PMmloop10),
-                                    *__restrict__ pPOm10 = TB(T_POmloop10);
-        const int ua = n - a - 2;
-        const int ri = i - 1;
-#pragma unroll 2
-        for (int bq = 1; bq < b; ++bq) {
-            // R3: cell (i, j, d, l) with d=k+bq (arm length b-bq), 2D term at (k, d-1)
-            const int b3 = b - bq;
-            const int m3 = ua - b3;
-            const int o3 = s_cb[b3] - s_tet[m3] + ((ri * (2 * m3 + 2 - i)) >> 1) + (k + bq - j - 2);
-            const int4 w3 = __ldg(&W3[(bq - 1) * n1 + k]);
-            // R4: cell (i, j, k, d) with d=k+bq (arm length bq), 2D term at (d+1, l)
-            const int m4 = ua - bq;
-            const int o4 = s_cb[bq] - s_tet[m4] + ((ri * (2 * m4 + 2 - i)) >> 1) + (k - j - 2);
-            const int4 w4 = __ldg(&W3[(b - bq - 1) * n1 + k + bq + 1]);
-            aPK3 = amin(aPK3, ld16(pPK, o3), w3.y);
-            aPfR1 = amin(aPfR1, ld16(pPfR, o3), w3.y);
-            aPfMp = amin(aPfMp, ld16(pMpp, o3), w3.y);
-            const int x3 = ld16(pPRm00, o3);
-            aPRm00 = amin(aPRm00, x3, w3.x);
-            aPRm10 = amin(aPRm10, x3, w3.z);
-            aPMm00 = amin(aPMm00, ld16(pPMm00, o3), w3.x);
-            aPfR2 = amin(aPfR2, ld16(pPfR, o4), w4.y);
-            aPfO2 = amin(aPfO2, ld16(pPfO, o4), w4.y);
-            const int x4 = ld16(pPRm00, o4);
-            aPRm00 = amin(aPRm00, x4, w4.x);
-            aPRm01 = amin(aPRm01, x4, w4.z);
-            aPMm01 = amin(aPMm01, ld16(pPMm00, o4), w4.z);
-            aPMm10 = amin(aPMm10, ld16(pPMm10, o4), w4.x);
-            const int y4 = ld16(pPOm00, o4);
-            aPOm00 = amin(aPOm00, y4, w4.x);
-            aPOm01 = amin(aPOm01, y4, w4.z);
-            aPOm10 = amin(aPOm10, ld16(pPOm10, o4), w4.x);
-        }
-    }
-
-    // ---------------- same-cell assembly, reference order (src/pseudo_loop.cc:85-127) ----------------
+    const int16_t *__restrict__ sc = q.scratch + C.c;
+    const int64_t ss = q.scratch_stride;
+#define GET(id) ((int)__ldg(sc + (int64_t)(id) * ss))
+    const int off0 = OFF(a, b, i, k);
     int16_t *w4 = q.t4;
-#define PUT(tbl, val) ccj_put16(w4 + (int64_t)(tbl) * st4 + off0, (val))
-    auto ccj_put16 = [](int16_t *dst, int mn) -> int {
+    auto put16 = [](int16_t *dst, int mn) -> int {
         int v = CCJ_INTERN_INF;
         if (mn < CCJ_INF / 2) {
             if (mn >= CCJ_INTERN_INF) mn = CCJ_INTERN_INF;
@@ -266,13 +487,12 @@ __global__ void __launch_bounds__(K4_THREADS) k_4d_v2(const ccj_model *__restric
         *dst = (int16_t)v;
         return v;
     };
-    const int II = CCJ_INTERN_INF;
-    PUT(T_PLmloop00, min(II + bp, aPLm00));
-    PUT(T_PLmloop01, aPLm01);
-    PUT(T_PLmloop10, aPLm10);
-    PUT(T_PRmloop00, min(II + bp, aPRm00));
+#define PUT(tbl, val) put16(w4 + (int64_t)(tbl) * st4 + off0, (val))
+    PUT(T_PLmloop00, min(II + bp, min(GET(Q_PLm00a), GET(Q_PLm00b))));
+    PUT(T_PLmloop01, GET(Q_PLm01));
+    PUT(T_PLmloop10, min(GET(Q_PLm10a), GET(Q_PLm10b)));
+    PUT(T_PRmloop00, min(II + bp, min(GET(Q_PRm00a), GET(Q_PRm00b))));
     {
-        // neighbours (i,j,k,l-1) and (i,j,k+1,l): valid iff b>=1
         int e01 = INF, e10 = INF, f01 = INF;
         if (b >= 1) {
             const int oA = OFF(a, b - 1, i, k);      // (i,j,k,l-1)
@@ -281,102 +501,48 @@ __global__ void __launch_bounds__(K4_THREADS) k_4d_v2(const ccj_model *__restric
             e10 = ld16(TB(T_PRmloop10), oB) + cp;
             f01 = ld16(TB(T_PMmloop01), oB) + cp;
         }
-        PUT(T_PRmloop01, min(e01, aPRm01));
-        PUT(T_PRmloop10, min(e10, aPRm10));
-        PUT(T_PMmloop00, min(II + bp, aPMm00));
-        PUT(T_PMmloop01, min(f01, aPMm01));
+        PUT(T_PRmloop01, min(e01, GET(Q_PRm01)));
+        PUT(T_PRmloop10, min(e10, GET(Q_PRm10)));
+        PUT(T_PMmloop00, min(II + bp, min(GET(Q_PMm00a), GET(Q_PMm00b))));
+        PUT(T_PMmloop01, min(f01, GET(Q_PMm01)));
         int g10 = INF;
         if (a >= 1) g10 = ld16(TB(T_PMmloop10), OFF(a - 1, b, i, k)) + cp;  // (i,j-1,k,l)
-        PUT(T_PMmloop10, min(g10, aPMm10));
+        PUT(T_PMmloop10, min(g10, min(GET(Q_PMm10a), GET(Q_PMm10b))));
     }
-    PUT(T_POmloop00, min(II + bp, aPOm00));
-    PUT(T_POmloop01, aPOm01);
-    PUT(T_POmloop10, aPOm10);
+    PUT(T_POmloop00, min(II + bp, min(GET(Q_POm00a), GET(Q_POm00b))));
+    PUT(T_POmloop01, GET(Q_POm01));
+    PUT(T_POmloop10, min(GET(Q_POm10a), GET(Q_POm10b)));
 
     const int8_t *__restrict__ S = q.S;
-    const int *__restrict__ estP = q.estP;
     auto ptype = [&](int x, int y) { return __ldg(&M->pair[S[x]][S[y]]); };
-
-    // ---- PL (src/pseudo_loop.cc:232-253, get_PLiloop :682-703, get_PLmloop :705-715) ----
-    int vPL;
-    {
+    // a window partial of 32767 stands for "INF or clamped": identical after the final clamp
+    int vPL, vPR, vPM, vPO;
+    {  // PL (src/pseudo_loop.cc:232-253)
         int mn = INF;
-        if (ptype(i, j) > 0) {
-            if (a >= 2) {
-                const int o = OFF(a - 2, b, i + 1, k);  // (i+1,j-1,k,l)
-                if (a > CCJ_TURN) {  // can_pair(i,j)
-                    if (a > CCJ_TURN + 2) mn = ld16(TB(T_PL), o) + __ldg(&estP[a * n1 + i]);
-                    const int slot = ccj_tri(i, j);
-                    const uint32_t *__restrict__ lst = q.inlist + (int64_t)slot * CCJ_WIN;
-                    const int cnt = __ldg(&q.incnt[slot]);
-                    const int16_t *__restrict__ pPL = TB(T_PL);
-                    for (int e = 0; e < cnt; ++e) {
-                        const uint32_t en = __ldg(&lst[e]);
-                        const int x = (en >> 16) & 0xff, y = en >> 24;
-                        const int mm = m + x + y, ii = i + x;
-                        const int o2 = s_cb[b] - s_tet[mm] + (((ii - 1) * (2 * mm + 2 - ii)) >> 1) + (k - j + y - 2);
-                        mn = min(mn, (int)(int16_t)(en & 0xffff) + ld16(pPL, o2));
-                    }
-                }
-                mn = min(mn, min(ld16(TB(T_PLmloop10), o), ld16(TB(T_PLmloop01), o)) + apbp + bp);
-                if (a >= CCJ_TURN + 1) mn = min(mn, ld16(TB(T_PfromL), o));
-            }
-            // a<2: get_PLmloop / PfromL read an invalid index -> INF
+        if (ptype(i, j) > 0 && a >= 2) {
+            const int o = OFF(a - 2, b, i + 1, k);  // (i+1,j-1,k,l)
+            mn = GET(Q_PLw);
+            mn = min(mn, min(ld16(TB(T_PLmloop10), o), ld16(TB(T_PLmloop01), o)) + apbp + bp);
+            if (a >= CCJ_TURN + 1) mn = min(mn, ld16(TB(T_PfromL), o));
         }
         vPL = PUT(T_PL, mn);
     }
-    // ---- PR (src/pseudo_loop.cc:255-275, get_PRiloop :717-738) ----
-    int vPR;
-    {
+    {  // PR (:255-275)
         int mn = INF;
-        if (ptype(k, l) > 0) {
-            if (b >= 2) {
-                const int o = OFF(a, b - 2, i, k + 1);  // (i,j,k+1,l-1)
-                if (b > CCJ_TURN) {
-                    if (b > CCJ_TURN + 2) mn = ld16(TB(T_PR), o) + __ldg(&estP[b * n1 + k]);
-                    const int slot = ccj_tri(k, l);
-                    const uint32_t *__restrict__ lst = q.inlist + (int64_t)slot * CCJ_WIN;
-                    const int cnt = __ldg(&q.incnt[slot]);
-                    const int16_t *__restrict__ pPR = TB(T_PR);
-                    const int rr = ((i - 1));
-                    for (int e = 0; e < cnt; ++e) {
-                        const uint32_t en = __ldg(&lst[e]);
-                        const int x = (en >> 16) & 0xff, y = en >> 24;
-                        const int mm = m + x + y;
-                        const int o2 = s_cb[b - x - y] - s_tet[mm] + ((rr * (2 * mm + 2 - i)) >> 1) + (k + x - j - 2);
-                        mn = min(mn, (int)(int16_t)(en & 0xffff) + ld16(pPR, o2));
-                    }
-                }
-                mn = min(mn, min(ld16(TB(T_PRmloop10), o), ld16(TB(T_PRmloop01), o)) + apbp + bp);
-                if (b >= CCJ_TURN + 1) mn = min(mn, ld16(TB(T_PfromR), o));
-            }
+        if (ptype(k, l) > 0 && b >= 2) {
+            const int o = OFF(a, b - 2, i, k + 1);  // (i,j,k+1,l-1)
+            mn = GET(Q_PRw);
+            mn = min(mn, min(ld16(TB(T_PRmloop10), o), ld16(TB(T_PRmloop01), o)) + apbp + bp);
+            if (b >= CCJ_TURN + 1) mn = min(mn, ld16(TB(T_PfromR), o));
         }
         vPR = PUT(T_PR, mn);
     }
-    // ---- PM (src/pseudo_loop.cc:277-300, get_PMiloop :752-773) ----
-    int vPM;
-    {
+    {  // PM (:277-300)
         int mn = INF;
         if (ptype(j, k) > 0) {
             if (a >= 1 && b >= 1) {
                 const int o = OFF(a - 1, b - 1, i, k + 1);  // (i,j-1,k+1,l)
-                if (k - j > CCJ_TURN) {                     // can_pair(j,k)
-                    mn = ld16(TB(T_PM), o) + __ldg(&estP[(k - j + 2) * n1 + (j - 1)]);
-                    const int slot = ccj_tri(j, k);
-                    const uint32_t *__restrict__ lst = q.outlist + (int64_t)slot * CCJ_WIN;
-                    const int cnt = __ldg(&q.outcnt[slot]);
-                    const int16_t *__restrict__ pPM = TB(T_PM);
-                    const int rr = i - 1;
-                    for (int e = 0; e < cnt; ++e) {
-                        const uint32_t en = __ldg(&lst[e]);
-                        const int x = (en >> 16) & 0xff, y = en >> 24;
-                        if (x < a && y < b) {
-                            const int mm = m + x + y;
-                            const int o2 = s_cb[b - y] - s_tet[mm] + ((rr * (2 * mm + 2 - i)) >> 1) + (k + y - j + x - 2);
-                            mn = min(mn, (int)(int16_t)(en & 0xffff) + ld16(pPM, o2));
-                        }
-                    }
-                }
+                mn = GET(Q_PMw);
                 mn = min(mn, min(ld16(TB(T_PMmloop10), o), ld16(TB(T_PMmloop01), o)) + apbp + bp);
                 mn = min(mn, ld16(TB(T_PfromM), o));
             }
@@ -384,31 +550,28 @@ __global__ void __launch_bounds__(K4_THREADS) k_4d_v2(const ccj_model *__restric
         }
         vPM = PUT(T_PM, mn);
     }
-    // ---- PO (src/pseudo_loop.cc:302-322, get_POiloop :787-808: window dead) ----
-    int vPO;
-    {
+    {  // PO (:302-322; the window of get_POiloop is dead, :787-808)
         int mn = INF;
-        if (ptype(i, l) > 0) {
-            if (a >= 1 && b >= 1) {
-                const int o = OFF(a - 1, b - 1, i + 1, k);  // (i+1,j,k,l-1)
-                mn = ld16(TB(T_PO), o) + __ldg(&estP[(l - i) * n1 + i]);  // l-i>3 always here
-                mn = min(mn, min(ld16(TB(T_POmloop10), o), ld16(TB(T_POmloop01), o)) + apbp + bp);
-                mn = min(mn, ld16(TB(T_PfromO), o));
-            }
+        if (ptype(i, l) > 0 && a >= 1 && b >= 1) {
+            const int o = OFF(a - 1, b - 1, i + 1, k);  // (i+1,j,k,l-1)
+            mn = ld16(TB(T_PO), o) + __ldg(&q.estP[(l - i) * n1 + i]);
+            mn = min(mn, min(ld16(TB(T_POmloop10), o), ld16(TB(T_POmloop01), o)) + apbp + bp);
+            mn = min(mn, ld16(TB(T_PfromO), o));
         }
         vPO = PUT(T_PO, mn);
     }
-    PUT(T_PfromL, min(min(aPfL1, aPfL2), min(vPR + PB, min(vPM + PB, vPO + PB))));
-    PUT(T_PfromR, min(min(aPfR1, aPfR2), min(vPM + PB, vPO + PB)));
-    PUT(T_PfromM, aPfM);
-    PUT(T_PfromMprime, aPfMp + PB);
-    PUT(T_PfromO, min(min(aPfO1, aPfO2), min(vPL + PB, vPR + PB)));
-    PUT(T_PK, min(min(aPK1, aPK3), min(min(vPL + PB, vPM + PB), min(vPR + PB, vPO + PB))));
+    PUT(T_PfromL, min(min(GET(Q_PfL1), GET(Q_PfL2)), min(vPR + PB, min(vPM + PB, vPO + PB))));
+    PUT(T_PfromR, min(min(GET(Q_PfR1), GET(Q_PfR2)), min(vPM + PB, vPO + PB)));
+    PUT(T_PfromM, GET(Q_PfM));
+    PUT(T_PfromMprime, GET(Q_PfMp) + PB);
+    PUT(T_PfromO, min(min(GET(Q_PfO1), GET(Q_PfO2)), min(vPL + PB, vPR + PB)));
+    PUT(T_PK, min(min(GET(Q_PK1), GET(Q_PK3)), min(min(vPL + PB, vPM + PB), min(vPR + PB, vPO + PB))));
     w4[(int64_t)T_MPP * st4 + off0] = (int16_t)min(vPL, vPR);
 #undef PUT
+#undef GET
+}
 #undef OFF
 #undef TB
-}
 
 void launch_prep(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cudaStream_t st) {
     if (d.nmax < 2) return;
@@ -421,7 +584,11 @@ void launch_4d_tuned(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int 
     const int m = d.nmax - t - 2;
     if (m < 1) return;
     const int ncell = m * (m + 1) / 2;
-    k_4d_v2<<<dim3((ncell + K4_THREADS - 1) / K4_THREADS, t + 1, d.nseq), K4_THREADS, 0, st>>>(M, seqs, t);
+    const int bx = (ncell + K4_THREADS - 1) / K4_THREADS;
+    k_roles<<<dim3(bx, t + 1, d.nseq * ROLE_COUNT), K4_THREADS, 0, st>>>(M, seqs, t);
+    k_final<<<dim3(bx, t + 1, d.nseq), K4_THREADS, 0, st>>>(M, seqs, t);
 }
+
+int fill4_partials() { return Q_COUNT; }
 
 }  // namespace ccj

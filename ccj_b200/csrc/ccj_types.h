@@ -110,6 +110,8 @@ struct ccj_seq {
     uint32_t *inlist;    // interior-loop partners INSIDE closing pair (i,j): slot tri(i,j)*CCJ_WIN, see ccj_fill4.cu
     uint32_t *outlist;   // interior-loop partners OUTSIDE inner pair (j,k)
     int32_t *incnt, *outcnt;  // entries per slot
+    int16_t *scratch;    // per-level partial minima: [partial id][cell of the level], see ccj_fill4.cu
+    int64_t scratch_stride;   // cells of the largest level
     int32_t *tb_stack;   // traceback stack, 5 ints per node
     int32_t tb_cap;      // capacity in nodes
     int32_t pad2_;
@@ -135,6 +137,16 @@ CCJ_HD int64_t ccj_idx4(int n, int i, int j, int k, int l) {
     const int a = j - i, b = l - k;
     const int64_t m = n - a - b - 2;
     return ccj_cb(n, b) - ccj_tet(m) + (int64_t)(i - 1) * (2 * m + 2 - i) / 2 + (k - j - 2);
+}
+
+// cells of the largest level of a length-n fold: max_t (t+1) * m(m+1)/2, m = n-t-2
+CCJ_HD int64_t ccj_level_max(int n) {
+    int64_t best = 0;
+    for (int t = 0; t <= n - 3; ++t) {
+        const int64_t m = n - t - 2, c = (int64_t)(t + 1) * m * (m + 1) / 2;
+        if (c > best) best = c;
+    }
+    return best;
 }
 
 CCJ_HD bool ccj_valid4(int i, int j, int k, int l) { return i <= j && j < k - 1 && k <= l; }
