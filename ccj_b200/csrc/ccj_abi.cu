@@ -179,7 +179,8 @@ void enqueue_fill(ccj_ctx *ctx, ccj::LaunchDims d) {
     ccj::launch_init(ctx->d_model, ctx->d_seqs, d, ctx->stream);
     if (tuned) ccj::launch_prep(ctx->d_model, ctx->d_seqs, d, ctx->stream);
     for (int s = 0; s < d.nmax; ++s) {
-        ccj::launch_P(ctx->d_model, ctx->d_seqs, d, s, ctx->stream);
+        if (tuned) ccj::launch_P_tuned(ctx->d_model, ctx->d_seqs, d, s, ctx->stream);
+        else ccj::launch_P(ctx->d_model, ctx->d_seqs, d, s, ctx->stream);
         ccj::launch_2d(ctx->d_model, ctx->d_seqs, d, s, ctx->stream);
         if (tuned) ccj::launch_4d_tuned(ctx->d_model, ctx->d_seqs, d, s, ctx->stream);
         else ccj::launch_4d(ctx->d_model, ctx->d_seqs, d, s, ctx->stream);
@@ -395,7 +396,11 @@ int ccj_batch_fill_profiled(ccj_ctx *ctx, float *kernel_ms) {
     ccj::launch_init(ctx->d_model, ctx->d_seqs, d, st); mark(3);
     if (tuned) { ccj::launch_prep(ctx->d_model, ctx->d_seqs, d, st); mark(3); }
     for (int s = 0; s < d.nmax; ++s) {
-        if (s >= 3 && s <= d.nmax - 1) { ccj::launch_P(ctx->d_model, ctx->d_seqs, d, s, st); mark(1); }
+        if (s >= 3 && s <= d.nmax - 1) {
+            if (tuned) ccj::launch_P_tuned(ctx->d_model, ctx->d_seqs, d, s, st);
+            else ccj::launch_P(ctx->d_model, ctx->d_seqs, d, s, st);
+            mark(1);
+        }
         ccj::launch_2d(ctx->d_model, ctx->d_seqs, d, s, st); mark(2);
         if (d.nmax - s - 2 >= 1) {
             if (tuned) ccj::launch_4d_tuned(ctx->d_model, ctx->d_seqs, d, s, st);

@@ -565,10 +565,49 @@ __global__ void __launch_bounds__(K4_THREADS) k_final(const ccj_model *__restric
     PUT(T_PfromM, GET(Q_PfM));
     PUT(T_PfromMprime, GET(Q_PfMp) + PB);
     PUT(T_PfromO, min(min(GET(Q_PfO1), GET(Q_PfO2)), min(vPL + PB, vPR + PB)));
-    PUT(T_PK, min(min(GET(Q_PK1), GET(Q_PK3)), min(min(vPL + PB, vPM + PB), min(vPR + PB, vPO + PB))));
+    const int vPK = PUT(T_PK, min(min(GET(Q_PK1), GET(Q_PK3)), min(min(vPL + PB, vPM + PB), min(vPR + PB, vPO + PB))));
     w4[(int64_t)T_MPP * st4 + off0] = (int16_t)min(vPL, vPR);
+    w4[(int64_t)T_PKG * st4 + ccj_pkg_idx(n, i, j, k, l)] = (int16_t)vPK;  // scattered: one store per cell
 #undef PUT
 #undef GET
+}
+
+// P(i,l) = min_{i<=j<d<k<l} PK(i,j,d+1,k) + PK(j+1,d,k+1,l)  (src/pseudo_loop.cc:166-179).
+// blockIdx.x -> i, blockIdx.y -> j; warps take the distances delta=k-d, lanes walk d: the first factor is then
+// contiguous in the main layout (row i of slab (j-i, delta-1)) and the second in the T_PKG copy.
+__global__ void __launch_bounds__(256) k_P_tuned(const ccj_seq *__restrict__ seqs, int s) {
+    const ccj_seq q = seqs[blockIdx.z];
+    const int n = q.n;
+    const int i = 1 + blockIdx.x, l = i + s;
+    if (l > n) return;
+    const int j = i + blockIdx.y;
+    if (j > l - 3) return;  // needs j < d < k < l
+    const int16_t *__restrict__ F = q.t4 + (int64_t)T_PK * q.stride4;
+    const int16_t *__restrict__ G = q.t4 + (int64_t)T_PKG * q.stride4;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int a1 = j - i;
+    const int s2 = l - j - 1;  // span of the second factor's block (i2=j+1, l)
+    const int64_t gblk = (ccj_pent(n - 2) - ccj_pent(n - (j + 1) - 1)) + ccj_tet(s2 - 2) - (j + 1);
+    int mn = CCJ_INF;
+    for (int dl = 1 + wid; dl <= l - j - 2; dl += nw) {  // dl = k-d
+        const int b1 = dl - 1;
+        const int64_t m1 = n - a1 - b1 - 2;
+        // first factor (i, j, d+1, d+dl): offset = F0 + d
+        const int64_t F0 = ccj_cb(n, b1) - ccj_tet(m1) + (int64_t)(i - 1) * (2 * m1 + 2 - i) / 2 + (1 - j - 2);
+        // second factor (j+1, d, d+dl+1, l): gap g2 = dl+1, offset = G0 + d
+        const int64_t g2 = dl + 1;
+        const int64_t G0 = gblk + ((int64_t)s2 * (s2 - 1) / 2 - (s2 - g2 + 1) * (s2 - g2 + 2) / 2);
+        const int dmax = l - dl - 1;  // k = d+dl < l
+        for (int d = j + 1 + lane; d <= dmax; d += 32) mn = min(mn, (int)__ldg(F + F0 + d) + (int)__ldg(G + G0 + d));
+    }
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    __shared__ int sm[8];
+    if (lane == 0) sm[wid] = mn;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int x = 1; x < nw; ++x) mn = min(mn, sm[x]);
+        if (mn < CCJ_INF / 2) atomicMin(&q.t2[T2_P * q.stride2 + ccj_idx2(n, i, l)], mn);
+    }
 }
 #undef OFF
 #undef TB
@@ -590,5 +629,10 @@ void launch_4d_tuned(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int 
 }
 
 int fill4_partials() { return Q_COUNT; }
+
+void launch_P_tuned(const ccj_model *, const ccj_seq *seqs, LaunchDims d, int s, cudaStream_t st) {
+    if (s < 3 || s > d.nmax - 1) return;
+    k_P_tuned<<<dim3(d.nmax - s, s - 2, d.nseq), 256, 0, st>>>(seqs, s);
+}
 
 }  // namespace ccj

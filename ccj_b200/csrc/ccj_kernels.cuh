@@ -23,6 +23,7 @@ void launch_4d(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cud
 // tuned level kernel (ccj_fill4.cu) + its per-sequence precomputation (e_stP table, window partner lists)
 void launch_prep(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cudaStream_t st);
 void launch_4d_tuned(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st);
+void launch_P_tuned(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int s, cudaStream_t st);
 bool fill4_tuned_supported(int nmax);
 int fill4_partials();  // int16 partial minima per cell in the per-level scratch
 // exterior W (src/W_final.cc:68-77)

@@ -28,7 +28,8 @@ enum ccj_table4 {
     T_PMmloop00, T_PMmloop01, T_PMmloop10, T_POmloop00, T_POmloop01, T_POmloop10,
     CCJ_NT4 = 22,
     T_MPP = 22,       /* internal: min(PL,PR) of the cell = get_PfromMdoubleprime without PB (pseudo_loop.cc:675-678) */
-    CCJ_NT4_STORE = 23
+    T_PKG = 23,       /* internal: second copy of PK in the layout compute_P's 2nd factor walks (ccj_pkg_idx) */
+    CCJ_NT4_STORE = 24
 };
 
 // ---- 2D tables ----------------------------------------------------------------------------------
@@ -147,6 +148,14 @@ CCJ_HD int64_t ccj_level_max(int n) {
         if (c > best) best = c;
     }
     return best;
+}
+
+// PK copy for compute_P's second factor PK(j+1,d,k+1,l) (src/pseudo_loop.cc:171): nesting [i][l][gap][j], j
+// fastest, so that for fixed (i,l,gap) consecutive j are consecutive in memory.
+//   block (i,l), s=l-i: gaps g=2..s, gap g holds j=i..l-g
+CCJ_HD int64_t ccj_pkg_idx(int n, int i, int j, int k, int l) {
+    const int64_t s = l - i, g = k - j;
+    return (ccj_pent(n - 2) - ccj_pent(n - i - 1)) + ccj_tet(s - 2) + (s * (s - 1) / 2 - (s - g + 1) * (s - g + 2) / 2) + (j - i);
 }
 
 CCJ_HD bool ccj_valid4(int i, int j, int k, int l) { return i <= j && j < k - 1 && k <= l; }
