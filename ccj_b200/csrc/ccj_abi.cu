@@ -25,7 +25,7 @@ struct SeqPlan {
 };
 
 // the per-sequence device buffers behind ccj_seq, in arena order
-enum { TAB_T4 = 0, TAB_T2, TAB_W3, TAB_ESTP, TAB_INLIST, TAB_OUTLIST, TAB_INCNT, TAB_OUTCNT, TAB_SCRATCH, TAB_FTYPE, TAB_TBSTACK,
+enum { TAB_T4 = 0, TAB_T2, TAB_W3, TAB_ESTP, TAB_INLIST, TAB_OUTLIST, TAB_INCNT, TAB_OUTCNT, TAB_LAY, TAB_SCRATCH, TAB_FTYPE, TAB_TBSTACK,
        TAB_COUNT };
 size_t tab_bytes(int n, int which) {
     const size_t tri = (size_t)n * (n - 1) / 2 + 1;
@@ -38,6 +38,7 @@ size_t tab_bytes(int n, int which) {
         case TAB_OUTLIST: return align_up(tri * CCJ_WIN * sizeof(uint32_t), 256);
         case TAB_INCNT:
         case TAB_OUTCNT: return align_up(tri * sizeof(int32_t), 256);
+        case TAB_LAY: return align_up((size_t)(2 * n + 4) * sizeof(int32_t), 256);
         case TAB_SCRATCH: return align_up((size_t)ccj_level_max(n) * ccj::fill4_partials() * sizeof(int16_t) + 64, 256);
         case TAB_FTYPE: return align_up((size_t)n + 2, 256);
         case TAB_TBSTACK: return align_up(sizeof(int32_t) * 5 * (size_t)(16 * n + 64), 256);
@@ -67,6 +68,8 @@ void plan_seq(int n, SeqPlan &p) {
 struct ccj_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t s_win = nullptr, s_2d = nullptr;  // side streams of the fill: interior windows, P + 2D tables
+    std::vector<cudaEvent_t> dep;                  // dependency events of the captured launch sequence
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
     bool model_ok = false;
@@ -174,18 +177,57 @@ bool use_tuned(int nmax) {
     return !(g && g[0] == '1') && ccj::fill4_tuned_supported(nmax);
 }
 
+// Tuned path, three streams (all inside the captured graph):
+//   main : k_roles(t) -> k_final(t)                       (4D level t; needs 2D spans <= t-1)
+//   s_win: k_windows(t)                                   (reads 4D levels <= t-2 only -> runs one level ahead)
+//   s_2d : k_P(s) -> k_2d(s)                              (needs PK of levels <= s-3 -> runs beside roles(s-2..s))
 void enqueue_fill(ccj_ctx *ctx, ccj::LaunchDims d) {
-    const bool tuned = use_tuned(d.nmax);
-    ccj::launch_init(ctx->d_model, ctx->d_seqs, d, ctx->stream);
-    if (tuned) ccj::launch_prep(ctx->d_model, ctx->d_seqs, d, ctx->stream);
-    for (int s = 0; s < d.nmax; ++s) {
-        if (tuned) ccj::launch_P_tuned(ctx->d_model, ctx->d_seqs, d, s, ctx->stream);
-        else ccj::launch_P(ctx->d_model, ctx->d_seqs, d, s, ctx->stream);
-        ccj::launch_2d(ctx->d_model, ctx->d_seqs, d, s, ctx->stream);
-        if (tuned) ccj::launch_4d_tuned(ctx->d_model, ctx->d_seqs, d, s, ctx->stream);
-        else ccj::launch_4d(ctx->d_model, ctx->d_seqs, d, s, ctx->stream);
+    const ccj_model *M = ctx->d_model;
+    const ccj_seq *Q = ctx->d_seqs;
+    cudaStream_t s0 = ctx->stream;
+    if (!use_tuned(d.nmax)) {
+        ccj::launch_init(M, Q, d, s0);
+        for (int s = 0; s < d.nmax; ++s) {
+            ccj::launch_P(M, Q, d, s, s0);
+            ccj::launch_2d(M, Q, d, s, s0);
+            ccj::launch_4d(M, Q, d, s, s0);
+        }
+        ccj::launch_W(M, Q, d, s0);
+        return;
     }
-    ccj::launch_W(ctx->d_model, ctx->d_seqs, d, ctx->stream);
+    const int nm = d.nmax;
+    while ((int)ctx->dep.size() < 3 * nm + 2) {
+        cudaEvent_t e;
+        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        ctx->dep.push_back(e);
+    }
+    cudaEvent_t *evF = ctx->dep.data(), *evD = evF + nm, *evW = evD + nm, evPrep = ctx->dep[3 * nm];
+    cudaStream_t sw = ctx->s_win, s2 = ctx->s_2d;
+    ccj::launch_init(M, Q, d, s0);
+    ccj::launch_prep(M, Q, d, s0);
+    cudaEventRecord(evPrep, s0);
+    const int last_level = nm - 3;
+    if (last_level >= 0) cudaStreamWaitEvent(sw, evPrep, 0);
+    cudaStreamWaitEvent(s2, evPrep, 0);
+    for (int s = 0; s < nm; ++s) {
+        if (s >= 3 && s - 3 <= last_level) cudaStreamWaitEvent(s2, evF[s - 3], 0);
+        ccj::launch_P_tuned(M, Q, d, s, s2);
+        ccj::launch_2d(M, Q, d, s, s2);
+        cudaEventRecord(evD[s], s2);
+        if (s <= last_level) {
+            if (s >= 2) cudaStreamWaitEvent(sw, evF[s - 2], 0);
+            ccj::launch_4d_windows(M, Q, d, s, sw);
+            cudaEventRecord(evW[s], sw);
+            if (s >= 1) cudaStreamWaitEvent(s0, evD[s - 1], 0);
+            ccj::launch_4d_roles(M, Q, d, s, s0);
+            cudaStreamWaitEvent(s0, evW[s], 0);
+            ccj::launch_4d_final(M, Q, d, s, s0);
+            cudaEventRecord(evF[s], s0);
+        }
+    }
+    cudaStreamWaitEvent(s0, evD[nm - 1], 0);
+    if (last_level >= 0) cudaStreamWaitEvent(s0, evW[last_level], 0);
+    ccj::launch_W(M, Q, d, s0);
 }
 
 }  // namespace
@@ -203,6 +245,8 @@ int ccj_ctx_create(int device, ccj_ctx **out) {
     ccj_ctx *ctx = new ccj_ctx();
     ctx->device = device;
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->s_win, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->s_2d, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
         cudaMalloc((void **)&ctx->d_model, sizeof(ccj_model)) != cudaSuccess) {
         delete ctx;
@@ -223,6 +267,9 @@ void ccj_ctx_destroy(ccj_ctx *ctx) {
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (cudaEvent_t e : ctx->dep) cudaEventDestroy(e);
+    if (ctx->s_win) cudaStreamDestroy(ctx->s_win);
+    if (ctx->s_2d) cudaStreamDestroy(ctx->s_2d);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx->h_model;
     delete ctx;
@@ -327,6 +374,7 @@ int ccj_batch_prepare(ccj_ctx *ctx, const char *seqs, const int64_t *offsets, in
         q.outlist = reinterpret_cast<uint32_t *>(t + tab_offset(n, TAB_OUTLIST));
         q.incnt = reinterpret_cast<int32_t *>(t + tab_offset(n, TAB_INCNT));
         q.outcnt = reinterpret_cast<int32_t *>(t + tab_offset(n, TAB_OUTCNT));
+        q.lay = reinterpret_cast<int32_t *>(t + tab_offset(n, TAB_LAY));
         q.scratch = reinterpret_cast<int16_t *>(t + tab_offset(n, TAB_SCRATCH));
         q.scratch_stride = ccj_level_max(n);
         q.ftype_out = reinterpret_cast<int8_t *>(t + tab_offset(n, TAB_FTYPE));

@@ -18,6 +18,9 @@
 
 namespace ccj {
 
+#define K4_THREADS 128
+#define K4_MAXN 448  // int32 offsets and the shared layout tables
+
 // ---------------------------------------------------------------------------------------------
 // per-sequence precomputation: e_stP table and window partner lists
 // entry = (uint16)energy | x<<16 | y<<24,  x,y in 1..29
@@ -40,6 +43,11 @@ __global__ void __launch_bounds__(128) k_prep(const ccj_model *M, const ccj_seq 
     const int n = c.q.n;
     const int j = blockIdx.x + 2;
     if (j > n) return;
+    if (blockIdx.x == 0 && n <= K4_MAXN)
+        for (int x = threadIdx.x; x <= n; x += blockDim.x) {
+            c.q.lay[x] = (int)ccj_tet(x);
+            c.q.lay[n + 1 + x] = x <= n - 3 ? (int)ccj_cb(n, x) : 0;
+        }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int8_t *S = c.q.S;
     for (int i = 1 + wid; i < j; i += nw) {
@@ -93,18 +101,15 @@ __global__ void __launch_bounds__(128) k_prep(const ccj_model *M, const ccj_seq 
 // Saturating a partial at 32767 is exact: every later operation is +non-negative constant / min, and the
 // final store clamps at 32767 anyway (Matrix4D::set, src/matrices.hh:188-191).
 // ---------------------------------------------------------------------------------------------
-#define K4_THREADS 128
-#define K4_MAXN 448  // int32 offsets and the shared tables below
-
 enum {  // partial ids in the scratch
     Q_PK1 = 0, Q_PfL2, Q_PfM, Q_PLm00a, Q_PLm01, Q_PLm10a, Q_PMm00a,              // role L1
     Q_PfL1, Q_PfO1, Q_PLm00b, Q_PLm10b, Q_PMm10a, Q_POm00a, Q_POm10a,               // role L2
     Q_PK3, Q_PfR1, Q_PfMp, Q_PRm00a, Q_PRm10, Q_PMm00b,                              // role R3
     Q_PfR2, Q_PfO2, Q_PRm00b, Q_PRm01, Q_PMm01, Q_PMm10b, Q_POm00b, Q_POm01, Q_POm10b,  // role R4
-    Q_PLw, Q_PRw, Q_PMw,                                                              // windows
+    Q_PLw, Q_PRw, Q_PMw, Q_PRw_odd, Q_PMw_odd,  // windows; PR/PM double-buffered by level parity (Q_PRw + 2*(t&1))
     Q_COUNT
 };
-enum { ROLE_L1 = 0, ROLE_L2, ROLE_R3, ROLE_R4, ROLE_WL, ROLE_WR, ROLE_WM, ROLE_COUNT };
+enum { ROLE_L1 = 0, ROLE_L2, ROLE_R3, ROLE_R4, ROLE_WL, ROLE_COUNT };
 
 __device__ __forceinline__ int ld16(const int16_t *__restrict__ p, int off) { return (int)__ldg(p + off); }
 __device__ __forceinline__ int16_t sat16(int x) { return (int16_t)max(min(x, 32767), -32768); }
@@ -118,8 +123,8 @@ __device__ __forceinline__ bool cell_setup(const ccj_seq &q, int t, int a, int b
     const int n = q.n;
     const int m = n - t - 2;
     for (int x = threadIdx.x; x <= n; x += K4_THREADS) {
-        s_tet[x] = (int)ccj_tet(x);
-        s_cb[x] = x <= n - 3 ? (int)ccj_cb(n, x) : 0;
+        s_tet[x] = __ldg(&q.lay[x]);
+        s_cb[x] = __ldg(&q.lay[n + 1 + x]);
     }
     __syncthreads();
     const int ncell = m * (m + 1) / 2;
@@ -388,7 +393,7 @@ __global__ void __launch_bounds__(K4_THREADS) k_roles(const ccj_model *__restric
         }
         SAVE(Q_PfR2, aPfR); SAVE(Q_PfO2, aPfO); SAVE(Q_PRm00b, aPRm00); SAVE(Q_PRm01, aPRm01); SAVE(Q_PMm01, aPMm01);
         SAVE(Q_PMm10b, aPMm10); SAVE(Q_POm00b, aPOm00); SAVE(Q_POm01, aPOm01); SAVE(Q_POm10b, aPOm10);
-    } else if (role == ROLE_WL) {
+    } else {
         // get_PLiloop (src/pseudo_loop.cc:682-703); the closing-pair test of compute_PL is applied by k_final
         int mn = INF;
         if (a > CCJ_TURN && __ldg(&M->pair[q.S[i]][q.S[j]]) > 0) {
@@ -408,50 +413,130 @@ __global__ void __launch_bounds__(K4_THREADS) k_roles(const ccj_model *__restric
             }
         }
         SAVE(Q_PLw, mn);
-    } else if (role == ROLE_WR) {
-        // get_PRiloop (src/pseudo_loop.cc:717-738)
-        int mn = INF;
-        if (b > CCJ_TURN && __ldg(&M->pair[q.S[k]][q.S[l]]) > 0) {
-            const int16_t *__restrict__ pPR = TB(T_PR);
-            if (b > CCJ_TURN + 2) mn = ld16(pPR, OFF(a, b - 2, i, k + 1)) + __ldg(&q.estP[b * n1 + k]);
-            const int slot = ccj_tri(k, l);
-            const uint32_t *__restrict__ lst = q.inlist + (int64_t)slot * CCJ_WIN;
-            const int cnt = __ldg(&q.incnt[slot]);
-            const int rr = i - 1, kc = k - j - 2;
-#pragma unroll 4
-            for (int e = 0; e < cnt; ++e) {
-                const uint32_t en = __ldg(&lst[e]);
-                const int x = (en >> 16) & 0xff, y = en >> 24;
-                const int mm = m + x + y;
-                const int o2 = s_cb[b - x - y] - s_tet[mm] + ((rr * (2 * mm + 2 - i)) >> 1) + (kc + x);
-                mn = min(mn, (int)(int16_t)(en & 0xffff) + ld16(pPR, o2));
+    }
+#undef SAVE
+}
+
+// PR and PM interior windows (get_PRiloop :717-738, get_PMiloop :752-773).
+// Neighbouring cells have different closing pairs, so thread-per-cell ran these lists at 8/32 active lanes.
+// Here a block takes 128 consecutive cells of a slab: phase 1 (thread per cell) evaluates the gates, the
+// stacking term and compacts the cells that have a list into shared memory; phase 2 gives each such cell to
+// a whole warp: the lanes walk the partner list (coalesced), each lane gathers its own PR/PM neighbour and
+// the warp reduces with __reduce_min_sync.  Offsets use  R(m',i) = (i-1)m' + (i-1)(2-i)/2, so with s=x+y
+//   PR: off = [cb(b-s) - tet(m+s) + s] + (i-1)s - y + K      PM: off = cb(b-y) + [-tet(m+s) + s] + (i-1)s + K
+// and the bracketed terms are per-block tables.
+__global__ void __launch_bounds__(K4_THREADS) k_windows(const ccj_model *__restrict__ M, const ccj_seq *__restrict__ seqs, int t) {
+    __shared__ int s_T[64];    // PR: cb(b-s)-tet(m+s)+s   PM: -tet(m+s)+s
+    __shared__ int s_C[32];    // PM: cb(b-y)
+    __shared__ int it_slot[K4_THREADS], it_cnt[K4_MAXN > K4_THREADS ? K4_THREADS : K4_THREADS], it_K[K4_THREADS],
+        it_rr[K4_THREADS], it_mn[K4_THREADS], it_c[K4_THREADS];
+    __shared__ int n_items;
+    const int role = blockIdx.z & 1;  // 0: PR, 1: PM
+    const ccj_seq q = seqs[blockIdx.z >> 1];
+    const int n = q.n;
+    const int m = n - t - 2;
+    if (m < 1) return;
+    const int ncell = m * (m + 1) / 2;
+    if ((int)(blockIdx.x * K4_THREADS) >= ncell) return;
+    const int a = blockIdx.y, b = t - a;
+    const int qid = (role == 0 ? Q_PRw : Q_PMw) + 2 * (t & 1);  // double-buffered: runs ahead of k_final
+    int16_t *__restrict__ out = q.scratch + (int64_t)qid * q.scratch_stride + (int64_t)a * ncell;
+    const int p = blockIdx.x * K4_THREADS + threadIdx.x;
+    if (role == 0 ? (b <= CCJ_TURN) : (a < 1 || b < 1)) {
+        // gate fails for the whole slab: PRiloop needs can_pair(k,l), PMiloop's terms need i<j and k<l
+        if (p < ncell) out[p] = 32767;
+        return;
+    }
+    const int *__restrict__ lay = q.lay;
+    if (threadIdx.x < 60) {
+        const int s = threadIdx.x;
+        int v = 0;
+        if (m + s <= n) {
+            v = -__ldg(&lay[m + s]) + s;
+            if (role == 0) v = (b - s >= 0) ? v + __ldg(&lay[n + 1 + b - s]) : 0;
+        }
+        s_T[s] = v;
+    } else if (threadIdx.x >= 64 && threadIdx.x < 96) {
+        const int y = threadIdx.x - 64;
+        s_C[y] = (b - y >= 0) ? __ldg(&lay[n + 1 + b - y]) : 0;
+    }
+    if (threadIdx.x == 0) n_items = 0;
+    __syncthreads();
+    const int16_t *__restrict__ t4 = q.t4;
+    const int64_t st4 = q.stride4;
+    const int n1 = n + 1;
+    const int INF = CCJ_INF;
+    const int8_t *__restrict__ S = q.S;
+    const int16_t *__restrict__ pX = t4 + (int64_t)(role == 0 ? T_PR : T_PM) * st4;
+    // ---- phase 1: thread per cell ----
+    if (p < ncell) {
+        int r = (int)(((2 * m + 1) - sqrtf((float)((2 * m + 1) * (2 * m + 1) - 8 * p))) * 0.5f);
+        if (r < 0) r = 0;
+        if (r > m - 1) r = m - 1;
+        while (r > 0 && r * (2 * m + 1 - r) / 2 > p) --r;
+        while ((r + 1) * (2 * m - r) / 2 <= p) ++r;
+        const int i = r + 1, kk = p - r * (2 * m + 1 - r) / 2;
+        const int j = i + a, k = j + 2 + kk, l = k + b;
+        const int rr = i - 1;
+        // K = cell-constant part of every offset: (i-1)m + (i-1)(2-i)/2 + (k-j-2)
+        const int K = rr * m + ((rr * (2 - i)) >> 1) + kk;
+        int mn = INF, slot = -1, cnt = 0;
+        if (role == 0) {
+            if (__ldg(&M->pair[S[k]][S[l]]) > 0) {
+                if (b > CCJ_TURN + 2) {  // PR(i,j,k+1,l-1): x=y=1, s=2
+                    const int o = s_T[2] + rr * 2 - 1 + K;
+                    mn = ld16(pX, o) + __ldg(&q.estP[b * n1 + k]);
+                }
+                slot = ccj_tri(k, l);
+                cnt = __ldg(&q.incnt[slot]);
+            }
+        } else {
+            if (k - j > CCJ_TURN && __ldg(&M->pair[S[j]][S[k]]) > 0) {
+                // PM(i,j-1,k+1,l): x=y=1, s=2
+                const int o = s_C[1] + s_T[2] + rr * 2 + K;
+                mn = ld16(pX, o) + __ldg(&q.estP[(k - j + 2) * n1 + (j - 1)]);
+                slot = ccj_tri(j, k);
+                cnt = __ldg(&q.outcnt[slot]);
             }
         }
-        SAVE(Q_PRw, mn);
-    } else {
-        // get_PMiloop (src/pseudo_loop.cc:752-773)
+        if (cnt > 0) {
+            const int pos = atomicAdd(&n_items, 1);
+            it_slot[pos] = slot; it_cnt[pos] = cnt; it_K[pos] = K; it_rr[pos] = rr; it_mn[pos] = mn; it_c[pos] = p;
+        } else {
+            out[p] = sat16(mn);
+        }
+    }
+    __syncthreads();
+    // ---- phase 2: warp per listed cell ----
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int items = n_items;
+    const uint32_t *__restrict__ lists = role == 0 ? q.inlist : q.outlist;
+    for (int it = wid; it < items; it += K4_THREADS / 32) {
+        const uint32_t *__restrict__ lst = lists + (int64_t)it_slot[it] * CCJ_WIN;
+        const int cnt = it_cnt[it], K = it_K[it], rr = it_rr[it];
         int mn = INF;
-        if (k - j > CCJ_TURN && a >= 1 && b >= 1 && __ldg(&M->pair[q.S[j]][q.S[k]]) > 0) {
-            const int16_t *__restrict__ pPM = TB(T_PM);
-            mn = ld16(pPM, OFF(a - 1, b - 1, i, k + 1)) + __ldg(&q.estP[(k - j + 2) * n1 + (j - 1)]);
-            const int slot = ccj_tri(j, k);
-            const uint32_t *__restrict__ lst = q.outlist + (int64_t)slot * CCJ_WIN;
-            const int cnt = __ldg(&q.outcnt[slot]);
-            const int rr = i - 1, kc = k - j - 2;
-#pragma unroll 4
-            for (int e = 0; e < cnt; ++e) {
+        if (role == 0) {
+#pragma unroll 2
+            for (int e = lane; e < cnt; e += 32) {
                 const uint32_t en = __ldg(&lst[e]);
-                const int x = (en >> 16) & 0xff, y = en >> 24;
+                const int x = (en >> 16) & 0xff, y = en >> 24, s = x + y;
+                const int o = s_T[s] + rr * s - y + K;
+                mn = min(mn, (int)(int16_t)(en & 0xffff) + ld16(pX, o));
+            }
+        } else {
+#pragma unroll 2
+            for (int e = lane; e < cnt; e += 32) {
+                const uint32_t en = __ldg(&lst[e]);
+                const int x = (en >> 16) & 0xff, y = en >> 24, s = x + y;
                 if (x < a && y < b) {
-                    const int mm = m + x + y;
-                    const int o2 = s_cb[b - y] - s_tet[mm] + ((rr * (2 * mm + 2 - i)) >> 1) + (kc + y + x);
-                    mn = min(mn, (int)(int16_t)(en & 0xffff) + ld16(pPM, o2));
+                    const int o = s_C[y] + s_T[s] + rr * s + K;
+                    mn = min(mn, (int)(int16_t)(en & 0xffff) + ld16(pX, o));
                 }
             }
         }
-        SAVE(Q_PMw, mn);
+        mn = __reduce_min_sync(0xffffffffu, mn);
+        if (lane == 0) out[it_c[it]] = sat16(min(mn, it_mn[it]));
     }
-#undef SAVE
 }
 
 // same-cell assembly in the reference's order (src/pseudo_loop.cc:85-127) from the partial minima
@@ -531,7 +616,7 @@ __global__ void __launch_bounds__(K4_THREADS) k_final(const ccj_model *__restric
         int mn = INF;
         if (ptype(k, l) > 0 && b >= 2) {
             const int o = OFF(a, b - 2, i, k + 1);  // (i,j,k+1,l-1)
-            mn = GET(Q_PRw);
+            mn = GET(Q_PRw + 2 * (t & 1));
             mn = min(mn, min(ld16(TB(T_PRmloop10), o), ld16(TB(T_PRmloop01), o)) + apbp + bp);
             if (b >= CCJ_TURN + 1) mn = min(mn, ld16(TB(T_PfromR), o));
         }
@@ -542,7 +627,7 @@ __global__ void __launch_bounds__(K4_THREADS) k_final(const ccj_model *__restric
         if (ptype(j, k) > 0) {
             if (a >= 1 && b >= 1) {
                 const int o = OFF(a - 1, b - 1, i, k + 1);  // (i,j-1,k+1,l)
-                mn = GET(Q_PMw);
+                mn = GET(Q_PMw + 2 * (t & 1));
                 mn = min(mn, min(ld16(TB(T_PMmloop10), o), ld16(TB(T_PMmloop01), o)) + apbp + bp);
                 mn = min(mn, ld16(TB(T_PfromM), o));
             }
@@ -576,32 +661,43 @@ __global__ void __launch_bounds__(K4_THREADS) k_final(const ccj_model *__restric
 // blockIdx.x -> i, blockIdx.y -> j; warps take the distances delta=k-d, lanes walk d: the first factor is then
 // contiguous in the main layout (row i of slab (j-i, delta-1)) and the second in the T_PKG copy.
 __global__ void __launch_bounds__(256) k_P_tuned(const ccj_seq *__restrict__ seqs, int s) {
+    __shared__ int s_tet[K4_MAXN + 4];
+    __shared__ int s_cb[K4_MAXN + 4];
+    __shared__ int sm[8];
     const ccj_seq q = seqs[blockIdx.z];
     const int n = q.n;
     const int i = 1 + blockIdx.x, l = i + s;
     if (l > n) return;
     const int j = i + blockIdx.y;
     if (j > l - 3) return;  // needs j < d < k < l
+    for (int x = threadIdx.x; x <= n; x += 256) {
+        s_tet[x] = __ldg(&q.lay[x]);
+        s_cb[x] = __ldg(&q.lay[n + 1 + x]);
+    }
+    __syncthreads();
     const int16_t *__restrict__ F = q.t4 + (int64_t)T_PK * q.stride4;
     const int16_t *__restrict__ G = q.t4 + (int64_t)T_PKG * q.stride4;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int a1 = j - i;
     const int s2 = l - j - 1;  // span of the second factor's block (i2=j+1, l)
-    const int64_t gblk = (ccj_pent(n - 2) - ccj_pent(n - (j + 1) - 1)) + ccj_tet(s2 - 2) - (j + 1);
+    // block base of (i2=j+1, l) in the T_PKG copy: Pent(n-2)-Pent(n-i2-1) = Cb(i2-2)  (see ccj_cb)
+    const int gblk = s_cb[j - 1] + s_tet[s2 - 2] + s2 * (s2 - 1) / 2 - (j + 1);
+    const int ua = n - a1 - 2, ri = i - 1;
     int mn = CCJ_INF;
-    for (int dl = 1 + wid; dl <= l - j - 2; dl += nw) {  // dl = k-d
-        const int b1 = dl - 1;
-        const int64_t m1 = n - a1 - b1 - 2;
-        // first factor (i, j, d+1, d+dl): offset = F0 + d
-        const int64_t F0 = ccj_cb(n, b1) - ccj_tet(m1) + (int64_t)(i - 1) * (2 * m1 + 2 - i) / 2 + (1 - j - 2);
-        // second factor (j+1, d, d+dl+1, l): gap g2 = dl+1, offset = G0 + d
-        const int64_t g2 = dl + 1;
-        const int64_t G0 = gblk + ((int64_t)s2 * (s2 - 1) / 2 - (s2 - g2 + 1) * (s2 - g2 + 2) / 2);
-        const int dmax = l - dl - 1;  // k = d+dl < l
-        for (int d = j + 1 + lane; d <= dmax; d += 32) mn = min(mn, (int)__ldg(F + F0 + d) + (int)__ldg(G + G0 + d));
+    // flatten (dl, d): warps take distances dl=k-d, lanes walk d; two distances in flight per warp
+    for (int dl = 1 + wid; dl <= l - j - 2; dl += nw) {
+        const int b1 = dl - 1, m1 = ua - b1;
+        const int F0 = s_cb[b1] - s_tet[m1] + ((ri * (2 * m1 + 2 - i)) >> 1) + (1 - j - 2);  // (i, j, d+1, d+dl)
+        const int G0 = gblk - (s2 - dl) * (s2 - dl + 1) / 2;                                  // (j+1, d, d+dl+1, l)
+        const int dmax = l - dl - 1;
+        int d = j + 1 + lane;
+        for (; d + 32 <= dmax; d += 64) {
+            const int f0 = __ldg(F + F0 + d), g0 = __ldg(G + G0 + d), f1 = __ldg(F + F0 + d + 32), g1 = __ldg(G + G0 + d + 32);
+            mn = min(mn, min(f0 + g0, f1 + g1));
+        }
+        if (d <= dmax) mn = min(mn, (int)__ldg(F + F0 + d) + (int)__ldg(G + G0 + d));
     }
     mn = __reduce_min_sync(0xffffffffu, mn);
-    __shared__ int sm[8];
     if (lane == 0) sm[wid] = mn;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -609,8 +705,6 @@ __global__ void __launch_bounds__(256) k_P_tuned(const ccj_seq *__restrict__ seq
         if (mn < CCJ_INF / 2) atomicMin(&q.t2[T2_P * q.stride2 + ccj_idx2(n, i, l)], mn);
     }
 }
-#undef OFF
-#undef TB
 
 void launch_prep(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cudaStream_t st) {
     if (d.nmax < 2) return;
@@ -619,13 +713,28 @@ void launch_prep(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cudaStre
 
 bool fill4_tuned_supported(int nmax) { return nmax <= K4_MAXN; }
 
-void launch_4d_tuned(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st) {
+static bool level_dims(LaunchDims d, int t, int &bx) {
     const int m = d.nmax - t - 2;
-    if (m < 1) return;
-    const int ncell = m * (m + 1) / 2;
-    const int bx = (ncell + K4_THREADS - 1) / K4_THREADS;
-    k_roles<<<dim3(bx, t + 1, d.nseq * ROLE_COUNT), K4_THREADS, 0, st>>>(M, seqs, t);
-    k_final<<<dim3(bx, t + 1, d.nseq), K4_THREADS, 0, st>>>(M, seqs, t);
+    if (m < 1) return false;
+    bx = (m * (m + 1) / 2 + K4_THREADS - 1) / K4_THREADS;
+    return true;
+}
+void launch_4d_roles(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st) {
+    int bx;
+    if (level_dims(d, t, bx)) k_roles<<<dim3(bx, t + 1, d.nseq * ROLE_COUNT), K4_THREADS, 0, st>>>(M, seqs, t);
+}
+void launch_4d_windows(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st) {
+    int bx;
+    if (level_dims(d, t, bx)) k_windows<<<dim3(bx, t + 1, d.nseq * 2), K4_THREADS, 0, st>>>(M, seqs, t);
+}
+void launch_4d_final(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st) {
+    int bx;
+    if (level_dims(d, t, bx)) k_final<<<dim3(bx, t + 1, d.nseq), K4_THREADS, 0, st>>>(M, seqs, t);
+}
+void launch_4d_tuned(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st) {
+    launch_4d_roles(M, seqs, d, t, st);
+    launch_4d_windows(M, seqs, d, t, st);
+    launch_4d_final(M, seqs, d, t, st);
 }
 
 int fill4_partials() { return Q_COUNT; }

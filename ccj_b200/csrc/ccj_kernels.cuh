@@ -23,6 +23,11 @@ void launch_4d(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cud
 // tuned level kernel (ccj_fill4.cu) + its per-sequence precomputation (e_stP table, window partner lists)
 void launch_prep(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cudaStream_t st);
 void launch_4d_tuned(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st);
+// the three parts of launch_4d_tuned, for callers that overlap them on different streams:
+// windows(t) only reads levels <= t-2, roles(t) levels <= t-1, final(t) needs both
+void launch_4d_roles(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st);
+void launch_4d_windows(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st);
+void launch_4d_final(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st);
 void launch_P_tuned(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int s, cudaStream_t st);
 bool fill4_tuned_supported(int nmax);
 int fill4_partials();  // int16 partial minima per cell in the per-level scratch

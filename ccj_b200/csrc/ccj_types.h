@@ -111,6 +111,7 @@ struct ccj_seq {
     uint32_t *inlist;    // interior-loop partners INSIDE closing pair (i,j): slot tri(i,j)*CCJ_WIN, see ccj_fill4.cu
     uint32_t *outlist;   // interior-loop partners OUTSIDE inner pair (j,k)
     int32_t *incnt, *outcnt;  // entries per slot
+    int32_t *lay;        // layout tables: lay[x]=Tet(x), lay[n+1+x]=Cb(x), x=0..n (int32; tuned path, n<=448)
     int16_t *scratch;    // per-level partial minima: [partial id][cell of the level], see ccj_fill4.cu
     int64_t scratch_stride;   // cells of the largest level
     int32_t *tb_stack;   // traceback stack, 5 ints per node
