@@ -93,6 +93,9 @@ def load_library(path: Optional[os.PathLike] = None) -> C.CDLL:
     lib.ccj_table2_len.restype = C.c_int64
     lib.ccj_batch_fill_profiled.argtypes = [vp, C.POINTER(C.c_float)]
     lib.ccj_count_terms.argtypes = [C.c_char_p, i32, i32, i64p]
+    i32p = C.POINTER(C.c_int32)
+    lib.ccj_table4_get.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32p]
+    lib.ccj_table2_get.argtypes = [vp, i32, i32, i32, i32, i32p]
     u64p = C.POINTER(C.c_uint64)
     lib.ccj_table4_hash.argtypes = [vp, i32, i32, u64p, i64p, C.POINTER(C.c_int32)]
     lib.ccj_table2_hash.argtypes = [vp, i32, i32, u64p, i64p, i64p]

@@ -613,6 +613,39 @@ int ccj_export_table2(ccj_ctx *ctx, int seq_index, int table, int32_t *out, int6
     return 0;
 }
 
+int ccj_table4_get(ccj_ctx *ctx, int seq_index, int table, int i, int j, int k, int l, int32_t *value) {
+    if (!ctx || !value || table < 0 || table >= CCJ_NT4) return CCJ_ERR_ARG;
+    if (!ctx->filled || seq_index < 0 || seq_index >= (int)ctx->plan.size())
+        return fail(ctx, CCJ_ERR_STATE, "no filled wave / bad sequence index");
+    const SeqPlan &p = ctx->plan[seq_index];
+    const int n = p.n;
+    if (!ccj_valid4(i, j, k, l) || i < 1 || l > n) {
+        *value = CCJ_INF;
+        return 0;
+    }
+    CU(cudaSetDevice(ctx->device));
+    const char *d_tab = ctx->d_arena + ctx->in_total + ctx->out_total + p.tab_off;
+    int16_t v = 0;
+    CU(cudaMemcpy(&v, d_tab + ((size_t)table * ccj_cells4(n) + (size_t)ccj_idx4(n, i, j, k, l)) * sizeof(int16_t),
+                  sizeof v, cudaMemcpyDeviceToHost));
+    *value = v;
+    return 0;
+}
+
+int ccj_table2_get(ccj_ctx *ctx, int seq_index, int table, int i, int j, int32_t *value) {
+    if (!ctx || !value || table < 0 || table >= CCJ_NT2) return CCJ_ERR_ARG;
+    if (!ctx->filled || seq_index < 0 || seq_index >= (int)ctx->plan.size())
+        return fail(ctx, CCJ_ERR_STATE, "no filled wave / bad sequence index");
+    const SeqPlan &p = ctx->plan[seq_index];
+    const int n = p.n;
+    if (i < 1 || j > n || i > j) return fail(ctx, CCJ_ERR_ARG, "need 1 <= i <= j <= n");
+    CU(cudaSetDevice(ctx->device));
+    const char *d_tab = ctx->d_arena + ctx->in_total + ctx->out_total + p.tab_off + tab_offset(n, TAB_T2);
+    CU(cudaMemcpy(value, d_tab + ((size_t)table * ccj_stride2(n) + (size_t)ccj_idx2(n, i, j)) * sizeof(int32_t),
+                  sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 static void fnv_add(uint64_t &h, uint64_t v) {
     h ^= v;
     h *= 1099511628211ULL;

@@ -111,7 +111,13 @@ enum {  // partial ids in the scratch
 };
 enum { ROLE_L1 = 0, ROLE_L2, ROLE_R3, ROLE_R4, ROLE_WL, ROLE_COUNT };
 
-__device__ __forceinline__ int ld16(const int16_t *__restrict__ p, int off) { return (int)__ldg(p + off); }
+// streaming read of a gap-table entry: read-only path, and ask L2 to fetch the whole 256-byte chunk -- the
+// neighbouring warps of the block need the adjacent 64-byte runs of the same slab row
+__device__ __forceinline__ int ld16(const int16_t *__restrict__ p, int off) {
+    int v;
+    asm("ld.global.nc.L2::256B.s16 %0, [%1];" : "=r"(v) : "l"(p + off));
+    return v;
+}
 __device__ __forceinline__ int16_t sat16(int x) { return (int16_t)max(min(x, 32767), -32768); }
 
 struct Cell {

@@ -90,6 +90,10 @@ int ccj_export_table4(ccj_ctx *ctx, int seq_index, int table, int16_t *out, int6
 int ccj_export_table2(ccj_ctx *ctx, int seq_index, int table, int32_t *out, int64_t out_len);
 int64_t ccj_table4_len(int n);
 int64_t ccj_table2_len(int n);
+/* one entry with the reference getters' semantics: Matrix4D::get (INF for an invalid index,
+ * src/matrices.hh:177-182) / the raw TriangleMatrix or node value of (i,j), 1<=i<=j<=n */
+int ccj_table4_get(ccj_ctx *ctx, int seq_index, int table, int i, int j, int k, int l, int32_t *value);
+int ccj_table2_get(ccj_ctx *ctx, int seq_index, int table, int i, int j, int32_t *value);
 /* FNV-1a 64 over the exported values (uint16 / uint32 each), the hash oracle/ref_dump.cc prints */
 int ccj_table4_hash(ccj_ctx *ctx, int seq_index, int table, uint64_t *hash, int64_t *finite, int32_t *min_value);
 int ccj_table2_hash(ccj_ctx *ctx, int seq_index, int table, uint64_t *hash, int64_t *finite, int64_t *sum);

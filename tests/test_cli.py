@@ -1,0 +1,74 @@
+"""The CCJ command line (ccj_b200/bin/CCJ) is a drop-in for the reference binary: option handling is
+checked on the CPU (against oracle/_ref/CCJ when it is present, else against the recorded behaviour),
+folds on the GPU against the golden vectors."""
+import subprocess
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+CLI = ROOT / "ccj_b200" / "bin" / "CCJ"
+REF = ROOT / "oracle" / "_ref" / "CCJ"
+
+HELP_HEAD = "Usage: CCJ [options] [sequence]\nPseudoknotted minimum free energy folding of RNAs\n"
+
+
+@pytest.fixture(scope="module")
+def cli(library):
+    from ccj_b200 import build
+    build.build_cli()
+    assert CLI.exists()
+    return CLI
+
+
+def run(exe, args, stdin=None, cwd=ROOT):
+    p = subprocess.run([str(exe)] + list(args), input=stdin, capture_output=True, text=True, cwd=str(cwd))
+    # the program name in getopt messages is argv[0]: normalise it
+    return p.returncode, p.stdout, p.stderr.replace(str(exe), "CCJ")
+
+
+OPTION_CASES = [["--help"], ["-h"], ["-V"], ["--version"], ["--foo"], ["-d"], ["-d", "x", "ACGU"], ["-d1", "-d2", "ACGU"],
+                ["-P", "/nonexistent", "ACGU"], ["-i", "somefile"], ["ACGN"], ["--noGU", "--noGU", "ACGU"]]
+
+
+@pytest.mark.parametrize("args", OPTION_CASES)
+def test_option_handling_matches_reference(cli, args):
+    mine = run(cli, args)
+    if REF.exists():
+        assert mine == run(REF, args), args
+    if args[0] in ("--help", "-h"):
+        assert mine[0] == 0 and mine[1].startswith(HELP_HEAD) and "--noGU" in mine[1]
+    if args[0] in ("-V", "--version"):
+        assert mine == (0, "CCJ 1.0\n", "")
+    if args == ["--foo"]:
+        assert mine[0] == 1 and "unrecognized option '--foo'" in mine[2]
+    if args == ["-P", "/nonexistent", "ACGU"]:
+        assert mine == (1, "", "Not a valid parameter file!\n")
+    if args == ["-i", "somefile"]:
+        assert mine == (1, "sequence is missing\n", "")
+    if args == ["ACGN"]:
+        assert mine == (1, "Sequence contains character N that is not G,C,A,U, or T.\n", "")
+
+
+def test_empty_stdin(cli):
+    assert run(cli, [], stdin="\n") == (1, "sequence is missing\n", "")
+
+
+@pytest.mark.gpu
+def test_cli_folds_match_golden(cli, golden_folds):
+    recs = [r for r in golden_folds if len(r["seq"]) <= 60][:40] + [r for r in golden_folds if r["rc"] != 0][:4]
+    for r in recs:
+        args = ["-P", str(ROOT / "params" / r["par"]), "-d", str(r["dangles"])] + r["extra"] + [r["seq"]]
+        assert run(cli, args) == (r["rc"], r["stdout"], r["stderr"]), r["seq"]
+
+
+@pytest.mark.gpu
+def test_cli_input_conventions(cli):
+    """stdin input, lower case, T->U, default parameter file relative to the cwd, extra positionals ignored."""
+    want = "GCAACGAUGACAUACAUCGCUAGUCGACGC\n....(((((.....)))))........... (-2.32)\n"  # DP09 default, SURVEY App. C
+    assert run(cli, [], stdin="gcaacgatgacatacatcgctagtcgacgc\n") == (0, want, "")
+    assert run(cli, ["GCAACGAUGACAUACAUCGCUAGUCGACGC", "ignored"]) == (0, want, "")
+    rc, out, _ = run(cli, ["--noConv", "GCAACGATGACATACATCGCTAGTCGACGC"])
+    assert (rc, out) == (0, "GCAACGATGACATACATCGCTAGTCGACGC\n....(((((.....)))))........... (-4.4)\n")
+    # run from a directory without params/: the default file is cwd-relative, exactly like the reference
+    assert run(cli, ["ACGU"], cwd="/tmp")[0] == 1
