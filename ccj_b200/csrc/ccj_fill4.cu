@@ -18,7 +18,9 @@
 
 namespace ccj {
 
+#ifndef K4_THREADS
 #define K4_THREADS 128
+#endif
 #define K4_MAXN 448  // int32 offsets and the shared layout tables
 
 // ---------------------------------------------------------------------------------------------
@@ -155,11 +157,13 @@ __device__ __forceinline__ bool cell_setup(const ccj_seq &q, int t, int a, int b
 #define OFF(aa, bb, ii, kx) (s_cb[bb] - s_tet[n - (aa) - (bb)-2] + ((((ii)-1) * (2 * (n - (aa) - (bb)-2) + 2 - (ii))) >> 1) + ((kx) - (ii) - (aa)-2))
 #define U4 4
 
-__global__ void __launch_bounds__(K4_THREADS) k_roles(const ccj_model *__restrict__ M, const ccj_seq *__restrict__ seqs, int t) {
+__global__ void __launch_bounds__(K4_THREADS) k_roles(const ccj_model *__restrict__ M, const ccj_seq *__restrict__ seqs, int t,
+                                                       int only_role) {
     __shared__ int s_tet[K4_MAXN + 4];
     __shared__ int s_cb[K4_MAXN + 4];
-    const int role = blockIdx.z % ROLE_COUNT;
-    const ccj_seq q = seqs[blockIdx.z / ROLE_COUNT];
+    // only_role == 0: blockIdx.z enumerates (sequence, role); else every block runs `only_role`
+    const int role = only_role ? only_role : (int)(blockIdx.z % ROLE_COUNT);
+    const ccj_seq q = seqs[only_role ? blockIdx.z : blockIdx.z / ROLE_COUNT];
     const int n = q.n;
     if (n - t - 2 < 1) return;
     {
@@ -727,7 +731,7 @@ static bool level_dims(LaunchDims d, int t, int &bx) {
 }
 void launch_4d_roles(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st) {
     int bx;
-    if (level_dims(d, t, bx)) k_roles<<<dim3(bx, t + 1, d.nseq * ROLE_COUNT), K4_THREADS, 0, st>>>(M, seqs, t);
+    if (level_dims(d, t, bx)) k_roles<<<dim3(bx, t + 1, d.nseq * ROLE_COUNT), K4_THREADS, 0, st>>>(M, seqs, t, 0);
 }
 void launch_4d_windows(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st) {
     int bx;
