@@ -252,9 +252,10 @@ class Context:
 
     def fill_profiled(self):
         """Fill launched kernel by kernel; returns summed device ms of (K_4D, K_P, K_2D, other)."""
-        ms = (C.c_float * 4)()
+        ms = (C.c_float * 6)()
         self._check(self._lib.ccj_batch_fill_profiled(self._h, ms))
-        return {"k4d_ms": ms[0], "kP_ms": ms[1], "k2d_ms": ms[2], "other_ms": ms[3],
+        return {"k4d_ms": ms[0] + ms[4] + ms[5], "k4d_split_ms": ms[0], "k4d_window_ms": ms[4], "k4d_final_ms": ms[5],
+                "kP_ms": ms[1], "k2d_ms": ms[2], "other_ms": ms[3],
                 "total_ms": float(self._lib.ccj_last_fill_ms(self._h))}
 
     def traceback(self) -> float:

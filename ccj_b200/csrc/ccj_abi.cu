@@ -25,12 +25,16 @@ struct SeqPlan {
 };
 
 // the per-sequence device buffers behind ccj_seq, in arena order
-enum { TAB_T4 = 0, TAB_T2, TAB_W3, TAB_ESTP, TAB_INLIST, TAB_OUTLIST, TAB_INCNT, TAB_OUTCNT, TAB_LAY, TAB_SCRATCH, TAB_FTYPE, TAB_TBSTACK,
+enum { TAB_T4 = 0, TAB_G1, TAB_G2, TAB_G3, TAB_G4, TAB_T2, TAB_W3, TAB_ESTP, TAB_INLIST, TAB_OUTLIST, TAB_INCNT, TAB_OUTCNT, TAB_LAY, TAB_SCRATCH, TAB_FTYPE, TAB_TBSTACK,
        TAB_COUNT };
 size_t tab_bytes(int n, int which) {
     const size_t tri = (size_t)n * (n - 1) / 2 + 1;
     switch (which) {
         case TAB_T4: return align_up((size_t)ccj_cells4(n) * CCJ_NT4_STORE * sizeof(int16_t) + 16, 256);
+        case TAB_G1:
+        case TAB_G2:
+        case TAB_G3: return align_up((size_t)ccj_cells4(n) * 6 * sizeof(int16_t) + 64, 256);
+        case TAB_G4: return align_up((size_t)ccj_cells4(n) * 8 * sizeof(int16_t) + 64, 256);
         case TAB_T2: return align_up((size_t)ccj_stride2(n) * CCJ_NT2 * sizeof(int32_t), 256);
         case TAB_W3: return align_up((size_t)ccj_stride2(n) * 4 * sizeof(int32_t), 256);
         case TAB_ESTP: return align_up((size_t)ccj_stride2(n) * sizeof(int32_t), 256);
@@ -366,6 +370,10 @@ int ccj_batch_prepare(ccj_ctx *ctx, const char *seqs, const int64_t *offsets, in
         char *t = d_tab + p.tab_off;
         q.t4 = reinterpret_cast<int16_t *>(t + tab_offset(n, TAB_T4));
         q.stride4 = ccj_cells4(n);
+        q.g1 = reinterpret_cast<int16_t *>(t + tab_offset(n, TAB_G1));
+        q.g2 = reinterpret_cast<int16_t *>(t + tab_offset(n, TAB_G2));
+        q.g3 = reinterpret_cast<int16_t *>(t + tab_offset(n, TAB_G3));
+        q.g4 = reinterpret_cast<int16_t *>(t + tab_offset(n, TAB_G4));
         q.t2 = reinterpret_cast<int32_t *>(t + tab_offset(n, TAB_T2));
         q.stride2 = ccj_stride2(n);
         q.w3 = reinterpret_cast<int32_t *>(t + tab_offset(n, TAB_W3));
@@ -432,7 +440,7 @@ int ccj_batch_fill_profiled(ccj_ctx *ctx, float *kernel_ms) {
     ccj::LaunchDims d;
     d.nseq = (int)ctx->plan.size();
     d.nmax = ctx->nmax;
-    const int nlaunch = ccj::fill_launch_count(d.nmax) + 1;
+    const int nlaunch = 3 * ccj::fill_launch_count(d.nmax) + 8;
     std::vector<cudaEvent_t> ev((size_t)nlaunch + 1);
     std::vector<int> kind;
     for (auto &e : ev) CU(cudaEventCreate(&e));
@@ -451,15 +459,19 @@ int ccj_batch_fill_profiled(ccj_ctx *ctx, float *kernel_ms) {
         }
         ccj::launch_2d(ctx->d_model, ctx->d_seqs, d, s, st); mark(2);
         if (d.nmax - s - 2 >= 1) {
-            if (tuned) ccj::launch_4d_tuned(ctx->d_model, ctx->d_seqs, d, s, st);
-            else ccj::launch_4d(ctx->d_model, ctx->d_seqs, d, s, st);
-            mark(0);
+            if (tuned) {
+                ccj::launch_4d_roles(ctx->d_model, ctx->d_seqs, d, s, st); mark(0);
+                ccj::launch_4d_windows(ctx->d_model, ctx->d_seqs, d, s, st); mark(4);
+                ccj::launch_4d_final(ctx->d_model, ctx->d_seqs, d, s, st); mark(5);
+            } else {
+                ccj::launch_4d(ctx->d_model, ctx->d_seqs, d, s, st); mark(0);
+            }
         }
     }
     ccj::launch_W(ctx->d_model, ctx->d_seqs, d, st); mark(3);
     CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
-    for (int k = 0; k < 4; ++k) kernel_ms[k] = 0.f;
+    for (int k = 0; k < 6; ++k) kernel_ms[k] = 0.f;
     for (size_t y = 0; y < kind.size(); ++y) {
         float ms = 0.f;
         CU(cudaEventElapsedTime(&ms, ev[y], ev[y + 1]));
@@ -467,7 +479,7 @@ int ccj_batch_fill_profiled(ccj_ctx *ctx, float *kernel_ms) {
     }
     CU(cudaEventElapsedTime(&ctx->fill_ms, ev[0], ev[x - 1]));
     for (auto &e : ev) cudaEventDestroy(e);
-    ctx->fill_launches = nlaunch;
+    ctx->fill_launches = (int)kind.size();
     ctx->filled = true;
     ctx->traced = false;
     return 0;

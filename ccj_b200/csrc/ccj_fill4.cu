@@ -120,6 +120,15 @@ __device__ __forceinline__ int ld16(const int16_t *__restrict__ p, int off) {
     asm("ld.global.nc.L2::256B.s16 %0, [%1];" : "=r"(v) : "l"(p + off));
     return v;
 }
+__device__ __forceinline__ int lo16(int w) { return (int)(int16_t)(w & 0xffff); }
+__device__ __forceinline__ int hi16(int w) { return w >> 16; }
+struct R12 { int w0, w1, w2; };  // one 12-byte read-group record (6 int16)
+__device__ __forceinline__ R12 ldr12(const int *__restrict__ g, int off) {
+    const int *p = g + (int64_t)off * 3;
+    R12 r;
+    r.w0 = __ldg(p); r.w1 = __ldg(p + 1); r.w2 = __ldg(p + 2);
+    return r;
+}
 __device__ __forceinline__ int16_t sat16(int x) { return (int16_t)max(min(x, 32767), -32768); }
 
 struct Cell {
@@ -184,108 +193,98 @@ __global__ void __launch_bounds__(K4_THREADS) k_roles(const ccj_model *__restric
 
     if (role == ROLE_L1) {
         // X(i,d,k,l), d=i+ap, with the 2D record of (d+1, j)   [src/pseudo_loop.cc:184-187,357-361,399-402,
-        // 449-458,468-471,481-487,548-551]
+        // 449-458,468-471,481-487,548-551]; record g1 = PK PfromL PfromMprime | PLmloop00 PLmloop10 PMmloop00
         int aPK = INF, aPfL = INF, aPfM = INF, aPLm00 = INF, aPLm01 = INF, aPLm10 = INF, aPMm00 = INF;
         if (a >= 1) {
-            const int16_t *__restrict__ pPK = TB(T_PK), *__restrict__ pPfL = TB(T_PfromL), *__restrict__ pPfMp = TB(T_PfromMprime),
-                          *__restrict__ pPLm00 = TB(T_PLmloop00), *__restrict__ pPLm10 = TB(T_PLmloop10),
-                          *__restrict__ pPMm00 = TB(T_PMmloop00);
+            const int *__restrict__ G = reinterpret_cast<const int *>(q.g1);
             {  // d=i
-                const int o = OFF(0, b, i, k);
+                const R12 r = ldr12(G, OFF(0, b, i, k));
                 const int4 w = __ldg(&W3[(a - 1) * n1 + i + 1]);
-                const int x = ld16(pPLm00, o);
+                const int x = hi16(r.w1);
                 aPLm00 = min(aPLm00, x + w.x);
                 aPLm01 = min(aPLm01, x + w.z);
-                aPMm00 = min(aPMm00, ld16(pPMm00, o) + w.x);
+                aPMm00 = min(aPMm00, hi16(r.w2) + w.x);
             }
             const int ub = n - b - 2, cbb = s_cb[b], ri = i - 1, kc = k - i - 2;
             int ap = 1;
             for (; ap + U4 <= a; ap += U4) {
-                int o[U4];
+                R12 r[U4];
                 int4 w[U4];
-                int v0[U4], v1[U4], v2[U4], v3[U4], v4[U4], v5[U4];
 #pragma unroll
                 for (int u = 0; u < U4; ++u) {
                     const int m1 = ub - ap - u;
-                    o[u] = cbb - s_tet[m1] + ((ri * (2 * m1 + 2 - i)) >> 1) + (kc - ap - u);
+                    const int o = cbb - s_tet[m1] + ((ri * (2 * m1 + 2 - i)) >> 1) + (kc - ap - u);
+                    r[u] = ldr12(G, o);
                     w[u] = __ldg(&W3[(a - ap - u - 1) * n1 + i + ap + u + 1]);
                 }
 #pragma unroll
                 for (int u = 0; u < U4; ++u) {
-                    v0[u] = ld16(pPK, o[u]); v1[u] = ld16(pPfL, o[u]); v2[u] = ld16(pPfMp, o[u]);
-                    v3[u] = ld16(pPLm00, o[u]); v4[u] = ld16(pPLm10, o[u]); v5[u] = ld16(pPMm00, o[u]);
-                }
-#pragma unroll
-                for (int u = 0; u < U4; ++u) {
-                    aPK = min(aPK, v0[u] + w[u].y); aPfL = min(aPfL, v1[u] + w[u].y); aPfM = min(aPfM, v2[u] + w[u].y);
-                    aPLm00 = min(aPLm00, v3[u] + w[u].x); aPLm01 = min(aPLm01, v3[u] + w[u].z);
-                    aPLm10 = min(aPLm10, v4[u] + w[u].x); aPMm00 = min(aPMm00, v5[u] + w[u].x);
+                    aPK = min(aPK, lo16(r[u].w0) + w[u].y); aPfL = min(aPfL, hi16(r[u].w0) + w[u].y);
+                    aPfM = min(aPfM, lo16(r[u].w1) + w[u].y);
+                    const int x = hi16(r[u].w1);
+                    aPLm00 = min(aPLm00, x + w[u].x); aPLm01 = min(aPLm01, x + w[u].z);
+                    aPLm10 = min(aPLm10, lo16(r[u].w2) + w[u].x); aPMm00 = min(aPMm00, hi16(r[u].w2) + w[u].x);
                 }
             }
             for (; ap < a; ++ap) {
                 const int m1 = ub - ap;
-                const int o1 = cbb - s_tet[m1] + ((ri * (2 * m1 + 2 - i)) >> 1) + (kc - ap);
+                const R12 r = ldr12(G, cbb - s_tet[m1] + ((ri * (2 * m1 + 2 - i)) >> 1) + (kc - ap));
                 const int4 w1 = __ldg(&W3[(a - ap - 1) * n1 + i + ap + 1]);
-                aPK = min(aPK, ld16(pPK, o1) + w1.y); aPfL = min(aPfL, ld16(pPfL, o1) + w1.y);
-                aPfM = min(aPfM, ld16(pPfMp, o1) + w1.y);
-                const int x1 = ld16(pPLm00, o1);
+                aPK = min(aPK, lo16(r.w0) + w1.y); aPfL = min(aPfL, hi16(r.w0) + w1.y); aPfM = min(aPfM, lo16(r.w1) + w1.y);
+                const int x1 = hi16(r.w1);
                 aPLm00 = min(aPLm00, x1 + w1.x); aPLm01 = min(aPLm01, x1 + w1.z);
-                aPLm10 = min(aPLm10, ld16(pPLm10, o1) + w1.x); aPMm00 = min(aPMm00, ld16(pPMm00, o1) + w1.x);
+                aPLm10 = min(aPLm10, lo16(r.w2) + w1.x); aPMm00 = min(aPMm00, hi16(r.w2) + w1.x);
             }
         }
         SAVE(Q_PK1, aPK); SAVE(Q_PfL2, aPfL); SAVE(Q_PfM, aPfM); SAVE(Q_PLm00a, aPLm00); SAVE(Q_PLm01, aPLm01);
         SAVE(Q_PLm10a, aPLm10); SAVE(Q_PMm00a, aPMm00);
     } else if (role == ROLE_L2) {
         // X(d,j,k,l), d=i+ap, with the 2D record of (i, d-1)   [:357-359,425-428,450-453,481-483,581-584,599-602,632-635]
+        // record g2 = PfromL PfromO | PLmloop00 PMmloop00 | POmloop00 -
         int aPfL = INF, aPfO = INF, aPLm00 = INF, aPLm10 = INF, aPMm10 = INF, aPOm00 = INF, aPOm10 = INF;
         if (a >= 1) {
-            const int16_t *__restrict__ pPfL = TB(T_PfromL), *__restrict__ pPfO = TB(T_PfromO), *__restrict__ pPLm00 = TB(T_PLmloop00),
-                          *__restrict__ pPMm00 = TB(T_PMmloop00), *__restrict__ pPOm00 = TB(T_POmloop00);
+            const int *__restrict__ G = reinterpret_cast<const int *>(q.g2);
             {  // d=j
-                const int o = OFF(0, b, j, k);
+                const R12 r = ldr12(G, OFF(0, b, j, k));
                 const int4 w = __ldg(&W3[(a - 1) * n1 + i]);
-                const int x = ld16(pPLm00, o);
+                const int x = lo16(r.w1);
                 aPLm00 = min(aPLm00, x + w.x);
                 aPLm10 = min(aPLm10, x + w.z);
-                aPMm10 = min(aPMm10, ld16(pPMm00, o) + w.z);
-                const int y = ld16(pPOm00, o);
+                aPMm10 = min(aPMm10, hi16(r.w1) + w.z);
+                const int y = lo16(r.w2);
                 aPOm00 = min(aPOm00, y + w.x);
                 aPOm10 = min(aPOm10, y + w.z);
             }
             const int ub = n - b - 2, cbb = s_cb[b], kc = k - j - 2;
             int ap = 1;
             for (; ap + U4 <= a; ap += U4) {
-                int o[U4];
+                R12 r[U4];
                 int4 w[U4];
-                int v0[U4], v1[U4], v2[U4], v3[U4], v4[U4];
 #pragma unroll
                 for (int u = 0; u < U4; ++u) {
                     const int d = i + ap + u, m2 = ub - (a - ap - u);
-                    o[u] = cbb - s_tet[m2] + (((d - 1) * (2 * m2 + 2 - d)) >> 1) + kc;
+                    r[u] = ldr12(G, cbb - s_tet[m2] + (((d - 1) * (2 * m2 + 2 - d)) >> 1) + kc);
                     w[u] = __ldg(&W3[(ap + u - 1) * n1 + i]);
                 }
 #pragma unroll
                 for (int u = 0; u < U4; ++u) {
-                    v0[u] = ld16(pPfL, o[u]); v1[u] = ld16(pPfO, o[u]); v2[u] = ld16(pPLm00, o[u]);
-                    v3[u] = ld16(pPMm00, o[u]); v4[u] = ld16(pPOm00, o[u]);
-                }
-#pragma unroll
-                for (int u = 0; u < U4; ++u) {
-                    aPfL = min(aPfL, v0[u] + w[u].y); aPfO = min(aPfO, v1[u] + w[u].y);
-                    aPLm00 = min(aPLm00, v2[u] + w[u].x); aPLm10 = min(aPLm10, v2[u] + w[u].z);
-                    aPMm10 = min(aPMm10, v3[u] + w[u].z);
-                    aPOm00 = min(aPOm00, v4[u] + w[u].x); aPOm10 = min(aPOm10, v4[u] + w[u].z);
+                    aPfL = min(aPfL, lo16(r[u].w0) + w[u].y); aPfO = min(aPfO, hi16(r[u].w0) + w[u].y);
+                    const int x = lo16(r[u].w1);
+                    aPLm00 = min(aPLm00, x + w[u].x); aPLm10 = min(aPLm10, x + w[u].z);
+                    aPMm10 = min(aPMm10, hi16(r[u].w1) + w[u].z);
+                    const int y = lo16(r[u].w2);
+                    aPOm00 = min(aPOm00, y + w[u].x); aPOm10 = min(aPOm10, y + w[u].z);
                 }
             }
             for (; ap < a; ++ap) {
                 const int d = i + ap, m2 = ub - (a - ap);
-                const int o2 = cbb - s_tet[m2] + (((d - 1) * (2 * m2 + 2 - d)) >> 1) + kc;
+                const R12 r = ldr12(G, cbb - s_tet[m2] + (((d - 1) * (2 * m2 + 2 - d)) >> 1) + kc);
                 const int4 w2 = __ldg(&W3[(ap - 1) * n1 + i]);
-                aPfL = min(aPfL, ld16(pPfL, o2) + w2.y); aPfO = min(aPfO, ld16(pPfO, o2) + w2.y);
-                const int x2 = ld16(pPLm00, o2);
+                aPfL = min(aPfL, lo16(r.w0) + w2.y); aPfO = min(aPfO, hi16(r.w0) + w2.y);
+                const int x2 = lo16(r.w1);
                 aPLm00 = min(aPLm00, x2 + w2.x); aPLm10 = min(aPLm10, x2 + w2.z);
-                aPMm10 = min(aPMm10, ld16(pPMm00, o2) + w2.z);
-                const int y2 = ld16(pPOm00, o2);
+                aPMm10 = min(aPMm10, hi16(r.w1) + w2.z);
+                const int y2 = lo16(r.w2);
                 aPOm00 = min(aPOm00, y2 + w2.x); aPOm10 = min(aPOm10, y2 + w2.z);
             }
         }
@@ -293,112 +292,100 @@ __global__ void __launch_bounds__(K4_THREADS) k_roles(const ccj_model *__restric
         SAVE(Q_POm00a, aPOm00); SAVE(Q_POm10a, aPOm10);
     } else if (role == ROLE_R3) {
         // X(i,j,d,l), d=k+bq, with the 2D record of (k, d-1)   [:189-192,379-381,412-415,499-503,534-537,552-555]
+        // record g3 = PK PfromR | min(PL,PR) PRmloop00 | PMmloop00 -
         int aPK = INF, aPfR = INF, aPfMp = INF, aPRm00 = INF, aPRm10 = INF, aPMm00 = INF;
         if (b >= 1) {
-            const int16_t *__restrict__ pPK = TB(T_PK), *__restrict__ pPfR = TB(T_PfromR), *__restrict__ pMpp = TB(T_MPP),
-                          *__restrict__ pPRm00 = TB(T_PRmloop00), *__restrict__ pPMm00 = TB(T_PMmloop00);
+            const int *__restrict__ G = reinterpret_cast<const int *>(q.g3);
             {  // d=l
-                const int o = OFF(a, 0, i, l);
+                const R12 r = ldr12(G, OFF(a, 0, i, l));
                 const int4 w = __ldg(&W3[(b - 1) * n1 + k]);
-                const int x = ld16(pPRm00, o);
+                const int x = hi16(r.w1);
                 aPRm00 = min(aPRm00, x + w.x);
                 aPRm10 = min(aPRm10, x + w.z);
-                aPMm00 = min(aPMm00, ld16(pPMm00, o) + w.x);
+                aPMm00 = min(aPMm00, lo16(r.w2) + w.x);
             }
             const int ua = n - a - 2, ri = i - 1, kc = k - j - 2;
             int bq = 1;
             for (; bq + U4 <= b; bq += U4) {
-                int o[U4];
+                R12 r[U4];
                 int4 w[U4];
-                int v0[U4], v1[U4], v2[U4], v3[U4], v4[U4];
 #pragma unroll
                 for (int u = 0; u < U4; ++u) {
                     const int b3 = b - bq - u, m3 = ua - b3;
-                    o[u] = s_cb[b3] - s_tet[m3] + ((ri * (2 * m3 + 2 - i)) >> 1) + (kc + bq + u);
+                    r[u] = ldr12(G, s_cb[b3] - s_tet[m3] + ((ri * (2 * m3 + 2 - i)) >> 1) + (kc + bq + u));
                     w[u] = __ldg(&W3[(bq + u - 1) * n1 + k]);
                 }
 #pragma unroll
                 for (int u = 0; u < U4; ++u) {
-                    v0[u] = ld16(pPK, o[u]); v1[u] = ld16(pPfR, o[u]); v2[u] = ld16(pMpp, o[u]);
-                    v3[u] = ld16(pPRm00, o[u]); v4[u] = ld16(pPMm00, o[u]);
-                }
-#pragma unroll
-                for (int u = 0; u < U4; ++u) {
-                    aPK = min(aPK, v0[u] + w[u].y); aPfR = min(aPfR, v1[u] + w[u].y); aPfMp = min(aPfMp, v2[u] + w[u].y);
-                    aPRm00 = min(aPRm00, v3[u] + w[u].x); aPRm10 = min(aPRm10, v3[u] + w[u].z);
-                    aPMm00 = min(aPMm00, v4[u] + w[u].x);
+                    aPK = min(aPK, lo16(r[u].w0) + w[u].y); aPfR = min(aPfR, hi16(r[u].w0) + w[u].y);
+                    aPfMp = min(aPfMp, lo16(r[u].w1) + w[u].y);
+                    const int x = hi16(r[u].w1);
+                    aPRm00 = min(aPRm00, x + w[u].x); aPRm10 = min(aPRm10, x + w[u].z);
+                    aPMm00 = min(aPMm00, lo16(r[u].w2) + w[u].x);
                 }
             }
             for (; bq < b; ++bq) {
                 const int b3 = b - bq, m3 = ua - b3;
-                const int o3 = s_cb[b3] - s_tet[m3] + ((ri * (2 * m3 + 2 - i)) >> 1) + (kc + bq);
+                const R12 r = ldr12(G, s_cb[b3] - s_tet[m3] + ((ri * (2 * m3 + 2 - i)) >> 1) + (kc + bq));
                 const int4 w3 = __ldg(&W3[(bq - 1) * n1 + k]);
-                aPK = min(aPK, ld16(pPK, o3) + w3.y); aPfR = min(aPfR, ld16(pPfR, o3) + w3.y);
-                aPfMp = min(aPfMp, ld16(pMpp, o3) + w3.y);
-                const int x3 = ld16(pPRm00, o3);
+                aPK = min(aPK, lo16(r.w0) + w3.y); aPfR = min(aPfR, hi16(r.w0) + w3.y); aPfMp = min(aPfMp, lo16(r.w1) + w3.y);
+                const int x3 = hi16(r.w1);
                 aPRm00 = min(aPRm00, x3 + w3.x); aPRm10 = min(aPRm10, x3 + w3.z);
-                aPMm00 = min(aPMm00, ld16(pPMm00, o3) + w3.x);
+                aPMm00 = min(aPMm00, lo16(r.w2) + w3.x);
             }
         }
         SAVE(Q_PK3, aPK); SAVE(Q_PfR1, aPfR); SAVE(Q_PfMp, aPfMp); SAVE(Q_PRm00a, aPRm00); SAVE(Q_PRm10, aPRm10);
         SAVE(Q_PMm00b, aPMm00);
     } else if (role == ROLE_R4) {
         // X(i,j,k,d), d=k+bq, with the 2D record of (d+1, l)   [:382-383,429-432,504-507,520-523,567-570,585-588,
-        // 603-606,618-621,636-639]
+        // 603-606,618-621,636-639]; record g4 = PfromR PfromO | PRmloop00 PMmloop00 | PMmloop10 POmloop00 | POmloop10 -
         int aPfR = INF, aPfO = INF, aPRm00 = INF, aPRm01 = INF, aPMm01 = INF, aPMm10 = INF, aPOm00 = INF, aPOm01 = INF,
             aPOm10 = INF;
         if (b >= 1) {
-            const int16_t *__restrict__ pPfR = TB(T_PfromR), *__restrict__ pPfO = TB(T_PfromO), *__restrict__ pPRm00 = TB(T_PRmloop00),
-                          *__restrict__ pPMm00 = TB(T_PMmloop00), *__restrict__ pPMm10 = TB(T_PMmloop10),
-                          *__restrict__ pPOm00 = TB(T_POmloop00), *__restrict__ pPOm10 = TB(T_POmloop10);
+            const int4 *__restrict__ G = reinterpret_cast<const int4 *>(q.g4);
             {  // d=k
-                const int o = OFF(a, 0, i, k);
+                const int4 r = __ldg(&G[OFF(a, 0, i, k)]);
                 const int4 w = __ldg(&W3[(b - 1) * n1 + k + 1]);
-                const int x = ld16(pPRm00, o);
+                const int x = lo16(r.y);
                 aPRm00 = min(aPRm00, x + w.x);
                 aPRm01 = min(aPRm01, x + w.z);
-                aPMm01 = min(aPMm01, ld16(pPMm00, o) + w.z);
-                const int y = ld16(pPOm00, o);
+                aPMm01 = min(aPMm01, hi16(r.y) + w.z);
+                const int y = hi16(r.z);
                 aPOm00 = min(aPOm00, y + w.x);
                 aPOm01 = min(aPOm01, y + w.z);
             }
             const int ua = n - a - 2, ri = i - 1, kc = k - j - 2;
             int bq = 1;
             for (; bq + U4 <= b; bq += U4) {
-                int o[U4];
-                int4 w[U4];
-                int v0[U4], v1[U4], v2[U4], v3[U4], v4[U4], v5[U4], v6[U4];
+                int4 r[U4], w[U4];
 #pragma unroll
                 for (int u = 0; u < U4; ++u) {
                     const int b4 = bq + u, m4 = ua - b4;
-                    o[u] = s_cb[b4] - s_tet[m4] + ((ri * (2 * m4 + 2 - i)) >> 1) + kc;
+                    r[u] = __ldg(&G[s_cb[b4] - s_tet[m4] + ((ri * (2 * m4 + 2 - i)) >> 1) + kc]);
                     w[u] = __ldg(&W3[(b - b4 - 1) * n1 + k + b4 + 1]);
                 }
 #pragma unroll
                 for (int u = 0; u < U4; ++u) {
-                    v0[u] = ld16(pPfR, o[u]); v1[u] = ld16(pPfO, o[u]); v2[u] = ld16(pPRm00, o[u]); v3[u] = ld16(pPMm00, o[u]);
-                    v4[u] = ld16(pPMm10, o[u]); v5[u] = ld16(pPOm00, o[u]); v6[u] = ld16(pPOm10, o[u]);
-                }
-#pragma unroll
-                for (int u = 0; u < U4; ++u) {
-                    aPfR = min(aPfR, v0[u] + w[u].y); aPfO = min(aPfO, v1[u] + w[u].y);
-                    aPRm00 = min(aPRm00, v2[u] + w[u].x); aPRm01 = min(aPRm01, v2[u] + w[u].z);
-                    aPMm01 = min(aPMm01, v3[u] + w[u].z); aPMm10 = min(aPMm10, v4[u] + w[u].x);
-                    aPOm00 = min(aPOm00, v5[u] + w[u].x); aPOm01 = min(aPOm01, v5[u] + w[u].z);
-                    aPOm10 = min(aPOm10, v6[u] + w[u].x);
+                    aPfR = min(aPfR, lo16(r[u].x) + w[u].y); aPfO = min(aPfO, hi16(r[u].x) + w[u].y);
+                    const int x = lo16(r[u].y);
+                    aPRm00 = min(aPRm00, x + w[u].x); aPRm01 = min(aPRm01, x + w[u].z);
+                    aPMm01 = min(aPMm01, hi16(r[u].y) + w[u].z); aPMm10 = min(aPMm10, lo16(r[u].z) + w[u].x);
+                    const int y = hi16(r[u].z);
+                    aPOm00 = min(aPOm00, y + w[u].x); aPOm01 = min(aPOm01, y + w[u].z);
+                    aPOm10 = min(aPOm10, lo16(r[u].w) + w[u].x);
                 }
             }
             for (; bq < b; ++bq) {
                 const int m4 = ua - bq;
-                const int o4 = s_cb[bq] - s_tet[m4] + ((ri * (2 * m4 + 2 - i)) >> 1) + kc;
+                const int4 r = __ldg(&G[s_cb[bq] - s_tet[m4] + ((ri * (2 * m4 + 2 - i)) >> 1) + kc]);
                 const int4 w4 = __ldg(&W3[(b - bq - 1) * n1 + k + bq + 1]);
-                aPfR = min(aPfR, ld16(pPfR, o4) + w4.y); aPfO = min(aPfO, ld16(pPfO, o4) + w4.y);
-                const int x4 = ld16(pPRm00, o4);
+                aPfR = min(aPfR, lo16(r.x) + w4.y); aPfO = min(aPfO, hi16(r.x) + w4.y);
+                const int x4 = lo16(r.y);
                 aPRm00 = min(aPRm00, x4 + w4.x); aPRm01 = min(aPRm01, x4 + w4.z);
-                aPMm01 = min(aPMm01, ld16(pPMm00, o4) + w4.z); aPMm10 = min(aPMm10, ld16(pPMm10, o4) + w4.x);
-                const int y4 = ld16(pPOm00, o4);
+                aPMm01 = min(aPMm01, hi16(r.y) + w4.z); aPMm10 = min(aPMm10, lo16(r.z) + w4.x);
+                const int y4 = hi16(r.z);
                 aPOm00 = min(aPOm00, y4 + w4.x); aPOm01 = min(aPOm01, y4 + w4.z);
-                aPOm10 = min(aPOm10, ld16(pPOm10, o4) + w4.x);
+                aPOm10 = min(aPOm10, lo16(r.w) + w4.x);
             }
         }
         SAVE(Q_PfR2, aPfR); SAVE(Q_PfO2, aPfO); SAVE(Q_PRm00b, aPRm00); SAVE(Q_PRm01, aPRm01); SAVE(Q_PMm01, aPMm01);
@@ -583,10 +570,11 @@ __global__ void __launch_bounds__(K4_THREADS) k_final(const ccj_model *__restric
         return v;
     };
 #define PUT(tbl, val) put16(w4 + (int64_t)(tbl) * st4 + off0, (val))
-    PUT(T_PLmloop00, min(II + bp, min(GET(Q_PLm00a), GET(Q_PLm00b))));
+    const int vPLm00 = PUT(T_PLmloop00, min(II + bp, min(GET(Q_PLm00a), GET(Q_PLm00b))));
     PUT(T_PLmloop01, GET(Q_PLm01));
-    PUT(T_PLmloop10, min(GET(Q_PLm10a), GET(Q_PLm10b)));
-    PUT(T_PRmloop00, min(II + bp, min(GET(Q_PRm00a), GET(Q_PRm00b))));
+    const int vPLm10 = PUT(T_PLmloop10, min(GET(Q_PLm10a), GET(Q_PLm10b)));
+    const int vPRm00 = PUT(T_PRmloop00, min(II + bp, min(GET(Q_PRm00a), GET(Q_PRm00b))));
+    int vPMm00, vPMm10;
     {
         int e01 = INF, e10 = INF, f01 = INF;
         if (b >= 1) {
@@ -598,15 +586,15 @@ __global__ void __launch_bounds__(K4_THREADS) k_final(const ccj_model *__restric
         }
         PUT(T_PRmloop01, min(e01, GET(Q_PRm01)));
         PUT(T_PRmloop10, min(e10, GET(Q_PRm10)));
-        PUT(T_PMmloop00, min(II + bp, min(GET(Q_PMm00a), GET(Q_PMm00b))));
+        vPMm00 = PUT(T_PMmloop00, min(II + bp, min(GET(Q_PMm00a), GET(Q_PMm00b))));
         PUT(T_PMmloop01, min(f01, GET(Q_PMm01)));
         int g10 = INF;
         if (a >= 1) g10 = ld16(TB(T_PMmloop10), OFF(a - 1, b, i, k)) + cp;  // (i,j-1,k,l)
-        PUT(T_PMmloop10, min(g10, min(GET(Q_PMm10a), GET(Q_PMm10b))));
+        vPMm10 = PUT(T_PMmloop10, min(g10, min(GET(Q_PMm10a), GET(Q_PMm10b))));
     }
-    PUT(T_POmloop00, min(II + bp, min(GET(Q_POm00a), GET(Q_POm00b))));
+    const int vPOm00 = PUT(T_POmloop00, min(II + bp, min(GET(Q_POm00a), GET(Q_POm00b))));
     PUT(T_POmloop01, GET(Q_POm01));
-    PUT(T_POmloop10, min(GET(Q_POm10a), GET(Q_POm10b)));
+    const int vPOm10 = PUT(T_POmloop10, min(GET(Q_POm10a), GET(Q_POm10b)));
 
     const int8_t *__restrict__ S = q.S;
     auto ptype = [&](int x, int y) { return __ldg(&M->pair[S[x]][S[y]]); };
@@ -655,14 +643,27 @@ __global__ void __launch_bounds__(K4_THREADS) k_final(const ccj_model *__restric
         }
         vPO = PUT(T_PO, mn);
     }
-    PUT(T_PfromL, min(min(GET(Q_PfL1), GET(Q_PfL2)), min(vPR + PB, min(vPM + PB, vPO + PB))));
-    PUT(T_PfromR, min(min(GET(Q_PfR1), GET(Q_PfR2)), min(vPM + PB, vPO + PB)));
+    const int vPfL = PUT(T_PfromL, min(min(GET(Q_PfL1), GET(Q_PfL2)), min(vPR + PB, min(vPM + PB, vPO + PB))));
+    const int vPfR = PUT(T_PfromR, min(min(GET(Q_PfR1), GET(Q_PfR2)), min(vPM + PB, vPO + PB)));
     PUT(T_PfromM, GET(Q_PfM));
-    PUT(T_PfromMprime, GET(Q_PfMp) + PB);
-    PUT(T_PfromO, min(min(GET(Q_PfO1), GET(Q_PfO2)), min(vPL + PB, vPR + PB)));
+    const int vPfMp = PUT(T_PfromMprime, GET(Q_PfMp) + PB);
+    const int vPfO = PUT(T_PfromO, min(min(GET(Q_PfO1), GET(Q_PfO2)), min(vPL + PB, vPR + PB)));
     const int vPK = PUT(T_PK, min(min(GET(Q_PK1), GET(Q_PK3)), min(min(vPL + PB, vPM + PB), min(vPR + PB, vPO + PB))));
     w4[(int64_t)T_MPP * st4 + off0] = (int16_t)min(vPL, vPR);
     w4[(int64_t)T_PKG * st4 + ccj_pkg_idx(n, i, j, k, l)] = (int16_t)vPK;  // scattered: one store per cell
+    // read-group records (layout in ccj_types.h); consecutive cells -> consecutive records, coalesced
+    {
+        const int vMpp = min(vPL, vPR);
+        auto pk2 = [](int lo, int hi) { return (int)((uint32_t)(uint16_t)(int16_t)lo | ((uint32_t)(uint16_t)(int16_t)hi << 16)); };
+        int *r1 = reinterpret_cast<int *>(q.g1) + (int64_t)off0 * 3;
+        r1[0] = pk2(vPK, vPfL); r1[1] = pk2(vPfMp, vPLm00); r1[2] = pk2(vPLm10, vPMm00);
+        int *r2 = reinterpret_cast<int *>(q.g2) + (int64_t)off0 * 3;
+        r2[0] = pk2(vPfL, vPfO); r2[1] = pk2(vPLm00, vPMm00); r2[2] = pk2(vPOm00, 0);
+        int *r3 = reinterpret_cast<int *>(q.g3) + (int64_t)off0 * 3;
+        r3[0] = pk2(vPK, vPfR); r3[1] = pk2(vMpp, vPRm00); r3[2] = pk2(vPMm00, 0);
+        int4 *r4 = reinterpret_cast<int4 *>(q.g4) + off0;
+        *r4 = make_int4(pk2(vPfR, vPfO), pk2(vPRm00, vPMm00), pk2(vPMm10, vPOm00), pk2(vPOm10, 0));
+    }
 #undef PUT
 #undef GET
 }

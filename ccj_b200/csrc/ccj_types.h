@@ -111,6 +111,14 @@ struct ccj_seq {
     uint32_t *inlist;    // interior-loop partners INSIDE closing pair (i,j): slot tri(i,j)*CCJ_WIN, see ccj_fill4.cu
     uint32_t *outlist;   // interior-loop partners OUTSIDE inner pair (j,k)
     int32_t *incnt, *outcnt;  // entries per slot
+    // "read-group" copies of the gap tables (tuned path): the tables one split-point pattern reads at the SAME
+    // cell are interleaved as one record per cell, so a pattern step is one 12/16-byte read per cell instead
+    // of 5-7 two-byte reads from as many arrays (ccj_fill4.cu).  Indexed by ccj_idx4 * record length.
+    //   g1 (12 B): PK PfromL PfromMprime PLmloop00 PLmloop10 PMmloop00          read as X(i,d,k,l)
+    //   g2 (12 B): PfromL PfromO PLmloop00 PMmloop00 POmloop00 -                read as X(d,j,k,l)
+    //   g3 (12 B): PK PfromR min(PL,PR) PRmloop00 PMmloop00 -                   read as X(i,j,d,l)
+    //   g4 (16 B): PfromR PfromO PRmloop00 PMmloop00 PMmloop10 POmloop00 POmloop10 -   read as X(i,j,k,d)
+    int16_t *g1, *g2, *g3, *g4;
     int32_t *lay;        // layout tables: lay[x]=Tet(x), lay[n+1+x]=Cb(x), x=0..n (int32; tuned path, n<=448)
     int16_t *scratch;    // per-level partial minima: [partial id][cell of the level], see ccj_fill4.cu
     int64_t scratch_stride;   // cells of the largest level

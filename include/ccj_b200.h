@@ -107,7 +107,8 @@ int64_t ccj_layout_index(int n, int i, int j, int k, int l);
 
 /* Measurement helpers.
  * ccj_batch_fill_profiled: same work as ccj_batch_fill but launched kernel by kernel (no graph) with a
- * CUDA event pair around every launch; kernel_ms[0..3] = summed device time of K_4D, K_P, K_2D, other.
+ * CUDA event pair around every launch; kernel_ms[0..5] = summed device time of the gap-table split-point
+ * kernel (or the whole generic level kernel), K_P, K_2D, other, gap-table window kernel, gap-table assembly.
  * ccj_count_terms (host only): the algorithmic work of one fold as SURVEY.md 8d defines it:
  * out[0]=cells C(n+1,4), out[1]=split terms, out[2]=P terms, out[3]=interior-window terms this
  * sequence evaluates (can_pair-gated), all exact. */
