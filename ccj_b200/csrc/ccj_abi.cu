@@ -248,9 +248,14 @@ int ccj_ctx_create(int device, ccj_ctx **out) {
     if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) return CCJ_ERR_CUDA;
     ccj_ctx *ctx = new ccj_ctx();
     ctx->device = device;
-    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->s_win, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->s_2d, cudaStreamNonBlocking) != cudaSuccess ||
+    // the main stream carries the bandwidth-bound split-point kernels and the assembly (the critical path);
+    // the side streams only fill the issue slots it leaves idle -> lower priority
+    int prio_lo = 0, prio_hi = 0;
+    if (cudaSetDevice(device) == cudaSuccess) cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaSetDevice(device) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&ctx->s_win, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&ctx->s_2d, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
         cudaMalloc((void **)&ctx->d_model, sizeof(ccj_model)) != cudaSuccess) {
         delete ctx;

@@ -108,7 +108,8 @@ enum {  // partial ids in the scratch
     Q_PfL1, Q_PfO1, Q_PLm00b, Q_PLm10b, Q_PMm10a, Q_POm00a, Q_POm10a,               // role L2
     Q_PK3, Q_PfR1, Q_PfMp, Q_PRm00a, Q_PRm10, Q_PMm00b,                              // role R3
     Q_PfR2, Q_PfO2, Q_PRm00b, Q_PRm01, Q_PMm01, Q_PMm10b, Q_POm00b, Q_POm01, Q_POm10b,  // role R4
-    Q_PLw, Q_PRw, Q_PMw, Q_PRw_odd, Q_PMw_odd,  // windows; PR/PM double-buffered by level parity (Q_PRw + 2*(t&1))
+    Q_PLw, Q_PRw, Q_PMw, Q_PLw_odd, Q_PRw_odd, Q_PMw_odd,  // windows, double-buffered by level parity (Q_xx + 3*(t&1)):
+                                                              // the window kernels run one level ahead of k_final
     Q_COUNT
 };
 enum { ROLE_L1 = 0, ROLE_L2, ROLE_R3, ROLE_R4, ROLE_WL, ROLE_COUNT };
@@ -164,15 +165,17 @@ __device__ __forceinline__ bool cell_setup(const ccj_seq &q, int t, int a, int b
 
 #define TB(tbl) (t4 + (int64_t)(tbl) * st4)
 #define OFF(aa, bb, ii, kx) (s_cb[bb] - s_tet[n - (aa) - (bb)-2] + ((((ii)-1) * (2 * (n - (aa) - (bb)-2) + 2 - (ii))) >> 1) + ((kx) - (ii) - (aa)-2))
+#ifndef U4
 #define U4 4
+#endif
 
 __global__ void __launch_bounds__(K4_THREADS) k_roles(const ccj_model *__restrict__ M, const ccj_seq *__restrict__ seqs, int t,
                                                        int only_role) {
     __shared__ int s_tet[K4_MAXN + 4];
     __shared__ int s_cb[K4_MAXN + 4];
     // only_role == 0: blockIdx.z enumerates (sequence, role); else every block runs `only_role`
-    const int role = only_role ? only_role : (int)(blockIdx.z % ROLE_COUNT);
-    const ccj_seq q = seqs[only_role ? blockIdx.z : blockIdx.z / ROLE_COUNT];
+    const int role = only_role ? only_role : (int)(blockIdx.z % 4);  // the PL window moved to k_winLR
+    const ccj_seq q = seqs[only_role ? blockIdx.z : blockIdx.z / 4];
     const int n = q.n;
     if (n - t - 2 < 1) return;
     {
@@ -428,15 +431,15 @@ __global__ void __launch_bounds__(K4_THREADS) k_windows(const ccj_model *__restr
     __shared__ int it_slot[K4_THREADS], it_cnt[K4_MAXN > K4_THREADS ? K4_THREADS : K4_THREADS], it_K[K4_THREADS],
         it_rr[K4_THREADS], it_mn[K4_THREADS], it_c[K4_THREADS];
     __shared__ int n_items;
-    const int role = blockIdx.z & 1;  // 0: PR, 1: PM
-    const ccj_seq q = seqs[blockIdx.z >> 1];
+    const int role = 1;  // 0: PR (now k_winR), 1: PM
+    const ccj_seq q = seqs[blockIdx.z];
     const int n = q.n;
     const int m = n - t - 2;
     if (m < 1) return;
     const int ncell = m * (m + 1) / 2;
     if ((int)(blockIdx.x * K4_THREADS) >= ncell) return;
     const int a = blockIdx.y, b = t - a;
-    const int qid = (role == 0 ? Q_PRw : Q_PMw) + 2 * (t & 1);  // double-buffered: runs ahead of k_final
+    const int qid = (role == 0 ? Q_PRw : Q_PMw) + 3 * (t & 1);  // double-buffered: runs ahead of k_final
     int16_t *__restrict__ out = q.scratch + (int64_t)qid * q.scratch_stride + (int64_t)a * ncell;
     const int p = blockIdx.x * K4_THREADS + threadIdx.x;
     if (role == 0 ? (b <= CCJ_TURN) : (a < 1 || b < 1)) {
@@ -536,6 +539,102 @@ __global__ void __launch_bounds__(K4_THREADS) k_windows(const ccj_model *__restr
     }
 }
 
+// PL and PR interior windows (get_PLiloop :682-703, get_PRiloop :717-738).
+// Cells of a slab that share the closing pair share its partner list: for PL these are the cells of one row
+// (i,j fixed, k running), for PR the cells of one transposed row (k,l fixed, i running; read from the
+// transposed copy T_PRT).  A warp takes 32 consecutive cells in that order (1-3 such runs).  Per run the
+// lanes first turn the partner list, 32 entries at a time, into (offset, energy) pairs in shared memory (one
+// coalesced read, unpacked once), then all lanes walk those pairs: every candidate is one broadcast LDS, one
+// coalesced 64-byte load and one add-min per warp.
+#define WTILE 64
+__global__ void __launch_bounds__(K4_THREADS) k_winLR(const ccj_model *__restrict__ M, const ccj_seq *__restrict__ seqs, int t) {
+    __shared__ int s_T[64];                       // PL: cb(b)-tet(m+s)      PR: cb(b-s)-tet(m+s)
+    __shared__ int2 tile[K4_THREADS / 32][WTILE];  // per warp: (offset, energy) of the current list tile
+    const int role = blockIdx.z & 1;              // 0: PL (main order, T_PL)   1: PR (transposed order, T_PRT)
+    const ccj_seq q = seqs[blockIdx.z >> 1];
+    const int n = q.n;
+    const int m = n - t - 2;
+    if (m < 1) return;
+    const int ncell = m * (m + 1) / 2;
+    if ((int)(blockIdx.x * K4_THREADS) >= ncell) return;
+    const int a = blockIdx.y, b = t - a;
+    const int arm = role == 0 ? a : b;            // length of the arm whose closing pair carries the window
+    int16_t *__restrict__ out =
+        q.scratch + (int64_t)((role == 0 ? Q_PLw : Q_PRw) + 3 * (t & 1)) * q.scratch_stride + (int64_t)a * ncell;
+    const int pT = blockIdx.x * K4_THREADS + threadIdx.x;
+    if (arm <= CCJ_TURN) {  // can_pair fails for the whole slab
+        if (pT < ncell) out[pT] = 32767;
+        return;
+    }
+    const int *__restrict__ lay = q.lay;
+    if (threadIdx.x < 60) {
+        const int s = threadIdx.x;
+        int v = 0;
+        if (m + s <= n) {
+            if (role == 0) v = __ldg(&lay[n + 1 + b]) - __ldg(&lay[m + s]);
+            else if (b - s >= 0) v = __ldg(&lay[n + 1 + b - s]) - __ldg(&lay[m + s]);
+        }
+        s_T[s] = v;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const bool valid = pT < ncell;
+    const int pc = valid ? pT : ncell - 1;
+    int r = (int)(((2 * m + 1) - sqrtf((float)((2 * m + 1) * (2 * m + 1) - 8 * pc))) * 0.5f);
+    if (r < 0) r = 0;
+    if (r > m - 1) r = m - 1;
+    while (r > 0 && r * (2 * m + 1 - r) / 2 > pc) --r;
+    while ((r + 1) * (2 * m - r) / 2 <= pc) ++r;
+    const int row = r;                                  // PL: i-1          PR: kr = n-b-k
+    const int pos = pc - r * (2 * m + 1 - r) / 2;       // PL: k-j-2        PR: i-1
+    const int16_t *__restrict__ pX = q.t4 + (int64_t)(role == 0 ? T_PL : T_PRT) * q.stride4;
+    const int8_t *__restrict__ S = q.S;
+    const int n1 = n + 1;
+    const int INF = CCJ_INF;
+    int mn = INF;
+    const int r_lo = __shfl_sync(0xffffffffu, row, 0), r_hi = __shfl_sync(0xffffffffu, row, 31);
+    for (int c = r_lo; c <= r_hi; ++c) {  // warp-uniform
+        // closing pair (p5,p3) of this run
+        const int p5 = role == 0 ? c + 1 : n - b - c;
+        const int p3 = p5 + arm;
+        if (__ldg(&M->pair[S[p5]][S[p3]]) == 0) continue;
+        const bool mine = valid && row == c;
+        if (arm > CCJ_TURN + 2) {  // stacking term, x=y=1 (PL(i+1,j-1,k,l) / PR(i,j,k+1,l-1))
+            const int mm = m + 2;
+            const int rw = c + 2;  // PL: row of i+1   PR: transposed row kr+1
+            const int o = s_T[2] + (((rw - 1) * (2 * mm + 2 - rw)) >> 1) + pos + (role == 0 ? 1 : 0);
+            if (mine) mn = min(mn, ld16(pX, o) + __ldg(&q.estP[arm * n1 + p5]));
+        }
+        const int slot = ccj_tri(p5, p3);
+        const uint32_t *__restrict__ lst = q.inlist + (int64_t)slot * CCJ_WIN;
+        const int cnt = __ldg(&q.incnt[slot]);
+        for (int e0 = 0; e0 < cnt; e0 += WTILE) {
+            const int ne = min(WTILE, cnt - e0);
+            __syncwarp();
+            for (int e = lane; e < ne; e += 32) {
+                const uint32_t en = __ldg(&lst[e0 + e]);
+                const int x = (en >> 16) & 0xff, y = en >> 24, sxy = x + y;
+                const int mm = m + sxy;
+                // PL target (i+x, j-y, k, l): slab (a-s, b), row i+x, position k-(j-y)-2 = pos + y
+                // PR target (i, j, k+x, l-y): slab (a, b-s), transposed row kr+y, position i-1 = pos
+                const int rw = role == 0 ? c + 1 + x : c + y + 1;
+                int o = s_T[sxy] + (((rw - 1) * (2 * mm + 2 - rw)) >> 1);
+                if (role == 0) o += y;
+                tile[wid][e] = make_int2(o, (int)(int16_t)(en & 0xffff));
+            }
+            __syncwarp();
+            if (mine) {
+#pragma unroll 4
+                for (int e = 0; e < ne; ++e) {
+                    const int2 oe = tile[wid][e];
+                    mn = min(mn, oe.y + ld16(pX, oe.x + pos));
+                }
+            }
+        }
+    }
+    if (valid) out[pT] = sat16(mn);
+}
+
 // same-cell assembly in the reference's order (src/pseudo_loop.cc:85-127) from the partial minima
 __global__ void __launch_bounds__(K4_THREADS) k_final(const ccj_model *__restrict__ M, const ccj_seq *__restrict__ seqs, int t) {
     __shared__ int s_tet[K4_MAXN + 4];
@@ -604,7 +703,7 @@ __global__ void __launch_bounds__(K4_THREADS) k_final(const ccj_model *__restric
         int mn = INF;
         if (ptype(i, j) > 0 && a >= 2) {
             const int o = OFF(a - 2, b, i + 1, k);  // (i+1,j-1,k,l)
-            mn = GET(Q_PLw);
+            mn = GET(Q_PLw + 3 * (t & 1));
             mn = min(mn, min(ld16(TB(T_PLmloop10), o), ld16(TB(T_PLmloop01), o)) + apbp + bp);
             if (a >= CCJ_TURN + 1) mn = min(mn, ld16(TB(T_PfromL), o));
         }
@@ -614,7 +713,10 @@ __global__ void __launch_bounds__(K4_THREADS) k_final(const ccj_model *__restric
         int mn = INF;
         if (ptype(k, l) > 0 && b >= 2) {
             const int o = OFF(a, b - 2, i, k + 1);  // (i,j,k+1,l-1)
-            mn = GET(Q_PRw + 2 * (t & 1));
+            // the PR window kernel walks the slab transposed (i fastest): its partial sits at the transposed index
+            const int kr = n - b - k, mloc = n - t - 2;
+            const int pT = ((kr * (2 * mloc + 1 - kr)) >> 1) + (i - 1);
+            mn = (int)__ldg(q.scratch + (int64_t)(Q_PRw + 3 * (t & 1)) * ss + (int64_t)a * (mloc * (mloc + 1) / 2) + pT);
             mn = min(mn, min(ld16(TB(T_PRmloop10), o), ld16(TB(T_PRmloop01), o)) + apbp + bp);
             if (b >= CCJ_TURN + 1) mn = min(mn, ld16(TB(T_PfromR), o));
         }
@@ -625,7 +727,7 @@ __global__ void __launch_bounds__(K4_THREADS) k_final(const ccj_model *__restric
         if (ptype(j, k) > 0) {
             if (a >= 1 && b >= 1) {
                 const int o = OFF(a - 1, b - 1, i, k + 1);  // (i,j-1,k+1,l)
-                mn = GET(Q_PMw + 2 * (t & 1));
+                mn = GET(Q_PMw + 3 * (t & 1));
                 mn = min(mn, min(ld16(TB(T_PMmloop10), o), ld16(TB(T_PMmloop01), o)) + apbp + bp);
                 mn = min(mn, ld16(TB(T_PfromM), o));
             }
@@ -651,6 +753,10 @@ __global__ void __launch_bounds__(K4_THREADS) k_final(const ccj_model *__restric
     const int vPK = PUT(T_PK, min(min(GET(Q_PK1), GET(Q_PK3)), min(min(vPL + PB, vPM + PB), min(vPR + PB, vPO + PB))));
     w4[(int64_t)T_MPP * st4 + off0] = (int16_t)min(vPL, vPR);
     w4[(int64_t)T_PKG * st4 + ccj_pkg_idx(n, i, j, k, l)] = (int16_t)vPK;  // scattered: one store per cell
+    {   // PR transposed inside the slab: row kr=n-b-k, position i-1 (scattered: one store per cell)
+        const int kr = n - b - k, mloc = n - t - 2;
+        w4[(int64_t)T_PRT * st4 + (off0 - C.p) + ((kr * (2 * mloc + 1 - kr)) >> 1) + (i - 1)] = (int16_t)vPR;
+    }
     // read-group records (layout in ccj_types.h); consecutive cells -> consecutive records, coalesced
     {
         const int vMpp = min(vPL, vPR);
@@ -732,11 +838,13 @@ static bool level_dims(LaunchDims d, int t, int &bx) {
 }
 void launch_4d_roles(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st) {
     int bx;
-    if (level_dims(d, t, bx)) k_roles<<<dim3(bx, t + 1, d.nseq * ROLE_COUNT), K4_THREADS, 0, st>>>(M, seqs, t, 0);
+    if (level_dims(d, t, bx)) k_roles<<<dim3(bx, t + 1, d.nseq * 4), K4_THREADS, 0, st>>>(M, seqs, t, 0);
 }
 void launch_4d_windows(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st) {
     int bx;
-    if (level_dims(d, t, bx)) k_windows<<<dim3(bx, t + 1, d.nseq * 2), K4_THREADS, 0, st>>>(M, seqs, t);
+    if (!level_dims(d, t, bx)) return;
+    k_winLR<<<dim3(bx, t + 1, d.nseq * 2), K4_THREADS, 0, st>>>(M, seqs, t);
+    k_windows<<<dim3(bx, t + 1, d.nseq), K4_THREADS, 0, st>>>(M, seqs, t);
 }
 void launch_4d_final(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st) {
     int bx;

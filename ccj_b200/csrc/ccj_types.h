@@ -29,7 +29,8 @@ enum ccj_table4 {
     CCJ_NT4 = 22,
     T_MPP = 22,       /* internal: min(PL,PR) of the cell = get_PfromMdoubleprime without PB (pseudo_loop.cc:675-678) */
     T_PKG = 23,       /* internal: second copy of PK in the layout compute_P's 2nd factor walks (ccj_pkg_idx) */
-    CCJ_NT4_STORE = 24
+    T_PRT = 24,       /* internal: PR transposed inside every (a,b) slab (i fastest), read by the PR interior window */
+    CCJ_NT4_STORE = 25
 };
 
 // ---- 2D tables ----------------------------------------------------------------------------------
