@@ -42,7 +42,7 @@ size_t tab_bytes(int n, int which) {
         case TAB_OUTLIST: return align_up(tri * CCJ_WIN * sizeof(uint32_t), 256);
         case TAB_INCNT:
         case TAB_OUTCNT: return align_up(tri * sizeof(int32_t), 256);
-        case TAB_LAY: return align_up((size_t)(2 * n + 4) * sizeof(int32_t), 256);
+        case TAB_LAY: return align_up((size_t)(3 * n + 8) * sizeof(int32_t), 256);
         case TAB_SCRATCH: return align_up((size_t)ccj_level_max(n) * ccj::fill4_partials() * sizeof(int16_t) + 64, 256);
         case TAB_FTYPE: return align_up((size_t)n + 2, 256);
         case TAB_TBSTACK: return align_up(sizeof(int32_t) * 5 * (size_t)(16 * n + 64), 256);

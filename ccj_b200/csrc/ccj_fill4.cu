@@ -49,6 +49,9 @@ __global__ void __launch_bounds__(128) k_prep(const ccj_model *M, const ccj_seq 
         for (int x = threadIdx.x; x <= n; x += blockDim.x) {
             c.q.lay[x] = (int)ccj_tet(x);
             c.q.lay[n + 1 + x] = x <= n - 3 ? (int)ccj_cb(n, x) : 0;
+            int64_t bj = 0;  // basej[x] of ccj_pmm_idx
+            for (int jj = 1; jj < x; ++jj) bj += (int64_t)jj * ((int64_t)(n - jj - 1) * (n - jj) / 2);
+            c.q.lay[2 * n + 2 + x] = (int)bj;
         }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int8_t *S = c.q.S;
@@ -417,125 +420,87 @@ __global__ void __launch_bounds__(K4_THREADS) k_roles(const ccj_model *__restric
 #undef SAVE
 }
 
-// PR and PM interior windows (get_PRiloop :717-738, get_PMiloop :752-773).
-// Neighbouring cells have different closing pairs, so thread-per-cell ran these lists at 8/32 active lanes.
-// Here a block takes 128 consecutive cells of a slab: phase 1 (thread per cell) evaluates the gates, the
-// stacking term and compacts the cells that have a list into shared memory; phase 2 gives each such cell to
-// a whole warp: the lanes walk the partner list (coalesced), each lane gathers its own PR/PM neighbour and
-// the warp reduces with __reduce_min_sync.  Offsets use  R(m',i) = (i-1)m' + (i-1)(2-i)/2, so with s=x+y
-//   PR: off = [cb(b-s) - tet(m+s) + s] + (i-1)s - y + K      PM: off = cb(b-y) + [-tet(m+s) + s] + (i-1)s + K
-// and the bracketed terms are per-block tables.
-__global__ void __launch_bounds__(K4_THREADS) k_windows(const ccj_model *__restrict__ M, const ccj_seq *__restrict__ seqs, int t) {
-    __shared__ int s_T[64];    // PR: cb(b-s)-tet(m+s)+s   PM: -tet(m+s)+s
-    __shared__ int s_C[32];    // PM: cb(b-y)
-    __shared__ int it_slot[K4_THREADS], it_cnt[K4_MAXN > K4_THREADS ? K4_THREADS : K4_THREADS], it_K[K4_THREADS],
-        it_rr[K4_THREADS], it_mn[K4_THREADS], it_c[K4_THREADS];
-    __shared__ int n_items;
-    const int role = 1;  // 0: PR (now k_winR), 1: PM
+#define WTILE 64
+#define WB 8      // window candidates in flight per lane
+// PM interior window (get_PMiloop, src/pseudo_loop.cc:752-773).  The partner list belongs to the INNER pair
+// (j,k); the cells of one level that share it are (j-a, j, k, k+t-a) for a = amin..amax, contiguous in the
+// T_PMM copy.  One warp per (j,k): the lanes first turn 64 list entries into (offset, energy, bounds) in
+// shared memory, then walk them with the lanes spread over a: one broadcast LDS.128, one coalesced load and
+// one add-min per candidate and warp.
+__global__ void __launch_bounds__(K4_THREADS) k_winM(const ccj_model *__restrict__ M, const ccj_seq *__restrict__ seqs, int t) {
+    __shared__ int4 tile[K4_THREADS / 32][WTILE];  // (offset - a, energy, x, t - y)
     const ccj_seq q = seqs[blockIdx.z];
     const int n = q.n;
     const int m = n - t - 2;
     if (m < 1) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int j = blockIdx.y + 1;
+    const int k = j + 2 + blockIdx.x * (K4_THREADS / 32) + wid;
+    if (j > n || k > n) return;
+    const int A = j - 1, B = n - k;
+    const int amin = max(0, t - B), amax = min(t, A);
+    if (amin > amax) return;
     const int ncell = m * (m + 1) / 2;
-    if ((int)(blockIdx.x * K4_THREADS) >= ncell) return;
-    const int a = blockIdx.y, b = t - a;
-    const int qid = (role == 0 ? Q_PRw : Q_PMw) + 3 * (t & 1);  // double-buffered: runs ahead of k_final
-    int16_t *__restrict__ out = q.scratch + (int64_t)qid * q.scratch_stride + (int64_t)a * ncell;
-    const int p = blockIdx.x * K4_THREADS + threadIdx.x;
-    if (role == 0 ? (b <= CCJ_TURN) : (a < 1 || b < 1)) {
-        // gate fails for the whole slab: PRiloop needs can_pair(k,l), PMiloop's terms need i<j and k<l
-        if (p < ncell) out[p] = 32767;
-        return;
-    }
-    const int *__restrict__ lay = q.lay;
-    if (threadIdx.x < 60) {
-        const int s = threadIdx.x;
-        int v = 0;
-        if (m + s <= n) {
-            v = -__ldg(&lay[m + s]) + s;
-            if (role == 0) v = (b - s >= 0) ? v + __ldg(&lay[n + 1 + b - s]) : 0;
-        }
-        s_T[s] = v;
-    } else if (threadIdx.x >= 64 && threadIdx.x < 96) {
-        const int y = threadIdx.x - 64;
-        s_C[y] = (b - y >= 0) ? __ldg(&lay[n + 1 + b - y]) : 0;
-    }
-    if (threadIdx.x == 0) n_items = 0;
-    __syncthreads();
-    const int16_t *__restrict__ t4 = q.t4;
-    const int64_t st4 = q.stride4;
+    int16_t *__restrict__ out = q.scratch + (int64_t)(Q_PMw + 3 * (t & 1)) * q.scratch_stride;
+    const int32_t *__restrict__ basej = q.lay + 2 * n + 2;
+    const int16_t *__restrict__ pX = q.t4 + (int64_t)T_PMM * q.stride4;
+    const int8_t *__restrict__ S = q.S;
     const int n1 = n + 1;
     const int INF = CCJ_INF;
-    const int8_t *__restrict__ S = q.S;
-    const int16_t *__restrict__ pX = t4 + (int64_t)(role == 0 ? T_PR : T_PM) * st4;
-    // ---- phase 1: thread per cell ----
-    if (p < ncell) {
-        int r = (int)(((2 * m + 1) - sqrtf((float)((2 * m + 1) * (2 * m + 1) - 8 * p))) * 0.5f);
-        if (r < 0) r = 0;
-        if (r > m - 1) r = m - 1;
-        while (r > 0 && r * (2 * m + 1 - r) / 2 > p) --r;
-        while ((r + 1) * (2 * m - r) / 2 <= p) ++r;
-        const int i = r + 1, kk = p - r * (2 * m + 1 - r) / 2;
-        const int j = i + a, k = j + 2 + kk, l = k + b;
-        const int rr = i - 1;
-        // K = cell-constant part of every offset: (i-1)m + (i-1)(2-i)/2 + (k-j-2)
-        const int K = rr * m + ((rr * (2 - i)) >> 1) + kk;
-        int mn = INF, slot = -1, cnt = 0;
-        if (role == 0) {
-            if (__ldg(&M->pair[S[k]][S[l]]) > 0) {
-                if (b > CCJ_TURN + 2) {  // PR(i,j,k+1,l-1): x=y=1, s=2
-                    const int o = s_T[2] + rr * 2 - 1 + K;
-                    mn = ld16(pX, o) + __ldg(&q.estP[b * n1 + k]);
-                }
-                slot = ccj_tri(k, l);
-                cnt = __ldg(&q.incnt[slot]);
-            }
-        } else {
-            if (k - j > CCJ_TURN && __ldg(&M->pair[S[j]][S[k]]) > 0) {
-                // PM(i,j-1,k+1,l): x=y=1, s=2
-                const int o = s_C[1] + s_T[2] + rr * 2 + K;
-                mn = ld16(pX, o) + __ldg(&q.estP[(k - j + 2) * n1 + (j - 1)]);
-                slot = ccj_tri(j, k);
-                cnt = __ldg(&q.outcnt[slot]);
-            }
-        }
-        if (cnt > 0) {
-            const int pos = atomicAdd(&n_items, 1);
-            it_slot[pos] = slot; it_cnt[pos] = cnt; it_K[pos] = K; it_rr[pos] = rr; it_mn[pos] = mn; it_c[pos] = p;
-        } else {
-            out[p] = sat16(mn);
-        }
+    const bool gate = (k - j > CCJ_TURN) && __ldg(&M->pair[S[j]][S[k]]) > 0;
+    const int slot = ccj_tri(j, k);
+    const uint32_t *__restrict__ lst = q.outlist + (int64_t)slot * CCJ_WIN;
+    const int cnt = gate ? __ldg(&q.outcnt[slot]) : 0;
+    int stack_base = 0, stack_e = 0;
+    if (gate && t >= 2) {  // PM(i,j-1,k+1,l) + e_stP(j-1,k+1): needs a>=1, b>=1
+        stack_base = (int)ccj_pmm_idx(n, basej, j - 1, k + 1, t - 2, 0) - 1;  // + a  (a' = a-1)
+        stack_e = __ldg(&q.estP[(k - j + 2) * n1 + (j - 1)]);
     }
-    __syncthreads();
-    // ---- phase 2: warp per listed cell ----
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int items = n_items;
-    const uint32_t *__restrict__ lists = role == 0 ? q.inlist : q.outlist;
-    for (int it = wid; it < items; it += K4_THREADS / 32) {
-        const uint32_t *__restrict__ lst = lists + (int64_t)it_slot[it] * CCJ_WIN;
-        const int cnt = it_cnt[it], K = it_K[it], rr = it_rr[it];
+    for (int a0 = amin; a0 <= amax; a0 += 32) {
+        const int a = a0 + lane;
+        const bool have = a <= amax;
+        const int b = t - a;
         int mn = INF;
-        if (role == 0) {
-#pragma unroll 2
-            for (int e = lane; e < cnt; e += 32) {
-                const uint32_t en = __ldg(&lst[e]);
-                const int x = (en >> 16) & 0xff, y = en >> 24, s = x + y;
-                const int o = s_T[s] + rr * s - y + K;
-                mn = min(mn, (int)(int16_t)(en & 0xffff) + ld16(pX, o));
-            }
-        } else {
-#pragma unroll 2
-            for (int e = lane; e < cnt; e += 32) {
-                const uint32_t en = __ldg(&lst[e]);
-                const int x = (en >> 16) & 0xff, y = en >> 24, s = x + y;
-                if (x < a && y < b) {
-                    const int o = s_C[y] + s_T[s] + rr * s + K;
-                    mn = min(mn, (int)(int16_t)(en & 0xffff) + ld16(pX, o));
+        if (gate) {
+            if (have && a >= 1 && b >= 1) mn = ld16(pX, stack_base + a) + stack_e;
+            for (int e0 = 0; e0 < cnt; e0 += WTILE) {
+                const int ne = min(WTILE, cnt - e0);
+                __syncwarp();
+                for (int e = lane; e < ne; e += 32) {
+                    const uint32_t en = __ldg(&lst[e0 + e]);
+                    const int x = (en >> 16) & 0xff, y = en >> 24;
+                    int off = 0;
+                    if (t - x - y >= 0 && j - x >= 1 && k + y <= n)
+                        off = (int)ccj_pmm_idx(n, basej, j - x, k + y, t - x - y, 0) - x;  // + a  (a' = a-x)
+                    tile[wid][e] = make_int4(off, (int)(int16_t)(en & 0xffff), x, t - y);
+                }
+                __syncwarp();
+                const int16_t *pb = pX + a;
+                asm volatile("" : "+l"(pb));
+                int e = 0;
+                for (; e + WB <= ne; e += WB) {  // WB candidates in flight per lane
+                    int v[WB], en[WB];
+#pragma unroll
+                    for (int u = 0; u < WB; ++u) {
+                        const int4 oe = tile[wid][e + u];
+                        const bool ok = have && a > oe.z && a < oe.w;
+                        v[u] = ok ? ld16(pb, oe.x) : 0;
+                        en[u] = ok ? oe.y : INF;
+                    }
+#pragma unroll
+                    for (int u = 0; u < WB; ++u) mn = min(mn, en[u] + v[u]);
+                }
+                for (; e < ne; ++e) {
+                    const int4 oe = tile[wid][e];
+                    if (have && a > oe.z && a < oe.w) mn = min(mn, oe.y + ld16(pb, oe.x));
                 }
             }
         }
-        mn = __reduce_min_sync(0xffffffffu, mn);
-        if (lane == 0) out[it_c[it]] = sat16(min(mn, it_mn[it]));
+        if (have) {
+            const int i = j - a;
+            const int p = (((i - 1) * (2 * m + 2 - i)) >> 1) + (k - j - 2);
+            out[(int64_t)a * ncell + p] = sat16(mn);
+        }
     }
 }
 
@@ -546,7 +511,6 @@ __global__ void __launch_bounds__(K4_THREADS) k_windows(const ccj_model *__restr
 // lanes first turn the partner list, 32 entries at a time, into (offset, energy) pairs in shared memory (one
 // coalesced read, unpacked once), then all lanes walk those pairs: every candidate is one broadcast LDS, one
 // coalesced 64-byte load and one add-min per warp.
-#define WTILE 64
 __global__ void __launch_bounds__(K4_THREADS) k_winLR(const ccj_model *__restrict__ M, const ccj_seq *__restrict__ seqs, int t) {
     __shared__ int s_T[64];                       // PL: cb(b)-tet(m+s)      PR: cb(b-s)-tet(m+s)
     __shared__ int2 tile[K4_THREADS / 32][WTILE];  // per warp: (offset, energy) of the current list tile
@@ -624,10 +588,23 @@ __global__ void __launch_bounds__(K4_THREADS) k_winLR(const ccj_model *__restric
             }
             __syncwarp();
             if (mine) {
-#pragma unroll 4
-                for (int e = 0; e < ne; ++e) {
+                const int16_t *pb = pX + pos;  // per-thread base held in a register pair: one IMAD.WIDE per candidate
+                asm volatile("" : "+l"(pb));
+                int e = 0;
+                for (; e + WB <= ne; e += WB) {  // WB candidates in flight per lane
+                    int v[WB], en[WB];
+#pragma unroll
+                    for (int u = 0; u < WB; ++u) {
+                        const int2 oe = tile[wid][e + u];
+                        v[u] = ld16(pb, oe.x);
+                        en[u] = oe.y;
+                    }
+#pragma unroll
+                    for (int u = 0; u < WB; ++u) mn = min(mn, en[u] + v[u]);
+                }
+                for (; e < ne; ++e) {
                     const int2 oe = tile[wid][e];
-                    mn = min(mn, oe.y + ld16(pX, oe.x + pos));
+                    mn = min(mn, oe.y + ld16(pb, oe.x));
                 }
             }
         }
@@ -753,6 +730,7 @@ __global__ void __launch_bounds__(K4_THREADS) k_final(const ccj_model *__restric
     const int vPK = PUT(T_PK, min(min(GET(Q_PK1), GET(Q_PK3)), min(min(vPL + PB, vPM + PB), min(vPR + PB, vPO + PB))));
     w4[(int64_t)T_MPP * st4 + off0] = (int16_t)min(vPL, vPR);
     w4[(int64_t)T_PKG * st4 + ccj_pkg_idx(n, i, j, k, l)] = (int16_t)vPK;  // scattered: one store per cell
+    w4[(int64_t)T_PMM * st4 + ccj_pmm_idx(n, q.lay + 2 * n + 2, j, k, t, a)] = (int16_t)vPM;  // scattered
     {   // PR transposed inside the slab: row kr=n-b-k, position i-1 (scattered: one store per cell)
         const int kr = n - b - k, mloc = n - t - 2;
         w4[(int64_t)T_PRT * st4 + (off0 - C.p) + ((kr * (2 * mloc + 1 - kr)) >> 1) + (i - 1)] = (int16_t)vPR;
@@ -844,7 +822,8 @@ void launch_4d_windows(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, in
     int bx;
     if (!level_dims(d, t, bx)) return;
     k_winLR<<<dim3(bx, t + 1, d.nseq * 2), K4_THREADS, 0, st>>>(M, seqs, t);
-    k_windows<<<dim3(bx, t + 1, d.nseq), K4_THREADS, 0, st>>>(M, seqs, t);
+    const int nm = d.nmax, wpb = K4_THREADS / 32;
+    k_winM<<<dim3((nm + wpb - 1) / wpb, nm, d.nseq), K4_THREADS, 0, st>>>(M, seqs, t);
 }
 void launch_4d_final(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st) {
     int bx;

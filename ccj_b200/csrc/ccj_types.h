@@ -30,7 +30,8 @@ enum ccj_table4 {
     T_MPP = 22,       /* internal: min(PL,PR) of the cell = get_PfromMdoubleprime without PB (pseudo_loop.cc:675-678) */
     T_PKG = 23,       /* internal: second copy of PK in the layout compute_P's 2nd factor walks (ccj_pkg_idx) */
     T_PRT = 24,       /* internal: PR transposed inside every (a,b) slab (i fastest), read by the PR interior window */
-    CCJ_NT4_STORE = 25
+    T_PMM = 25,       /* internal: PM keyed by its pair (j,k): nesting [j][k][level][a], read by the PM interior window */
+    CCJ_NT4_STORE = 26
 };
 
 // ---- 2D tables ----------------------------------------------------------------------------------
@@ -120,7 +121,7 @@ struct ccj_seq {
     //   g3 (12 B): PK PfromR min(PL,PR) PRmloop00 PMmloop00 -                   read as X(i,j,d,l)
     //   g4 (16 B): PfromR PfromO PRmloop00 PMmloop00 PMmloop10 POmloop00 POmloop10 -   read as X(i,j,k,d)
     int16_t *g1, *g2, *g3, *g4;
-    int32_t *lay;        // layout tables: lay[x]=Tet(x), lay[n+1+x]=Cb(x), x=0..n (int32; tuned path, n<=448)
+    int32_t *lay;        // layout tables: lay[x]=Tet(x), lay[n+1+x]=Cb(x), x=0..n; lay[2n+2+j]=basej[j] of ccj_pmm_idx (int32; tuned path, n<=448)
     int16_t *scratch;    // per-level partial minima: [partial id][cell of the level], see ccj_fill4.cu
     int64_t scratch_stride;   // cells of the largest level
     int32_t *tb_stack;   // traceback stack, 5 ints per node
@@ -166,6 +167,23 @@ CCJ_HD int64_t ccj_level_max(int n) {
 CCJ_HD int64_t ccj_pkg_idx(int n, int i, int j, int k, int l) {
     const int64_t s = l - i, g = k - j;
     return (ccj_pent(n - 2) - ccj_pent(n - i - 1)) + ccj_tet(s - 2) + (s * (s - 1) / 2 - (s - g + 1) * (s - g + 2) / 2) + (j - i);
+}
+
+// PM copy for the PM interior window (get_PMiloop, src/pseudo_loop.cc:752-773): all cells with the same inner
+// pair (j,k) form one block of (A+1)(B+1) entries, A=j-1, B=n-k, ordered by level t=a+b and then by a, so the
+// cells (i,j,k,l) of ONE level that share (j,k) -- the only ones that share a partner list -- are contiguous.
+//   basej[j] = sum_{j'<j} j' * T(n-j'-1)   (precomputed per sequence length; T(x)=x(x+1)/2)
+CCJ_HD int64_t ccj_pmm_idx(int n, const int32_t *basej, int j, int k, int t, int a) {
+    const int64_t A = j - 1, B = n - k;
+    auto T = [](int64_t x) { return x * (x + 1) / 2; };
+    const int64_t blockbase = (int64_t)basej[j] + (int64_t)j * (T(n - j - 1) - T(n - k + 1));
+    const int64_t lo = A < B ? A : B, hi = A < B ? B : A;
+    int64_t S;
+    if (t <= lo) S = T(t);
+    else if (t <= hi) S = T(lo + 1) + (t - lo - 1) * (lo + 1);
+    else S = T(lo + 1) + (hi - lo) * (lo + 1) + (t - hi - 1) * (A + B + 1) - (T(t - 1) - T(hi));
+    const int64_t amin = t - B > 0 ? t - B : 0;
+    return blockbase + S + (a - amin);
 }
 
 CCJ_HD bool ccj_valid4(int i, int j, int k, int l) { return i <= j && j < k - 1 && k <= l; }
