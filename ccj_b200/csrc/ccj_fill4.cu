@@ -421,7 +421,9 @@ __global__ void __launch_bounds__(K4_THREADS) k_roles(const ccj_model *__restric
 }
 
 #define WTILE 64
+#ifndef WB
 #define WB 8      // window candidates in flight per lane
+#endif
 // PM interior window (get_PMiloop, src/pseudo_loop.cc:752-773).  The partner list belongs to the INNER pair
 // (j,k); the cells of one level that share it are (j-a, j, k, k+t-a) for a = amin..amax, contiguous in the
 // T_PMM copy.  One warp per (j,k): the lanes first turn 64 list entries into (offset, energy, bounds) in
