@@ -432,7 +432,7 @@ int ccj_batch_fill(ccj_ctx *ctx) {
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaGetLastError());
     CU(cudaEventElapsedTime(&ctx->fill_ms, ctx->ev0, ctx->ev1));
-    ctx->fill_launches = ccj::fill_launch_count(d.nmax);
+    ctx->fill_launches = ccj::fill_launch_count(d.nmax, use_tuned(d.nmax));
     ctx->filled = true;
     ctx->traced = false;
     return 0;
@@ -445,7 +445,7 @@ int ccj_batch_fill_profiled(ccj_ctx *ctx, float *kernel_ms) {
     ccj::LaunchDims d;
     d.nseq = (int)ctx->plan.size();
     d.nmax = ctx->nmax;
-    const int nlaunch = 3 * ccj::fill_launch_count(d.nmax) + 8;
+    const int nlaunch = ccj::fill_launch_count(d.nmax, true) + 8;
     std::vector<cudaEvent_t> ev((size_t)nlaunch + 1);
     std::vector<int> kind;
     for (auto &e : ev) CU(cudaEventCreate(&e));

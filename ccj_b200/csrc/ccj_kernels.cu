@@ -149,12 +149,12 @@ void launch_traceback(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cud
     k_traceback<<<d.nseq, 32, 0, st>>>(M, seqs);
 }
 
-int fill_launch_count(int nmax) {
-    int c = 2;  // init + W
+int fill_launch_count(int nmax, bool tuned) {
+    int c = tuned ? 3 : 2;  // init (+ prep) + W
     for (int s = 0; s < nmax; ++s) {
-        if (s >= 3 && s <= nmax - 1) ++c;
-        ++c;
-        if (nmax - s - 2 >= 1) ++c;
+        if (s >= 3 && s <= nmax - 1) ++c;           // K_P
+        ++c;                                        // K_2D
+        if (nmax - s - 2 >= 1) c += tuned ? 4 : 1;  // level: split roles, PL/PR windows, PM window, assembly
     }
     return c;
 }

@@ -37,6 +37,6 @@ void launch_W(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cudaStream_
 void launch_traceback(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cudaStream_t st);
 
 // number of kernel launches the fill of a wave with longest sequence nmax issues (for gpu_launches)
-int fill_launch_count(int nmax);
+int fill_launch_count(int nmax, bool tuned);
 
 }  // namespace ccj
