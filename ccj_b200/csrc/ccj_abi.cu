@@ -412,7 +412,7 @@ int ccj_batch_fill(ccj_ctx *ctx) {
     ccj::LaunchDims d;
     d.nseq = (int)ctx->plan.size();
     d.nmax = ctx->nmax;
-    const std::pair<int, int> key(d.nmax, d.nseq);
+    const std::pair<int, int> key(d.nmax, d.nseq * 2 + (use_tuned(d.nmax) ? 1 : 0));  // the env toggle changes the launch sequence
     auto it = ctx->graphs.find(key);
     if (it == ctx->graphs.end()) {
         // capture the per-level launch sequence once per wave shape

@@ -129,3 +129,31 @@ def test_structure_is_consistent_with_pairs_at_benchmark_size(ctx_factory):
                 depth += (ch == o) - (ch == c)
                 assert depth >= 0
             assert depth == 0
+
+
+def _all_hashes(ctx):
+    out = {name: ctx.table4_hash(0, name) for name in ccj_b200.TABLE4}
+    out.update({name: ctx.table2_hash(0, name) for name in ccj_b200.TABLE2[:8]})
+    return out
+
+
+@pytest.mark.parametrize("n", [97, 230])
+def test_tuned_kernels_equal_generic_kernels(ctx_factory, monkeypatch, n):
+    """The tuned level kernels (read-group records, window lists, transposed copies) against the generic
+    one-thread-per-cell kernel that calls ccj_cell4d, on every table -- also beyond n=213, where the
+    reference itself aborts (SURVEY.md finding 2) and cannot serve as the oracle."""
+    rng = random.Random(4000 + n)
+    seq = "".join(rng.choice("ACGU") for _ in range(n))
+    ctx = ctx_factory()
+    ctx.prepare([seq])
+    ctx.fill()
+    ctx.traceback()
+    tuned, fold_t = _all_hashes(ctx), ctx.fetch()[0]
+    monkeypatch.setenv("CCJ_FILL_GENERIC", "1")
+    ctx.prepare([seq])
+    ctx.fill()
+    ctx.traceback()
+    generic, fold_g = _all_hashes(ctx), ctx.fetch()[0]
+    monkeypatch.delenv("CCJ_FILL_GENERIC")
+    assert tuned == generic
+    assert fold_t == fold_g
