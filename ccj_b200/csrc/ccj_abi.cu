@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -25,9 +26,10 @@ struct SeqPlan {
 };
 
 // the per-sequence device buffers behind ccj_seq, in arena order
-enum { TAB_T4 = 0, TAB_G1, TAB_G2, TAB_G3, TAB_G4, TAB_T2, TAB_W3, TAB_ESTP, TAB_INLIST, TAB_OUTLIST, TAB_INCNT, TAB_OUTCNT, TAB_LAY, TAB_SCRATCH, TAB_FTYPE, TAB_TBSTACK,
+enum { TAB_T4 = 0, TAB_G1, TAB_G2, TAB_G3, TAB_G4, TAB_T2, TAB_W3, TAB_ESTP, TAB_INLIST, TAB_OUTLIST, TAB_INCNT, TAB_OUTCNT, TAB_LAY, TAB_SCRATCH,
+       TAB_PLW, TAB_PRW, TAB_PMW, TAB_WSCR, TAB_PMLEV, TAB_PLIST, TAB_PCUM, TAB_PMLIST, TAB_PMSTART, TAB_FTYPE, TAB_TBSTACK,
        TAB_COUNT };
-size_t tab_bytes(int n, int which) {
+size_t tab_bytes_uncached(int n, int which) {
     const size_t tri = (size_t)n * (n - 1) / 2 + 1;
     switch (which) {
         case TAB_T4: return align_up((size_t)ccj_cells4(n) * CCJ_NT4_STORE * sizeof(int16_t) + 16, 256);
@@ -38,22 +40,46 @@ size_t tab_bytes(int n, int which) {
         case TAB_T2: return align_up((size_t)ccj_stride2(n) * CCJ_NT2 * sizeof(int32_t), 256);
         case TAB_W3: return align_up((size_t)ccj_stride2(n) * 4 * sizeof(int32_t), 256);
         case TAB_ESTP: return align_up((size_t)ccj_stride2(n) * sizeof(int32_t), 256);
-        case TAB_INLIST:
-        case TAB_OUTLIST: return align_up(tri * CCJ_WIN * sizeof(uint32_t), 256);
+        case TAB_INLIST: return align_up(tri * CCJ_WIN_IN * sizeof(uint32_t), 256);
+        case TAB_OUTLIST: return align_up(tri * CCJ_WIN_OUT * 2 * sizeof(uint32_t), 256);
         case TAB_INCNT:
         case TAB_OUTCNT: return align_up(tri * sizeof(int32_t), 256);
-        case TAB_LAY: return align_up((size_t)(3 * n + 8) * sizeof(int32_t), 256);
+        case TAB_LAY: return align_up((size_t)(5 * (n + 1) + 8) * sizeof(int32_t), 256);
         case TAB_SCRATCH: return align_up((size_t)ccj_level_max(n) * ccj::fill4_partials() * sizeof(int16_t) + 64, 256);
+        case TAB_PLW:
+        case TAB_PRW: return align_up((size_t)ccj_winlr_quads(n) * 4 * sizeof(int16_t) + 64, 256);
+        case TAB_PMW: return align_up(((size_t)ccj_pmw_level_quads(n) * (size_t)(n > 2 ? n - 2 : 1) + 16) * 16, 256);  // 16 bytes per quad: 4 values + 4 masks
+        case TAB_WSCR: return align_up(((size_t)ccj_winlr_level_max(n) * 4 + (size_t)ccj_pmw_level_quads(n) * 8) * sizeof(int16_t) + 64, 256);
+        case TAB_PMLEV: return align_up((size_t)(n + 1) * (n + 1) * sizeof(int32_t) + 64, 256);
+        case TAB_PLIST: return align_up((size_t)(n + 1) * (n + 1) * sizeof(int32_t), 256);
+        case TAB_PCUM: return align_up((size_t)(n + 1) * (n + 2) * sizeof(int32_t), 256);
+        case TAB_PMLIST: return align_up(tri * sizeof(int32_t), 256);
+        case TAB_PMSTART: return align_up((size_t)(n + 4) * sizeof(int32_t), 256);
         case TAB_FTYPE: return align_up((size_t)n + 2, 256);
         case TAB_TBSTACK: return align_up(sizeof(int32_t) * 5 * (size_t)(16 * n + 64), 256);
     }
     return 0;
 }
-size_t tab_offset(int n, int which) {
-    size_t o = 0;
-    for (int x = 0; x < which; ++x) o += tab_bytes(n, x);
-    return o;
+// the window layouts need O(n^2) host loops to size: memoise per length
+struct TabSizes { size_t bytes[TAB_COUNT]; size_t off[TAB_COUNT + 1]; int64_t wscr_lr; int32_t wtot4; };
+const TabSizes &tab_sizes(int n) {
+    static std::mutex mu;
+    static std::map<int, TabSizes> cache;
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(n);
+    if (it != cache.end()) return it->second;
+    TabSizes z;
+    z.off[0] = 0;
+    for (int x = 0; x < TAB_COUNT; ++x) {
+        z.bytes[x] = tab_bytes_uncached(n, x);
+        z.off[x + 1] = z.off[x] + z.bytes[x];
+    }
+    z.wscr_lr = ccj_winlr_level_max(n);
+    z.wtot4 = (int32_t)ccj_pmw_level_quads(n);
+    return cache.emplace(n, z).first->second;
 }
+size_t tab_bytes(int n, int which) { return tab_sizes(n).bytes[which]; }
+size_t tab_offset(int n, int which) { return tab_sizes(n).off[which]; }
 
 // per-sequence byte needs
 void plan_seq(int n, SeqPlan &p) {
@@ -390,6 +416,17 @@ int ccj_batch_prepare(ccj_ctx *ctx, const char *seqs, const int64_t *offsets, in
         q.lay = reinterpret_cast<int32_t *>(t + tab_offset(n, TAB_LAY));
         q.scratch = reinterpret_cast<int16_t *>(t + tab_offset(n, TAB_SCRATCH));
         q.scratch_stride = ccj_level_max(n);
+        q.plw = reinterpret_cast<int16_t *>(t + tab_offset(n, TAB_PLW));
+        q.prw = reinterpret_cast<int16_t *>(t + tab_offset(n, TAB_PRW));
+        q.pmw = reinterpret_cast<int16_t *>(t + tab_offset(n, TAB_PMW));
+        q.wscr = reinterpret_cast<int16_t *>(t + tab_offset(n, TAB_WSCR));
+        q.wscr_lr = tab_sizes(n).wscr_lr;
+        q.wtot4 = tab_sizes(n).wtot4;
+        q.pmlev4 = reinterpret_cast<int32_t *>(t + tab_offset(n, TAB_PMLEV));
+        q.plist = reinterpret_cast<int32_t *>(t + tab_offset(n, TAB_PLIST));
+        q.pcum = reinterpret_cast<int32_t *>(t + tab_offset(n, TAB_PCUM));
+        q.pmlist = reinterpret_cast<int32_t *>(t + tab_offset(n, TAB_PMLIST));
+        q.pmstart = reinterpret_cast<int32_t *>(t + tab_offset(n, TAB_PMSTART));
         q.ftype_out = reinterpret_cast<int8_t *>(t + tab_offset(n, TAB_FTYPE));
         q.tb_stack = reinterpret_cast<int32_t *>(t + tab_offset(n, TAB_TBSTACK));
         q.tb_cap = 16 * n + 64;

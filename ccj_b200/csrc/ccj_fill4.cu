@@ -16,6 +16,8 @@
 #include "ccj_kernels.cuh"
 #include "ccj_cells4.cuh"
 
+#include <algorithm>
+
 namespace ccj {
 
 #ifndef K4_THREADS
@@ -38,6 +40,74 @@ __device__ __forceinline__ bool pack_entry(int e, int x, int y, uint32_t &out, i
     return true;
 }
 
+// layout tables, PM row offsets and the per-arm lists of pairs; one block per sequence, before k_prep
+__global__ void __launch_bounds__(256) k_prep_lay(const ccj_model *M, const ccj_seq *seqs) {
+    __shared__ int s_row[K4_MAXN + 4];
+    const ccj_seq q = seqs[blockIdx.x];
+    const int n = q.n;
+    if (n > K4_MAXN || n < 1) return;
+    const int n1 = n + 1;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int *lay = q.lay;
+    for (int x = threadIdx.x; x <= n; x += blockDim.x) {
+        lay[x] = (int)ccj_tet(x);
+        lay[n1 + x] = x <= n - 3 ? (int)ccj_cb(n, x) : 0;
+        lay[2 * n1 + x] = (int)ccj_h4(x);
+    }
+    // PM rows: quads of row (j,k) inside a level
+    for (int j = threadIdx.x + 1; j <= n; j += blockDim.x) {
+        int sum = 0;
+        for (int k = j + 2; k <= n; ++k) sum += ccj_pmw_w4(n, j, k);
+        s_row[j] = sum;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int x = 0; x <= n; ++x) { acc += lay[2 * n1 + x]; lay[3 * n1 + x] = acc; }
+        acc = 0;
+        for (int b = 0; b <= n; ++b) { lay[4 * n1 + b] = acc; if (n - b - 2 >= 0) acc += lay[3 * n1 + n - b - 2]; }
+        acc = 0;
+        for (int j = 1; j <= n; ++j) { const int v = s_row[j]; s_row[j] = acc; acc += v; }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x + 1; j <= n; j += blockDim.x) {
+        int acc = s_row[j];
+        for (int k = j + 2; k <= n; ++k) { q.pmlev4[j * n1 + k] = acc; acc += ccj_pmw_w4(n, j, k); }
+    }
+    __syncthreads();
+    // pairs (i,i+s) per arm length s
+    const int8_t *S = q.S;
+    for (int s = wid; s <= n; s += nw) {
+        int *pl = q.plist + s * n1, *pc = q.pcum + s * (n + 2);
+        int cnt = 0;
+        if (lane == 0) pc[0] = 0;
+        for (int i0 = 1; i0 <= n; i0 += 32) {
+            const int i = i0 + lane;
+            const bool ok = i + s <= n && s > CCJ_TURN && M->pair[S[i]][S[i + s]] > 0;
+            const unsigned bal = __ballot_sync(0xffffffffu, ok);
+            const int before = __popc(bal & ((1u << lane) - 1));
+            if (ok) pl[cnt + before] = i;
+            if (i <= n) pc[i] = cnt + before + (ok ? 1 : 0);
+            cnt += __popc(bal);
+        }
+        if (lane == 0) { pc[n + 1] = cnt; s_row[s] = cnt; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int s = 0; s <= n; ++s) { q.pmstart[s] = acc; acc += s_row[s]; }
+        q.pmstart[n + 1] = acc;
+    }
+    __syncthreads();
+    for (int s = wid; s <= n; s += nw) {
+        const int base = q.pmstart[s], cnt = s_row[s];
+        for (int x = lane; x < cnt; x += 32) {
+            const int i = q.plist[s * n1 + x];
+            q.pmlist[base + x] = i | ((i + s) << 16);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128) k_prep(const ccj_model *M, const ccj_seq *seqs) {
     ccj_cx c;
     c.M = M;
@@ -45,24 +115,17 @@ __global__ void __launch_bounds__(128) k_prep(const ccj_model *M, const ccj_seq 
     const int n = c.q.n;
     const int j = blockIdx.x + 2;
     if (j > n) return;
-    if (blockIdx.x == 0 && n <= K4_MAXN)
-        for (int x = threadIdx.x; x <= n; x += blockDim.x) {
-            c.q.lay[x] = (int)ccj_tet(x);
-            c.q.lay[n + 1 + x] = x <= n - 3 ? (int)ccj_cb(n, x) : 0;
-            int64_t bj = 0;  // basej[x] of ccj_pmm_idx
-            for (int jj = 1; jj < x; ++jj) bj += (int64_t)jj * ((int64_t)(n - jj - 1) * (n - jj) / 2);
-            c.q.lay[2 * n + 2 + x] = (int)bj;
-        }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int8_t *S = c.q.S;
+    const int n1 = n + 1;
     for (int i = 1 + wid; i < j; i += nw) {
         const int ij = ccj_idx2(n, i, j);
         if (lane == 0) c.q.estP[ij] = (j - i >= 2) ? ccj_e_stP(M, S, i, j) : CCJ_INF;
         const int slot = ccj_tri(i, j);
         int nin = 0, nout = 0;
         if (ccj_can_pair(c, i, j)) {
-            uint32_t *il = c.q.inlist + (int64_t)slot * CCJ_WIN;
-            uint32_t *ol = c.q.outlist + (int64_t)slot * CCJ_WIN;
+            uint32_t *il = c.q.inlist + (int64_t)slot * CCJ_WIN_IN;
+            uint2 *ol = reinterpret_cast<uint2 *>(c.q.outlist) + (int64_t)slot * CCJ_WIN_OUT;
             for (int s0 = 0; s0 < CCJ_WIN; s0 += 32) {
                 const int s = s0 + lane;
                 const int x = s / 29 + 1, y = s % 29 + 1;
@@ -79,14 +142,22 @@ __global__ void __launch_bounds__(128) k_prep(const ccj_model *M, const ccj_seq 
                 nin += __popc(bal);
                 // outside (i,j) as inner pair (j,k):=(i,j): d=i-x, dp=j+y  (get_PMiloop window)
                 ok = false;
+                int pm4 = 0;
                 if (s < CCJ_WIN) {
                     const int d = i - x, dp = j + y;
-                    if (d >= 1 && dp <= n && ccj_can_pair(c, d, dp))
+                    if (d >= 1 && dp <= n && ccj_can_pair(c, d, dp)) {
                         ok = pack_entry(ccj_e_intP(M, S, d, i, j, dp), x, y, ent, c.q.status);
+                        if (n <= K4_MAXN) pm4 = c.q.pmlev4[d * n1 + dp];
+                    }
                 }
                 bal = __ballot_sync(0xffffffffu, ok);
-                if (ok) ol[nout + __popc(bal & ((1u << lane) - 1))] = ent;
+                if (ok) ol[nout + __popc(bal & ((1u << lane) - 1))] = make_uint2(ent, (uint32_t)pm4);
                 nout += __popc(bal);
+            }
+            // zero entries up to the next multiple of 8: the window kernels read whole 8-entry batches
+            if (lane < 8) {
+                if (nin + lane < ((nin + 7) & ~7)) il[nin + lane] = 0;
+                if (nout + lane < ((nout + 7) & ~7)) ol[nout + lane] = make_uint2(0u, 0u);
             }
         }
         if (lane == 0) {
@@ -111,11 +182,9 @@ enum {  // partial ids in the scratch
     Q_PfL1, Q_PfO1, Q_PLm00b, Q_PLm10b, Q_PMm10a, Q_POm00a, Q_POm10a,               // role L2
     Q_PK3, Q_PfR1, Q_PfMp, Q_PRm00a, Q_PRm10, Q_PMm00b,                              // role R3
     Q_PfR2, Q_PfO2, Q_PRm00b, Q_PRm01, Q_PMm01, Q_PMm10b, Q_POm00b, Q_POm01, Q_POm10b,  // role R4
-    Q_PLw, Q_PRw, Q_PMw, Q_PLw_odd, Q_PRw_odd, Q_PMw_odd,  // windows, double-buffered by level parity (Q_xx + 3*(t&1)):
-                                                              // the window kernels run one level ahead of k_final
-    Q_COUNT
+    Q_COUNT  // the window partials live in ccj_seq::wscr, in the window layouts
 };
-enum { ROLE_L1 = 0, ROLE_L2, ROLE_R3, ROLE_R4, ROLE_WL, ROLE_COUNT };
+enum { ROLE_L1 = 0, ROLE_L2, ROLE_R3, ROLE_R4, ROLE_COUNT };
 
 // streaming read of a gap-table entry: read-only path, and ask L2 to fetch the whole 256-byte chunk -- the
 // neighbouring warps of the block need the adjacent 64-byte runs of the same slab row
@@ -172,7 +241,7 @@ __device__ __forceinline__ bool cell_setup(const ccj_seq &q, int t, int a, int b
 #define U4 4
 #endif
 
-__global__ void __launch_bounds__(K4_THREADS) k_roles(const ccj_model *__restrict__ M, const ccj_seq *__restrict__ seqs, int t,
+__global__ void __launch_bounds__(K4_THREADS, 8) k_roles(const ccj_model *__restrict__ M, const ccj_seq *__restrict__ seqs, int t,
                                                        int only_role) {
     __shared__ int s_tet[K4_MAXN + 4];
     __shared__ int s_cb[K4_MAXN + 4];
@@ -396,234 +465,266 @@ __global__ void __launch_bounds__(K4_THREADS) k_roles(const ccj_model *__restric
         }
         SAVE(Q_PfR2, aPfR); SAVE(Q_PfO2, aPfO); SAVE(Q_PRm00b, aPRm00); SAVE(Q_PRm01, aPRm01); SAVE(Q_PMm01, aPMm01);
         SAVE(Q_PMm10b, aPMm10); SAVE(Q_POm00b, aPOm00); SAVE(Q_POm01, aPOm01); SAVE(Q_POm10b, aPOm10);
-    } else {
-        // get_PLiloop (src/pseudo_loop.cc:682-703); the closing-pair test of compute_PL is applied by k_final
-        int mn = INF;
-        if (a > CCJ_TURN && __ldg(&M->pair[q.S[i]][q.S[j]]) > 0) {
-            const int16_t *__restrict__ pPL = TB(T_PL);
-            if (a > CCJ_TURN + 2) mn = ld16(pPL, OFF(a - 2, b, i + 1, k)) + __ldg(&q.estP[a * n1 + i]);
-            const int slot = ccj_tri(i, j);
-            const uint32_t *__restrict__ lst = q.inlist + (int64_t)slot * CCJ_WIN;
-            const int cnt = __ldg(&q.incnt[slot]);
-            const int cbb = s_cb[b], kc = k - j - 2;
-#pragma unroll 4
-            for (int e = 0; e < cnt; ++e) {
-                const uint32_t en = __ldg(&lst[e]);
-                const int x = (en >> 16) & 0xff, y = en >> 24;
-                const int mm = m + x + y, ii = i + x;
-                const int o2 = cbb - s_tet[mm] + (((ii - 1) * (2 * mm + 2 - ii)) >> 1) + (kc + y);
-                mn = min(mn, (int)(int16_t)(en & 0xffff) + ld16(pPL, o2));
-            }
-        }
-        SAVE(Q_PLw, mn);
     }
 #undef SAVE
 }
 
-#define WTILE 64
-#ifndef WB
-#define WB 8      // window candidates in flight per lane
-#endif
-// PM interior window (get_PMiloop, src/pseudo_loop.cc:752-773).  The partner list belongs to the INNER pair
-// (j,k); the cells of one level that share it are (j-a, j, k, k+t-a) for a = amin..amax, contiguous in the
-// T_PMM copy.  One warp per (j,k): the lanes first turn 64 list entries into (offset, energy, bounds) in
-// shared memory, then walk them with the lanes spread over a: one broadcast LDS.128, one coalesced load and
-// one add-min per candidate and warp.
-__global__ void __launch_bounds__(K4_THREADS) k_winM(const ccj_model *__restrict__ M, const ccj_seq *__restrict__ seqs, int t) {
-    __shared__ int4 tile[K4_THREADS / 32][WTILE];  // (offset - a, energy, x, t - y)
-    const ccj_seq q = seqs[blockIdx.z];
-    const int n = q.n;
-    const int m = n - t - 2;
-    if (m < 1) return;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int j = blockIdx.y + 1;
-    const int k = j + 2 + blockIdx.x * (K4_THREADS / 32) + wid;
-    if (j > n || k > n) return;
-    const int A = j - 1, B = n - k;
-    const int amin = max(0, t - B), amax = min(t, A);
-    if (amin > amax) return;
-    const int ncell = m * (m + 1) / 2;
-    int16_t *__restrict__ out = q.scratch + (int64_t)(Q_PMw + 3 * (t & 1)) * q.scratch_stride;
-    const int32_t *__restrict__ basej = q.lay + 2 * n + 2;
-    const int16_t *__restrict__ pX = q.t4 + (int64_t)T_PMM * q.stride4;
-    const int8_t *__restrict__ S = q.S;
-    const int n1 = n + 1;
-    const int INF = CCJ_INF;
-    const bool gate = (k - j > CCJ_TURN) && __ldg(&M->pair[S[j]][S[k]]) > 0;
-    const int slot = ccj_tri(j, k);
-    const uint32_t *__restrict__ lst = q.outlist + (int64_t)slot * CCJ_WIN;
-    const int cnt = gate ? __ldg(&q.outcnt[slot]) : 0;
-    int stack_base = 0, stack_e = 0;
-    if (gate && t >= 2) {  // PM(i,j-1,k+1,l) + e_stP(j-1,k+1): needs a>=1, b>=1
-        stack_base = (int)ccj_pmm_idx(n, basej, j - 1, k + 1, t - 2, 0) - 1;  // + a  (a' = a-1)
-        stack_e = __ldg(&q.estP[(k - j + 2) * n1 + (j - 1)]);
-    }
-    for (int a0 = amin; a0 <= amax; a0 += 32) {
-        const int a = a0 + lane;
-        const bool have = a <= amax;
-        const int b = t - a;
-        int mn = INF;
-        if (gate) {
-            if (have && a >= 1 && b >= 1) mn = ld16(pX, stack_base + a) + stack_e;
-            for (int e0 = 0; e0 < cnt; e0 += WTILE) {
-                const int ne = min(WTILE, cnt - e0);
-                __syncwarp();
-                for (int e = lane; e < ne; e += 32) {
-                    const uint32_t en = __ldg(&lst[e0 + e]);
-                    const int x = (en >> 16) & 0xff, y = en >> 24;
-                    int off = 0;
-                    if (t - x - y >= 0 && j - x >= 1 && k + y <= n)
-                        off = (int)ccj_pmm_idx(n, basej, j - x, k + y, t - x - y, 0) - x;  // + a  (a' = a-x)
-                    tile[wid][e] = make_int4(off, (int)(int16_t)(en & 0xffff), x, t - y);
-                }
-                __syncwarp();
-                const int16_t *pb = pX + a;
-                asm volatile("" : "+l"(pb));
-                int e = 0;
-                for (; e + WB <= ne; e += WB) {  // WB candidates in flight per lane
-                    int v[WB], en[WB];
-#pragma unroll
-                    for (int u = 0; u < WB; ++u) {
-                        const int4 oe = tile[wid][e + u];
-                        const bool ok = have && a > oe.z && a < oe.w;
-                        v[u] = ok ? ld16(pb, oe.x) : 0;
-                        en[u] = ok ? oe.y : INF;
-                    }
-#pragma unroll
-                    for (int u = 0; u < WB; ++u) mn = min(mn, en[u] + v[u]);
-                }
-                for (; e < ne; ++e) {
-                    const int4 oe = tile[wid][e];
-                    if (have && a > oe.z && a < oe.w) mn = min(mn, oe.y + ld16(pb, oe.x));
-                }
-            }
-        }
-        if (have) {
-            const int i = j - a;
-            const int p = (((i - 1) * (2 * m + 2 - i)) >> 1) + (k - j - 2);
-            out[(int64_t)a * ncell + p] = sat16(mn);
-        }
-    }
+#define WB 8      // window candidates in flight per lane (FENCE8 assumes 8)
+// keep the compiler from sinking the WB loads of a batch to their uses: all of them must be in flight together
+#define FENCE8(v) asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]))
+#define FENCE8X(v) asm volatile("" : "+r"(v[0].x), "+r"(v[1].x), "+r"(v[2].x), "+r"(v[3].x), "+r"(v[4].x), "+r"(v[5].x), "+r"(v[6].x), "+r"(v[7].x))
+#define WGRP 8    // lanes per run: one pass covers 8 quads = 32 cells
+#define WRUNS (K4_THREADS / WGRP)
+
+__device__ __forceinline__ int2 ldq(const int2 *p, int off) {
+    int2 v;
+    asm("ld.global.nc.L2::256B.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p + off));
+    return v;
+}
+__device__ __forceinline__ int pack_sat(int lo, int hi) {
+    return (int)((uint32_t)(uint16_t)sat16(lo) | ((uint32_t)(uint16_t)sat16(hi) << 16));
 }
 
+// packed int16x2 arithmetic (VIADDMNMX.S16x2 / VIMNMX.S16x2): two cells per instruction, no unpacking
+__device__ __forceinline__ int addmin2(int a, int b, int c) {  // min(a+b, c) per half
+    int r, s;
+    asm("add.s16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    asm("min.s16x2 %0, %1, %2;" : "=r"(s) : "r"(r), "r"(c));
+    return s;
+}
+__device__ __forceinline__ int addmax2(int a, int b, int c) {  // max(a+b, c) per half
+    int r, s;
+    asm("add.s16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    asm("max.s16x2 %0, %1, %2;" : "=r"(s) : "r"(r), "r"(c));
+    return s;
+}
+__device__ __forceinline__ int min2(int a, int b) {
+    int s;
+    asm("min.s16x2 %0, %1, %2;" : "=r"(s) : "r"(a), "r"(b));
+    return s;
+}
+__device__ __forceinline__ int splat16(int e) { return (int)__byte_perm((unsigned)e, 0u, 0x1010); }
+// A window candidate is value + energy with the sum saturated at 32767 ("INF or clamped", see k_final).  In
+// 16 bits:  min(value, 32767 - max(energy,0)) + energy  -- exact, and it cannot wrap upwards.
+#define WIN_INF2 0x7fff7fff
+
 // PL and PR interior windows (get_PLiloop :682-703, get_PRiloop :717-738).
-// Cells of a slab that share the closing pair share its partner list: for PL these are the cells of one row
-// (i,j fixed, k running), for PR the cells of one transposed row (k,l fixed, i running; read from the
-// transposed copy T_PRT).  A warp takes 32 consecutive cells in that order (1-3 such runs).  Per run the
-// lanes first turn the partner list, 32 entries at a time, into (offset, energy) pairs in shared memory (one
-// coalesced read, unpacked once), then all lanes walk those pairs: every candidate is one broadcast LDS, one
-// coalesced 64-byte load and one add-min per warp.
-__global__ void __launch_bounds__(K4_THREADS) k_winLR(const ccj_model *__restrict__ M, const ccj_seq *__restrict__ seqs, int t) {
-    __shared__ int s_T[64];                       // PL: cb(b)-tet(m+s)      PR: cb(b-s)-tet(m+s)
-    __shared__ int2 tile[K4_THREADS / 32][WTILE];  // per warp: (offset, energy) of the current list tile
-    const int role = blockIdx.z & 1;              // 0: PL (main order, T_PL)   1: PR (transposed order, T_PRT)
+// Cells that share the closing pair share its partner list: for PL the cells of one row of the slab (i,j
+// fixed, k running), for PR the cells of one transposed row (k,l fixed, i running).  Both are runs of the
+// window layouts PLW / PRW (ccj_types.h), where the run of every candidate starts on the same quad phase:
+// a group of 8 lanes takes one run of a PAIRED row (per-arm pair lists from k_prep_lay, so no lane idles on
+// an unpairable row) and 32 of its cells.  The 8 lanes decode 8 list entries at a time into (source run,
+// energy, clamp) in shared memory; every candidate is then one 8-byte load and four packed int16x2
+// instructions per lane (4 cells).  Results go to the wscr partial in the same layout, 8 bytes per lane.
+//   blockIdx.x -> (pass, chunk of 16 paired rows), blockIdx.y -> a, blockIdx.z -> (sequence, PL|PR)
+__global__ void __launch_bounds__(K4_THREADS) k_winLR(const ccj_model *__restrict__ M, const ccj_seq *__restrict__ seqs, int t, int nchunk) {
+    __shared__ int s_T[64];              // quad offset of source slab (a-s,b) resp. (a,b-s), plus H4(m+s)
+    __shared__ int s_h4[K4_MAXN + 4];
+    __shared__ int4 tile[WRUNS][WGRP];   // (source run start, energy x2, clamp x2, -)
+    const int role = blockIdx.z & 1;     // 0: PL   1: PR
     const ccj_seq q = seqs[blockIdx.z >> 1];
-    const int n = q.n;
+    const int n = q.n, n1 = n + 1;
     const int m = n - t - 2;
     if (m < 1) return;
-    const int ncell = m * (m + 1) / 2;
-    if ((int)(blockIdx.x * K4_THREADS) >= ncell) return;
     const int a = blockIdx.y, b = t - a;
-    const int arm = role == 0 ? a : b;            // length of the arm whose closing pair carries the window
-    int16_t *__restrict__ out =
-        q.scratch + (int64_t)((role == 0 ? Q_PLw : Q_PRw) + 3 * (t & 1)) * q.scratch_stride + (int64_t)a * ncell;
-    const int pT = blockIdx.x * K4_THREADS + threadIdx.x;
-    if (arm <= CCJ_TURN) {  // can_pair fails for the whole slab
-        if (pT < ncell) out[pT] = 32767;
-        return;
-    }
+    const int arm = role == 0 ? a : b;   // length of the arm whose closing pair carries the window
+    if (arm <= CCJ_TURN) return;
+    const int chunk = blockIdx.x % nchunk, pass = blockIdx.x / nchunk;
+    if (pass * (4 * WGRP) >= m) return;
+    const int *__restrict__ pc = q.pcum + arm * (n + 2);
+    // paired 5' ends of this slab: PL i in 1..m, PR k in a+3..n-b
+    const int first = role == 0 ? 0 : __ldg(&pc[a + 2]);
+    const int last = role == 0 ? __ldg(&pc[m]) : __ldg(&pc[n - b]);
+    if (first + chunk * WRUNS >= last) return;
     const int *__restrict__ lay = q.lay;
-    if (threadIdx.x < 60) {
+    for (int x = threadIdx.x; x <= n; x += K4_THREADS) s_h4[x] = __ldg(&lay[2 * n1 + x]);
+    if (threadIdx.x < 64) {
         const int s = threadIdx.x;
         int v = 0;
-        if (m + s <= n) {
-            if (role == 0) v = __ldg(&lay[n + 1 + b]) - __ldg(&lay[m + s]);
-            else if (b - s >= 0) v = __ldg(&lay[n + 1 + b - s]) - __ldg(&lay[m + s]);
+        if (m + s <= n - 2) {
+            const int bb = role == 0 ? b : b - s;
+            if (bb >= 0 && n - bb - 2 >= m + s)
+                v = __ldg(&lay[4 * n1 + bb]) + __ldg(&lay[3 * n1 + n - bb - 2]) - __ldg(&lay[3 * n1 + m + s]) + __ldg(&lay[2 * n1 + m + s]);
         }
         s_T[s] = v;
     }
     __syncthreads();
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const bool valid = pT < ncell;
-    const int pc = valid ? pT : ncell - 1;
-    int r = (int)(((2 * m + 1) - sqrtf((float)((2 * m + 1) * (2 * m + 1) - 8 * pc))) * 0.5f);
-    if (r < 0) r = 0;
-    if (r > m - 1) r = m - 1;
-    while (r > 0 && r * (2 * m + 1 - r) / 2 > pc) --r;
-    while ((r + 1) * (2 * m - r) / 2 <= pc) ++r;
-    const int row = r;                                  // PL: i-1          PR: kr = n-b-k
-    const int pos = pc - r * (2 * m + 1 - r) / 2;       // PL: k-j-2        PR: i-1
-    const int16_t *__restrict__ pX = q.t4 + (int64_t)(role == 0 ? T_PL : T_PRT) * q.stride4;
-    const int8_t *__restrict__ S = q.S;
-    const int n1 = n + 1;
-    const int INF = CCJ_INF;
-    int mn = INF;
-    const int r_lo = __shfl_sync(0xffffffffu, row, 0), r_hi = __shfl_sync(0xffffffffu, row, 31);
-    for (int c = r_lo; c <= r_hi; ++c) {  // warp-uniform
-        // closing pair (p5,p3) of this run
-        const int p5 = role == 0 ? c + 1 : n - b - c;
-        const int p3 = p5 + arm;
-        if (__ldg(&M->pair[S[p5]][S[p3]]) == 0) continue;
-        const bool mine = valid && row == c;
-        if (arm > CCJ_TURN + 2) {  // stacking term, x=y=1 (PL(i+1,j-1,k,l) / PR(i,j,k+1,l-1))
-            const int mm = m + 2;
-            const int rw = c + 2;  // PL: row of i+1   PR: transposed row kr+1
-            const int o = s_T[2] + (((rw - 1) * (2 * mm + 2 - rw)) >> 1) + pos + (role == 0 ? 1 : 0);
-            if (mine) mn = min(mn, ld16(pX, o) + __ldg(&q.estP[arm * n1 + p5]));
+    const int grp = threadIdx.x / WGRP, gl = threadIdx.x & (WGRP - 1);
+    const int idx = first + chunk * WRUNS + grp;
+    const int p5 = __ldg(&q.plist[arm * n1 + min(idx, last - 1)]);
+    const int c = role == 0 ? p5 - 1 : n - b - p5;     // row of the run: i-1 resp. kr=n-b-k
+    const int zc = m - c;                               // its length
+    const bool gact = idx < last && pass * (4 * WGRP) < zc;   // the group has cells in this pass
+    const int qd = pass * WGRP + gl;                    // this lane's quad of the run
+    const int2 *src = reinterpret_cast<const int2 *>(role == 0 ? q.plw : q.prw) + qd;
+    asm volatile("" : "+l"(src));  // per-lane base in a register pair: one IMAD.WIDE per candidate
+    const int own = s_T[0] - s_h4[zc];                  // the run's own (not yet written) quads
+    int acc0 = WIN_INF2, acc1 = WIN_INF2;
+    if (gact && arm > CCJ_TURN + 2) {  // stacking term, x=y=1 (PL(i+1,j-1,k,l) / PR(i,j,k+1,l-1))
+        const int2 w = ldq(src, s_T[2] - s_h4[zc + 1]);
+        const int e = __ldg(&q.estP[arm * n1 + p5]);
+        const int ee = splat16(e), cc = splat16(32767 - max(e, 0));
+        acc0 = addmin2(min2(w.x, cc), ee, acc0);
+        acc1 = addmin2(min2(w.y, cc), ee, acc1);
+    }
+    const int keep0 = acc0, keep1 = acc1;
+    const int slot = ccj_tri(p5, p5 + arm);
+    const uint32_t *__restrict__ lst = q.inlist + (int64_t)slot * CCJ_WIN_IN;
+    const int cnt = gact ? __ldg(&q.incnt[slot]) : 0;
+    const int cmax = __reduce_max_sync(0xffffffffu, cnt);
+    for (int e0 = 0; e0 < cmax; e0 += WGRP) {
+        int4 d = make_int4(own, 0, WIN_INF2, 0);
+        if (cnt > 0) {  // lane gl decodes entry e0+gl; past the end the last entry again (min is idempotent)
+            const uint32_t en = __ldg(&lst[min(e0 + gl, cnt - 1)]);
+            const int x = (en >> 16) & 0xff, y = en >> 24, e = (int)(int16_t)(en & 0xffff);
+            // PL source (i+x, j-y, k, l): slab (a-s, b), row c+x, length zc+y, same position (n-b)-k
+            // PR source (i, j, k+x, l-y): slab (a, b-s), row kr+y, length zc+x, same position i-1
+            d = make_int4(s_T[x + y] - s_h4[zc + (role == 0 ? y : x)], splat16(e), splat16(32767 - max(e, 0)), 0);
         }
-        const int slot = ccj_tri(p5, p3);
-        const uint32_t *__restrict__ lst = q.inlist + (int64_t)slot * CCJ_WIN;
-        const int cnt = __ldg(&q.incnt[slot]);
-        for (int e0 = 0; e0 < cnt; e0 += WTILE) {
-            const int ne = min(WTILE, cnt - e0);
-            __syncwarp();
-            for (int e = lane; e < ne; e += 32) {
-                const uint32_t en = __ldg(&lst[e0 + e]);
-                const int x = (en >> 16) & 0xff, y = en >> 24, sxy = x + y;
-                const int mm = m + sxy;
-                // PL target (i+x, j-y, k, l): slab (a-s, b), row i+x, position k-(j-y)-2 = pos + y
-                // PR target (i, j, k+x, l-y): slab (a, b-s), transposed row kr+y, position i-1 = pos
-                const int rw = role == 0 ? c + 1 + x : c + y + 1;
-                int o = s_T[sxy] + (((rw - 1) * (2 * mm + 2 - rw)) >> 1);
-                if (role == 0) o += y;
-                tile[wid][e] = make_int2(o, (int)(int16_t)(en & 0xffff));
-            }
-            __syncwarp();
-            if (mine) {
-                const int16_t *pb = pX + pos;  // per-thread base held in a register pair: one IMAD.WIDE per candidate
-                asm volatile("" : "+l"(pb));
-                int e = 0;
-                for (; e + WB <= ne; e += WB) {  // WB candidates in flight per lane
-                    int v[WB], en[WB];
+        __syncwarp();
+        tile[grp][gl] = d;
+        __syncwarp();
+        int2 w[WB];
 #pragma unroll
-                    for (int u = 0; u < WB; ++u) {
-                        const int2 oe = tile[wid][e + u];
-                        v[u] = ld16(pb, oe.x);
-                        en[u] = oe.y;
-                    }
+        for (int u = 0; u < WB; ++u) w[u] = ldq(src, tile[grp][u].x);
+        FENCE8X(w);
 #pragma unroll
-                    for (int u = 0; u < WB; ++u) mn = min(mn, en[u] + v[u]);
-                }
-                for (; e < ne; ++e) {
-                    const int2 oe = tile[wid][e];
-                    mn = min(mn, oe.y + ld16(pb, oe.x));
-                }
-            }
+        for (int u = 0; u < WB; ++u) {
+            const int4 d2 = tile[grp][u];
+            acc0 = addmin2(min2(w[u].x, d2.z), d2.y, acc0);
+            acc1 = addmin2(min2(w[u].y, d2.z), d2.y, acc1);
         }
     }
-    if (valid) out[pT] = sat16(mn);
+    if (gact && 4 * qd < zc) {
+        if (cnt == 0) { acc0 = keep0; acc1 = keep1; }
+        int2 *__restrict__ out = reinterpret_cast<int2 *>(q.wscr + (int64_t)((t & 1) * 2 + role) * q.wscr_lr);
+        out[a * s_h4[m] + (s_h4[m] - s_h4[zc]) + qd] = make_int2(acc0, acc1);
+    }
+}
+
+__device__ __forceinline__ int4 ldq4(const int4 *p, int off) {
+    int4 v;
+    asm("ld.global.nc.L2::256B.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p + off));
+    return v;
+}
+
+// every entry of PMW starts as (32767, "not a source"): rows are padded and read past their ends
+__global__ void __launch_bounds__(256) k_fill_pmw(const ccj_seq *seqs) {
+    const ccj_seq q = seqs[blockIdx.y];
+    if (q.n > K4_MAXN || q.n < 3) return;
+    const int64_t quads = (int64_t)q.wtot4 * (q.n - 2) + 16;
+    int4 *p = reinterpret_cast<int4 *>(q.pmw);
+    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < quads; x += (int64_t)gridDim.x * blockDim.x)
+        p[x] = make_int4(WIN_INF2, WIN_INF2, WIN_INF2, WIN_INF2);
+}
+
+// PM interior window (get_PMiloop, src/pseudo_loop.cc:752-773).  The partner list belongs to the INNER pair
+// (j,k); the cells of one level that share it are (j-a, j, k, k+t-a), one row of the PMW layout, and a
+// candidate (j-x, k+y) keeps i and l, i.e. the position inside the row.  A group of 8 lanes takes 32 cells of
+// the row of one PAIRED (j,k) (pairs ordered by span: the rows that exist on level t are a prefix).
+// A candidate is valid for j-t+y < i < j-x only (d>i, dp<l in the reference's loops), i.e. for the cells of
+// the source row with a'>=1 and b'>=1: PMW stores next to every value a mask half (-32768 for such a cell,
+// 32767 for the two end cells and the padding), and the candidate is max(value+energy, mask) -- still two
+// cells per instruction.  The 8 lanes of a group decode 8 list entries at a time into shared memory.
+//   blockIdx.x -> (pass, chunk of 16 pairs), blockIdx.y -> sequence
+__global__ void __launch_bounds__(K4_THREADS) k_winM(const ccj_model *__restrict__ M, const ccj_seq *__restrict__ seqs, int t, int nchunk) {
+    __shared__ int4 tile[WRUNS][WGRP];   // (source row start, energy x2, clamp x2, first quad | quads-1 << 16)
+    const ccj_seq q = seqs[blockIdx.y];
+    const int n = q.n, n1 = n + 1;
+    const int m = n - t - 2;
+    if (m < 1) return;
+    const int chunk = blockIdx.x % nchunk, pass = blockIdx.x / nchunk;
+    const int nact = __ldg(&q.pmstart[n - t]);  // pairs with span <= n-1-t: (j-1)+(n-k) >= t
+    if (chunk * WRUNS >= nact) return;
+    const int grp = threadIdx.x / WGRP, gl = threadIdx.x & (WGRP - 1);
+    const int g = min(chunk * WRUNS + grp, nact - 1);
+    const int jk = __ldg(&q.pmlist[g]);
+    const int j = jk & 0xffff, k = jk >> 16;
+    const int B = n - k;
+    const int ilo = max(j - t, 1), ihi = j - max(0, t - B);   // i of the row's cells
+    const int qlo = (ilo - 1) >> 2, qhi = (ihi - 1) >> 2;
+    const int qd = qlo + pass * WGRP + gl;                     // absolute quad of (i-1)
+    const bool gact = chunk * WRUNS + grp < nact && qlo + pass * WGRP <= qhi;  // the group has cells in this pass
+    const int p0 = 4 * qd;                                     // i-1 of the lane's first cell
+    const int wtot4 = q.wtot4;
+    const int4 *src = reinterpret_cast<const int4 *>(q.pmw) + qd;
+    asm volatile("" : "+l"(src));
+    const int INF = CCJ_INF;
+    const int own = t * wtot4 + __ldg(&q.pmlev4[j * n1 + k]) - qlo;   // the row's own (not yet written) quads
+    int acc0 = WIN_INF2, acc1 = WIN_INF2;
+    if (gact && t >= 2 && j >= 2 && k < n) {
+        // PM(i,j-1,k+1,l) + e_stP(j-1,k+1) for a>=1, b>=1: unlike the list candidates this one may read the end
+        // cells of its source row (a'=0, b'=0), so it is masked by position, once per lane, in 32 bits
+        const int lo1 = max(j - t + 1, ilo) - 1, cnt1 = min(j - 1, ihi) - 1 - lo1 + 1;
+        if (cnt1 > 0 && p0 + 3 >= lo1 && p0 < lo1 + cnt1) {
+            const int qls = (max(j - t + 1, 1) - 1) >> 2;
+            const int4 w = ldq4(src, (t - 2) * wtot4 + __ldg(&q.pmlev4[(j - 1) * n1 + k + 1]) - qls);
+            const int e = __ldg(&q.estP[(k - j + 2) * n1 + (j - 1)]);
+            const int dl = p0 - lo1;
+            const int m0 = lo16(w.x) + ((unsigned)dl < (unsigned)cnt1 ? e : INF);
+            const int m1 = hi16(w.x) + ((unsigned)(dl + 1) < (unsigned)cnt1 ? e : INF);
+            const int m2 = lo16(w.z) + ((unsigned)(dl + 2) < (unsigned)cnt1 ? e : INF);
+            const int m3 = hi16(w.z) + ((unsigned)(dl + 3) < (unsigned)cnt1 ? e : INF);
+            acc0 = pack_sat(m0, m1);
+            acc1 = pack_sat(m2, m3);
+        }
+    }
+    const int slot = ccj_tri(j, k);
+    const uint2 *__restrict__ lst = reinterpret_cast<const uint2 *>(q.outlist) + (int64_t)slot * CCJ_WIN_OUT;
+    const int cnt = gact ? __ldg(&q.outcnt[slot]) : 0;
+    const int cmax = __reduce_max_sync(0xffffffffu, cnt);
+    for (int e0 = 0; e0 < cmax; e0 += WGRP) {
+        int4 d = make_int4(own, 0, WIN_INF2, 0);  // no candidate: the own row is all "not a source"
+        if (e0 + gl < cnt) {  // lane gl decodes entry e0+gl of its group's list
+            const uint2 L = __ldg(&lst[e0 + gl]);
+            const int x = (L.x >> 16) & 0xff, y = L.x >> 24, e = (int)(int16_t)(L.x & 0xffff);
+            const int tl = t - x - y;                               // level of the source row (j-x, k+y)
+            const int il = max(j - t + y, 1), ih = j - x - max(0, tl - (B - y));   // its cells
+            if (tl >= 0 && ih >= il) {
+                const int qls = (il - 1) >> 2, qhs = (ih - 1) >> 2;
+                d = make_int4(tl * wtot4 + (int)L.y - qls, splat16(e), splat16(32767 - max(e, 0)), qls | ((qhs - qls) << 16));
+            }
+        }
+        __syncwarp();
+        tile[grp][gl] = d;
+        __syncwarp();
+        int4 w[WB];
+#pragma unroll
+        for (int u = 0; u < WB; ++u) {
+            const int4 d2 = tile[grp][u];
+            // quads outside the source row belong to other rows: read the own row instead
+            const bool ok = (unsigned)(qd - (d2.w & 0xffff)) <= (unsigned)(d2.w >> 16);
+            w[u] = ldq4(src, ok ? d2.x : own);
+        }
+#pragma unroll
+        for (int u = 0; u < WB; ++u) {
+            const int4 d2 = tile[grp][u];
+            acc0 = min2(acc0, addmax2(min2(w[u].x, d2.z), d2.y, w[u].y));
+            acc1 = min2(acc1, addmax2(min2(w[u].z, d2.z), d2.y, w[u].w));
+        }
+    }
+    if (gact && qd <= qhi) {
+        int2 *__restrict__ out = reinterpret_cast<int2 *>(q.wscr + 4 * q.wscr_lr + (int64_t)(t & 1) * 4 * wtot4);
+        out[own - t * wtot4 + qd] = make_int2(acc0, acc1);
+    }
 }
 
 // same-cell assembly in the reference's order (src/pseudo_loop.cc:85-127) from the partial minima
-__global__ void __launch_bounds__(K4_THREADS) k_final(const ccj_model *__restrict__ M, const ccj_seq *__restrict__ seqs, int t) {
+__global__ void __launch_bounds__(K4_THREADS, 8) k_final(const ccj_model *__restrict__ M, const ccj_seq *__restrict__ seqs, int t) {
     __shared__ int s_tet[K4_MAXN + 4];
     __shared__ int s_cb[K4_MAXN + 4];
+    __shared__ int s_hh[K4_MAXN + 4];   // HH4
+    __shared__ int s_cw[K4_MAXN + 4];   // CbW4
     const ccj_seq q = seqs[blockIdx.z];
     const int n = q.n;
     if (n - t - 2 < 1) return;
     {
         const int m0 = n - t - 2;
         if ((int)(blockIdx.x * K4_THREADS) >= m0 * (m0 + 1) / 2) return;
+    }
+    for (int x = threadIdx.x; x <= n; x += K4_THREADS) {
+        s_hh[x] = __ldg(&q.lay[3 * (n + 1) + x]);
+        s_cw[x] = __ldg(&q.lay[4 * (n + 1) + x]);
     }
     Cell C;
     if (!cell_setup(q, t, blockIdx.y, blockIdx.x, s_tet, s_cb, C)) return;
@@ -632,12 +733,17 @@ __global__ void __launch_bounds__(K4_THREADS) k_final(const ccj_model *__restric
     const int64_t st4 = q.stride4;
     const int n1 = n + 1;
     const int INF = CCJ_INF, II = CCJ_INTERN_INF;
+    auto H4 = [](int x) { return ((x >> 2) + 1) * (2 * (x >> 2) + (x & 3)); };
     const int bp = M->bp_penalty, cp = M->cp_penalty, PB = M->PB_penalty, apbp = M->ap_penalty + M->bp_penalty;
     const int16_t *__restrict__ sc = q.scratch + C.c;
     const int64_t ss = q.scratch_stride;
 #define GET(id) ((int)__ldg(sc + (int64_t)(id) * ss))
     const int off0 = OFF(a, b, i, k);
     int16_t *w4 = q.t4;
+    const int mloc = n - t - 2, kr = n - b - k;
+    const int h4m = H4(mloc);
+    // entry of (j,k)'s row of level t that holds this cell (ccj_types.h, PMW)
+    const int pmrow = 4 * (__ldg(&q.pmlev4[j * n1 + k]) - ((max(j - t, 1) - 1) >> 2)) + (i - 1);
     auto put16 = [](int16_t *dst, int mn) -> int {
         int v = CCJ_INTERN_INF;
         if (mn < CCJ_INF / 2) {
@@ -682,7 +788,8 @@ __global__ void __launch_bounds__(K4_THREADS) k_final(const ccj_model *__restric
         int mn = INF;
         if (ptype(i, j) > 0 && a >= 2) {
             const int o = OFF(a - 2, b, i + 1, k);  // (i+1,j-1,k,l)
-            mn = GET(Q_PLw + 3 * (t & 1));
+            // window partial, PLW layout: row i-1, position (n-b)-k; rows with a<=TURN have no window
+            mn = a > CCJ_TURN ? (int)__ldg(q.wscr + (int64_t)((t & 1) * 2) * q.wscr_lr + 4 * (a * h4m + h4m - H4(mloc - i + 1)) + (n - b - k)) : 32767;
             mn = min(mn, min(ld16(TB(T_PLmloop10), o), ld16(TB(T_PLmloop01), o)) + apbp + bp);
             if (a >= CCJ_TURN + 1) mn = min(mn, ld16(TB(T_PfromL), o));
         }
@@ -692,10 +799,8 @@ __global__ void __launch_bounds__(K4_THREADS) k_final(const ccj_model *__restric
         int mn = INF;
         if (ptype(k, l) > 0 && b >= 2) {
             const int o = OFF(a, b - 2, i, k + 1);  // (i,j,k+1,l-1)
-            // the PR window kernel walks the slab transposed (i fastest): its partial sits at the transposed index
-            const int kr = n - b - k, mloc = n - t - 2;
-            const int pT = ((kr * (2 * mloc + 1 - kr)) >> 1) + (i - 1);
-            mn = (int)__ldg(q.scratch + (int64_t)(Q_PRw + 3 * (t & 1)) * ss + (int64_t)a * (mloc * (mloc + 1) / 2) + pT);
+            // window partial, PRW layout: row kr=n-b-k, position i-1
+            mn = b > CCJ_TURN ? (int)__ldg(q.wscr + (int64_t)((t & 1) * 2 + 1) * q.wscr_lr + 4 * (a * h4m + h4m - H4(mloc - kr)) + (i - 1)) : 32767;
             mn = min(mn, min(ld16(TB(T_PRmloop10), o), ld16(TB(T_PRmloop01), o)) + apbp + bp);
             if (b >= CCJ_TURN + 1) mn = min(mn, ld16(TB(T_PfromR), o));
         }
@@ -706,7 +811,8 @@ __global__ void __launch_bounds__(K4_THREADS) k_final(const ccj_model *__restric
         if (ptype(j, k) > 0) {
             if (a >= 1 && b >= 1) {
                 const int o = OFF(a - 1, b - 1, i, k + 1);  // (i,j-1,k+1,l)
-                mn = GET(Q_PMw + 3 * (t & 1));
+                // window partial, PMW row layout of this level
+                mn = k - j > CCJ_TURN ? (int)__ldg(q.wscr + 4 * q.wscr_lr + (int64_t)(t & 1) * 4 * q.wtot4 + pmrow) : 32767;
                 mn = min(mn, min(ld16(TB(T_PMmloop10), o), ld16(TB(T_PMmloop01), o)) + apbp + bp);
                 mn = min(mn, ld16(TB(T_PfromM), o));
             }
@@ -732,10 +838,15 @@ __global__ void __launch_bounds__(K4_THREADS) k_final(const ccj_model *__restric
     const int vPK = PUT(T_PK, min(min(GET(Q_PK1), GET(Q_PK3)), min(min(vPL + PB, vPM + PB), min(vPR + PB, vPO + PB))));
     w4[(int64_t)T_MPP * st4 + off0] = (int16_t)min(vPL, vPR);
     w4[(int64_t)T_PKG * st4 + ccj_pkg_idx(n, i, j, k, l)] = (int16_t)vPK;  // scattered: one store per cell
-    w4[(int64_t)T_PMM * st4 + ccj_pmm_idx(n, q.lay + 2 * n + 2, j, k, t, a)] = (int16_t)vPM;  // scattered
-    {   // PR transposed inside the slab: row kr=n-b-k, position i-1 (scattered: one store per cell)
-        const int kr = n - b - k, mloc = n - t - 2;
-        w4[(int64_t)T_PRT * st4 + (off0 - C.p) + ((kr * (2 * mloc + 1 - kr)) >> 1) + (i - 1)] = (int16_t)vPR;
+    {   // window copies (layouts in ccj_types.h); PLW is coalesced, PRW / PMW are one scattered store per cell
+        const int slab4 = s_cw[b] + s_hh[n - b - 2] - s_hh[mloc] + h4m;
+        q.plw[4 * (int64_t)(slab4 - H4(mloc - i + 1)) + (n - b - k)] = (int16_t)vPL;
+        q.prw[4 * (int64_t)(slab4 - H4(mloc - kr)) + (i - 1)] = (int16_t)vPR;
+        {   // value and, two halves further, the "is a window source" mask (a>=1 and b>=1)
+            int16_t *pq = q.pmw + 8 * ((int64_t)t * q.wtot4 + (pmrow >> 2)) + (pmrow & 1) + 2 * (pmrow & 2);
+            pq[0] = (int16_t)vPM;
+            pq[2] = (a >= 1 && b >= 1) ? (int16_t)-32768 : (int16_t)32767;
+        }
     }
     // read-group records (layout in ccj_types.h); consecutive cells -> consecutive records, coalesced
     {
@@ -805,6 +916,10 @@ __global__ void __launch_bounds__(256) k_P_tuned(const ccj_seq *__restrict__ seq
 
 void launch_prep(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cudaStream_t st) {
     if (d.nmax < 2) return;
+    if (d.nmax <= K4_MAXN) {
+        k_prep_lay<<<d.nseq, 256, 0, st>>>(M, seqs);
+        k_fill_pmw<<<dim3(296, d.nseq), 256, 0, st>>>(seqs);
+    }
     k_prep<<<dim3(d.nmax - 1, d.nseq), 128, 0, st>>>(M, seqs);
 }
 
@@ -821,11 +936,21 @@ void launch_4d_roles(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int 
     if (level_dims(d, t, bx)) k_roles<<<dim3(bx, t + 1, d.nseq * 4), K4_THREADS, 0, st>>>(M, seqs, t, 0);
 }
 void launch_4d_windows(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st) {
-    int bx;
-    if (!level_dims(d, t, bx)) return;
-    k_winLR<<<dim3(bx, t + 1, d.nseq * 2), K4_THREADS, 0, st>>>(M, seqs, t);
-    const int nm = d.nmax, wpb = K4_THREADS / 32;
-    k_winM<<<dim3((nm + wpb - 1) / wpb, nm, d.nseq), K4_THREADS, 0, st>>>(M, seqs, t);
+    const int nm = d.nmax, m = nm - t - 2;
+    if (m < 1) return;
+    {   // PL / PR: at most m paired rows per slab, runs of up to m cells
+        const int nchunk = (m + WRUNS - 1) / WRUNS, npass = (m + 4 * WGRP - 1) / (4 * WGRP);
+        k_winLR<<<dim3(nchunk * npass, t + 1, d.nseq * 2), K4_THREADS, 0, st>>>(M, seqs, t, nchunk);
+    }
+    {   // PM: pairs (j,k) with TURN < k-j <= n-1-t; a row has at most min(t+1, n-4-t) cells at any quad phase
+        long long rows = 0;
+        for (int s = CCJ_TURN + 1; s <= nm - 1 - t; ++s) rows += nm - s;
+        if (rows < 1) return;
+        const int cm = std::max(1, std::min(t + 1, nm - 4 - t));
+        const int nq = ((cm + 2) >> 2) + 1;
+        const int nchunk = (int)((rows + WRUNS - 1) / WRUNS), npass = (nq + WGRP - 1) / WGRP;
+        k_winM<<<dim3(nchunk * npass, d.nseq), K4_THREADS, 0, st>>>(M, seqs, t, nchunk);
+    }
 }
 void launch_4d_final(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st) {
     int bx;

@@ -150,11 +150,11 @@ void launch_traceback(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cud
 }
 
 int fill_launch_count(int nmax, bool tuned) {
-    int c = tuned ? 3 : 2;  // init (+ prep) + W
+    int c = tuned ? 5 : 2;  // init (+ layout prep + PMW fill + list prep) + W
     for (int s = 0; s < nmax; ++s) {
         if (s >= 3 && s <= nmax - 1) ++c;           // K_P
         ++c;                                        // K_2D
-        if (nmax - s - 2 >= 1) c += tuned ? 4 : 1;  // level: split roles, PL/PR windows, PM window, assembly
+        if (nmax - s - 2 >= 1) c += tuned ? (nmax - 1 - s > CCJ_TURN ? 4 : 3) : 1;  // level: split roles, PL/PR windows, PM window (if any pair is short enough), assembly
     }
     return c;
 }

@@ -29,9 +29,7 @@ enum ccj_table4 {
     CCJ_NT4 = 22,
     T_MPP = 22,       /* internal: min(PL,PR) of the cell = get_PfromMdoubleprime without PB (pseudo_loop.cc:675-678) */
     T_PKG = 23,       /* internal: second copy of PK in the layout compute_P's 2nd factor walks (ccj_pkg_idx) */
-    T_PRT = 24,       /* internal: PR transposed inside every (a,b) slab (i fastest), read by the PR interior window */
-    T_PMM = 25,       /* internal: PM keyed by its pair (j,k): nesting [j][k][level][a], read by the PM interior window */
-    CCJ_NT4_STORE = 26
+    CCJ_NT4_STORE = 24
 };
 
 // ---- 2D tables ----------------------------------------------------------------------------------
@@ -121,7 +119,19 @@ struct ccj_seq {
     //   g3 (12 B): PK PfromR min(PL,PR) PRmloop00 PMmloop00 -                   read as X(i,j,d,l)
     //   g4 (16 B): PfromR PfromO PRmloop00 PMmloop00 PMmloop10 POmloop00 POmloop10 -   read as X(i,j,k,d)
     int16_t *g1, *g2, *g3, *g4;
-    int32_t *lay;        // layout tables: lay[x]=Tet(x), lay[n+1+x]=Cb(x), x=0..n; lay[2n+2+j]=basej[j] of ccj_pmm_idx (int32; tuned path, n<=448)
+    int32_t *lay;        // layout tables, 5 arrays of n+1 ints: Tet(x), Cb(x), H4(x), HH4(x), CbW4(x)  (tuned path, n<=448)
+    // copies of PL / PR / PM for the interior windows, rows padded to 4 entries so that a lane moves 4 cells
+    // per 8-byte load ("window layouts" below); written by k_final, read by k_winLR / k_winM only
+    int16_t *plw, *prw, *pmw;
+    int16_t *wscr;       // window partial minima in the same row layouts: [parity][PL,PR] x wscr_lr, then [parity] x 4*wtot4
+    int64_t wscr_lr;     // entries of one PL/PR partial = largest padded level
+    int32_t *pmlev4;     // (n+1)^2: quad offset of row (j,k) inside one PM level (ccj_pmw_quad)
+    int32_t wtot4;       // quads of one PM level
+    int32_t npairs;      // unused on the host
+    int32_t *plist;      // plist[s*(n+1)+x], x=0..: the 5' ends i of the pairs (i,i+s), ascending
+    int32_t *pcum;       // pcum[s*(n+2)+x]: number of pairs (i,i+s) with i<=x
+    int32_t *pmlist;     // all pairs as j | k<<16, ordered by span k-j and then j
+    int32_t *pmstart;    // pmstart[s]: number of pairs with span < s, s=0..n+1
     int16_t *scratch;    // per-level partial minima: [partial id][cell of the level], see ccj_fill4.cu
     int64_t scratch_stride;   // cells of the largest level
     int32_t *tb_stack;   // traceback stack, 5 ints per node
@@ -130,6 +140,8 @@ struct ccj_seq {
 };
 #define CCJ_STATUS_INTS 8
 #define CCJ_WIN 841      /* 29*29 window slots of get_P{L,R,M}iloop (src/pseudo_loop.cc:694-700) */
+#define CCJ_WIN_IN 848   /* pitch of an inlist slot (4-byte entries, zero-padded to a multiple of 8) */
+#define CCJ_WIN_OUT 848  /* pitch of an outlist slot (8-byte entries: packed term, quad offset of the partner's PMW row) */
 CCJ_HD int ccj_tri(int i, int j) { return (j - 1) * (j - 2) / 2 + (i - 1); } /* 1<=i<j<=n -> [0, n(n-1)/2) */
 
 // ---- 4D layout ---------------------------------------------------------------------------------------
@@ -169,21 +181,33 @@ CCJ_HD int64_t ccj_pkg_idx(int n, int i, int j, int k, int l) {
     return (ccj_pent(n - 2) - ccj_pent(n - i - 1)) + ccj_tet(s - 2) + (s * (s - 1) / 2 - (s - g + 1) * (s - g + 2) / 2) + (j - i);
 }
 
-// PM copy for the PM interior window (get_PMiloop, src/pseudo_loop.cc:752-773): all cells with the same inner
-// pair (j,k) form one block of (A+1)(B+1) entries, A=j-1, B=n-k, ordered by level t=a+b and then by a, so the
-// cells (i,j,k,l) of ONE level that share (j,k) -- the only ones that share a partner list -- are contiguous.
-//   basej[j] = sum_{j'<j} j' * T(n-j'-1)   (precomputed per sequence length; T(x)=x(x+1)/2)
-CCJ_HD int64_t ccj_pmm_idx(int n, const int32_t *basej, int j, int k, int t, int a) {
-    const int64_t A = j - 1, B = n - k;
-    auto T = [](int64_t x) { return x * (x + 1) / 2; };
-    const int64_t blockbase = (int64_t)basej[j] + (int64_t)j * (T(n - j - 1) - T(n - k + 1));
-    const int64_t lo = A < B ? A : B, hi = A < B ? B : A;
-    int64_t S;
-    if (t <= lo) S = T(t);
-    else if (t <= hi) S = T(lo + 1) + (t - lo - 1) * (lo + 1);
-    else S = T(lo + 1) + (hi - lo) * (lo + 1) + (t - hi - 1) * (A + B + 1) - (T(t - 1) - T(hi));
-    const int64_t amin = t - B > 0 ? t - B : 0;
-    return blockbase + S + (a - amin);
+// ---- window layouts ------------------------------------------------------------------------------------
+// The interior windows (get_P{L,R,M}iloop, src/pseudo_loop.cc:682-773) read, for a run of cells that share a
+// closing pair, the SAME run shifted to another slab.  Their copies store every run with its start on a
+// 4-entry (8-byte) boundary and the coordinate that the window leaves unchanged as the position inside the
+// run, so that source and target quads line up and a lane moves 4 cells per load:
+//   PLW: slab (a,b), row r=i-1 (length m-r), position (n-b)-k       (window keeps k,l; source slab (a-s,b))
+//   PRW: slab (a,b), row kr=n-b-k (length m-kr), position i-1       (window keeps i,j; source slab (a,b-s))
+//        slab base = 4*(CbW4(b) + HH4(n-b-2) - HH4(m)), row start = 4*(H4(m) - H4(m-r))
+//        H4(x)  = quads of a triangle with rows 1..x, each padded to a multiple of 4
+//        HH4(x) = sum_{m<=x} H4(m),  CbW4(b) = sum_{b'<b} HH4(n-b'-2)
+//   PMW: level-major; row (j,k) of level t holds i=j-a, position (i-1) - 4*((max(j-t,1)-1)>>2)
+//        (window keeps i,l; source row (j-x,k+y) of level t-x-y); row pitch W4(j,k) quads, see ccj_pmw_w4.
+//        A PMW quad is 16 bytes: v0 v1 m0 m1 v2 v3 m2 m3, m = -32768 for a cell the window may read (a>=1, b>=1)
+//        and 32767 otherwise (end cells, padding), so that max(value+energy, mask) masks two cells at once
+CCJ_HD int64_t ccj_h4(int64_t x) { const int64_t q = x >> 2, r = x & 3; return (q + 1) * (2 * q + r); }
+inline int64_t ccj_hh4(int x) { int64_t s = 0; for (int m = 1; m <= x; ++m) s += ccj_h4(m); return s; }
+inline int64_t ccj_winlr_quads(int n) { int64_t s = 0; for (int b = 0; b <= n - 3; ++b) s += ccj_hh4(n - b - 2); return s; }
+inline int64_t ccj_winlr_level_max(int n) {  // entries of the largest padded level
+    int64_t best = 4;
+    for (int t = 0; t <= n - 3; ++t) { const int64_t c = 4 * (int64_t)(t + 1) * ccj_h4(n - t - 2); if (c > best) best = c; }
+    return best;
+}
+CCJ_HD int ccj_pmw_w4(int n, int j, int k) { const int A = j - 1, B = n - k; return (((A < B ? A : B) + 4) >> 2) + 1; }
+inline int64_t ccj_pmw_level_quads(int n) {
+    int64_t s = 0;
+    for (int j = 1; j <= n; ++j) for (int k = j + 2; k <= n; ++k) s += ccj_pmw_w4(n, j, k);
+    return s > 0 ? s : 1;
 }
 
 CCJ_HD bool ccj_valid4(int i, int j, int k, int l) { return i <= j && j < k - 1 && k <= l; }
