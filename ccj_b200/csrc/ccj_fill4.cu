@@ -517,10 +517,11 @@ __device__ __forceinline__ int splat16(int e) { return (int)__byte_perm((unsigne
 // energy, clamp) in shared memory; every candidate is then one 8-byte load and four packed int16x2
 // instructions per lane (4 cells).  Results go to the wscr partial in the same layout, 8 bytes per lane.
 //   blockIdx.x -> (pass, chunk of 16 paired rows), blockIdx.y -> a, blockIdx.z -> (sequence, PL|PR)
-__global__ void __launch_bounds__(K4_THREADS) k_winLR(const ccj_model *__restrict__ M, const ccj_seq *__restrict__ seqs, int t, int nchunk) {
+template <bool PIPE>
+__global__ void __launch_bounds__(K4_THREADS, PIPE ? 6 : 12) k_winLR(const ccj_model *__restrict__ M, const ccj_seq *__restrict__ seqs, int t, int nchunk) {
     __shared__ int s_T[64];              // quad offset of source slab (a-s,b) resp. (a,b-s), plus H4(m+s)
     __shared__ int s_h4[K4_MAXN + 4];
-    __shared__ int4 tile[WRUNS][WGRP];   // (source run start, energy x2, clamp x2, -)
+    __shared__ int4 tile[2][WRUNS][WGRP];   // double-buffered: (source run start, energy x2, clamp x2, -)
     const int role = blockIdx.z & 1;     // 0: PL   1: PR
     const ccj_seq q = seqs[blockIdx.z >> 1];
     const int n = q.n, n1 = n + 1;
@@ -571,30 +572,69 @@ __global__ void __launch_bounds__(K4_THREADS) k_winLR(const ccj_model *__restric
     const int slot = ccj_tri(p5, p5 + arm);
     const uint32_t *__restrict__ lst = q.inlist + (int64_t)slot * CCJ_WIN_IN;
     const int cnt = gact ? __ldg(&q.incnt[slot]) : 0;
-    const int cmax = __reduce_max_sync(0xffffffffu, cnt);
-    for (int e0 = 0; e0 < cmax; e0 += WGRP) {
-        int4 d = make_int4(own, 0, WIN_INF2, 0);
-        if (cnt > 0) {  // lane gl decodes entry e0+gl; past the end the last entry again (min is idempotent)
-            const uint32_t en = __ldg(&lst[min(e0 + gl, cnt - 1)]);
-            const int x = (en >> 16) & 0xff, y = en >> 24, e = (int)(int16_t)(en & 0xffff);
-            // PL source (i+x, j-y, k, l): slab (a-s, b), row c+x, length zc+y, same position (n-b)-k
-            // PR source (i, j, k+x, l-y): slab (a, b-s), row kr+y, length zc+x, same position i-1
-            d = make_int4(s_T[x + y] - s_h4[zc + (role == 0 ? y : x)], splat16(e), splat16(32767 - max(e, 0)), 0);
+    const int nb = (__reduce_max_sync(0xffffffffu, cnt) + WGRP - 1) / WGRP;   // batches of 8 candidates, warp-uniform
+    // PIPE (small waves): software pipeline over the batches -- while batch b is consumed, the loads of batch b+1
+    // are in flight and the list entry of batch b+2 is on its way.
+    // lane gl fetches entry 8b+gl of its group's list; past the end the last entry again (min is idempotent)
+    auto fetch = [&](int bb) -> uint32_t { return cnt > 0 ? __ldg(&lst[min(bb * WGRP + gl, cnt - 1)]) : 0u; };
+    auto decode = [&](uint32_t en) -> int4 {
+        if (cnt == 0) return make_int4(own, 0, WIN_INF2, 0);
+        const int x = (en >> 16) & 0xff, y = en >> 24, e = (int)(int16_t)(en & 0xffff);
+        // PL source (i+x, j-y, k, l): slab (a-s, b), row c+x, length zc+y, same position (n-b)-k
+        // PR source (i, j, k+x, l-y): slab (a, b-s), row kr+y, length zc+x, same position i-1
+        return make_int4(s_T[x + y] - s_h4[zc + (role == 0 ? y : x)], splat16(e), splat16(32767 - max(e, 0)), 0);
+    };
+#define ISSUE(W_, buf)                                                        \
+    _Pragma("unroll") for (int u = 0; u < WB; ++u) W_[u] = ldq(src, tile[buf][grp][u].x)
+#define CONSUME(W_, buf)                                                      \
+    _Pragma("unroll") for (int u = 0; u < WB; ++u) {                         \
+        const int4 d2 = tile[buf][grp][u];                                   \
+        acc0 = addmin2(min2(W_[u].x, d2.z), d2.y, acc0);                      \
+        acc1 = addmin2(min2(W_[u].y, d2.z), d2.y, acc1);                      \
+    }
+    if (PIPE) {
+        int2 wa[WB], wb[WB];
+        uint32_t pre = 0;
+        if (nb > 0) {
+            tile[0][grp][gl] = decode(fetch(0));
+            pre = fetch(1);
+            __syncwarp();
+            ISSUE(wa, 0);
         }
-        __syncwarp();
-        tile[grp][gl] = d;
-        __syncwarp();
-        int2 w[WB];
-#pragma unroll
-        for (int u = 0; u < WB; ++u) w[u] = ldq(src, tile[grp][u].x);
-        FENCE8X(w);
-#pragma unroll
-        for (int u = 0; u < WB; ++u) {
-            const int4 d2 = tile[grp][u];
-            acc0 = addmin2(min2(w[u].x, d2.z), d2.y, acc0);
-            acc1 = addmin2(min2(w[u].y, d2.z), d2.y, acc1);
+        for (int bb = 0; bb < nb; bb += 2) {
+            if (bb + 1 < nb) {
+                tile[1][grp][gl] = decode(pre);
+                pre = fetch(bb + 2);
+                __syncwarp();
+                ISSUE(wb, 1);
+            }
+            CONSUME(wa, 0);
+            __syncwarp();
+            if (bb + 1 < nb) {
+                if (bb + 2 < nb) {
+                    tile[0][grp][gl] = decode(pre);
+                    pre = fetch(bb + 3);
+                    __syncwarp();
+                    ISSUE(wa, 0);
+                }
+                CONSUME(wb, 1);
+                __syncwarp();
+            }
+        }
+    } else {  // waves with many sequences hide the latency with occupancy: plain loop, fewer registers
+        for (int bb = 0; bb < nb; ++bb) {
+            const int4 d = decode(fetch(bb));
+            __syncwarp();
+            tile[0][grp][gl] = d;
+            __syncwarp();
+            int2 w[WB];
+            ISSUE(w, 0);
+            FENCE8X(w);
+            CONSUME(w, 0);
         }
     }
+#undef ISSUE
+#undef CONSUME
     if (gact && 4 * qd < zc) {
         if (cnt == 0) { acc0 = keep0; acc1 = keep1; }
         int2 *__restrict__ out = reinterpret_cast<int2 *>(q.wscr + (int64_t)((t & 1) * 2 + role) * q.wscr_lr);
@@ -627,8 +667,9 @@ __global__ void __launch_bounds__(256) k_fill_pmw(const ccj_seq *seqs) {
 // 32767 for the two end cells and the padding), and the candidate is max(value+energy, mask) -- still two
 // cells per instruction.  The 8 lanes of a group decode 8 list entries at a time into shared memory.
 //   blockIdx.x -> (pass, chunk of 16 pairs), blockIdx.y -> sequence
-__global__ void __launch_bounds__(K4_THREADS) k_winM(const ccj_model *__restrict__ M, const ccj_seq *__restrict__ seqs, int t, int nchunk) {
-    __shared__ int4 tile[WRUNS][WGRP];   // (source row start, energy x2, clamp x2, first quad | quads-1 << 16)
+template <bool PIPE>
+__global__ void __launch_bounds__(K4_THREADS, PIPE ? 4 : 10) k_winM(const ccj_model *__restrict__ M, const ccj_seq *__restrict__ seqs, int t, int nchunk) {
+    __shared__ int4 tile[2][WRUNS][WGRP];   // (source row start, energy x2, clamp x2, first quad | quads-1 << 16)
     const ccj_seq q = seqs[blockIdx.y];
     const int n = q.n, n1 = n + 1;
     const int m = n - t - 2;
@@ -672,37 +713,76 @@ __global__ void __launch_bounds__(K4_THREADS) k_winM(const ccj_model *__restrict
     const int slot = ccj_tri(j, k);
     const uint2 *__restrict__ lst = reinterpret_cast<const uint2 *>(q.outlist) + (int64_t)slot * CCJ_WIN_OUT;
     const int cnt = gact ? __ldg(&q.outcnt[slot]) : 0;
-    const int cmax = __reduce_max_sync(0xffffffffu, cnt);
-    for (int e0 = 0; e0 < cmax; e0 += WGRP) {
-        int4 d = make_int4(own, 0, WIN_INF2, 0);  // no candidate: the own row is all "not a source"
-        if (e0 + gl < cnt) {  // lane gl decodes entry e0+gl of its group's list
-            const uint2 L = __ldg(&lst[e0 + gl]);
+    const int nb = (__reduce_max_sync(0xffffffffu, cnt) + WGRP - 1) / WGRP;   // batches of 8 candidates, warp-uniform
+    // lane gl fetches / decodes entry 8b+gl of its group's list
+    auto fetch = [&](int bb) -> uint2 { return bb * WGRP + gl < cnt ? __ldg(&lst[bb * WGRP + gl]) : make_uint2(0u, 0xffffffffu); };
+    auto decode = [&](uint2 L) -> int4 {
+        if (L.y != 0xffffffffu) {
             const int x = (L.x >> 16) & 0xff, y = L.x >> 24, e = (int)(int16_t)(L.x & 0xffff);
             const int tl = t - x - y;                               // level of the source row (j-x, k+y)
             const int il = max(j - t + y, 1), ih = j - x - max(0, tl - (B - y));   // its cells
             if (tl >= 0 && ih >= il) {
                 const int qls = (il - 1) >> 2, qhs = (ih - 1) >> 2;
-                d = make_int4(tl * wtot4 + (int)L.y - qls, splat16(e), splat16(32767 - max(e, 0)), qls | ((qhs - qls) << 16));
+                return make_int4(tl * wtot4 + (int)L.y - qls, splat16(e), splat16(32767 - max(e, 0)), qls | ((qhs - qls) << 16));
             }
         }
-        __syncwarp();
-        tile[grp][gl] = d;
-        __syncwarp();
-        int4 w[WB];
-#pragma unroll
-        for (int u = 0; u < WB; ++u) {
-            const int4 d2 = tile[grp][u];
-            // quads outside the source row belong to other rows: read the own row instead
-            const bool ok = (unsigned)(qd - (d2.w & 0xffff)) <= (unsigned)(d2.w >> 16);
-            w[u] = ldq4(src, ok ? d2.x : own);
+        return make_int4(own, 0, WIN_INF2, 0);  // no candidate: the own row is all "not a source"
+    };
+#define ISSUE(W_, buf)                                                                             \
+    _Pragma("unroll") for (int u = 0; u < WB; ++u) {                                              \
+        const int4 d2 = tile[buf][grp][u];                                                        \
+        /* quads outside the source row belong to other rows: read the own row instead */         \
+        const bool ok = (unsigned)(qd - (d2.w & 0xffff)) <= (unsigned)(d2.w >> 16);               \
+        W_[u] = ldq4(src, ok ? d2.x : own);                                                        \
+    }
+#define CONSUME(W_, buf)                                                                           \
+    _Pragma("unroll") for (int u = 0; u < WB; ++u) {                                              \
+        const int4 d2 = tile[buf][grp][u];                                                        \
+        acc0 = min2(acc0, addmax2(min2(W_[u].x, d2.z), d2.y, W_[u].y));                             \
+        acc1 = min2(acc1, addmax2(min2(W_[u].z, d2.z), d2.y, W_[u].w));                             \
+    }
+    if (PIPE) {  // see k_winLR
+        int4 wa[WB], wb[WB];
+        uint2 pre = make_uint2(0u, 0xffffffffu);
+        if (nb > 0) {
+            tile[0][grp][gl] = decode(fetch(0));
+            pre = fetch(1);
+            __syncwarp();
+            ISSUE(wa, 0);
         }
-#pragma unroll
-        for (int u = 0; u < WB; ++u) {
-            const int4 d2 = tile[grp][u];
-            acc0 = min2(acc0, addmax2(min2(w[u].x, d2.z), d2.y, w[u].y));
-            acc1 = min2(acc1, addmax2(min2(w[u].z, d2.z), d2.y, w[u].w));
+        for (int bb = 0; bb < nb; bb += 2) {
+            if (bb + 1 < nb) {
+                tile[1][grp][gl] = decode(pre);
+                pre = fetch(bb + 2);
+                __syncwarp();
+                ISSUE(wb, 1);
+            }
+            CONSUME(wa, 0);
+            __syncwarp();
+            if (bb + 1 < nb) {
+                if (bb + 2 < nb) {
+                    tile[0][grp][gl] = decode(pre);
+                    pre = fetch(bb + 3);
+                    __syncwarp();
+                    ISSUE(wa, 0);
+                }
+                CONSUME(wb, 1);
+                __syncwarp();
+            }
+        }
+    } else {
+        for (int bb = 0; bb < nb; ++bb) {
+            const int4 d = decode(fetch(bb));
+            __syncwarp();
+            tile[0][grp][gl] = d;
+            __syncwarp();
+            int4 w[WB];
+            ISSUE(w, 0);
+            CONSUME(w, 0);
         }
     }
+#undef ISSUE
+#undef CONSUME
     if (gact && qd <= qhi) {
         int2 *__restrict__ out = reinterpret_cast<int2 *>(q.wscr + 4 * q.wscr_lr + (int64_t)(t & 1) * 4 * wtot4);
         out[own - t * wtot4 + qd] = make_int2(acc0, acc1);
@@ -938,9 +1018,12 @@ void launch_4d_roles(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int 
 void launch_4d_windows(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st) {
     const int nm = d.nmax, m = nm - t - 2;
     if (m < 1) return;
+    const bool pipe = d.nseq < 4;  // few sequences: latency-bound, use the software-pipelined variants
     {   // PL / PR: at most m paired rows per slab, runs of up to m cells
         const int nchunk = (m + WRUNS - 1) / WRUNS, npass = (m + 4 * WGRP - 1) / (4 * WGRP);
-        k_winLR<<<dim3(nchunk * npass, t + 1, d.nseq * 2), K4_THREADS, 0, st>>>(M, seqs, t, nchunk);
+        const dim3 grid(nchunk * npass, t + 1, d.nseq * 2);
+        if (pipe) k_winLR<true><<<grid, K4_THREADS, 0, st>>>(M, seqs, t, nchunk);
+        else k_winLR<false><<<grid, K4_THREADS, 0, st>>>(M, seqs, t, nchunk);
     }
     {   // PM: pairs (j,k) with TURN < k-j <= n-1-t; a row has at most min(t+1, n-4-t) cells at any quad phase
         long long rows = 0;
@@ -949,7 +1032,9 @@ void launch_4d_windows(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, in
         const int cm = std::max(1, std::min(t + 1, nm - 4 - t));
         const int nq = ((cm + 2) >> 2) + 1;
         const int nchunk = (int)((rows + WRUNS - 1) / WRUNS), npass = (nq + WGRP - 1) / WGRP;
-        k_winM<<<dim3(nchunk * npass, d.nseq), K4_THREADS, 0, st>>>(M, seqs, t, nchunk);
+        const dim3 grid(nchunk * npass, d.nseq);
+        if (pipe) k_winM<true><<<grid, K4_THREADS, 0, st>>>(M, seqs, t, nchunk);
+        else k_winM<false><<<grid, K4_THREADS, 0, st>>>(M, seqs, t, nchunk);
     }
 }
 void launch_4d_final(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st) {
