@@ -1,0 +1,907 @@
+// ccj_oracle -- CPU restatement of the CCJ MFE fill (reference: mateog4712/CCJ, src/).
+//
+// TEST INFRASTRUCTURE ONLY.  Nothing in the product (ccj_b200/) includes, links or executes this file; it is the
+// checker behind tests/test_oracle.py, tests/test_gpu_parity.py and __graft_entry__.smoke().
+//
+// What it restates: every table of the fill -- V/VM, WM, WMv, WMp (src/s_energy_matrix.cc), P, WBP, WPP and the
+// 22 four-dimensional gap tables (src/pseudo_loop.cc:69-848) -- in the reference's own sweep order
+// (W_final::ccj, src/W_final.cc:58-77), the exterior W, and the loop energies of the vendored ViennaRNA headers
+// the fill calls.  Plain loops over plain arrays, one function per reference function, each citing file:line.
+// The traceback is not restated: structures are pinned by the compiled reference (oracle/_ref/CCJ) and the
+// golden folds it produced (tests/golden/).
+//
+// Parity of THIS file is pinned: tests/test_oracle.py compares its table hashes and energies with the golden
+// vectors written by the compiled reference (tests/golden/table_hashes.json, folds.json), and with
+// oracle/_ref/ccj_ref_dump where that binary exists.
+//
+// The scaled energy parameters are read from the text dump that `ccj_ref_dump params` writes
+// (tests/golden/params_*.txt.gz, unpacked), so the oracle shares no parameter-file reader with the product.
+//
+//   ccj_oracle hash   <params.txt> <dangles> <noGU 0|1> <sequence>   table hashes, format of `ccj_ref_dump hash`, + "W <dcal>"
+//   ccj_oracle energy <params.txt> <dangles> <noGU 0|1> <sequence>   W[n] in dcal/mol
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+static const int INF = 10000000;  // src/matrices.hh:10
+static const int TURN = 3;        // src/ViennaRNA/params/constants.h:27
+static const int MAXLOOP = 30;    // src/ViennaRNA/params/constants.h:29
+static const int MAX_NINIO = 300; // src/ViennaRNA/params/constants.h (MAX_NINIO)
+
+// pseudoknot penalties, src/h_globals.hh:7-25
+static const int PS_penalty = -138, PSM_penalty = 1007, PSP_penalty = 1500, PB_penalty = 246, PUP_penalty = 6,
+                 PPS_penalty = 96;
+static const double e_stP_penalty = 0.89, e_intP_penalty = 0.74;
+static const int b_penalty = 3, ap_penalty = 341, bp_penalty = 56, cp_penalty = 12;
+
+// ---- scaled parameters (vrna_param_t fields the path reads; src/ViennaRNA/params/basic.h:57-118) --------------
+struct Params {
+    int stack[8][8], hairpin[31], bulge[31], internal_loop[31];
+    int mismatchExt[8][5][5], mismatchI[8][5][5], mismatch1nI[8][5][5], mismatch23I[8][5][5], mismatchH[8][5][5],
+        mismatchM[8][5][5];
+    int dangle5[8][5], dangle3[8][5];
+    int int11[8][8][5][5], int21[8][8][5][5][5], int22[8][8][5][5][5][5];
+    int ninio[5], MLbase, MLintern[8], MLclosing, TerminalAU;
+    double lxc;
+    std::string Tetraloops, Triloops, Hexaloops;
+    int Tetraloop_E[64], Triloop_E[64], Hexaloop_E[64];
+    int special_hp, dangles;
+};
+static Params P;
+
+static void load_params(const char *path) {
+    std::ifstream in(path);
+    if (!in) { fprintf(stderr, "ccj_oracle: cannot read %s\n", path); exit(2); }
+    std::string line;
+    while (std::getline(in, line)) {
+        std::istringstream ss(line);
+        std::string name;
+        ss >> name;
+        if (name == "Tetraloops" || name == "Triloops" || name == "Hexaloops") {
+            // "Name <string>|": the string itself contains blanks and ends before the bar
+            const size_t a = line.find(' ') + 1, b = line.rfind('|');
+            std::string v = line.substr(a, b - a);
+            (name == "Tetraloops" ? P.Tetraloops : name == "Triloops" ? P.Triloops : P.Hexaloops) = v;
+            continue;
+        }
+        if (name == "lxc") { ss >> P.lxc; continue; }
+        std::vector<long> v;
+        long x;
+        while (ss >> x) v.push_back(x);
+        if (v.empty()) continue;
+        const int val = (int)v.back();
+#define IDX(k) ((int)v[k])
+        if (name == "stack") P.stack[IDX(0)][IDX(1)] = val;
+        else if (name == "hairpin") P.hairpin[IDX(0)] = val;
+        else if (name == "bulge") P.bulge[IDX(0)] = val;
+        else if (name == "internal_loop") P.internal_loop[IDX(0)] = val;
+        else if (name == "mismatchExt") P.mismatchExt[IDX(0)][IDX(1)][IDX(2)] = val;
+        else if (name == "mismatchI") P.mismatchI[IDX(0)][IDX(1)][IDX(2)] = val;
+        else if (name == "mismatch1nI") P.mismatch1nI[IDX(0)][IDX(1)][IDX(2)] = val;
+        else if (name == "mismatch23I") P.mismatch23I[IDX(0)][IDX(1)][IDX(2)] = val;
+        else if (name == "mismatchH") P.mismatchH[IDX(0)][IDX(1)][IDX(2)] = val;
+        else if (name == "mismatchM") P.mismatchM[IDX(0)][IDX(1)][IDX(2)] = val;
+        else if (name == "dangle5") P.dangle5[IDX(0)][IDX(1)] = val;
+        else if (name == "dangle3") P.dangle3[IDX(0)][IDX(1)] = val;
+        else if (name == "int11") P.int11[IDX(0)][IDX(1)][IDX(2)][IDX(3)] = val;
+        else if (name == "int21") P.int21[IDX(0)][IDX(1)][IDX(2)][IDX(3)][IDX(4)] = val;
+        else if (name == "int22") P.int22[IDX(0)][IDX(1)][IDX(2)][IDX(3)][IDX(4)][IDX(5)] = val;
+        else if (name == "ninio") P.ninio[IDX(0)] = val;
+        else if (name == "MLbase") P.MLbase = val;
+        else if (name == "MLintern") P.MLintern[IDX(0)] = val;
+        else if (name == "MLclosing") P.MLclosing = val;
+        else if (name == "TerminalAU") P.TerminalAU = val;
+        else if (name == "Tetraloop_E") P.Tetraloop_E[IDX(0)] = val;
+        else if (name == "Triloop_E") P.Triloop_E[IDX(0)] = val;
+        else if (name == "Hexaloop_E") P.Hexaloop_E[IDX(0)] = val;
+        else if (name == "special_hp") P.special_hp = val;
+#undef IDX
+    }
+}
+
+// ---- sequence encoding and pair matrix (src/ViennaRNA/pair_mat.h:20-38, 80-100, 159-183) -----------------------
+static int n;
+static std::string seq;
+static std::vector<short> S, S1;
+static int pairm[8][8];
+static int rtype[8] = {0, 2, 1, 4, 3, 6, 5, 7};
+
+static int encode_char(char c) {
+    switch (toupper(c)) {
+        case 'A': return 1;
+        case 'C': return 2;
+        case 'G': return 3;
+        case 'U':
+        case 'T': return 4;
+    }
+    return 0;
+}
+static void make_pair_matrix(bool noGU) {
+    static const int BP[8][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 5, 0, 0, 5}, {0, 0, 0, 1, 0, 0, 0, 0},
+                                 {0, 0, 2, 0, 3, 0, 0, 0}, {0, 6, 0, 4, 0, 0, 0, 6}, {0, 0, 0, 0, 0, 0, 2, 0},
+                                 {0, 0, 0, 0, 0, 1, 0, 0}, {0, 6, 0, 0, 5, 0, 0, 0}};
+    for (int i = 0; i < 8; ++i)
+        for (int j = 0; j < 8; ++j) pairm[i][j] = BP[i][j];
+    if (noGU) pairm[3][4] = pairm[4][3] = 0;
+    for (int i = 0; i < 8; ++i)
+        for (int j = 0; j < 8; ++j) rtype[pairm[i][j]] = pairm[j][i];
+}
+static void encode(const std::string &s) {
+    seq = s;
+    n = (int)s.size();
+    S.assign(n + 2, 0);
+    S1.assign(n + 2, 0);
+    for (int i = 1; i <= n; ++i) S[i] = S1[i] = (short)encode_char(s[i - 1]);
+    S[n + 1] = S[1];
+    S[0] = (short)n;
+    S1[n + 1] = S1[1];
+    S1[0] = S1[n];
+}
+
+// ---- loop energies -------------------------------------------------------------------------------------------
+// src/ViennaRNA/loops/hairpin.h:148-200
+static int E_Hairpin(int size, int type, int si1, int sj1, const char *string) {
+    int energy;
+    if (size <= 30) energy = P.hairpin[size];
+    else energy = P.hairpin[30] + (int)(P.lxc * log((size) / 30.));
+    if (size < 3) return energy;
+    if (string && P.special_hp) {
+        if (size == 4) {
+            char tl[7] = {0};
+            memcpy(tl, string, 6);
+            const char *ts = strstr(P.Tetraloops.c_str(), tl);
+            if (ts) return P.Tetraloop_E[(ts - P.Tetraloops.c_str()) / 7];
+        } else if (size == 6) {
+            char tl[9] = {0};
+            memcpy(tl, string, 8);
+            const char *ts = strstr(P.Hexaloops.c_str(), tl);
+            if (ts) return P.Hexaloop_E[(ts - P.Hexaloops.c_str()) / 9];
+        } else if (size == 3) {
+            char tl[6] = {0};
+            memcpy(tl, string, 5);
+            const char *ts = strstr(P.Triloops.c_str(), tl);
+            if (ts) return P.Triloop_E[(ts - P.Triloops.c_str()) / 6];
+            return energy + (type > 2 ? P.TerminalAU : 0);
+        }
+    }
+    energy += P.mismatchH[type][si1][sj1];
+    return energy;
+}
+// src/ViennaRNA/loops/internal.h:478-569
+static int E_IntLoop(int n1, int n2, int type, int type_2, int si1, int sj1, int sp1, int sq1) {
+    int nl, ns, u, energy = INF;
+    if (n1 > n2) { nl = n1; ns = n2; } else { nl = n2; ns = n1; }
+    if (nl == 0) return P.stack[type][type_2];
+    if (ns == 0) {
+        energy = (nl <= MAXLOOP) ? P.bulge[nl] : (P.bulge[30] + (int)(P.lxc * log(nl / 30.)));
+        if (nl == 1) energy += P.stack[type][type_2];
+        else {
+            if (type > 2) energy += P.TerminalAU;
+            if (type_2 > 2) energy += P.TerminalAU;
+        }
+        return energy;
+    }
+    if (ns == 1) {
+        if (nl == 1) return P.int11[type][type_2][si1][sj1];
+        if (nl == 2) {
+            if (n1 == 1) energy = P.int21[type][type_2][si1][sq1][sj1];
+            else energy = P.int21[type_2][type][sq1][si1][sp1];
+            return energy;
+        }
+        energy = (nl + 1 <= MAXLOOP) ? P.internal_loop[nl + 1] : (P.internal_loop[30] + (int)(P.lxc * log((nl + 1) / 30.)));
+        energy += std::min(MAX_NINIO, (nl - ns) * P.ninio[2]);
+        energy += P.mismatch1nI[type][si1][sj1] + P.mismatch1nI[type_2][sq1][sp1];
+        return energy;
+    } else if (ns == 2) {
+        if (nl == 2) return P.int22[type][type_2][si1][sp1][sq1][sj1];
+        if (nl == 3) {
+            energy = P.internal_loop[5] + P.ninio[2];
+            energy += P.mismatch23I[type][si1][sj1] + P.mismatch23I[type_2][sq1][sp1];
+            return energy;
+        }
+    }
+    u = nl + ns;
+    energy = (u <= MAXLOOP) ? P.internal_loop[u] : (P.internal_loop[30] + (int)(P.lxc * log((u) / 30.)));
+    energy += std::min(MAX_NINIO, (nl - ns) * P.ninio[2]);
+    energy += P.mismatchI[type][si1][sj1] + P.mismatchI[type_2][sq1][sp1];
+    return energy;
+}
+// src/ViennaRNA/loops/multibranch.h:225-246
+static int E_MLstem(int type, int si1, int sj1) {
+    int energy = 0;
+    if (si1 >= 0 && sj1 >= 0) energy += P.mismatchM[type][si1][sj1];
+    else if (si1 >= 0) energy += P.dangle5[type][si1];
+    else if (sj1 >= 0) energy += P.dangle3[type][sj1];
+    if (type > 2) energy += P.TerminalAU;
+    energy += P.MLintern[type];
+    return energy;
+}
+// src/ViennaRNA/loops/external.c:383-402
+static int vrna_E_ext_stem(int type, int n5d, int n3d) {
+    int energy = 0;
+    if (n5d >= 0 && n3d >= 0) energy += P.mismatchExt[type][n5d][n3d];
+    else if (n5d >= 0) energy += P.dangle5[type][n5d];
+    else if (n3d >= 0) energy += P.dangle3[type][n3d];
+    if (type > 2) energy += P.TerminalAU;
+    return energy;
+}
+
+// ---- containers (src/matrices.hh:14-79 TriangleMatrix, :148-232 Matrix4D; src/h_struct.hh:94-103) ---------------
+static std::vector<int> tindex;  // TriangleMatrix::new_index(index, n+1)
+static int ij2(int i, int j) { return tindex[i] + j - i; }
+struct Tri {
+    std::vector<int> m;
+    void init() { m.assign((size_t)(n + 1) * (n + 2) / 2, INF + 1); }
+    int get(int i, int j) const { return i > j ? INF : m[ij2(i, j)]; }   // return_val_ = INF
+    int &at(int i, int j) { return m[ij2(i, j)]; }
+};
+static std::vector<size_t> index3D;  // Matrix4D::construct_index
+struct M4 {
+    std::vector<int16_t> m;
+    void init() { m.assign((size_t)n * (n + 1) * (n + 2) * (n + 3) / 24, (int16_t)32767); }
+    size_t index(int i, int j, int k, int l) const { return index3D[(size_t)(i - 1) * n * n + (size_t)(j - 1) * n + k - 1] + (l - k); }
+    int get(int i, int j, int k, int l) const {
+        if (!(i <= j && j < k - 1 && k <= l)) return INF;
+        return m[index(i, j, k, l)];
+    }
+    void set(int i, int j, int k, int l, int e) {
+        if (e >= 32767) e = 32767;
+        m[index(i, j, k, l)] = (int16_t)e;   // int16 narrowing like std::vector<energy_16t>
+    }
+};
+static void build_indices() {
+    tindex.assign(n + 2, 0);
+    const int nn = n + 1;
+    tindex[1] = 0;
+    for (int i = 2; i < nn; ++i) tindex[i] = tindex[i - 1] + nn - i + 1;
+    index3D.assign((size_t)n * n * n, 0);
+    size_t idx = 0;
+    for (int i = 0; i < n; ++i)
+        for (int j = i; j < n; ++j)
+            for (int k = j; k < n; ++k) {
+                index3D[(size_t)i * n * n + (size_t)j * n + k] = idx;
+                idx += (n - k);
+            }
+}
+
+// ---- nested part: src/s_energy_matrix.cc ----------------------------------------------------------------------
+static std::vector<int> Venergy;
+static std::vector<char> Vtype;
+static Tri WM, WMv, WMp;
+static int V_get(int i, int j) { return i >= j ? INF : Venergy[ij2(i, j)]; }        // s_energy_matrix.hh:37
+static int WM_get(int i, int j) { return i >= j ? INF : WM.m[ij2(i, j)]; }          // :39
+static int WMv_get(int i, int j) { return i >= j ? INF : WMv.m[ij2(i, j)]; }        // :40
+static int WMp_get(int i, int j) { return i >= j ? INF : WMp.m[ij2(i, j)]; }        // :41
+
+// s_energy_matrix::E_MLStem, src/s_energy_matrix.cc:54-112
+static int E_MLStem(int vij, int vi1j, int vij1, int vi1j1, int i, int j) {
+    int e = INF, en = INF;
+    int type = pairm[S[i]][S[j]];
+    en = vij;
+    if (en != INF) {
+        if (P.dangles == 2) {
+            const int mm5 = i > 1 ? S[i - 1] : -1;
+            const int mm3 = j < n ? S[j + 1] : -1;
+            en += E_MLstem(type, mm5, mm3);
+        } else {
+            en += E_MLstem(type, -1, -1);
+        }
+        e = std::min(e, en);
+    }
+    if (P.dangles == 1) {
+        const int mm5 = S[i], mm3 = S[j];
+        en = (j - i - 1 > TURN) ? vi1j : INF;
+        if (en != INF) {
+            en += P.MLbase;
+            type = pairm[S[i + 1]][S[j]];
+            en += E_MLstem(type, mm5, -1);
+            e = std::min(e, en);
+        }
+        en = (j - 1 - i > TURN) ? vij1 : INF;
+        if (en != INF) {
+            en += P.MLbase;
+            type = pairm[S[i]][S[j - 1]];
+            en += E_MLstem(type, -1, mm3);
+            e = std::min(e, en);
+        }
+        en = (j - 1 - i - 1 > TURN) ? vi1j1 : INF;
+        if (en != INF) {
+            en += 2 * P.MLbase;
+            type = pairm[S[i + 1]][S[j - 1]];
+            en += E_MLstem(type, mm5, mm3);
+            e = std::min(e, en);
+        }
+    }
+    return e;
+}
+// s_energy_matrix::E_MbLoop, src/s_energy_matrix.cc:122-205
+static int E_MbLoop(int WM2ij, int WM2ip1j, int WM2ijm1, int WM2ip1jm1, int i, int j) {
+    int e = INF, en = INF;
+    const int tt = pairm[S[j]][S[i]];
+    switch (P.dangles) {
+        case 2:
+            e = WM2ij;
+            if (e != INF) e += E_MLstem(tt, S[j - 1], S[i + 1]) + P.MLclosing;
+            break;
+        case 1:
+            e = WM2ij;
+            if (e != INF) e += E_MLstem(tt, -1, -1) + P.MLclosing;
+            en = WM2ip1j;
+            if (en != INF) en += E_MLstem(tt, -1, S[i + 1]) + P.MLclosing + P.MLbase;
+            e = std::min(e, en);
+            en = WM2ijm1;
+            if (en != INF) en += E_MLstem(tt, S[j - 1], -1) + P.MLclosing + P.MLbase;
+            e = std::min(e, en);
+            en = WM2ip1jm1;
+            if (en != INF) en += E_MLstem(tt, S[j - 1], S[i + 1]) + P.MLclosing + 2 * P.MLbase;
+            e = std::min(e, en);
+            break;
+        case 0:
+            e = WM2ij;
+            if (e != INF) e += E_MLstem(tt, -1, -1) + P.MLclosing;
+            break;
+    }
+    return e;
+}
+// s_energy_matrix::compute_energy_VM, src/s_energy_matrix.cc:243-268 (including the (k-1,j-1) index of :253)
+static int compute_energy_VM(int i, int j) {
+    int mn = INF;
+    for (int k = i + 1; k <= j - 3; ++k) {
+        int WM2ij = WM_get(i + 1, k - 1) + WMv_get(k, j - 1);
+        WM2ij = std::min(WM2ij, WM_get(i + 1, k - 1) + WMp_get(k, j - 1));
+        WM2ij = std::min(WM2ij, (k - i - 1) * P.MLbase + WMp_get(k, j - 1));
+        int WM2ip1j = WM_get(i + 2, k - 1) + WMv_get(k, j - 1);
+        WM2ip1j = std::min(WM2ip1j, WM_get(i + 2, k - 1) + WMp_get(k - 1, j - 1));
+        WM2ip1j = std::min(WM2ip1j, (k - (i + 1) - 1) * P.MLbase + WMp_get(k, j - 1));
+        int WM2ijm1 = WM_get(i + 1, k - 1) + WMv_get(k, j - 2);
+        WM2ijm1 = std::min(WM2ijm1, WM_get(i + 1, k - 1) + WMp_get(k, j - 2));
+        WM2ijm1 = std::min(WM2ijm1, (k - i - 1) * P.MLbase + WMp_get(k, j - 2));
+        int WM2ip1jm1 = WM_get(i + 2, k - 1) + WMv_get(k, j - 2);
+        WM2ip1jm1 = std::min(WM2ip1jm1, WM_get(i + 2, k - 1) + WMp_get(k, j - 2));
+        WM2ip1jm1 = std::min(WM2ip1jm1, (k - (i + 1) - 1) * P.MLbase + WMp_get(k, j - 2));
+        mn = std::min(mn, E_MbLoop(WM2ij, WM2ip1j, WM2ijm1, WM2ip1jm1, i, j));
+    }
+    return mn;
+}
+// s_energy_matrix::HairpinE, src/s_energy_matrix.cc:275-282
+static int HairpinE(int i, int j) {
+    const int ptype_closing = pairm[S[i]][S[j]];
+    if (ptype_closing == 0) return INF;
+    return E_Hairpin(j - i - 1, ptype_closing, S1[i + 1], S1[j - 1], seq.c_str() + (i - 1));
+}
+// s_energy_matrix::compute_internal, src/s_energy_matrix.cc:287-299
+static int compute_internal(int i, int j) {
+    int v_iloop = INF;
+    const int max_k = std::min(j - TURN - 2, i + MAXLOOP + 1);
+    const int ptype_closing = pairm[S[i]][S[j]];
+    for (int k = i + 1; k <= max_k; ++k) {
+        const int min_l = std::max(k + TURN + 1 + MAXLOOP + 2, k + j - i) - MAXLOOP - 2;
+        for (int l = j - 1; l >= min_l; --l) {
+            const int v = E_IntLoop(k - i - 1, j - l - 1, ptype_closing, rtype[pairm[S[k]][S[l]]], S1[i + 1], S1[j - 1],
+                                    S1[k - 1], S1[l + 1]) + V_get(k, l);
+            v_iloop = std::min(v_iloop, v);
+        }
+    }
+    return v_iloop;
+}
+// s_energy_matrix::compute_energy, src/s_energy_matrix.cc:315-358
+static void compute_energy(int i, int j) {
+    int mn = INF / 2, min_rank = -1, min_en[3];
+    min_en[0] = HairpinE(i, j);
+    min_en[1] = compute_internal(i, j);
+    min_en[2] = compute_energy_VM(i, j);
+    for (int k = 0; k < 3; ++k)
+        if (min_en[k] < mn) { mn = min_en[k]; min_rank = k; }
+    const char type = min_rank == 0 ? 'H' : min_rank == 1 ? 'I' : min_rank == 2 ? 'M' : 'N';
+    if (mn < INF / 2) {
+        Venergy[ij2(i, j)] = mn;
+        Vtype[ij2(i, j)] = type;
+    }
+}
+// s_energy_matrix::compute_WMv_WMp, src/s_energy_matrix.cc:206-218
+static void compute_WMv_WMp(int i, int j, int WMB) {
+    if (j - i + 1 < 4) return;
+    const int ij = ij2(i, j), ijminus1 = ij2(i, j - 1);
+    WMv.m[ij] = E_MLStem(V_get(i, j), V_get(i + 1, j), V_get(i, j - 1), V_get(i + 1, j - 1), i, j);
+    WMp.m[ij] = WMB + PSM_penalty + b_penalty;
+    WMv.m[ij] = std::min(WMv.m[ij], WMv.m[ijminus1] + P.MLbase);
+    WMp.m[ij] = std::min(WMp.m[ij], WMp.m[ijminus1] + P.MLbase);
+}
+// s_energy_matrix::compute_energy_WM, src/s_energy_matrix.cc:219-241
+static void compute_energy_WM(int i, int j, Tri &WMB) {
+    if (j - i + 1 < 4) return;
+    int m1 = INF, m2 = INF, m3 = INF, m4 = INF, m5 = INF;
+    for (int k = j - TURN - 1; k >= i; --k) {
+        const int wm_kj = E_MLStem(V_get(k, j), V_get(k + 1, j), V_get(k, j - 1), V_get(k + 1, j - 1), k, j);
+        const int wmb_kj = WMB.m[ij2(k, j)] + PSM_penalty + b_penalty;
+        m1 = std::min(m1, (k - i) * P.MLbase + wm_kj);
+        m2 = std::min(m2, (k - i) * P.MLbase + wmb_kj);
+        m3 = std::min(m3, WM_get(i, k - 1) + wm_kj);
+        m4 = std::min(m4, WM_get(i, k - 1) + wmb_kj);
+    }
+    m5 = std::min(m5, WM.m[ij2(i, j - 1)] + P.MLbase);
+    WM.m[ij2(i, j)] = std::min({m1, m2, m3, m4, m5});
+}
+
+// ---- pseudoknotted part: src/pseudo_loop.cc ---------------------------------------------------------------------
+static Tri Pm, WBP, WPP;
+static M4 PK, PL, PR, PM, PO, PfromL, PfromR, PfromM, PfromMprime, PfromO, PLmloop00, PLmloop01, PLmloop10, PRmloop00,
+    PRmloop01, PRmloop10, PMmloop00, PMmloop01, PMmloop10, POmloop00, POmloop01, POmloop10;
+static std::vector<char> can_pair_;
+// pseudo_loop::init_can_pair / can_pair, src/pseudo_loop.hh:117-136
+static void init_can_pair() {
+    can_pair_.assign((size_t)(n + 1) * (n + 1), 0);
+    for (int i = 1; i <= n; ++i)
+        for (int j = i + TURN + 1; j <= n; ++j) can_pair_[(size_t)i * (n + 1) + j] = pairm[S[i]][S[j]] > 0;
+}
+static bool can_pair(int i, int j) { return can_pair_[(size_t)i * (n + 1) + j]; }
+static int gamma2(int, int) { return 0; }          // src/pseudo_loop.hh:187-189
+static int beta2P(int, int) { return bp_penalty; } // src/pseudo_loop.cc:848-850
+static bool valid4(int i, int j, int k, int l) { return i <= j && j < k - 1 && k <= l; }
+
+// src/pseudo_loop.cc:647-661
+static int get_WB(int i, int j) {
+    if (i <= 0 || j <= 0 || i > n || j > n) return INF;
+    if (i > j) return 0;
+    return std::min(cp_penalty * (j - i + 1), WBP.get(i, j));
+}
+static int get_WP(int i, int j) {
+    if (i <= 0 || j <= 0 || i > n || j > n) return INF;
+    if (i > j) return 0;
+    return std::min(PUP_penalty * (j - i + 1), WPP.get(i, j));
+}
+// src/pseudo_loop.cc:822-841
+static int compute_int(int i, int j, int k, int l) {
+    const int ptype_closing = pairm[S[i]][S[j]];
+    return E_IntLoop(k - i - 1, j - l - 1, ptype_closing, rtype[pairm[S[k]][S[l]]], S1[i + 1], S1[j - 1], S1[k - 1], S1[l + 1]);
+}
+static int get_e_stP(int i, int j) {
+    if (i + 1 == j - 1) return INF;
+    return (int)lrint(e_stP_penalty * compute_int(i, j, i + 1, j - 1));
+}
+static int get_e_intP(int i, int ip, int jp, int j) { return (int)lrint(e_intP_penalty * compute_int(i, j, ip, jp)); }
+
+// src/pseudo_loop.cc:134-148
+static void compute_WBP(int i, int l) {
+    int b1 = INF, b2 = INF;
+    for (int d = i; d < l; ++d) {
+        b1 = std::min(b1, get_WB(i, d - 1) + V_get(d, l) + beta2P(l, d) + PPS_penalty);
+        b2 = std::min(b2, get_WB(i, d - 1) + Pm.get(d, l) + PSM_penalty + PPS_penalty);
+    }
+    const int b3 = WBP.get(i, l - 1) + cp_penalty;
+    const int mn = std::min({b1, b2, b3});
+    if (mn < INF / 2) WBP.at(i, l) = mn;
+}
+// src/pseudo_loop.cc:150-164
+static void compute_WPP(int i, int l) {
+    int b1 = INF, b2 = INF;
+    for (int d = i; d < l; ++d) {
+        b1 = std::min(b1, get_WP(i, d - 1) + V_get(d, l) + gamma2(l, d) + PPS_penalty);
+        b2 = std::min(b2, get_WP(i, d - 1) + Pm.get(d, l) + PSP_penalty + PPS_penalty);
+    }
+    const int b3 = WPP.get(i, l - 1) + PUP_penalty;
+    const int mn = std::min({b1, b2, b3});
+    if (mn < INF / 2) WPP.at(i, l) = mn;
+}
+// src/pseudo_loop.cc:166-179
+static void compute_P(int i, int l) {
+    int mn = INF;
+    for (int j = i; j < l; ++j)
+        for (int d = j + 1; d < l; ++d)
+            for (int k = d + 1; k < l; ++k) mn = std::min(mn, PK.get(i, j, d + 1, k) + PK.get(j + 1, d, k + 1, l));
+    if (mn < INF / 2) Pm.at(i, l) = mn;
+}
+// interior windows, src/pseudo_loop.cc:682-703, 717-738, 752-773, 787-808
+static int get_PLiloop(int i, int j, int k, int l) {
+    if (!valid4(i, j, k, l)) return INF;
+    if (!can_pair(i, j)) return INF;
+    int mn = INF;
+    if (i + TURN + 2 < j) mn = PL.get(i + 1, j - 1, k, l) + get_e_stP(i, j);
+    const int max_d = std::min(j, i + MAXLOOP);
+    for (int d = i + 1; d < max_d; ++d) {
+        const int min_dp = std::max(d + TURN, j - MAXLOOP);
+        for (int dp = j - 1; dp > min_dp; --dp) {
+            if (!can_pair(d, dp)) continue;
+            mn = std::min(mn, get_e_intP(i, d, dp, j) + PL.get(d, dp, k, l));
+        }
+    }
+    return mn;
+}
+static int get_PRiloop(int i, int j, int k, int l) {
+    if (!valid4(i, j, k, l)) return INF;
+    if (!can_pair(k, l)) return INF;
+    int mn = INF;
+    if (k + TURN + 2 < l) mn = PR.get(i, j, k + 1, l - 1) + get_e_stP(k, l);
+    const int max_d = std::min(l, k + MAXLOOP);
+    for (int d = k + 1; d < max_d; ++d) {
+        const int min_dp = std::max(d + TURN, l - MAXLOOP);
+        for (int dp = l - 1; dp > min_dp; --dp) {
+            if (!can_pair(d, dp)) continue;
+            mn = std::min(mn, get_e_intP(k, d, dp, l) + PR.get(i, j, d, dp));
+        }
+    }
+    return mn;
+}
+static int get_PMiloop(int i, int j, int k, int l) {
+    if (!valid4(i, j, k, l)) return INF;
+    if (!can_pair(j, k)) return INF;
+    int mn = INF;
+    if (i < j && k < l) mn = PM.get(i, j - 1, k + 1, l) + get_e_stP(j - 1, k + 1);
+    const int max_d = std::max(i, j - MAXLOOP);
+    for (int d = j - 1; d > max_d; --d) {
+        const int min_dp = std::min(l, k + MAXLOOP);
+        for (int dp = k + 1; dp < min_dp; ++dp) {
+            if (!can_pair(d, dp)) continue;
+            mn = std::min(mn, get_e_intP(d, j, k, dp) + PM.get(i, d, dp, l));
+        }
+    }
+    return mn;
+}
+static int get_POiloop(int i, int j, int k, int l) {
+    if (!valid4(i, j, k, l)) return INF;
+    if (!can_pair(i, l)) return INF;
+    int mn = INF;
+    if (i < j && k < l) mn = PO.get(i + 1, j, k, l - 1) + get_e_stP(i, l);
+    const int max_d = std::min(j, i + MAXLOOP);
+    for (int d = i + 1; d < max_d; ++d) {
+        const int min_dp = std::max(l - MAXLOOP, k);
+        for (int dp = l - 1; dp > min_dp; --dp) {
+            if (!can_pair(d, dp)) continue;
+            mn = std::min(mn, get_e_intP(i, d, dp, l) + PO.get(d, j, dp, k));   // (d,j,dp,k) as written at :803
+        }
+    }
+    return mn;
+}
+// src/pseudo_loop.cc:705-715, 740-750, 775-785, 810-820
+static int get_PLmloop(int i, int j, int k, int l) {
+    if (!valid4(i, j, k, l)) return INF;
+    return std::min(PLmloop10.get(i + 1, j - 1, k, l), PLmloop01.get(i + 1, j - 1, k, l)) + ap_penalty + beta2P(j, i);
+}
+static int get_PRmloop(int i, int j, int k, int l) {
+    if (!valid4(i, j, k, l)) return INF;
+    return std::min(PRmloop10.get(i, j, k + 1, l - 1), PRmloop01.get(i, j, k + 1, l - 1)) + ap_penalty + beta2P(l, k);
+}
+static int get_PMmloop(int i, int j, int k, int l) {
+    if (!valid4(i, j, k, l)) return INF;
+    return std::min(PMmloop10.get(i, j - 1, k + 1, l), PMmloop01.get(i, j - 1, k + 1, l)) + ap_penalty + beta2P(j, k);
+}
+static int get_POmloop(int i, int j, int k, int l) {
+    if (!valid4(i, j, k, l)) return INF;
+    return std::min(POmloop10.get(i + 1, j, k, l - 1), POmloop01.get(i + 1, j, k, l - 1)) + ap_penalty + beta2P(l, i);
+}
+// src/pseudo_loop.cc:663-680
+static int get_PfromMdoubleprime(int i, int j, int k, int l) {
+    if (!valid4(i, j, k, l)) return INF;
+    if (i == j && k == l) return pairm[S[i]][S[l]] == 0 ? INF : 0;
+    return std::min(PL.get(i, j, k, l) + gamma2(j, i) + PB_penalty, PR.get(i, j, k, l) + gamma2(l, k) + PB_penalty);
+}
+
+#define STORE(T, v) do { if ((v) < INF / 2) T.set(i, j, k, l, (v)); } while (0)
+// src/pseudo_loop.cc:181-230
+static void compute_PK(int i, int j, int k, int l) {
+    int b1 = INF, b2 = INF;
+    for (int d = i + 1; d < j; ++d) b1 = std::min(b1, PK.get(i, d, k, l) + get_WP(d + 1, j));
+    for (int d = k + 1; d < l; ++d) b2 = std::min(b2, PK.get(i, j, d, l) + get_WP(k, d - 1));
+    const int b3 = PL.get(i, j, k, l) + gamma2(j, i) + PB_penalty, b4 = PM.get(i, j, k, l) + gamma2(j, k) + PB_penalty;
+    const int b5 = PR.get(i, j, k, l) + gamma2(l, k) + PB_penalty, b6 = PO.get(i, j, k, l) + gamma2(l, i) + PB_penalty;
+    STORE(PK, std::min({b1, b2, b3, b4, b5, b6}));
+}
+// src/pseudo_loop.cc:232-253
+static void compute_PL(int i, int j, int k, int l) {
+    int b1 = INF, b2 = INF, b3 = INF;
+    if (pairm[S[i]][S[j]] > 0) {
+        b1 = get_PLiloop(i, j, k, l);
+        b2 = get_PLmloop(i, j, k, l) + bp_penalty;
+        if (j >= (i + TURN + 1)) b3 = PfromL.get(i + 1, j - 1, k, l) + gamma2(j, i);
+    }
+    STORE(PL, std::min({b1, b2, b3}));
+}
+// src/pseudo_loop.cc:255-275
+static void compute_PR(int i, int j, int k, int l) {
+    int b1 = INF, b2 = INF, b3 = INF;
+    if (pairm[S[k]][S[l]] > 0) {
+        b1 = get_PRiloop(i, j, k, l);
+        b2 = get_PRmloop(i, j, k, l) + bp_penalty;
+        if (l >= (k + TURN + 1)) b3 = PfromR.get(i, j, k + 1, l - 1) + gamma2(l, k);
+    }
+    STORE(PR, std::min({b1, b2, b3}));
+}
+// src/pseudo_loop.cc:277-300
+static void compute_PM(int i, int j, int k, int l) {
+    int b1 = INF, b2 = INF, b3 = INF, b4 = INF;
+    if (pairm[S[j]][S[k]] > 0) {
+        b1 = get_PMiloop(i, j, k, l);
+        b2 = get_PMmloop(i, j, k, l) + bp_penalty;
+        if (k >= (j + TURN - 1)) b3 = PfromM.get(i, j - 1, k + 1, l) + gamma2(j, k);
+        if (i == j && k == l) b4 = gamma2(i, l);
+    }
+    STORE(PM, std::min({b1, b2, b3, b4}));
+}
+// src/pseudo_loop.cc:302-322
+static void compute_PO(int i, int j, int k, int l) {
+    int b1 = INF, b2 = INF, b3 = INF;
+    if (pairm[S[i]][S[l]] > 0) {
+        b1 = get_POiloop(i, j, k, l);
+        b2 = get_POmloop(i, j, k, l) + bp_penalty;
+        if (l >= (i + TURN + 1)) b3 = PfromO.get(i + 1, j, k, l - 1) + gamma2(l, i);
+    }
+    STORE(PO, std::min({b1, b2, b3}));
+}
+// src/pseudo_loop.cc:354-374
+static void compute_PfromL(int i, int j, int k, int l) {
+    int b1 = INF, b2 = INF;
+    for (int d = i + 1; d < j; ++d) {
+        b1 = std::min(b1, PfromL.get(d, j, k, l) + get_WP(i, d - 1));
+        b2 = std::min(b2, PfromL.get(i, d, k, l) + get_WP(d + 1, j));
+    }
+    const int b3 = PR.get(i, j, k, l) + gamma2(l, k) + PB_penalty, b4 = PM.get(i, j, k, l) + gamma2(j, k) + PB_penalty;
+    const int b5 = PO.get(i, j, k, l) + gamma2(l, i) + PB_penalty;
+    STORE(PfromL, std::min({b1, b2, b3, b4, b5}));
+}
+// src/pseudo_loop.cc:376-394
+static void compute_PfromR(int i, int j, int k, int l) {
+    int b1 = INF, b2 = INF;
+    for (int d = k + 1; d < l; ++d) {
+        b1 = std::min(b1, PfromR.get(i, j, d, l) + get_WP(k, d - 1));
+        b2 = std::min(b2, PfromR.get(i, j, k, d) + get_WP(d + 1, l));
+    }
+    const int b3 = PM.get(i, j, k, l) + gamma2(j, k) + PB_penalty, b4 = PO.get(i, j, k, l) + gamma2(l, i) + PB_penalty;
+    STORE(PfromR, std::min({b1, b2, b3, b4}));
+}
+// src/pseudo_loop.cc:396-407
+static void compute_PfromM(int i, int j, int k, int l) {
+    int mn = INF;
+    for (int d = i + 1; d < j; ++d) mn = std::min(mn, PfromMprime.get(i, d, k, l) + get_WP(d + 1, j));
+    STORE(PfromM, mn);
+}
+// src/pseudo_loop.cc:409-420
+static void compute_PfromMprime(int i, int j, int k, int l) {
+    int mn = INF;
+    for (int d = k + 1; d < l; ++d) mn = std::min(mn, get_PfromMdoubleprime(i, j, d, l) + get_WP(k, d - 1));
+    STORE(PfromMprime, mn);
+}
+// src/pseudo_loop.cc:422-443
+static void compute_PfromO(int i, int j, int k, int l) {
+    int b1 = INF, b2 = INF;
+    for (int d = i + 1; d < j; ++d) b1 = std::min(b1, PfromO.get(d, j, k, l) + get_WP(i, d - 1));
+    for (int d = k + 1; d < l; ++d) b2 = std::min(b2, PfromO.get(i, j, k, d) + get_WP(d + 1, l));
+    const int b3 = PL.get(i, j, k, l) + gamma2(j, i) + PB_penalty, b4 = PR.get(i, j, k, l) + gamma2(l, k) + PB_penalty;
+    STORE(PfromO, std::min({b1, b2, b3, b4}));
+}
+// src/pseudo_loop.cc:445-463
+static void compute_PLmloop00(int i, int j, int k, int l) {
+    int mn = PL.get(i, j, k, l) + beta2P(j, i);
+    for (int d = i; d <= j; ++d) {
+        if (d > i) mn = std::min(mn, get_WB(i, d - 1) + PLmloop00.get(d, j, k, l));
+        if (d < j) mn = std::min(mn, PLmloop00.get(i, d, k, l) + get_WB(d + 1, j));
+    }
+    STORE(PLmloop00, mn);
+}
+// src/pseudo_loop.cc:465-476
+static void compute_PLmloop01(int i, int j, int k, int l) {
+    int mn = INF;
+    for (int d = i; d < j; ++d) mn = std::min(mn, PLmloop00.get(i, d, k, l) + WBP.get(d + 1, j));
+    STORE(PLmloop01, mn);
+}
+// src/pseudo_loop.cc:478-493
+static void compute_PLmloop10(int i, int j, int k, int l) {
+    int mn = INF;
+    for (int d = i + 1; d <= j; ++d) {
+        mn = std::min(mn, WBP.get(i, d - 1) + PLmloop00.get(d, j, k, l));
+        if (d < j) mn = std::min(mn, PLmloop10.get(i, d, k, l) + get_WB(d + 1, j));
+    }
+    STORE(PLmloop10, mn);
+}
+// src/pseudo_loop.cc:495-514
+static void compute_PRmloop00(int i, int j, int k, int l) {
+    int mn = PR.get(i, j, k, l) + beta2P(l, k);
+    for (int d = k; d <= l; ++d) {
+        if (d > k) mn = std::min(mn, get_WB(k, d - 1) + PRmloop00.get(i, j, d, l));
+        if (d < l) mn = std::min(mn, PRmloop00.get(i, j, k, d) + get_WB(d + 1, l));
+    }
+    STORE(PRmloop00, mn);
+}
+// src/pseudo_loop.cc:516-528
+static void compute_PRmloop01(int i, int j, int k, int l) {
+    int mn = PRmloop01.get(i, j, k, l - 1) + cp_penalty;
+    for (int d = k; d < l; ++d) mn = std::min(mn, PRmloop00.get(i, j, k, d) + WBP.get(d + 1, l));
+    STORE(PRmloop01, mn);
+}
+// src/pseudo_loop.cc:530-542
+static void compute_PRmloop10(int i, int j, int k, int l) {
+    int mn = PRmloop10.get(i, j, k + 1, l) + cp_penalty;
+    for (int d = k + 1; d <= l; ++d) mn = std::min(mn, WBP.get(k, d - 1) + PRmloop00.get(i, j, d, l));
+    STORE(PRmloop10, mn);
+}
+// src/pseudo_loop.cc:544-561
+static void compute_PMmloop00(int i, int j, int k, int l) {
+    int mn = PM.get(i, j, k, l) + beta2P(j, k);
+    for (int d = i; d < j; ++d) mn = std::min(mn, PMmloop00.get(i, d, k, l) + get_WB(d + 1, j));
+    for (int d = k + 1; d <= l; ++d) mn = std::min(mn, PMmloop00.get(i, j, d, l) + get_WB(k, d - 1));
+    STORE(PMmloop00, mn);
+}
+// src/pseudo_loop.cc:563-575
+static void compute_PMmloop01(int i, int j, int k, int l) {
+    int mn = PMmloop01.get(i, j, k + 1, l) + cp_penalty;
+    for (int d = k; d < l; ++d) mn = std::min(mn, PMmloop00.get(i, j, k, d) + WBP.get(d + 1, l));
+    STORE(PMmloop01, mn);
+}
+// src/pseudo_loop.cc:577-593
+static void compute_PMmloop10(int i, int j, int k, int l) {
+    int mn = PMmloop10.get(i, j - 1, k, l) + cp_penalty;
+    for (int d = i + 1; d <= j; ++d) mn = std::min(mn, WBP.get(i, d - 1) + PMmloop00.get(d, j, k, l));
+    for (int d = k + 1; d < l; ++d) mn = std::min(mn, PMmloop10.get(i, j, k, d) + get_WB(d + 1, l));
+    STORE(PMmloop10, mn);
+}
+// src/pseudo_loop.cc:595-613
+static void compute_POmloop00(int i, int j, int k, int l) {
+    int mn = PO.get(i, j, k, l) + beta2P(l, i);
+    for (int d = i + 1; d <= j; ++d) mn = std::min(mn, get_WB(i, d - 1) + POmloop00.get(d, j, k, l));
+    for (int d = k; d < l; ++d) mn = std::min(mn, POmloop00.get(i, j, k, d) + get_WB(d + 1, l));
+    STORE(POmloop00, mn);
+}
+// src/pseudo_loop.cc:615-627
+static void compute_POmloop01(int i, int j, int k, int l) {
+    int mn = INF;
+    for (int d = k; d < l; ++d) mn = std::min(mn, POmloop00.get(i, j, k, d) + WBP.get(d + 1, l));
+    STORE(POmloop01, mn);
+}
+// src/pseudo_loop.cc:629-645
+static void compute_POmloop10(int i, int j, int k, int l) {
+    int mn = INF;
+    for (int d = i + 1; d <= j; ++d) mn = std::min(mn, WBP.get(i, d - 1) + POmloop00.get(d, j, k, l));
+    for (int d = k + 1; d < l; ++d) mn = std::min(mn, POmloop10.get(i, j, k, d) + get_WB(d + 1, l));
+    STORE(POmloop10, mn);
+}
+#undef STORE
+
+// pseudo_loop::compute_energies, src/pseudo_loop.cc:69-132 -- the in-cell order matters: the mloop tables read
+// PL/PR/PM/PO of the SAME cell before those are computed (still 32767)
+static void compute_energies(int i, int l) {
+    compute_P(i, l);
+    compute_WBP(i, l);
+    compute_WPP(i, l);
+    for (int j = i; j < l; ++j)
+        for (int k = l; k >= j + 2; --k) {
+            compute_PLmloop00(i, j, k, l); compute_PLmloop01(i, j, k, l); compute_PLmloop10(i, j, k, l);
+            compute_PRmloop00(i, j, k, l); compute_PRmloop01(i, j, k, l); compute_PRmloop10(i, j, k, l);
+            compute_PMmloop00(i, j, k, l); compute_PMmloop01(i, j, k, l); compute_PMmloop10(i, j, k, l);
+            compute_POmloop00(i, j, k, l); compute_POmloop01(i, j, k, l); compute_POmloop10(i, j, k, l);
+            compute_PL(i, j, k, l); compute_PR(i, j, k, l); compute_PM(i, j, k, l); compute_PO(i, j, k, l);
+            compute_PfromL(i, j, k, l); compute_PfromR(i, j, k, l); compute_PfromM(i, j, k, l);
+            compute_PfromMprime(i, j, k, l); compute_PfromO(i, j, k, l);
+            compute_PK(i, j, k, l);
+        }
+}
+
+// ---- exterior loop: src/W_final.cc:58-77 and E_ext_Stem :118-173 --------------------------------------------------
+static int E_ext_Stem(int vij, int vi1j, int vij1, int vi1j1, int i, int j) {
+    int e = INF, en = INF;
+    int tt = pairm[S[i]][S[j]];
+    en = vij;
+    if (en != INF) {
+        if (P.dangles == 2) {
+            const int si1 = i > 1 ? S[i - 1] : -1;
+            const int sj1 = j < n ? S[j + 1] : -1;
+            en += vrna_E_ext_stem(tt, si1, sj1);
+        } else {
+            en += vrna_E_ext_stem(tt, -1, -1);
+        }
+        e = std::min(e, en);
+    }
+    if (P.dangles == 1) {
+        tt = pairm[S[i + 1]][S[j]];
+        en = (j - i - 1 > TURN) ? vi1j : INF;
+        if (en != INF) en += vrna_E_ext_stem(tt, S[i], -1);
+        e = std::min(e, en);
+        tt = pairm[S[i]][S[j - 1]];
+        en = (j - 1 - i > TURN) ? vij1 : INF;
+        if (en != INF) en += vrna_E_ext_stem(tt, -1, S[j]);
+        e = std::min(e, en);
+        tt = pairm[S[i + 1]][S[j - 1]];
+        en = (j - 1 - i - 1 > TURN) ? vi1j1 : INF;
+        if (en != INF) en += vrna_E_ext_stem(tt, S[i], S[j]);
+        e = std::min(e, en);
+    }
+    return e;
+}
+
+static std::vector<int> W;
+static void fold() {
+    build_indices();
+    Venergy.assign((size_t)(n + 1) * (n + 2) / 2, 10000);   // free_energy_node(), src/h_struct.hh:98-102
+    Vtype.assign(Venergy.size(), 'N');
+    WM.init(); WMv.init(); WMp.init(); Pm.init(); WBP.init(); WPP.init();
+    M4 *all[22] = {&PK, &PL, &PR, &PM, &PO, &PfromL, &PfromR, &PfromM, &PfromMprime, &PfromO, &PLmloop00, &PLmloop01,
+                   &PLmloop10, &PRmloop00, &PRmloop01, &PRmloop10, &PMmloop00, &PMmloop01, &PMmloop10, &POmloop00,
+                   &POmloop01, &POmloop10};
+    for (M4 *t : all) t->init();
+    init_can_pair();
+    // W_final::ccj, src/W_final.cc:60-67
+    for (int i = n; i >= 1; --i)
+        for (int j = i; j <= n; ++j) {
+            compute_energy(i, j);
+            compute_energies(i, j);
+            compute_WMv_WMp(i, j, Pm.get(i, j));
+            compute_energy_WM(i, j, Pm);
+        }
+    // src/W_final.cc:68-77
+    W.assign(n + 1, 0);
+    for (int j = TURN + 1; j <= n; ++j) {
+        int m1 = W[j - 1], m2 = INF, m3 = INF;
+        for (int k = 1; k <= j - TURN - 1; ++k) {
+            const int acc = (k > 1) ? W[k - 1] : 0;
+            m2 = std::min(m2, acc + E_ext_Stem(V_get(k, j), V_get(k + 1, j), V_get(k, j - 1), V_get(k + 1, j - 1), k, j));
+            m3 = std::min(m3, acc + std::min({Pm.get(k, j), Pm.get(k + 1, j), Pm.get(k, j - 1), Pm.get(k + 1, j - 1)}) + PS_penalty);
+        }
+        W[j] = std::min({m1, m2, m3});
+    }
+}
+
+// ---- output: same lines as `ccj_ref_dump hash` (oracle/ref_dump.cc) ----------------------------------------------
+struct Fnv {
+    uint64_t h = 1469598103934665603ULL;
+    void add(uint64_t v) { h ^= v; h *= 1099511628211ULL; }
+};
+
+int main(int argc, char **argv) {
+    if (argc < 6) {
+        fprintf(stderr, "usage: ccj_oracle hash|energy <params.txt> <dangles> <noGU> <sequence>\n");
+        return 2;
+    }
+    const std::string mode = argv[1];
+    load_params(argv[2]);
+    P.dangles = atoi(argv[3]);
+    make_pair_matrix(atoi(argv[4]) != 0);
+    encode(argv[5]);
+    fold();
+    if (mode == "energy") {
+        printf("%d\n", W[n]);
+        return 0;
+    }
+    static const char *names4[22] = {"PK", "PL", "PR", "PM", "PO", "PfromL", "PfromR", "PfromM", "PfromMprime", "PfromO",
+                                     "PLmloop00", "PLmloop01", "PLmloop10", "PRmloop00", "PRmloop01", "PRmloop10",
+                                     "PMmloop00", "PMmloop01", "PMmloop10", "POmloop00", "POmloop01", "POmloop10"};
+    M4 *all[22] = {&PK, &PL, &PR, &PM, &PO, &PfromL, &PfromR, &PfromM, &PfromMprime, &PfromO, &PLmloop00, &PLmloop01,
+                   &PLmloop10, &PRmloop00, &PRmloop01, &PRmloop10, &PMmloop00, &PMmloop01, &PMmloop10, &POmloop00,
+                   &POmloop01, &POmloop10};
+    printf("n %d\n", n);
+    for (int t = 0; t < 22; ++t) {
+        Fnv f;
+        long finite = 0;
+        int mn = 1 << 30;
+        for (int i = 1; i <= n; ++i)
+            for (int j = i; j <= n; ++j)
+                for (int k = j + 2; k <= n; ++k)
+                    for (int l = k; l <= n; ++l) {
+                        const int v = all[t]->get(i, j, k, l);
+                        f.add((uint16_t)(int16_t)v);
+                        if (v < 32767) { ++finite; if (v < mn) mn = v; }
+                    }
+        printf("%s %ld %d %016llx\n", names4[t], finite, finite ? mn : 0, (unsigned long long)f.h);
+    }
+    static const char *names2[8] = {"V", "Vtype", "WM", "WMv", "WMp", "P", "WBP", "WPP"};
+    for (int t = 0; t < 8; ++t) {
+        Fnv f;
+        long finite = 0;
+        long long sum = 0;
+        for (int i = 1; i <= n; ++i)
+            for (int j = i; j <= n; ++j) {
+                const int ij = ij2(i, j);
+                const int32_t v = t == 0 ? Venergy[ij] : t == 1 ? (int32_t)Vtype[ij] : t == 2 ? WM.m[ij] : t == 3 ? WMv.m[ij]
+                                : t == 4 ? WMp.m[ij] : t == 5 ? Pm.m[ij] : t == 6 ? WBP.m[ij] : WPP.m[ij];
+                f.add((uint32_t)v);
+                if (v < INF / 2) { ++finite; sum += v; }
+            }
+        printf("%s %ld %lld %016llx\n", names2[t], finite, sum, (unsigned long long)f.h);
+    }
+    printf("W %d\n", W[n]);
+    return 0;
+}

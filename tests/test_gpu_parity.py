@@ -157,3 +157,24 @@ def test_tuned_kernels_equal_generic_kernels(ctx_factory, monkeypatch, n):
     monkeypatch.delenv("CCJ_FILL_GENERIC")
     assert tuned == generic
     assert fold_t == fold_g
+
+
+@pytest.mark.parametrize("par,dangles,no_gu", [("rna_Turner04.par", 2, False), ("rna_Turner04.par", 1, False),
+                                               ("rna_Turner04.par", 0, True), ("rna_DirksPierce09.par", 2, False)])
+def test_cuda_matches_cpu_restatement(par, dangles, no_gu):
+    """CUDA path against oracle/ccj_oracle.cc (the independent CPU restatement): W[n] on random sequences and every
+    table hash on one of them."""
+    from oracle import oracle as orc
+    rng = random.Random(sum(map(ord, par)) + 10 * dangles)
+    seqs = ["".join(rng.choice("ACGU") for _ in range(rng.randint(12, 46))) for _ in range(6)]
+    with ccj_b200.Context(0, ccj_b200.default_par_file(par), dangles, no_gu) as ctx:
+        ctx.prepare(seqs)
+        ctx.fill()
+        ctx.traceback()
+        folds = ctx.fetch()
+        for s, f in zip(seqs, folds):
+            assert round(f.energy * 100) == orc.oracle_energy_dcal(s, par, dangles, no_gu), s
+        tables, _ = orc.oracle_hashes(seqs[0], par, dangles, no_gu)
+        for name, want in tables.items():
+            got = ctx.table2_hash(0, name) if name in ccj_b200.TABLE2 else ctx.table4_hash(0, name)
+            assert got == want, (name, seqs[0])
