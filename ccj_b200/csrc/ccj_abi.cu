@@ -208,7 +208,7 @@ bool use_tuned(int nmax) {
 }
 
 // Tuned path, three streams (all inside the captured graph):
-//   main : k_roles(t) -> k_final(t)                       (4D level t; needs 2D spans <= t-1)
+//   main : k_roles(t, even t: levels t and t+1) -> k_final(t)   (needs 2D spans <= t)
 //   s_win: k_windows(t)                                   (reads 4D levels <= t-2 only -> runs one level ahead)
 //   s_2d : k_P(s) -> k_2d(s)                              (needs PK of levels <= s-3 -> runs beside roles(s-2..s))
 void enqueue_fill(ccj_ctx *ctx, ccj::LaunchDims d) {
@@ -248,7 +248,7 @@ void enqueue_fill(ccj_ctx *ctx, ccj::LaunchDims d) {
             if (s >= 2) cudaStreamWaitEvent(sw, evF[s - 2], 0);
             ccj::launch_4d_windows(M, Q, d, s, sw);
             cudaEventRecord(evW[s], sw);
-            if (s >= 1) cudaStreamWaitEvent(s0, evD[s - 1], 0);
+            cudaStreamWaitEvent(s0, evD[s], 0);  // k_roles(s) also works on level s+1: 2D intervals up to span s
             ccj::launch_4d_roles(M, Q, d, s, s0);
             cudaStreamWaitEvent(s0, evW[s], 0);
             ccj::launch_4d_final(M, Q, d, s, s0);

@@ -238,16 +238,78 @@ __device__ __forceinline__ bool cell_setup(const ccj_seq &q, int t, int a, int b
 #define TB(tbl) (t4 + (int64_t)(tbl) * st4)
 #define OFF(aa, bb, ii, kx) (s_cb[bb] - s_tet[n - (aa) - (bb)-2] + ((((ii)-1) * (2 * (n - (aa) - (bb)-2) + 2 - (ii))) >> 1) + ((kx) - (ii) - (aa)-2))
 #ifndef U4
-#define U4 4
+#define U4 2
 #endif
 
-__global__ void __launch_bounds__(K4_THREADS, 8) k_roles(const ccj_model *__restrict__ M, const ccj_seq *__restrict__ seqs, int t,
-                                                       int only_role) {
+// ---- the four split-point roles: accumulators and the add-mins of ONE split point -------------------------------
+// *_first is the boundary split point that only some recurrences have (d=i, d=j, d=l, d=k), *_term a regular one.
+// r = read-group record of the source cell, w = {WB, WP, WBP} of the 2D interval next to it.
+// L1: X(i,d,k,l) with (d+1,j)   [src/pseudo_loop.cc:184-187,357-361,399-402,449-458,468-471,481-487,548-551]
+//     record g1 = PK PfromL | PfromMprime PLmloop00 | PLmloop10 PMmloop00
+struct AccL1 { int PK, PfL, PfM, PLm00, PLm01, PLm10, PMm00; };
+__device__ __forceinline__ void l1_first(AccL1 &A, const R12 &r, const int4 &w) {  // d=i
+    const int x = hi16(r.w1);
+    A.PLm00 = min(A.PLm00, x + w.x); A.PLm01 = min(A.PLm01, x + w.z); A.PMm00 = min(A.PMm00, hi16(r.w2) + w.x);
+}
+__device__ __forceinline__ void l1_term(AccL1 &A, const R12 &r, const int4 &w) {
+    A.PK = min(A.PK, lo16(r.w0) + w.y); A.PfL = min(A.PfL, hi16(r.w0) + w.y); A.PfM = min(A.PfM, lo16(r.w1) + w.y);
+    const int x = hi16(r.w1);
+    A.PLm00 = min(A.PLm00, x + w.x); A.PLm01 = min(A.PLm01, x + w.z);
+    A.PLm10 = min(A.PLm10, lo16(r.w2) + w.x); A.PMm00 = min(A.PMm00, hi16(r.w2) + w.x);
+}
+// L2: X(d,j,k,l) with (i,d-1)   [:357-359,425-428,450-453,481-483,581-584,599-602,632-635]
+//     record g2 = PfromL PfromO | PLmloop00 PMmloop00 | POmloop00 -
+struct AccL2 { int PfL, PfO, PLm00, PLm10, PMm10, POm00, POm10; };
+__device__ __forceinline__ void l2_first(AccL2 &A, const R12 &r, const int4 &w) {  // d=j
+    const int x = lo16(r.w1);
+    A.PLm00 = min(A.PLm00, x + w.x); A.PLm10 = min(A.PLm10, x + w.z); A.PMm10 = min(A.PMm10, hi16(r.w1) + w.z);
+    const int y = lo16(r.w2);
+    A.POm00 = min(A.POm00, y + w.x); A.POm10 = min(A.POm10, y + w.z);
+}
+__device__ __forceinline__ void l2_term(AccL2 &A, const R12 &r, const int4 &w) {
+    A.PfL = min(A.PfL, lo16(r.w0) + w.y); A.PfO = min(A.PfO, hi16(r.w0) + w.y);
+    l2_first(A, r, w);
+}
+// R3: X(i,j,d,l) with (k,d-1)   [:189-192,379-381,412-415,499-503,534-537,552-555]
+//     record g3 = PK PfromR | min(PL,PR) PRmloop00 | PMmloop00 -
+struct AccR3 { int PK, PfR, PfMp, PRm00, PRm10, PMm00; };
+__device__ __forceinline__ void r3_first(AccR3 &A, const R12 &r, const int4 &w) {  // d=l
+    const int x = hi16(r.w1);
+    A.PRm00 = min(A.PRm00, x + w.x); A.PRm10 = min(A.PRm10, x + w.z); A.PMm00 = min(A.PMm00, lo16(r.w2) + w.x);
+}
+__device__ __forceinline__ void r3_term(AccR3 &A, const R12 &r, const int4 &w) {
+    A.PK = min(A.PK, lo16(r.w0) + w.y); A.PfR = min(A.PfR, hi16(r.w0) + w.y); A.PfMp = min(A.PfMp, lo16(r.w1) + w.y);
+    r3_first(A, r, w);
+}
+// R4: X(i,j,k,d) with (d+1,l)   [:382-383,429-432,504-507,520-523,567-570,585-588,603-606,618-621,636-639]
+//     record g4 = PfromR PfromO | PRmloop00 PMmloop00 | PMmloop10 POmloop00 | POmloop10 -
+struct AccR4 { int PfR, PfO, PRm00, PRm01, PMm01, PMm10, POm00, POm01, POm10; };
+__device__ __forceinline__ void r4_first(AccR4 &A, const int4 &r, const int4 &w) {  // d=k
+    const int x = lo16(r.y);
+    A.PRm00 = min(A.PRm00, x + w.x); A.PRm01 = min(A.PRm01, x + w.z); A.PMm01 = min(A.PMm01, hi16(r.y) + w.z);
+    const int y = hi16(r.z);
+    A.POm00 = min(A.POm00, y + w.x); A.POm01 = min(A.POm01, y + w.z);
+}
+__device__ __forceinline__ void r4_term(AccR4 &A, const int4 &r, const int4 &w) {
+    A.PfR = min(A.PfR, lo16(r.x) + w.y); A.PfO = min(A.PfO, hi16(r.x) + w.y);
+    A.PMm10 = min(A.PMm10, lo16(r.z) + w.x); A.POm10 = min(A.POm10, lo16(r.w) + w.x);
+    r4_first(A, r, w);
+}
+
+// Split-point roles of TWO levels per launch.  A record X(i,d,k,l) that role L1 reads for the cell (i,j,k,l) of
+// level t is the very record the cell (i,j+1,k,l) of level t+1 needs at the same split point, only with the 2D
+// interval (d+1,j+1) instead of (d+1,j); likewise (i-1,j,k,l) for L2, (i,j,k-1,l) for R3 and (i,j,k,l+1) for R4.
+// Launched for even t, a thread therefore keeps two sets of accumulators: its own cell (all split points, sources
+// of levels <= t-1) and its level-t+1 partner (the same split points; the one remaining split point, whose source
+// is the level-t cell itself, is added by k_final(t+1)).  Every record is fetched from HBM once per two levels.
+#ifndef ROLES_MINB
+#define ROLES_MINB 8
+#endif
+__global__ void __launch_bounds__(K4_THREADS, ROLES_MINB) k_roles(const ccj_model *__restrict__ M, const ccj_seq *__restrict__ seqs, int t) {
     __shared__ int s_tet[K4_MAXN + 4];
     __shared__ int s_cb[K4_MAXN + 4];
-    // only_role == 0: blockIdx.z enumerates (sequence, role); else every block runs `only_role`
-    const int role = only_role ? only_role : (int)(blockIdx.z % 4);  // the PL window moved to k_winLR
-    const ccj_seq q = seqs[only_role ? blockIdx.z : blockIdx.z / 4];
+    const int role = (int)(blockIdx.z % 4);
+    const ccj_seq q = seqs[blockIdx.z / 4];
     const int n = q.n;
     if (n - t - 2 < 1) return;
     {
@@ -257,216 +319,179 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_roles(const ccj_model *__rest
     Cell C;
     if (!cell_setup(q, t, blockIdx.y, blockIdx.x, s_tet, s_cb, C)) return;
     const int a = C.a, b = C.b, i = C.i, j = C.j, k = C.k, l = C.l, m = C.m;
-    const int16_t *__restrict__ t4 = q.t4;
-    const int64_t st4 = q.stride4;
     const int4 *__restrict__ W3 = reinterpret_cast<const int4 *>(q.w3);
     const int n1 = n + 1;
     const int INF = CCJ_INF;
-    int16_t *__restrict__ sc = q.scratch + C.c;
     const int64_t ss = q.scratch_stride;
+    int16_t *__restrict__ sc = q.scratch + (int64_t)(t & 1) * Q_COUNT * ss + C.c;
+    // the level-t+1 partner: slab (a+1,b) for L1/L2, (a,b+1) for R3/R4, m2 = m-1 rows
+    const int m2 = m - 1, kk = k - j - 2;
+    const int ncell2 = m2 * (m2 + 1) / 2;
+    int16_t *__restrict__ sc2 = q.scratch + (int64_t)((t + 1) & 1) * Q_COUNT * ss;
 #define SAVE(id, v) sc[(int64_t)(id) * ss] = sat16(v)
+#define SAVE2(id, v) sc2[(int64_t)(id) * ss] = sat16(v)
+#define ROW2(ii) ((((ii)-1) * (2 * m2 + 2 - (ii))) >> 1)
 
     if (role == ROLE_L1) {
-        // X(i,d,k,l), d=i+ap, with the 2D record of (d+1, j)   [src/pseudo_loop.cc:184-187,357-361,399-402,
-        // 449-458,468-471,481-487,548-551]; record g1 = PK PfromL PfromMprime | PLmloop00 PLmloop10 PMmloop00
-        int aPK = INF, aPfL = INF, aPfM = INF, aPLm00 = INF, aPLm01 = INF, aPLm10 = INF, aPMm00 = INF;
+        AccL1 A = {INF, INF, INF, INF, INF, INF, INF}, A2 = A;
+        const bool two = m2 >= 1 && kk >= 1;   // partner (i,j+1,k,l)
         if (a >= 1) {
             const int *__restrict__ G = reinterpret_cast<const int *>(q.g1);
             {  // d=i
                 const R12 r = ldr12(G, OFF(0, b, i, k));
-                const int4 w = __ldg(&W3[(a - 1) * n1 + i + 1]);
-                const int x = hi16(r.w1);
-                aPLm00 = min(aPLm00, x + w.x);
-                aPLm01 = min(aPLm01, x + w.z);
-                aPMm00 = min(aPMm00, hi16(r.w2) + w.x);
+                l1_first(A, r, __ldg(&W3[(a - 1) * n1 + i + 1]));
+                l1_first(A2, r, __ldg(&W3[a * n1 + i + 1]));
             }
             const int ub = n - b - 2, cbb = s_cb[b], ri = i - 1, kc = k - i - 2;
             int ap = 1;
             for (; ap + U4 <= a; ap += U4) {
                 R12 r[U4];
-                int4 w[U4];
+                int4 w[U4], w2[U4];
 #pragma unroll
                 for (int u = 0; u < U4; ++u) {
                     const int m1 = ub - ap - u;
-                    const int o = cbb - s_tet[m1] + ((ri * (2 * m1 + 2 - i)) >> 1) + (kc - ap - u);
-                    r[u] = ldr12(G, o);
-                    w[u] = __ldg(&W3[(a - ap - u - 1) * n1 + i + ap + u + 1]);
+                    r[u] = ldr12(G, cbb - s_tet[m1] + ((ri * (2 * m1 + 2 - i)) >> 1) + (kc - ap - u));
+                    w[u] = __ldg(&W3[(a - ap - u - 1) * n1 + i + ap + u + 1]);   // (d+1, j)
+                    w2[u] = __ldg(&W3[(a - ap - u) * n1 + i + ap + u + 1]);      // (d+1, j+1)
                 }
 #pragma unroll
-                for (int u = 0; u < U4; ++u) {
-                    aPK = min(aPK, lo16(r[u].w0) + w[u].y); aPfL = min(aPfL, hi16(r[u].w0) + w[u].y);
-                    aPfM = min(aPfM, lo16(r[u].w1) + w[u].y);
-                    const int x = hi16(r[u].w1);
-                    aPLm00 = min(aPLm00, x + w[u].x); aPLm01 = min(aPLm01, x + w[u].z);
-                    aPLm10 = min(aPLm10, lo16(r[u].w2) + w[u].x); aPMm00 = min(aPMm00, hi16(r[u].w2) + w[u].x);
-                }
+                for (int u = 0; u < U4; ++u) { l1_term(A, r[u], w[u]); l1_term(A2, r[u], w2[u]); }
             }
             for (; ap < a; ++ap) {
                 const int m1 = ub - ap;
                 const R12 r = ldr12(G, cbb - s_tet[m1] + ((ri * (2 * m1 + 2 - i)) >> 1) + (kc - ap));
-                const int4 w1 = __ldg(&W3[(a - ap - 1) * n1 + i + ap + 1]);
-                aPK = min(aPK, lo16(r.w0) + w1.y); aPfL = min(aPfL, hi16(r.w0) + w1.y); aPfM = min(aPfM, lo16(r.w1) + w1.y);
-                const int x1 = hi16(r.w1);
-                aPLm00 = min(aPLm00, x1 + w1.x); aPLm01 = min(aPLm01, x1 + w1.z);
-                aPLm10 = min(aPLm10, lo16(r.w2) + w1.x); aPMm00 = min(aPMm00, hi16(r.w2) + w1.x);
+                l1_term(A, r, __ldg(&W3[(a - ap - 1) * n1 + i + ap + 1]));
+                l1_term(A2, r, __ldg(&W3[(a - ap) * n1 + i + ap + 1]));
             }
         }
-        SAVE(Q_PK1, aPK); SAVE(Q_PfL2, aPfL); SAVE(Q_PfM, aPfM); SAVE(Q_PLm00a, aPLm00); SAVE(Q_PLm01, aPLm01);
-        SAVE(Q_PLm10a, aPLm10); SAVE(Q_PMm00a, aPMm00);
+        SAVE(Q_PK1, A.PK); SAVE(Q_PfL2, A.PfL); SAVE(Q_PfM, A.PfM); SAVE(Q_PLm00a, A.PLm00); SAVE(Q_PLm01, A.PLm01);
+        SAVE(Q_PLm10a, A.PLm10); SAVE(Q_PMm00a, A.PMm00);
+        if (two) {
+            sc2 += (int64_t)(a + 1) * ncell2 + ROW2(i) + kk - 1;
+            SAVE2(Q_PK1, A2.PK); SAVE2(Q_PfL2, A2.PfL); SAVE2(Q_PfM, A2.PfM); SAVE2(Q_PLm00a, A2.PLm00);
+            SAVE2(Q_PLm01, A2.PLm01); SAVE2(Q_PLm10a, A2.PLm10); SAVE2(Q_PMm00a, A2.PMm00);
+        }
     } else if (role == ROLE_L2) {
-        // X(d,j,k,l), d=i+ap, with the 2D record of (i, d-1)   [:357-359,425-428,450-453,481-483,581-584,599-602,632-635]
-        // record g2 = PfromL PfromO | PLmloop00 PMmloop00 | POmloop00 -
-        int aPfL = INF, aPfO = INF, aPLm00 = INF, aPLm10 = INF, aPMm10 = INF, aPOm00 = INF, aPOm10 = INF;
+        AccL2 A = {INF, INF, INF, INF, INF, INF, INF}, A2 = A;
+        const bool two = m2 >= 1 && i >= 2;    // partner (i-1,j,k,l)
         if (a >= 1) {
             const int *__restrict__ G = reinterpret_cast<const int *>(q.g2);
             {  // d=j
                 const R12 r = ldr12(G, OFF(0, b, j, k));
-                const int4 w = __ldg(&W3[(a - 1) * n1 + i]);
-                const int x = lo16(r.w1);
-                aPLm00 = min(aPLm00, x + w.x);
-                aPLm10 = min(aPLm10, x + w.z);
-                aPMm10 = min(aPMm10, hi16(r.w1) + w.z);
-                const int y = lo16(r.w2);
-                aPOm00 = min(aPOm00, y + w.x);
-                aPOm10 = min(aPOm10, y + w.z);
+                l2_first(A, r, __ldg(&W3[(a - 1) * n1 + i]));
+                l2_first(A2, r, __ldg(&W3[a * n1 + i - 1]));
             }
             const int ub = n - b - 2, cbb = s_cb[b], kc = k - j - 2;
             int ap = 1;
             for (; ap + U4 <= a; ap += U4) {
                 R12 r[U4];
-                int4 w[U4];
+                int4 w[U4], w2[U4];
 #pragma unroll
                 for (int u = 0; u < U4; ++u) {
-                    const int d = i + ap + u, m2 = ub - (a - ap - u);
-                    r[u] = ldr12(G, cbb - s_tet[m2] + (((d - 1) * (2 * m2 + 2 - d)) >> 1) + kc);
-                    w[u] = __ldg(&W3[(ap + u - 1) * n1 + i]);
+                    const int d = i + ap + u, mm = ub - (a - ap - u);
+                    r[u] = ldr12(G, cbb - s_tet[mm] + (((d - 1) * (2 * mm + 2 - d)) >> 1) + kc);
+                    w[u] = __ldg(&W3[(ap + u - 1) * n1 + i]);       // (i, d-1)
+                    w2[u] = __ldg(&W3[(ap + u) * n1 + i - 1]);      // (i-1, d-1)
                 }
 #pragma unroll
-                for (int u = 0; u < U4; ++u) {
-                    aPfL = min(aPfL, lo16(r[u].w0) + w[u].y); aPfO = min(aPfO, hi16(r[u].w0) + w[u].y);
-                    const int x = lo16(r[u].w1);
-                    aPLm00 = min(aPLm00, x + w[u].x); aPLm10 = min(aPLm10, x + w[u].z);
-                    aPMm10 = min(aPMm10, hi16(r[u].w1) + w[u].z);
-                    const int y = lo16(r[u].w2);
-                    aPOm00 = min(aPOm00, y + w[u].x); aPOm10 = min(aPOm10, y + w[u].z);
-                }
+                for (int u = 0; u < U4; ++u) { l2_term(A, r[u], w[u]); l2_term(A2, r[u], w2[u]); }
             }
             for (; ap < a; ++ap) {
-                const int d = i + ap, m2 = ub - (a - ap);
-                const R12 r = ldr12(G, cbb - s_tet[m2] + (((d - 1) * (2 * m2 + 2 - d)) >> 1) + kc);
-                const int4 w2 = __ldg(&W3[(ap - 1) * n1 + i]);
-                aPfL = min(aPfL, lo16(r.w0) + w2.y); aPfO = min(aPfO, hi16(r.w0) + w2.y);
-                const int x2 = lo16(r.w1);
-                aPLm00 = min(aPLm00, x2 + w2.x); aPLm10 = min(aPLm10, x2 + w2.z);
-                aPMm10 = min(aPMm10, hi16(r.w1) + w2.z);
-                const int y2 = lo16(r.w2);
-                aPOm00 = min(aPOm00, y2 + w2.x); aPOm10 = min(aPOm10, y2 + w2.z);
+                const int d = i + ap, mm = ub - (a - ap);
+                const R12 r = ldr12(G, cbb - s_tet[mm] + (((d - 1) * (2 * mm + 2 - d)) >> 1) + kc);
+                l2_term(A, r, __ldg(&W3[(ap - 1) * n1 + i]));
+                l2_term(A2, r, __ldg(&W3[ap * n1 + i - 1]));
             }
         }
-        SAVE(Q_PfL1, aPfL); SAVE(Q_PfO1, aPfO); SAVE(Q_PLm00b, aPLm00); SAVE(Q_PLm10b, aPLm10); SAVE(Q_PMm10a, aPMm10);
-        SAVE(Q_POm00a, aPOm00); SAVE(Q_POm10a, aPOm10);
+        SAVE(Q_PfL1, A.PfL); SAVE(Q_PfO1, A.PfO); SAVE(Q_PLm00b, A.PLm00); SAVE(Q_PLm10b, A.PLm10); SAVE(Q_PMm10a, A.PMm10);
+        SAVE(Q_POm00a, A.POm00); SAVE(Q_POm10a, A.POm10);
+        if (two) {
+            sc2 += (int64_t)(a + 1) * ncell2 + ROW2(i - 1) + kk;
+            SAVE2(Q_PfL1, A2.PfL); SAVE2(Q_PfO1, A2.PfO); SAVE2(Q_PLm00b, A2.PLm00); SAVE2(Q_PLm10b, A2.PLm10);
+            SAVE2(Q_PMm10a, A2.PMm10); SAVE2(Q_POm00a, A2.POm00); SAVE2(Q_POm10a, A2.POm10);
+        }
     } else if (role == ROLE_R3) {
-        // X(i,j,d,l), d=k+bq, with the 2D record of (k, d-1)   [:189-192,379-381,412-415,499-503,534-537,552-555]
-        // record g3 = PK PfromR | min(PL,PR) PRmloop00 | PMmloop00 -
-        int aPK = INF, aPfR = INF, aPfMp = INF, aPRm00 = INF, aPRm10 = INF, aPMm00 = INF;
+        AccR3 A = {INF, INF, INF, INF, INF, INF}, A2 = A;
+        const bool two = m2 >= 1 && kk >= 1;   // partner (i,j,k-1,l)
         if (b >= 1) {
             const int *__restrict__ G = reinterpret_cast<const int *>(q.g3);
             {  // d=l
                 const R12 r = ldr12(G, OFF(a, 0, i, l));
-                const int4 w = __ldg(&W3[(b - 1) * n1 + k]);
-                const int x = hi16(r.w1);
-                aPRm00 = min(aPRm00, x + w.x);
-                aPRm10 = min(aPRm10, x + w.z);
-                aPMm00 = min(aPMm00, lo16(r.w2) + w.x);
+                r3_first(A, r, __ldg(&W3[(b - 1) * n1 + k]));
+                r3_first(A2, r, __ldg(&W3[b * n1 + k - 1]));
             }
             const int ua = n - a - 2, ri = i - 1, kc = k - j - 2;
             int bq = 1;
             for (; bq + U4 <= b; bq += U4) {
                 R12 r[U4];
-                int4 w[U4];
+                int4 w[U4], w2[U4];
 #pragma unroll
                 for (int u = 0; u < U4; ++u) {
                     const int b3 = b - bq - u, m3 = ua - b3;
                     r[u] = ldr12(G, s_cb[b3] - s_tet[m3] + ((ri * (2 * m3 + 2 - i)) >> 1) + (kc + bq + u));
-                    w[u] = __ldg(&W3[(bq + u - 1) * n1 + k]);
+                    w[u] = __ldg(&W3[(bq + u - 1) * n1 + k]);       // (k, d-1)
+                    w2[u] = __ldg(&W3[(bq + u) * n1 + k - 1]);      // (k-1, d-1)
                 }
 #pragma unroll
-                for (int u = 0; u < U4; ++u) {
-                    aPK = min(aPK, lo16(r[u].w0) + w[u].y); aPfR = min(aPfR, hi16(r[u].w0) + w[u].y);
-                    aPfMp = min(aPfMp, lo16(r[u].w1) + w[u].y);
-                    const int x = hi16(r[u].w1);
-                    aPRm00 = min(aPRm00, x + w[u].x); aPRm10 = min(aPRm10, x + w[u].z);
-                    aPMm00 = min(aPMm00, lo16(r[u].w2) + w[u].x);
-                }
+                for (int u = 0; u < U4; ++u) { r3_term(A, r[u], w[u]); r3_term(A2, r[u], w2[u]); }
             }
             for (; bq < b; ++bq) {
                 const int b3 = b - bq, m3 = ua - b3;
                 const R12 r = ldr12(G, s_cb[b3] - s_tet[m3] + ((ri * (2 * m3 + 2 - i)) >> 1) + (kc + bq));
-                const int4 w3 = __ldg(&W3[(bq - 1) * n1 + k]);
-                aPK = min(aPK, lo16(r.w0) + w3.y); aPfR = min(aPfR, hi16(r.w0) + w3.y); aPfMp = min(aPfMp, lo16(r.w1) + w3.y);
-                const int x3 = hi16(r.w1);
-                aPRm00 = min(aPRm00, x3 + w3.x); aPRm10 = min(aPRm10, x3 + w3.z);
-                aPMm00 = min(aPMm00, lo16(r.w2) + w3.x);
+                r3_term(A, r, __ldg(&W3[(bq - 1) * n1 + k]));
+                r3_term(A2, r, __ldg(&W3[bq * n1 + k - 1]));
             }
         }
-        SAVE(Q_PK3, aPK); SAVE(Q_PfR1, aPfR); SAVE(Q_PfMp, aPfMp); SAVE(Q_PRm00a, aPRm00); SAVE(Q_PRm10, aPRm10);
-        SAVE(Q_PMm00b, aPMm00);
-    } else if (role == ROLE_R4) {
-        // X(i,j,k,d), d=k+bq, with the 2D record of (d+1, l)   [:382-383,429-432,504-507,520-523,567-570,585-588,
-        // 603-606,618-621,636-639]; record g4 = PfromR PfromO | PRmloop00 PMmloop00 | PMmloop10 POmloop00 | POmloop10 -
-        int aPfR = INF, aPfO = INF, aPRm00 = INF, aPRm01 = INF, aPMm01 = INF, aPMm10 = INF, aPOm00 = INF, aPOm01 = INF,
-            aPOm10 = INF;
+        SAVE(Q_PK3, A.PK); SAVE(Q_PfR1, A.PfR); SAVE(Q_PfMp, A.PfMp); SAVE(Q_PRm00a, A.PRm00); SAVE(Q_PRm10, A.PRm10);
+        SAVE(Q_PMm00b, A.PMm00);
+        if (two) {
+            sc2 += (int64_t)a * ncell2 + ROW2(i) + kk - 1;
+            SAVE2(Q_PK3, A2.PK); SAVE2(Q_PfR1, A2.PfR); SAVE2(Q_PfMp, A2.PfMp); SAVE2(Q_PRm00a, A2.PRm00);
+            SAVE2(Q_PRm10, A2.PRm10); SAVE2(Q_PMm00b, A2.PMm00);
+        }
+    } else {
+        AccR4 A = {INF, INF, INF, INF, INF, INF, INF, INF, INF}, A2 = A;
+        const bool two = m2 >= 1 && l + 1 <= n;   // partner (i,j,k,l+1)
         if (b >= 1) {
             const int4 *__restrict__ G = reinterpret_cast<const int4 *>(q.g4);
             {  // d=k
                 const int4 r = __ldg(&G[OFF(a, 0, i, k)]);
-                const int4 w = __ldg(&W3[(b - 1) * n1 + k + 1]);
-                const int x = lo16(r.y);
-                aPRm00 = min(aPRm00, x + w.x);
-                aPRm01 = min(aPRm01, x + w.z);
-                aPMm01 = min(aPMm01, hi16(r.y) + w.z);
-                const int y = hi16(r.z);
-                aPOm00 = min(aPOm00, y + w.x);
-                aPOm01 = min(aPOm01, y + w.z);
+                r4_first(A, r, __ldg(&W3[(b - 1) * n1 + k + 1]));
+                r4_first(A2, r, __ldg(&W3[b * n1 + k + 1]));
             }
             const int ua = n - a - 2, ri = i - 1, kc = k - j - 2;
             int bq = 1;
             for (; bq + U4 <= b; bq += U4) {
-                int4 r[U4], w[U4];
+                int4 r[U4], w[U4], w2[U4];
 #pragma unroll
                 for (int u = 0; u < U4; ++u) {
                     const int b4 = bq + u, m4 = ua - b4;
                     r[u] = __ldg(&G[s_cb[b4] - s_tet[m4] + ((ri * (2 * m4 + 2 - i)) >> 1) + kc]);
-                    w[u] = __ldg(&W3[(b - b4 - 1) * n1 + k + b4 + 1]);
+                    w[u] = __ldg(&W3[(b - b4 - 1) * n1 + k + b4 + 1]);   // (d+1, l)
+                    w2[u] = __ldg(&W3[(b - b4) * n1 + k + b4 + 1]);      // (d+1, l+1)
                 }
 #pragma unroll
-                for (int u = 0; u < U4; ++u) {
-                    aPfR = min(aPfR, lo16(r[u].x) + w[u].y); aPfO = min(aPfO, hi16(r[u].x) + w[u].y);
-                    const int x = lo16(r[u].y);
-                    aPRm00 = min(aPRm00, x + w[u].x); aPRm01 = min(aPRm01, x + w[u].z);
-                    aPMm01 = min(aPMm01, hi16(r[u].y) + w[u].z); aPMm10 = min(aPMm10, lo16(r[u].z) + w[u].x);
-                    const int y = hi16(r[u].z);
-                    aPOm00 = min(aPOm00, y + w[u].x); aPOm01 = min(aPOm01, y + w[u].z);
-                    aPOm10 = min(aPOm10, lo16(r[u].w) + w[u].x);
-                }
+                for (int u = 0; u < U4; ++u) { r4_term(A, r[u], w[u]); r4_term(A2, r[u], w2[u]); }
             }
             for (; bq < b; ++bq) {
                 const int m4 = ua - bq;
                 const int4 r = __ldg(&G[s_cb[bq] - s_tet[m4] + ((ri * (2 * m4 + 2 - i)) >> 1) + kc]);
-                const int4 w4 = __ldg(&W3[(b - bq - 1) * n1 + k + bq + 1]);
-                aPfR = min(aPfR, lo16(r.x) + w4.y); aPfO = min(aPfO, hi16(r.x) + w4.y);
-                const int x4 = lo16(r.y);
-                aPRm00 = min(aPRm00, x4 + w4.x); aPRm01 = min(aPRm01, x4 + w4.z);
-                aPMm01 = min(aPMm01, hi16(r.y) + w4.z); aPMm10 = min(aPMm10, lo16(r.z) + w4.x);
-                const int y4 = hi16(r.z);
-                aPOm00 = min(aPOm00, y4 + w4.x); aPOm01 = min(aPOm01, y4 + w4.z);
-                aPOm10 = min(aPOm10, lo16(r.w) + w4.x);
+                r4_term(A, r, __ldg(&W3[(b - bq - 1) * n1 + k + bq + 1]));
+                r4_term(A2, r, __ldg(&W3[(b - bq) * n1 + k + bq + 1]));
             }
         }
-        SAVE(Q_PfR2, aPfR); SAVE(Q_PfO2, aPfO); SAVE(Q_PRm00b, aPRm00); SAVE(Q_PRm01, aPRm01); SAVE(Q_PMm01, aPMm01);
-        SAVE(Q_PMm10b, aPMm10); SAVE(Q_POm00b, aPOm00); SAVE(Q_POm01, aPOm01); SAVE(Q_POm10b, aPOm10);
+        SAVE(Q_PfR2, A.PfR); SAVE(Q_PfO2, A.PfO); SAVE(Q_PRm00b, A.PRm00); SAVE(Q_PRm01, A.PRm01); SAVE(Q_PMm01, A.PMm01);
+        SAVE(Q_PMm10b, A.PMm10); SAVE(Q_POm00b, A.POm00); SAVE(Q_POm01, A.POm01); SAVE(Q_POm10b, A.POm10);
+        if (two) {
+            sc2 += (int64_t)a * ncell2 + ROW2(i) + kk;
+            SAVE2(Q_PfR2, A2.PfR); SAVE2(Q_PfO2, A2.PfO); SAVE2(Q_PRm00b, A2.PRm00); SAVE2(Q_PRm01, A2.PRm01);
+            SAVE2(Q_PMm01, A2.PMm01); SAVE2(Q_PMm10b, A2.PMm10); SAVE2(Q_POm00b, A2.POm00); SAVE2(Q_POm01, A2.POm01);
+            SAVE2(Q_POm10b, A2.POm10);
+        }
     }
 #undef SAVE
+#undef SAVE2
+#undef ROW2
 }
 
 #define WB 8      // window candidates in flight per lane (FENCE8 assumes 8)
@@ -790,7 +815,7 @@ __global__ void __launch_bounds__(K4_THREADS, PIPE ? 4 : 10) k_winM(const ccj_mo
 }
 
 // same-cell assembly in the reference's order (src/pseudo_loop.cc:85-127) from the partial minima
-__global__ void __launch_bounds__(K4_THREADS, 8) k_final(const ccj_model *__restrict__ M, const ccj_seq *__restrict__ seqs, int t) {
+__global__ void __launch_bounds__(K4_THREADS, 8) k_final(const ccj_model *__restrict__ M, const ccj_seq *__restrict__ seqs, int t, int tail) {
     __shared__ int s_tet[K4_MAXN + 4];
     __shared__ int s_cb[K4_MAXN + 4];
     __shared__ int s_hh[K4_MAXN + 4];   // HH4
@@ -815,10 +840,44 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_final(const ccj_model *__rest
     const int INF = CCJ_INF, II = CCJ_INTERN_INF;
     auto H4 = [](int x) { return ((x >> 2) + 1) * (2 * (x >> 2) + (x & 3)); };
     const int bp = M->bp_penalty, cp = M->cp_penalty, PB = M->PB_penalty, apbp = M->ap_penalty + M->bp_penalty;
-    const int16_t *__restrict__ sc = q.scratch + C.c;
     const int64_t ss = q.scratch_stride;
+    const int16_t *__restrict__ sc = q.scratch + (int64_t)(t & 1) * Q_COUNT * ss + C.c;
 #define GET(id) ((int)__ldg(sc + (int64_t)(id) * ss))
     const int off0 = OFF(a, b, i, k);
+    // partial minima of the four split-point roles.  tail (odd levels): k_roles(t-1) left them for the sources of
+    // levels <= t-2 (nothing for a role without split points); the one split point per role whose source is a
+    // level-(t-1) cell is added here.
+    AccL1 L1 = {INF, INF, INF, INF, INF, INF, INF};
+    AccL2 L2 = {INF, INF, INF, INF, INF, INF, INF};
+    AccR3 R3 = {INF, INF, INF, INF, INF, INF};
+    AccR4 R4 = {INF, INF, INF, INF, INF, INF, INF, INF, INF};
+    if (!tail || a >= 1) {
+        L1 = {GET(Q_PK1), GET(Q_PfL2), GET(Q_PfM), GET(Q_PLm00a), GET(Q_PLm01), GET(Q_PLm10a), GET(Q_PMm00a)};
+        L2 = {GET(Q_PfL1), GET(Q_PfO1), GET(Q_PLm00b), GET(Q_PLm10b), GET(Q_PMm10a), GET(Q_POm00a), GET(Q_POm10a)};
+    }
+    if (!tail || b >= 1) {
+        R3 = {GET(Q_PK3), GET(Q_PfR1), GET(Q_PfMp), GET(Q_PRm00a), GET(Q_PRm10), GET(Q_PMm00b)};
+        R4 = {GET(Q_PfR2), GET(Q_PfO2), GET(Q_PRm00b), GET(Q_PRm01), GET(Q_PMm01), GET(Q_PMm10b), GET(Q_POm00b), GET(Q_POm01), GET(Q_POm10b)};
+    }
+    if (tail) {
+        const int4 *__restrict__ W3 = reinterpret_cast<const int4 *>(q.w3);
+        if (a >= 1) {
+            const R12 r1 = ldr12(reinterpret_cast<const int *>(q.g1), OFF(a - 1, b, i, k));      // X(i,j-1,k,l) with (j,j)
+            const int4 w1 = __ldg(&W3[j]);
+            if (a == 1) l1_first(L1, r1, w1); else l1_term(L1, r1, w1);
+            const R12 r2 = ldr12(reinterpret_cast<const int *>(q.g2), OFF(a - 1, b, i + 1, k));  // X(i+1,j,k,l) with (i,i)
+            const int4 w2 = __ldg(&W3[i]);
+            if (a == 1) l2_first(L2, r2, w2); else l2_term(L2, r2, w2);
+        }
+        if (b >= 1) {
+            const R12 r3 = ldr12(reinterpret_cast<const int *>(q.g3), OFF(a, b - 1, i, k + 1));  // X(i,j,k+1,l) with (k,k)
+            const int4 w3 = __ldg(&W3[k]);
+            if (b == 1) r3_first(R3, r3, w3); else r3_term(R3, r3, w3);
+            const int4 r4 = __ldg(reinterpret_cast<const int4 *>(q.g4) + OFF(a, b - 1, i, k));   // X(i,j,k,l-1) with (l,l)
+            const int4 w4 = __ldg(&W3[l]);
+            if (b == 1) r4_first(R4, r4, w4); else r4_term(R4, r4, w4);
+        }
+    }
     int16_t *w4 = q.t4;
     const int mloc = n - t - 2, kr = n - b - k;
     const int h4m = H4(mloc);
@@ -834,10 +893,10 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_final(const ccj_model *__rest
         return v;
     };
 #define PUT(tbl, val) put16(w4 + (int64_t)(tbl) * st4 + off0, (val))
-    const int vPLm00 = PUT(T_PLmloop00, min(II + bp, min(GET(Q_PLm00a), GET(Q_PLm00b))));
-    PUT(T_PLmloop01, GET(Q_PLm01));
-    const int vPLm10 = PUT(T_PLmloop10, min(GET(Q_PLm10a), GET(Q_PLm10b)));
-    const int vPRm00 = PUT(T_PRmloop00, min(II + bp, min(GET(Q_PRm00a), GET(Q_PRm00b))));
+    const int vPLm00 = PUT(T_PLmloop00, min(II + bp, min(L1.PLm00, L2.PLm00)));
+    PUT(T_PLmloop01, L1.PLm01);
+    const int vPLm10 = PUT(T_PLmloop10, min(L1.PLm10, L2.PLm10));
+    const int vPRm00 = PUT(T_PRmloop00, min(II + bp, min(R3.PRm00, R4.PRm00)));
     int vPMm00, vPMm10;
     {
         int e01 = INF, e10 = INF, f01 = INF;
@@ -848,17 +907,17 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_final(const ccj_model *__rest
             e10 = ld16(TB(T_PRmloop10), oB) + cp;
             f01 = ld16(TB(T_PMmloop01), oB) + cp;
         }
-        PUT(T_PRmloop01, min(e01, GET(Q_PRm01)));
-        PUT(T_PRmloop10, min(e10, GET(Q_PRm10)));
-        vPMm00 = PUT(T_PMmloop00, min(II + bp, min(GET(Q_PMm00a), GET(Q_PMm00b))));
-        PUT(T_PMmloop01, min(f01, GET(Q_PMm01)));
+        PUT(T_PRmloop01, min(e01, R4.PRm01));
+        PUT(T_PRmloop10, min(e10, R3.PRm10));
+        vPMm00 = PUT(T_PMmloop00, min(II + bp, min(L1.PMm00, R3.PMm00)));
+        PUT(T_PMmloop01, min(f01, R4.PMm01));
         int g10 = INF;
         if (a >= 1) g10 = ld16(TB(T_PMmloop10), OFF(a - 1, b, i, k)) + cp;  // (i,j-1,k,l)
-        vPMm10 = PUT(T_PMmloop10, min(g10, min(GET(Q_PMm10a), GET(Q_PMm10b))));
+        vPMm10 = PUT(T_PMmloop10, min(g10, min(L2.PMm10, R4.PMm10)));
     }
-    const int vPOm00 = PUT(T_POmloop00, min(II + bp, min(GET(Q_POm00a), GET(Q_POm00b))));
-    PUT(T_POmloop01, GET(Q_POm01));
-    const int vPOm10 = PUT(T_POmloop10, min(GET(Q_POm10a), GET(Q_POm10b)));
+    const int vPOm00 = PUT(T_POmloop00, min(II + bp, min(L2.POm00, R4.POm00)));
+    PUT(T_POmloop01, R4.POm01);
+    const int vPOm10 = PUT(T_POmloop10, min(L2.POm10, R4.POm10));
 
     const int8_t *__restrict__ S = q.S;
     auto ptype = [&](int x, int y) { return __ldg(&M->pair[S[x]][S[y]]); };
@@ -910,12 +969,12 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_final(const ccj_model *__rest
         }
         vPO = PUT(T_PO, mn);
     }
-    const int vPfL = PUT(T_PfromL, min(min(GET(Q_PfL1), GET(Q_PfL2)), min(vPR + PB, min(vPM + PB, vPO + PB))));
-    const int vPfR = PUT(T_PfromR, min(min(GET(Q_PfR1), GET(Q_PfR2)), min(vPM + PB, vPO + PB)));
-    PUT(T_PfromM, GET(Q_PfM));
-    const int vPfMp = PUT(T_PfromMprime, GET(Q_PfMp) + PB);
-    const int vPfO = PUT(T_PfromO, min(min(GET(Q_PfO1), GET(Q_PfO2)), min(vPL + PB, vPR + PB)));
-    const int vPK = PUT(T_PK, min(min(GET(Q_PK1), GET(Q_PK3)), min(min(vPL + PB, vPM + PB), min(vPR + PB, vPO + PB))));
+    const int vPfL = PUT(T_PfromL, min(min(L2.PfL, L1.PfL), min(vPR + PB, min(vPM + PB, vPO + PB))));
+    const int vPfR = PUT(T_PfromR, min(min(R3.PfR, R4.PfR), min(vPM + PB, vPO + PB)));
+    PUT(T_PfromM, L1.PfM);
+    const int vPfMp = PUT(T_PfromMprime, R3.PfMp + PB);
+    const int vPfO = PUT(T_PfromO, min(min(L2.PfO, R4.PfO), min(vPL + PB, vPR + PB)));
+    const int vPK = PUT(T_PK, min(min(L1.PK, R3.PK), min(min(vPL + PB, vPM + PB), min(vPR + PB, vPO + PB))));
     w4[(int64_t)T_MPP * st4 + off0] = (int16_t)min(vPL, vPR);
     w4[(int64_t)T_PKG * st4 + ccj_pkg_idx(n, i, j, k, l)] = (int16_t)vPK;  // scattered: one store per cell
     {   // window copies (layouts in ccj_types.h); PLW is coalesced, PRW / PMW are one scattered store per cell
@@ -1013,7 +1072,7 @@ static bool level_dims(LaunchDims d, int t, int &bx) {
 }
 void launch_4d_roles(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st) {
     int bx;
-    if (level_dims(d, t, bx)) k_roles<<<dim3(bx, t + 1, d.nseq * 4), K4_THREADS, 0, st>>>(M, seqs, t, 0);
+    if ((t & 1) == 0 && level_dims(d, t, bx)) k_roles<<<dim3(bx, t + 1, d.nseq * 4), K4_THREADS, 0, st>>>(M, seqs, t);  // levels t and t+1
 }
 void launch_4d_windows(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st) {
     const int nm = d.nmax, m = nm - t - 2;
@@ -1039,7 +1098,7 @@ void launch_4d_windows(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, in
 }
 void launch_4d_final(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st) {
     int bx;
-    if (level_dims(d, t, bx)) k_final<<<dim3(bx, t + 1, d.nseq), K4_THREADS, 0, st>>>(M, seqs, t);
+    if (level_dims(d, t, bx)) k_final<<<dim3(bx, t + 1, d.nseq), K4_THREADS, 0, st>>>(M, seqs, t, t & 1);
 }
 void launch_4d_tuned(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st) {
     launch_4d_roles(M, seqs, d, t, st);
@@ -1047,7 +1106,7 @@ void launch_4d_tuned(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int 
     launch_4d_final(M, seqs, d, t, st);
 }
 
-int fill4_partials() { return Q_COUNT; }
+int fill4_partials() { return 2 * Q_COUNT; }  // two levels of partial minima (k_roles works on levels t and t+1)
 
 void launch_P_tuned(const ccj_model *, const ccj_seq *seqs, LaunchDims d, int s, cudaStream_t st) {
     if (s < 3 || s > d.nmax - 1) return;
