@@ -1005,50 +1005,76 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_final(const ccj_model *__rest
 }
 
 // P(i,l) = min_{i<=j<d<k<l} PK(i,j,d+1,k) + PK(j+1,d,k+1,l)  (src/pseudo_loop.cc:166-179).
-// blockIdx.x -> i, blockIdx.y -> j; warps take the distances delta=k-d, lanes walk d: the first factor is then
-// contiguous in the main layout (row i of slab (j-i, delta-1)) and the second in the T_PKG copy.
-__global__ void __launch_bounds__(256) k_P_tuned(const ccj_seq *__restrict__ seqs, int s) {
+// blockIdx.x -> i, warps (and blockIdx.y) -> j.  For fixed (i,j,l) the pairs (delta=k-d, d) form a triangle with
+// rows of length L, L-1, ..., 1 (L=l-j-2).  In the T_PKG copy the second factor of that whole triangle is ONE
+// contiguous run; the first factor is contiguous per row (row i of slab (j-i, delta-1)).  A warp walks the
+// flattened triangle of its j, 8 consecutive terms per lane: no lane idles on a short row, and the row base of
+// the first factor is recomputed only when a lane's run crosses into the next row.
+#define KP_RUN 8
+__global__ void __launch_bounds__(256) k_P_tuned(const ccj_seq *__restrict__ seqs, int s, int nj) {
     __shared__ int s_tet[K4_MAXN + 4];
     __shared__ int s_cb[K4_MAXN + 4];
     __shared__ int sm[8];
     const ccj_seq q = seqs[blockIdx.z];
-    const int n = q.n;
+    const int n = q.n, n1 = n + 1;
     const int i = 1 + blockIdx.x, l = i + s;
     if (l > n) return;
-    const int j = i + blockIdx.y;
-    if (j > l - 3) return;  // needs j < d < k < l
+    const int *__restrict__ lay = q.lay;
     for (int x = threadIdx.x; x <= n; x += 256) {
-        s_tet[x] = __ldg(&q.lay[x]);
-        s_cb[x] = __ldg(&q.lay[n + 1 + x]);
+        s_tet[x] = __ldg(&lay[x]);
+        s_cb[x] = __ldg(&lay[n1 + x]);
     }
     __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int16_t *__restrict__ F = q.t4 + (int64_t)T_PK * q.stride4;
-    const int16_t *__restrict__ G = q.t4 + (int64_t)T_PKG * q.stride4;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int a1 = j - i;
-    const int s2 = l - j - 1;  // span of the second factor's block (i2=j+1, l)
-    // block base of (i2=j+1, l) in the T_PKG copy: Pent(n-2)-Pent(n-i2-1) = Cb(i2-2)  (see ccj_cb)
-    const int gblk = s_cb[j - 1] + s_tet[s2 - 2] + s2 * (s2 - 1) / 2 - (j + 1);
-    const int ua = n - a1 - 2, ri = i - 1;
+    const int16_t *__restrict__ Gt = q.t4 + (int64_t)T_PKG * q.stride4;
+    const int ri = i - 1;
     int mn = CCJ_INF;
-    // flatten (dl, d): warps take distances dl=k-d, lanes walk d; two distances in flight per warp
-    for (int dl = 1 + wid; dl <= l - j - 2; dl += nw) {
-        const int b1 = dl - 1, m1 = ua - b1;
-        const int F0 = s_cb[b1] - s_tet[m1] + ((ri * (2 * m1 + 2 - i)) >> 1) + (1 - j - 2);  // (i, j, d+1, d+dl)
-        const int G0 = gblk - (s2 - dl) * (s2 - dl + 1) / 2;                                  // (j+1, d, d+dl+1, l)
-        const int dmax = l - dl - 1;
-        int d = j + 1 + lane;
-        for (; d + 32 <= dmax; d += 64) {
-            const int f0 = __ldg(F + F0 + d), g0 = __ldg(G + G0 + d), f1 = __ldg(F + F0 + d + 32), g1 = __ldg(G + G0 + d + 32);
-            mn = min(mn, min(f0 + g0, f1 + g1));
+    // Work items = (j, 256 consecutive terms of j's triangle), dealt round-robin to the warps: triangle sizes range
+    // from 1 to L(L+1)/2 terms, so neither "a warp per j" nor "the block per j" keeps the lanes busy.  The j with
+    // more than 256*p terms are a prefix (the triangles shrink with j), which makes the item list a double loop.
+    const int Lmax = l - i - 2, Tmax = Lmax * (Lmax + 1) / 2;
+    for (int p = 0; p * (32 * KP_RUN) < Tmax; ++p) {
+        int Lmin = (int)((sqrtf(1.f + 8.f * (float)(p * 32 * KP_RUN)) - 1.f) * 0.5f);
+        Lmin = max(Lmin, 1);
+        while (Lmin * (Lmin + 1) / 2 <= p * 32 * KP_RUN) ++Lmin;
+        while (Lmin > 1 && (Lmin - 1) * Lmin / 2 > p * 32 * KP_RUN) --Lmin;
+        const int jmax = l - 2 - Lmin;   // L = l-j-2 >= Lmin
+        for (int j = i + blockIdx.y + ((wid + p) & 7) * nj; j <= jmax; j += 8 * nj) {  // rotated: every warp gets large and small j
+            const int L = l - j - 2, T = L * (L + 1) / 2;
+            const int ua = n - (j - i) - 2;
+            // row r: delta = r+1, first factor (i,j,d+1,d+delta) in slab (j-i, r), m1 = ua-r, row i, position d-j-1
+            auto rowbase = [&](int r) { const int m1 = ua - r; return s_cb[r] - s_tet[m1] + ((ri * (2 * m1 + 2 - i)) >> 1); };
+            // second factor PK(j+1,d,d+delta+1,l): block (j+1,l) of the T_PKG copy starts at Cb(j-1) + Tet(l-j-3)  (ccj_pkg_idx)
+            const int16_t *__restrict__ G = Gt + (s_cb[j - 1] + s_tet[L - 1]);
+            const int q0 = (p * 32 + lane) * KP_RUN;
+            if (q0 >= T) continue;
+            // invert q0 = r(2L+1-r)/2 + kk  (rows r=0..L-1 of length L-r)
+            int r = (int)(((2 * L + 1) - sqrtf((float)((2 * L + 1) * (2 * L + 1) - 8 * q0))) * 0.5f);
+            r = max(0, min(r, L - 1));
+            while (r > 0 && r * (2 * L + 1 - r) / 2 > q0) --r;
+            while ((r + 1) * (2 * L - r) / 2 <= q0) ++r;
+            int kk = q0 - r * (2 * L + 1 - r) / 2;
+            int f0 = rowbase(r);
+            int idx[KP_RUN];
+#pragma unroll
+            for (int e = 0; e < KP_RUN; ++e) {  // addresses first (pure index arithmetic) ...
+                idx[e] = f0 + kk;
+                if (++kk == L - r) { ++r; kk = 0; f0 = rowbase(min(r, L - 1)); }
+            }
+            int v[KP_RUN];
+#pragma unroll
+            for (int e = 0; e < KP_RUN; ++e)   // ... then all 2*KP_RUN loads in flight together
+                v[e] = q0 + e < T ? (int)__ldg(F + idx[e]) + (int)__ldg(G + q0 + e) : CCJ_INF;
+#pragma unroll
+            for (int e = 0; e < KP_RUN; ++e) mn = min(mn, v[e]);
         }
-        if (d <= dmax) mn = min(mn, (int)__ldg(F + F0 + d) + (int)__ldg(G + G0 + d));
     }
     mn = __reduce_min_sync(0xffffffffu, mn);
     if (lane == 0) sm[wid] = mn;
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int x = 1; x < nw; ++x) mn = min(mn, sm[x]);
+        for (int x = 1; x < 8; ++x) mn = min(mn, sm[x]);
         if (mn < CCJ_INF / 2) atomicMin(&q.t2[T2_P * q.stride2 + ccj_idx2(n, i, l)], mn);
     }
 }
@@ -1110,7 +1136,10 @@ int fill4_partials() { return 2 * Q_COUNT; }  // two levels of partial minima (k
 
 void launch_P_tuned(const ccj_model *, const ccj_seq *seqs, LaunchDims d, int s, cudaStream_t st) {
     if (s < 3 || s > d.nmax - 1) return;
-    k_P_tuned<<<dim3(d.nmax - s, s - 2, d.nseq), 256, 0, st>>>(seqs, s);
+    // one block per (i, residue class of j); enough classes to fill the 148 SMs a few times when the wave is small
+    const int per = (d.nmax - s) * d.nseq;
+    const int nj = std::max(1, std::min(s - 2, (148 * 6 + per - 1) / per));
+    k_P_tuned<<<dim3(d.nmax - s, nj, d.nseq), 256, 0, st>>>(seqs, s, nj);
 }
 
 }  // namespace ccj
