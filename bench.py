@@ -232,11 +232,28 @@ def gpu_arm(args):
     bytes_4d = sum(x["bytes_4d"] for x in terms)
     peak, peak_src = hbm_peak()
     achieved = bytes_4d / (prof["k4d_ms"] / 1e3) / 1e9
+    # SURVEY.md 8d also defines the figure over the WHOLE fill (gap tables + compute_P, graph launch, all streams)
+    bytes_fill = bytes_4d + sum(x["bytes_P"] for x in terms)
+    fill_ms = ctx.fill()
+    # measured DRAM traffic: ncu dram__bytes_{read,write}.sum summed over every gap-table launch of one fold of this
+    # workload (profiles/r1_traffic.json, written by profiles/measure_traffic.py from the committed ncu launch list),
+    # scaled from its algorithmic bytes to this step's
+    traffic, traffic_src = None, None
+    tpath = ROOT / "profiles" / "r1_traffic.json"
+    if tpath.exists():
+        tj = json.loads(tpath.read_text())
+        traffic = tj["dram_bytes"] / tj["algorithmic_bytes"] * bytes_4d
+        traffic_src = tj.get("source")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "level-wavefront gap-table kernel(s), all launches of one step",
+                "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": "level-wavefront gap-table kernels (k_roles + k_winLR + k_winM + k_final), all launches of one step",
                 "algorithmic_bytes_per_step": bytes_4d, "kernel_ms_per_step": prof["k4d_ms"],
                 "kernel_share_of_fill": prof["k4d_ms"] / max(prof["total_ms"], 1e-9), "peak_source": peak_src,
-                "other_kernels_ms": {"P": prof["kP_ms"], "2D": prof["k2d_ms"], "other": prof["other_ms"]}}
+                "kernel_ms": {"roles": prof["k4d_split_ms"], "windows": prof["k4d_window_ms"], "final": prof["k4d_final_ms"],
+                              "P": prof["kP_ms"], "2D": prof["k2d_ms"], "other": prof["other_ms"]},
+                "whole_fill": {"algorithmic_bytes": bytes_fill, "ms": fill_ms,
+                               "achieved": bytes_fill / (fill_ms / 1e3) / 1e9,
+                               "frac": bytes_fill / (fill_ms / 1e3) / 1e9 / peak}}
 
     # --- CPU baseline on a bounded sample + parity of the GPU path on exactly that sample ---
     cpu = None

@@ -238,7 +238,7 @@ __device__ __forceinline__ bool cell_setup(const ccj_seq &q, int t, int a, int b
 #define TB(tbl) (t4 + (int64_t)(tbl) * st4)
 #define OFF(aa, bb, ii, kx) (s_cb[bb] - s_tet[n - (aa) - (bb)-2] + ((((ii)-1) * (2 * (n - (aa) - (bb)-2) + 2 - (ii))) >> 1) + ((kx) - (ii) - (aa)-2))
 #ifndef U4
-#define U4 2
+#define U4 3
 #endif
 
 // ---- the four split-point roles: accumulators and the add-mins of ONE split point -------------------------------
@@ -647,8 +647,10 @@ __global__ void __launch_bounds__(K4_THREADS, PIPE ? 6 : 12) k_winLR(const ccj_m
             }
         }
     } else {  // waves with many sequences hide the latency with occupancy: plain loop, fewer registers
+        uint32_t pre = nb > 0 ? fetch(0) : 0u;
         for (int bb = 0; bb < nb; ++bb) {
-            const int4 d = decode(fetch(bb));
+            const int4 d = decode(pre);
+            pre = fetch(bb + 1);   // the next batch's list entry is on its way while this batch is loaded and consumed
             __syncwarp();
             tile[0][grp][gl] = d;
             __syncwarp();
@@ -756,9 +758,9 @@ __global__ void __launch_bounds__(K4_THREADS, PIPE ? 4 : 10) k_winM(const ccj_mo
 #define ISSUE(W_, buf)                                                                             \
     _Pragma("unroll") for (int u = 0; u < WB; ++u) {                                              \
         const int4 d2 = tile[buf][grp][u];                                                        \
-        /* quads outside the source row belong to other rows: read the own row instead */         \
+        /* quads outside the source row belong to other rows: no load, "not a source" masks */    \
         const bool ok = (unsigned)(qd - (d2.w & 0xffff)) <= (unsigned)(d2.w >> 16);               \
-        W_[u] = ldq4(src, ok ? d2.x : own);                                                        \
+        W_[u] = ok ? ldq4(src, d2.x) : make_int4(WIN_INF2, WIN_INF2, WIN_INF2, WIN_INF2);         \
     }
 #define CONSUME(W_, buf)                                                                           \
     _Pragma("unroll") for (int u = 0; u < WB; ++u) {                                              \
@@ -796,8 +798,10 @@ __global__ void __launch_bounds__(K4_THREADS, PIPE ? 4 : 10) k_winM(const ccj_mo
             }
         }
     } else {
+        uint2 pre = fetch(0);
         for (int bb = 0; bb < nb; ++bb) {
-            const int4 d = decode(fetch(bb));
+            const int4 d = decode(pre);
+            pre = fetch(bb + 1);
             __syncwarp();
             tile[0][grp][gl] = d;
             __syncwarp();
