@@ -38,6 +38,7 @@ void cmdline_parser_print_help(void) {
 void cmdline_parser_free(struct args_info *a) {
     free(a->input_file_arg);
     free(a->paramFile_arg);
+    free(a->batch_file_arg);
     for (unsigned i = 0; i < a->inputs_num; ++i) free(a->inputs[i]);
     free(a->inputs);
     memset(a, 0, sizeof *a);
@@ -56,7 +57,8 @@ int cmdline_parser(int argc, char **argv, struct args_info *a) {
     static struct option longopts[] = {{"help", 0, nullptr, 'h'},        {"version", 0, nullptr, 'V'},
                                        {"input-file", 1, nullptr, 'i'},  {"dangles", 1, nullptr, 'd'},
                                        {"paramFile", 1, nullptr, 'P'},   {"noConv", 0, nullptr, 0},
-                                       {"noGU", 0, nullptr, 0},          {nullptr, 0, nullptr, 0}};
+                                       {"noGU", 0, nullptr, 0},          {"batch-file", 1, nullptr, 0},
+                                       {nullptr, 0, nullptr, 0}};
     const char *prog = argv[0];
     optarg = nullptr;
     optind = 0;
@@ -98,6 +100,10 @@ int cmdline_parser(int argc, char **argv, struct args_info *a) {
                     if (twice(prog, a->noGU_given, "noGU", '-')) { fail = true; break; }
                     a->noGU_given = 1;
                     a->noGU_flag = !a->noGU_flag;
+                } else if (strcmp(longopts[idx].name, "batch-file") == 0) {
+                    if (twice(prog, a->batch_file_given, "batch-file", '-')) { fail = true; break; }
+                    a->batch_file_given = 1;
+                    a->batch_file_arg = strdup(optarg);
                 }
                 break;
             default:  // '?': getopt_long printed the message

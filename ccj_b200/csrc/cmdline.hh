@@ -13,8 +13,9 @@ struct args_info {
     char *paramFile_arg;        // -P, --paramFile
     int noConv_flag;            // --noConv
     int noGU_flag;              // --noGU
+    char *batch_file_arg;       // --batch-file (ccj_b200 extension, SURVEY.md 8f: FASTA or one sequence per line)
     unsigned int help_given, version_given, input_file_given, dangles_given, paramFile_given, noConv_given,
-        noGU_given;
+        noGU_given, batch_file_given;
     char **inputs;              // unnamed options: [sequence]
     unsigned inputs_num;
 };

@@ -72,3 +72,31 @@ def test_cli_input_conventions(cli):
     assert (rc, out) == (0, "GCAACGATGACATACATCGCTAGTCGACGC\n....(((((.....)))))........... (-4.4)\n")
     # run from a directory without params/: the default file is cwd-relative, exactly like the reference
     assert run(cli, ["ACGU"], cwd="/tmp")[0] == 1
+
+
+@pytest.mark.gpu
+def test_cli_batch_file(cli, golden_folds, tmp_path):
+    """--batch-file (extension): FASTA and plain lists; per record the header, then exactly the
+    reference's output for that sequence; invalid / aborting records do not stop the batch."""
+    recs = [r for r in golden_folds if r["par"] == "rna_Turner04.par" and r["dangles"] == 2 and not r["extra"]
+            and 8 <= len(r["seq"]) <= 70]
+    ok = [r for r in recs if r["rc"] == 0][:12]
+    bad = [r for r in recs if r["rc"] != 0][:2]
+    use = ok[:6] + bad + ok[6:]
+    fa = tmp_path / "batch.fa"
+    lines = []
+    for x, r in enumerate(use):
+        s = r["seq"]
+        lines += [f">rec{x}", s[: len(s) // 2].lower(), s[len(s) // 2:]]      # wrapped, lower case
+    lines += [">broken", "ACGNNU"]
+    fa.write_text("\n".join(lines) + "\n")
+    rc, out, err = run(cli, ["-P", str(ROOT / "params" / "rna_Turner04.par"), "--batch-file", str(fa)])
+    want = "".join(f">rec{x}\n" + r["stdout"] for x, r in enumerate(use))
+    want += ">broken\nSequence contains character N that is not G,C,A,U, or T.\n"
+    assert out == want
+    assert err == "".join(r["stderr"] for r in use)
+    assert rc == 1
+    plain = tmp_path / "batch.txt"
+    plain.write_text("\n".join(r["seq"] for r in ok) + "\n")
+    rc, out, err = run(cli, ["-P", str(ROOT / "params" / "rna_Turner04.par"), "--batch-file", str(plain)])
+    assert (rc, out, err) == (0, "".join(r["stdout"] for r in ok), "")
