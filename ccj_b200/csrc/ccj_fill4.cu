@@ -546,7 +546,7 @@ template <bool PIPE>
 __global__ void __launch_bounds__(K4_THREADS, PIPE ? 6 : 12) k_winLR(const ccj_model *__restrict__ M, const ccj_seq *__restrict__ seqs, int t, int nchunk) {
     __shared__ int s_T[64];              // quad offset of source slab (a-s,b) resp. (a,b-s), plus H4(m+s)
     __shared__ int s_h4[K4_MAXN + 4];
-    __shared__ int4 tile[2][WRUNS][WGRP];   // double-buffered: (source run start, energy x2, clamp x2, -)
+    __shared__ int2 tile[2][WRUNS][WGRP];   // double-buffered: (source run start, energy | clamp << 16)
     const int role = blockIdx.z & 1;     // 0: PL   1: PR
     const ccj_seq q = seqs[blockIdx.z >> 1];
     const int n = q.n, n1 = n + 1;
@@ -602,62 +602,70 @@ __global__ void __launch_bounds__(K4_THREADS, PIPE ? 6 : 12) k_winLR(const ccj_m
     // are in flight and the list entry of batch b+2 is on its way.
     // lane gl fetches entry 8b+gl of its group's list; past the end the last entry again (min is idempotent)
     auto fetch = [&](int bb) -> uint32_t { return cnt > 0 ? __ldg(&lst[min(bb * WGRP + gl, cnt - 1)]) : 0u; };
-    auto decode = [&](uint32_t en) -> int4 {
-        if (cnt == 0) return make_int4(own, 0, WIN_INF2, 0);
+    auto decode = [&](uint32_t en) -> int2 {
+        if (cnt == 0) return make_int2(own, 0x7fff0000);
         const int x = (en >> 16) & 0xff, y = en >> 24, e = (int)(int16_t)(en & 0xffff);
         // PL source (i+x, j-y, k, l): slab (a-s, b), row c+x, length zc+y, same position (n-b)-k
         // PR source (i, j, k+x, l-y): slab (a, b-s), row kr+y, length zc+x, same position i-1
-        return make_int4(s_T[x + y] - s_h4[zc + (role == 0 ? y : x)], splat16(e), splat16(32767 - max(e, 0)), 0);
+        return make_int2(s_T[x + y] - s_h4[zc + (role == 0 ? y : x)], (e & 0xffff) | ((32767 - max(e, 0)) << 16));
     };
-#define ISSUE(W_, buf)                                                        \
-    _Pragma("unroll") for (int u = 0; u < WB; ++u) W_[u] = ldq(src, tile[buf][grp][u].x)
-#define CONSUME(W_, buf)                                                      \
+    // one LDS.64 per candidate (shared memory / L1 is the busiest unit of this kernel): the energy and its clamp
+    // travel as two halves of one word and are splatted with two PRMTs
+#define ISSUE(W_, EC_, buf)                                                   \
     _Pragma("unroll") for (int u = 0; u < WB; ++u) {                         \
-        const int4 d2 = tile[buf][grp][u];                                   \
-        acc0 = addmin2(min2(W_[u].x, d2.z), d2.y, acc0);                      \
-        acc1 = addmin2(min2(W_[u].y, d2.z), d2.y, acc1);                      \
+        const int2 d2 = tile[buf][grp][u];                                   \
+        W_[u] = ldq(src, d2.x);                                              \
+        EC_[u] = d2.y;                                                       \
+    }
+#define CONSUME(W_, EC_)                                                      \
+    _Pragma("unroll") for (int u = 0; u < WB; ++u) {                         \
+        const int ee = (int)__byte_perm((unsigned)EC_[u], 0u, 0x1010), cc = (int)__byte_perm((unsigned)EC_[u], 0u, 0x3232); \
+        acc0 = addmin2(min2(W_[u].x, cc), ee, acc0);                          \
+        acc1 = addmin2(min2(W_[u].y, cc), ee, acc1);                          \
     }
     if (PIPE) {
         int2 wa[WB], wb[WB];
+        int ea[WB], eb[WB];
         uint32_t pre = 0;
         if (nb > 0) {
             tile[0][grp][gl] = decode(fetch(0));
             pre = fetch(1);
             __syncwarp();
-            ISSUE(wa, 0);
+            ISSUE(wa, ea, 0);
         }
         for (int bb = 0; bb < nb; bb += 2) {
             if (bb + 1 < nb) {
                 tile[1][grp][gl] = decode(pre);
                 pre = fetch(bb + 2);
                 __syncwarp();
-                ISSUE(wb, 1);
+                ISSUE(wb, eb, 1);
             }
-            CONSUME(wa, 0);
+            CONSUME(wa, ea);
             __syncwarp();
             if (bb + 1 < nb) {
                 if (bb + 2 < nb) {
                     tile[0][grp][gl] = decode(pre);
                     pre = fetch(bb + 3);
                     __syncwarp();
-                    ISSUE(wa, 0);
+                    ISSUE(wa, ea, 0);
                 }
-                CONSUME(wb, 1);
+                CONSUME(wb, eb);
                 __syncwarp();
             }
         }
     } else {  // waves with many sequences hide the latency with occupancy: plain loop, fewer registers
         uint32_t pre = nb > 0 ? fetch(0) : 0u;
         for (int bb = 0; bb < nb; ++bb) {
-            const int4 d = decode(pre);
+            const int2 d = decode(pre);
             pre = fetch(bb + 1);   // the next batch's list entry is on its way while this batch is loaded and consumed
             __syncwarp();
             tile[0][grp][gl] = d;
             __syncwarp();
             int2 w[WB];
-            ISSUE(w, 0);
+            int ec[WB];
+            ISSUE(w, ec, 0);
             FENCE8X(w);
-            CONSUME(w, 0);
+            CONSUME(w, ec);
         }
     }
 #undef ISSUE
