@@ -704,7 +704,7 @@ __global__ void __launch_bounds__(256) k_fill_pmw(const ccj_seq *seqs) {
 //   blockIdx.x -> (pass, chunk of 16 pairs), blockIdx.y -> sequence
 template <bool PIPE>
 __global__ void __launch_bounds__(K4_THREADS, PIPE ? 4 : 10) k_winM(const ccj_model *__restrict__ M, const ccj_seq *__restrict__ seqs, int t, int nchunk) {
-    __shared__ int4 tile[2][WRUNS][WGRP];   // (source row start, energy x2, clamp x2, first quad | quads-1 << 16)
+    __shared__ int4 tile[2][WRUNS][WGRP];   // (source row start, energy | clamp << 16, first quad, quads - 1)
     const ccj_seq q = seqs[blockIdx.y];
     const int n = q.n, n1 = n + 1;
     const int m = n - t - 2;
@@ -758,50 +758,53 @@ __global__ void __launch_bounds__(K4_THREADS, PIPE ? 4 : 10) k_winM(const ccj_mo
             const int il = max(j - t + y, 1), ih = j - x - max(0, tl - (B - y));   // its cells
             if (tl >= 0 && ih >= il) {
                 const int qls = (il - 1) >> 2, qhs = (ih - 1) >> 2;
-                return make_int4(tl * wtot4 + (int)L.y - qls, splat16(e), splat16(32767 - max(e, 0)), qls | ((qhs - qls) << 16));
+                return make_int4(tl * wtot4 + (int)L.y - qls, (e & 0xffff) | ((32767 - max(e, 0)) << 16), qls, qhs - qls);
             }
         }
-        return make_int4(own, 0, WIN_INF2, 0);  // no candidate: the own row is all "not a source"
+        return make_int4(own, 0x7fff0000, 0x7fffffff, 0);  // no candidate: no quad is inside its (empty) source row
     };
-#define ISSUE(W_, buf)                                                                             \
+    // one LDS.128 per candidate: (source row start, energy | clamp << 16, first quad, quads - 1)
+#define ISSUE(W_, EC_, buf)                                                                       \
     _Pragma("unroll") for (int u = 0; u < WB; ++u) {                                              \
         const int4 d2 = tile[buf][grp][u];                                                        \
         /* quads outside the source row belong to other rows: no load, "not a source" masks */    \
-        const bool ok = (unsigned)(qd - (d2.w & 0xffff)) <= (unsigned)(d2.w >> 16);               \
+        const bool ok = (unsigned)(qd - d2.z) <= (unsigned)d2.w;                                  \
         W_[u] = ok ? ldq4(src, d2.x) : make_int4(WIN_INF2, WIN_INF2, WIN_INF2, WIN_INF2);         \
+        EC_[u] = d2.y;                                                                            \
     }
-#define CONSUME(W_, buf)                                                                           \
+#define CONSUME(W_, EC_)                                                                          \
     _Pragma("unroll") for (int u = 0; u < WB; ++u) {                                              \
-        const int4 d2 = tile[buf][grp][u];                                                        \
-        acc0 = min2(acc0, addmax2(min2(W_[u].x, d2.z), d2.y, W_[u].y));                             \
-        acc1 = min2(acc1, addmax2(min2(W_[u].z, d2.z), d2.y, W_[u].w));                             \
+        const int ee = (int)__byte_perm((unsigned)EC_[u], 0u, 0x1010), cc = (int)__byte_perm((unsigned)EC_[u], 0u, 0x3232); \
+        acc0 = min2(acc0, addmax2(min2(W_[u].x, cc), ee, W_[u].y));                               \
+        acc1 = min2(acc1, addmax2(min2(W_[u].z, cc), ee, W_[u].w));                               \
     }
     if (PIPE) {  // see k_winLR
         int4 wa[WB], wb[WB];
+        int ea[WB], eb[WB];
         uint2 pre = make_uint2(0u, 0xffffffffu);
         if (nb > 0) {
             tile[0][grp][gl] = decode(fetch(0));
             pre = fetch(1);
             __syncwarp();
-            ISSUE(wa, 0);
+            ISSUE(wa, ea, 0);
         }
         for (int bb = 0; bb < nb; bb += 2) {
             if (bb + 1 < nb) {
                 tile[1][grp][gl] = decode(pre);
                 pre = fetch(bb + 2);
                 __syncwarp();
-                ISSUE(wb, 1);
+                ISSUE(wb, eb, 1);
             }
-            CONSUME(wa, 0);
+            CONSUME(wa, ea);
             __syncwarp();
             if (bb + 1 < nb) {
                 if (bb + 2 < nb) {
                     tile[0][grp][gl] = decode(pre);
                     pre = fetch(bb + 3);
                     __syncwarp();
-                    ISSUE(wa, 0);
+                    ISSUE(wa, ea, 0);
                 }
-                CONSUME(wb, 1);
+                CONSUME(wb, eb);
                 __syncwarp();
             }
         }
@@ -814,8 +817,9 @@ __global__ void __launch_bounds__(K4_THREADS, PIPE ? 4 : 10) k_winM(const ccj_mo
             tile[0][grp][gl] = d;
             __syncwarp();
             int4 w[WB];
-            ISSUE(w, 0);
-            CONSUME(w, 0);
+            int ec[WB];
+            ISSUE(w, ec, 0);
+            CONSUME(w, ec);
         }
     }
 #undef ISSUE
