@@ -831,24 +831,32 @@ __global__ void __launch_bounds__(K4_THREADS, PIPE ? 4 : 10) k_winM(const ccj_mo
 }
 
 // same-cell assembly in the reference's order (src/pseudo_loop.cc:85-127) from the partial minima
+// layout tables read straight from global memory (L1-resident): k_final needs a dozen entries with block-uniform
+// indices, not worth staging in shared memory
+struct LayTab {
+    const int *p;
+    __device__ __forceinline__ int operator[](int x) const { return __ldg(p + x); }
+};
 __global__ void __launch_bounds__(K4_THREADS, 8) k_final(const ccj_model *__restrict__ M, const ccj_seq *__restrict__ seqs, int t, int tail) {
-    __shared__ int s_tet[K4_MAXN + 4];
-    __shared__ int s_cb[K4_MAXN + 4];
-    __shared__ int s_hh[K4_MAXN + 4];   // HH4
-    __shared__ int s_cw[K4_MAXN + 4];   // CbW4
     const ccj_seq q = seqs[blockIdx.z];
     const int n = q.n;
     if (n - t - 2 < 1) return;
-    {
-        const int m0 = n - t - 2;
-        if ((int)(blockIdx.x * K4_THREADS) >= m0 * (m0 + 1) / 2) return;
-    }
-    for (int x = threadIdx.x; x <= n; x += K4_THREADS) {
-        s_hh[x] = __ldg(&q.lay[3 * (n + 1) + x]);
-        s_cw[x] = __ldg(&q.lay[4 * (n + 1) + x]);
-    }
+    const LayTab s_tet{q.lay}, s_cb{q.lay + (n + 1)}, s_hh{q.lay + 3 * (n + 1)}, s_cw{q.lay + 4 * (n + 1)};
     Cell C;
-    if (!cell_setup(q, t, blockIdx.y, blockIdx.x, s_tet, s_cb, C)) return;
+    {   // decode of the thread's cell (cell_setup without the shared tables)
+        const int m = n - t - 2, ncell = m * (m + 1) / 2;
+        const int p = blockIdx.x * K4_THREADS + threadIdx.x;
+        if (p >= ncell) return;
+        int r = (int)(((2 * m + 1) - sqrtf((float)((2 * m + 1) * (2 * m + 1) - 8 * p))) * 0.5f);
+        r = max(0, min(r, m - 1));
+        while (r > 0 && r * (2 * m + 1 - r) / 2 > p) --r;
+        while ((r + 1) * (2 * m - r) / 2 <= p) ++r;
+        C.n = n; C.m = m; C.a = blockIdx.y; C.b = t - C.a;
+        C.i = r + 1;
+        C.j = C.i + C.a; C.k = C.j + 2 + (p - r * (2 * m + 1 - r) / 2); C.l = C.k + C.b;
+        C.p = p;
+        C.c = C.a * ncell + p;
+    }
     const int a = C.a, b = C.b, i = C.i, j = C.j, k = C.k, l = C.l;
     const int16_t *__restrict__ t4 = q.t4;
     const int64_t st4 = q.stride4;
@@ -992,7 +1000,11 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_final(const ccj_model *__rest
     const int vPfO = PUT(T_PfromO, min(min(L2.PfO, R4.PfO), min(vPL + PB, vPR + PB)));
     const int vPK = PUT(T_PK, min(min(L1.PK, R3.PK), min(min(vPL + PB, vPM + PB), min(vPR + PB, vPO + PB))));
     w4[(int64_t)T_MPP * st4 + off0] = (int16_t)min(vPL, vPR);
-    w4[(int64_t)T_PKG * st4 + ccj_pkg_idx(n, i, j, k, l)] = (int16_t)vPK;  // scattered: one store per cell
+    {   // ccj_pkg_idx(n,i,j,k,l) through the layout tables: block (i,l) starts at Cb(i-2) + Tet(l-i-2)
+        const int sp = l - i, g = k - j;
+        const int pkg = (i >= 2 ? s_cb[i - 2] : 0) + s_tet[sp - 2] + ((sp * (sp - 1) - (sp - g + 1) * (sp - g + 2)) >> 1) + (j - i);
+        w4[(int64_t)T_PKG * st4 + pkg] = (int16_t)vPK;  // scattered: one store per cell
+    }
     {   // window copies (layouts in ccj_types.h); PLW is coalesced, PRW / PMW are one scattered store per cell
         const int slab4 = s_cw[b] + s_hh[n - b - 2] - s_hh[mloc] + h4m;
         q.plw[4 * (int64_t)(slab4 - H4(mloc - i + 1)) + (n - b - k)] = (int16_t)vPL;
