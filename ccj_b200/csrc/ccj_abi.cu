@@ -557,6 +557,8 @@ int ccj_batch_fetch(ccj_ctx *ctx, ccj_result *results, int32_t *pairs, char *str
         const int32_t *st = reinterpret_cast<const int32_t *>(ctx->h_stage + p.out_off);
         const int32_t *W = st + CCJ_STATUS_INTS;
         const int32_t *pr = W + (n + 1);
+        if (st[5] != 0)  // k_prep met an interior-loop energy outside int16: the packed window lists cannot hold this model
+            return fail(ctx, CCJ_ERR_STATE, "energy model outside the range of the tuned kernels (set CCJ_FILL_GENERIC=1)");
         ccj_result &r = results[s];
         r.energy_dcal = W[n];
         r.status = st[0];

@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(256) k_prep_lay(const ccj_model *M, const ccj_
         int acc = 0;
         for (int s = 0; s <= n; ++s) { q.pmstart[s] = acc; acc += s_row[s]; }
         q.pmstart[n + 1] = acc;
+        q.status[6] = 1;   // the tuned fill is running: layout tables and T_PKG will be valid for the traceback
     }
     __syncthreads();
     for (int s = wid; s <= n; s += nw) {

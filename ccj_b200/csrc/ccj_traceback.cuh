@@ -12,6 +12,7 @@
 // the reference's evaluation order, and the winner is the lexicographic minimum (value, position),
 // which is exactly "first strictly smaller wins".
 #pragma once
+#include <math.h>
 #include "ccj_cells4.cuh"
 
 // node types (src/constants.hh:21-73)
@@ -313,10 +314,41 @@ CCJ_HD void ccj_tb_node(ccj_tb &T, const Par &par, int ni, int nj, int nk, int n
             // candidates (j,d,k) in lexicographic order; position packed as ((j-i)*s + (d-i))*s + (k-i)
             const int s = l - i + 1;
             ccj_best b = {INF, -1};
-            for (int j = i; j < l; ++j)
-                for (int d = j + 1; d < l; ++d)
-                    for (int k = d + 1 + L; k < l; k += NL)
-                        ccj_cand(b, ccj_P_term(c, i, l, j, d, k), ((j - i) * s + (d - i)) * s + (k - i));
+            if (c.q.status[6] == 1) {
+                // the tuned fill left the layout tables and the second PK copy (T_PKG): walk, per j, the flattened
+                // (delta=k-d, d) triangle like k_P_tuned -- the second factor is one contiguous run, the first one
+                // contiguous per row -- 8 consecutive terms per lane with all 16 loads in flight.  Same candidates,
+                // same (value, position) order as the loops below.
+                const int *lay = c.q.lay;
+                const int n1 = n + 1, ri = i - 1;
+                const int16_t *F = ccj_t4(c, T_PK), *Gt = ccj_t4(c, T_PKG);
+                for (int j = i; j <= l - 3; ++j) {
+                    const int Lr = l - j - 2, T = Lr * (Lr + 1) / 2, ua = n - (j - i) - 2;
+                    const int16_t *G = Gt + (lay[n1 + j - 1] + lay[Lr - 1]);
+                    for (int q0 = L * 8; q0 < T; q0 += NL * 8) {
+                        int r = (int)(((2 * Lr + 1) - sqrtf((float)((2 * Lr + 1) * (2 * Lr + 1) - 8 * q0))) * 0.5f);
+                        r = r < 0 ? 0 : (r > Lr - 1 ? Lr - 1 : r);
+                        while (r > 0 && r * (2 * Lr + 1 - r) / 2 > q0) --r;
+                        while ((r + 1) * (2 * Lr - r) / 2 <= q0) ++r;
+                        int kk = q0 - r * (2 * Lr + 1 - r) / 2;
+                        int idx[8], ord[8], val[8];
+                        for (int e = 0; e < 8; ++e) {
+                            const int m1 = ua - r, d = j + 1 + kk, k = d + r + 1;
+                            idx[e] = lay[n1 + r] - lay[m1] + ((ri * (2 * m1 + 2 - i)) >> 1) + kk;
+                            ord[e] = ((j - i) * s + (d - i)) * s + (k - i);
+                            if (++kk == Lr - r) { kk = 0; if (r < Lr - 1) ++r; }
+                        }
+                        for (int e = 0; e < 8; ++e) val[e] = q0 + e < T ? (int)F[idx[e]] + (int)G[q0 + e] : INF;
+                        for (int e = 0; e < 8; ++e)
+                            if (q0 + e < T) ccj_cand(b, val[e], ord[e]);
+                    }
+                }
+            } else {
+                for (int j = i; j < l; ++j)
+                    for (int d = j + 1; d < l; ++d)
+                        for (int k = d + 1 + L; k < l; k += NL)
+                            ccj_cand(b, ccj_P_term(c, i, l, j, d, k), ((j - i) * s + (d - i)) * s + (k - i));
+            }
             b = par.argmin(b);
             int best_j = 0, best_d = 0, best_k = 0;
             if (b.ord >= 0) {

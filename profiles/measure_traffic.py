@@ -26,10 +26,12 @@ for r in rows[1:]:
     per[name][r[im]] += v
     if r[im] == "gpu__time_duration.sum":
         launches[name] += 1
-dram = sum(k["dram__bytes_read.sum"] + k["dram__bytes_write.sum"] for k in per.values())
+GAP = ("k_roles", "k_winLR", "k_winM", "k_final")
+gap = {k: v for k, v in per.items() if k.startswith(GAP)}
+dram = sum(k["dram__bytes_read.sum"] + k["dram__bytes_write.sum"] for k in gap.values())
 alg = sum(ccj_b200.count_terms(s)["bytes_4d"] for s in bench.workload(0, count))
 out = {"dram_bytes": dram, "algorithmic_bytes": alg, "ratio": dram / alg,
-       "source": f"ncu dram__bytes_read+write over all {sum(launches.values())} gap-table launches of one fill of "
+       "source": f"ncu dram__bytes_read+write over all {sum(launches[k] for k in gap)} gap-table launches of one fill of "
                  f"{count} x 150-nt workload sequence(s) (profiles/traffic_workload.py)",
        "per_kernel": {k: {"launches": launches[k], "dram_read_GB": v["dram__bytes_read.sum"] / 1e9,
                           "dram_write_GB": v["dram__bytes_write.sum"] / 1e9,
