@@ -239,17 +239,27 @@ void enqueue_fill(ccj_ctx *ctx, ccj::LaunchDims d) {
     const int last_level = nm - 3;
     if (last_level >= 0) cudaStreamWaitEvent(sw, evPrep, 0);
     cudaStreamWaitEvent(s2, evPrep, 0);
+    // k_roles(s) works on levels s..s+KF-1 and needs the 2D tables up to span s+KF-2: the 2D stream runs `lead`
+    // spans ahead of the levels (P(s') only needs PK of levels <= s'-3, so there is room)
+    const int KFL = ccj::fill4_fused_levels(), lead = KFL - 2 > 0 ? KFL - 2 : 0;
+    auto span_step = [&](int sp) {
+        if (sp >= nm) return;
+        if (sp >= 3 && sp - 3 <= last_level) cudaStreamWaitEvent(s2, evF[sp - 3], 0);
+        ccj::launch_P_tuned(M, Q, d, sp, s2);
+        ccj::launch_2d(M, Q, d, sp, s2);
+        cudaEventRecord(evD[sp], s2);
+    };
+    for (int sp = 0; sp < lead; ++sp) span_step(sp);
     for (int s = 0; s < nm; ++s) {
-        if (s >= 3 && s - 3 <= last_level) cudaStreamWaitEvent(s2, evF[s - 3], 0);
-        ccj::launch_P_tuned(M, Q, d, s, s2);
-        ccj::launch_2d(M, Q, d, s, s2);
-        cudaEventRecord(evD[s], s2);
+        span_step(s + lead);
         if (s <= last_level) {
             if (s >= 2) cudaStreamWaitEvent(sw, evF[s - 2], 0);
             ccj::launch_4d_windows(M, Q, d, s, sw);
             cudaEventRecord(evW[s], sw);
-            cudaStreamWaitEvent(s0, evD[s], 0);  // k_roles(s) also works on level s+1: 2D intervals up to span s
-            ccj::launch_4d_roles(M, Q, d, s, s0);
+            if (s % KFL == 0) {
+                cudaStreamWaitEvent(s0, evD[std::min(s + lead, nm - 1)], 0);
+                ccj::launch_4d_roles(M, Q, d, s, s0);
+            }
             cudaStreamWaitEvent(s0, evW[s], 0);
             ccj::launch_4d_final(M, Q, d, s, s0);
             cudaEventRecord(evF[s], s0);
@@ -493,13 +503,20 @@ int ccj_batch_fill_profiled(ccj_ctx *ctx, float *kernel_ms) {
     const bool tuned = use_tuned(d.nmax);
     ccj::launch_init(ctx->d_model, ctx->d_seqs, d, st); mark(3);
     if (tuned) { ccj::launch_prep(ctx->d_model, ctx->d_seqs, d, st); mark(3); }
-    for (int s = 0; s < d.nmax; ++s) {
-        if (s >= 3 && s <= d.nmax - 1) {
-            if (tuned) ccj::launch_P_tuned(ctx->d_model, ctx->d_seqs, d, s, st);
-            else ccj::launch_P(ctx->d_model, ctx->d_seqs, d, s, st);
+    // same order as enqueue_fill on one stream: the 2D tables run `lead` spans ahead of the levels
+    const int lead = tuned ? std::max(ccj::fill4_fused_levels() - 2, 0) : 0;
+    auto span_step = [&](int sp) {
+        if (sp >= d.nmax) return;
+        if (sp >= 3 && sp <= d.nmax - 1) {
+            if (tuned) ccj::launch_P_tuned(ctx->d_model, ctx->d_seqs, d, sp, st);
+            else ccj::launch_P(ctx->d_model, ctx->d_seqs, d, sp, st);
             mark(1);
         }
-        ccj::launch_2d(ctx->d_model, ctx->d_seqs, d, s, st); mark(2);
+        ccj::launch_2d(ctx->d_model, ctx->d_seqs, d, sp, st); mark(2);
+    };
+    for (int sp = 0; sp < lead; ++sp) span_step(sp);
+    for (int s = 0; s < d.nmax; ++s) {
+        span_step(s + lead);
         if (d.nmax - s - 2 >= 1) {
             if (tuned) {
                 ccj::launch_4d_roles(ctx->d_model, ctx->d_seqs, d, s, st); mark(0);

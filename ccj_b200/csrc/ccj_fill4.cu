@@ -239,7 +239,7 @@ __device__ __forceinline__ bool cell_setup(const ccj_seq &q, int t, int a, int b
 #define TB(tbl) (t4 + (int64_t)(tbl) * st4)
 #define OFF(aa, bb, ii, kx) (s_cb[bb] - s_tet[n - (aa) - (bb)-2] + ((((ii)-1) * (2 * (n - (aa) - (bb)-2) + 2 - (ii))) >> 1) + ((kx) - (ii) - (aa)-2))
 #ifndef U4
-#define U4 3
+#define U4 2
 #endif
 
 // ---- the four split-point roles: accumulators and the add-mins of ONE split point -------------------------------
@@ -297,14 +297,18 @@ __device__ __forceinline__ void r4_term(AccR4 &A, const int4 &r, const int4 &w) 
     r4_first(A, r, w);
 }
 
-// Split-point roles of TWO levels per launch.  A record X(i,d,k,l) that role L1 reads for the cell (i,j,k,l) of
-// level t is the very record the cell (i,j+1,k,l) of level t+1 needs at the same split point, only with the 2D
-// interval (d+1,j+1) instead of (d+1,j); likewise (i-1,j,k,l) for L2, (i,j,k-1,l) for R3 and (i,j,k,l+1) for R4.
-// Launched for even t, a thread therefore keeps two sets of accumulators: its own cell (all split points, sources
-// of levels <= t-1) and its level-t+1 partner (the same split points; the one remaining split point, whose source
-// is the level-t cell itself, is added by k_final(t+1)).  Every record is fetched from HBM once per two levels.
+// Split-point roles of KF consecutive levels per launch.  A record X(i,d,k,l) that role L1 reads for the cell
+// (i,j,k,l) of level t is the very record the cells (i,j+1,k,l), (i,j+2,k,l) of levels t+1, t+2 need at the same
+// split point, only with the 2D interval (d+1,j+f) instead of (d+1,j); likewise (i-f,j,k,l) for L2, (i,j,k-f,l)
+// for R3 and (i,j,k,l+f) for R4.  Launched for t = 0 mod KF, a thread therefore keeps KF sets of accumulators:
+// its own cell (all split points: sources of levels <= t-1) and its partners on levels t+1..t+KF-1 (the same split
+// points; their remaining <= f split points, whose sources are cells of levels t..t+f-1, are added by k_final).
+// Every record is fetched from HBM once per KF levels.
+#ifndef KF
+#define KF 3
+#endif
 #ifndef ROLES_MINB
-#define ROLES_MINB 8
+#define ROLES_MINB 7
 #endif
 __global__ void __launch_bounds__(K4_THREADS, ROLES_MINB) k_roles(const ccj_model *__restrict__ M, const ccj_seq *__restrict__ seqs, int t) {
     __shared__ int s_tet[K4_MAXN + 4];
@@ -324,175 +328,184 @@ __global__ void __launch_bounds__(K4_THREADS, ROLES_MINB) k_roles(const ccj_mode
     const int n1 = n + 1;
     const int INF = CCJ_INF;
     const int64_t ss = q.scratch_stride;
-    int16_t *__restrict__ sc = q.scratch + (int64_t)(t & 1) * Q_COUNT * ss + C.c;
-    // the level-t+1 partner: slab (a+1,b) for L1/L2, (a,b+1) for R3/R4, m2 = m-1 rows
-    const int m2 = m - 1, kk = k - j - 2;
-    const int ncell2 = m2 * (m2 + 1) / 2;
-    int16_t *__restrict__ sc2 = q.scratch + (int64_t)((t + 1) & 1) * Q_COUNT * ss;
+    const int kk = k - j - 2;
+    // scratch slot of the partner on level t+f: plane (t+f) mod KF, slab aa, row ii, position pp of a triangle with m-f rows
+    auto slot = [&](int f, int aa, int ii, int pp) -> int16_t * {
+        const int mf = m - f;
+        return q.scratch + (int64_t)((t + f) % KF) * Q_COUNT * ss + (int64_t)aa * (mf * (mf + 1) / 2) + (((ii - 1) * (2 * mf + 2 - ii)) >> 1) + pp;
+    };
 #define SAVE(id, v) sc[(int64_t)(id) * ss] = sat16(v)
-#define SAVE2(id, v) sc2[(int64_t)(id) * ss] = sat16(v)
-#define ROW2(ii) ((((ii)-1) * (2 * m2 + 2 - (ii))) >> 1)
 
     if (role == ROLE_L1) {
-        AccL1 A = {INF, INF, INF, INF, INF, INF, INF}, A2 = A;
-        const bool two = m2 >= 1 && kk >= 1;   // partner (i,j+1,k,l)
+        AccL1 A[KF];
+#pragma unroll
+        for (int f = 0; f < KF; ++f) A[f] = {INF, INF, INF, INF, INF, INF, INF};
         if (a >= 1) {
             const int *__restrict__ G = reinterpret_cast<const int *>(q.g1);
-            {  // d=i
+            {  // d=i, 2D interval (i+1, j+f)
                 const R12 r = ldr12(G, OFF(0, b, i, k));
-                l1_first(A, r, __ldg(&W3[(a - 1) * n1 + i + 1]));
-                l1_first(A2, r, __ldg(&W3[a * n1 + i + 1]));
+#pragma unroll
+                for (int f = 0; f < KF; ++f) l1_first(A[f], r, __ldg(&W3[(a - 1 + f) * n1 + i + 1]));
             }
             const int ub = n - b - 2, cbb = s_cb[b], ri = i - 1, kc = k - i - 2;
             int ap = 1;
             for (; ap + U4 <= a; ap += U4) {
                 R12 r[U4];
-                int4 w[U4], w2[U4];
+                int4 w[KF][U4];
 #pragma unroll
                 for (int u = 0; u < U4; ++u) {
                     const int m1 = ub - ap - u;
                     r[u] = ldr12(G, cbb - s_tet[m1] + ((ri * (2 * m1 + 2 - i)) >> 1) + (kc - ap - u));
-                    w[u] = __ldg(&W3[(a - ap - u - 1) * n1 + i + ap + u + 1]);   // (d+1, j)
-                    w2[u] = __ldg(&W3[(a - ap - u) * n1 + i + ap + u + 1]);      // (d+1, j+1)
+#pragma unroll
+                    for (int f = 0; f < KF; ++f) w[f][u] = __ldg(&W3[(a - ap - u - 1 + f) * n1 + i + ap + u + 1]);   // (d+1, j+f)
                 }
 #pragma unroll
-                for (int u = 0; u < U4; ++u) { l1_term(A, r[u], w[u]); l1_term(A2, r[u], w2[u]); }
+                for (int u = 0; u < U4; ++u)
+#pragma unroll
+                    for (int f = 0; f < KF; ++f) l1_term(A[f], r[u], w[f][u]);
             }
             for (; ap < a; ++ap) {
                 const int m1 = ub - ap;
                 const R12 r = ldr12(G, cbb - s_tet[m1] + ((ri * (2 * m1 + 2 - i)) >> 1) + (kc - ap));
-                l1_term(A, r, __ldg(&W3[(a - ap - 1) * n1 + i + ap + 1]));
-                l1_term(A2, r, __ldg(&W3[(a - ap) * n1 + i + ap + 1]));
+#pragma unroll
+                for (int f = 0; f < KF; ++f) l1_term(A[f], r, __ldg(&W3[(a - ap - 1 + f) * n1 + i + ap + 1]));
             }
         }
-        SAVE(Q_PK1, A.PK); SAVE(Q_PfL2, A.PfL); SAVE(Q_PfM, A.PfM); SAVE(Q_PLm00a, A.PLm00); SAVE(Q_PLm01, A.PLm01);
-        SAVE(Q_PLm10a, A.PLm10); SAVE(Q_PMm00a, A.PMm00);
-        if (two) {
-            sc2 += (int64_t)(a + 1) * ncell2 + ROW2(i) + kk - 1;
-            SAVE2(Q_PK1, A2.PK); SAVE2(Q_PfL2, A2.PfL); SAVE2(Q_PfM, A2.PfM); SAVE2(Q_PLm00a, A2.PLm00);
-            SAVE2(Q_PLm01, A2.PLm01); SAVE2(Q_PLm10a, A2.PLm10); SAVE2(Q_PMm00a, A2.PMm00);
-        }
+#pragma unroll
+        for (int f = 0; f < KF; ++f)
+            if (m - f >= 1 && kk >= f) {   // partner (i,j+f,k,l)
+                int16_t *sc = slot(f, a + f, i, kk - f);
+                SAVE(Q_PK1, A[f].PK); SAVE(Q_PfL2, A[f].PfL); SAVE(Q_PfM, A[f].PfM); SAVE(Q_PLm00a, A[f].PLm00);
+                SAVE(Q_PLm01, A[f].PLm01); SAVE(Q_PLm10a, A[f].PLm10); SAVE(Q_PMm00a, A[f].PMm00);
+            }
     } else if (role == ROLE_L2) {
-        AccL2 A = {INF, INF, INF, INF, INF, INF, INF}, A2 = A;
-        const bool two = m2 >= 1 && i >= 2;    // partner (i-1,j,k,l)
+        AccL2 A[KF];
+#pragma unroll
+        for (int f = 0; f < KF; ++f) A[f] = {INF, INF, INF, INF, INF, INF, INF};
         if (a >= 1) {
             const int *__restrict__ G = reinterpret_cast<const int *>(q.g2);
-            {  // d=j
+            {  // d=j, 2D interval (i-f, j-1)
                 const R12 r = ldr12(G, OFF(0, b, j, k));
-                l2_first(A, r, __ldg(&W3[(a - 1) * n1 + i]));
-                l2_first(A2, r, __ldg(&W3[a * n1 + i - 1]));
+#pragma unroll
+                for (int f = 0; f < KF; ++f) l2_first(A[f], r, __ldg(&W3[(a - 1 + f) * n1 + i - f]));
             }
             const int ub = n - b - 2, cbb = s_cb[b], kc = k - j - 2;
             int ap = 1;
             for (; ap + U4 <= a; ap += U4) {
                 R12 r[U4];
-                int4 w[U4], w2[U4];
+                int4 w[KF][U4];
 #pragma unroll
                 for (int u = 0; u < U4; ++u) {
                     const int d = i + ap + u, mm = ub - (a - ap - u);
                     r[u] = ldr12(G, cbb - s_tet[mm] + (((d - 1) * (2 * mm + 2 - d)) >> 1) + kc);
-                    w[u] = __ldg(&W3[(ap + u - 1) * n1 + i]);       // (i, d-1)
-                    w2[u] = __ldg(&W3[(ap + u) * n1 + i - 1]);      // (i-1, d-1)
+#pragma unroll
+                    for (int f = 0; f < KF; ++f) w[f][u] = __ldg(&W3[(ap + u - 1 + f) * n1 + i - f]);   // (i-f, d-1)
                 }
 #pragma unroll
-                for (int u = 0; u < U4; ++u) { l2_term(A, r[u], w[u]); l2_term(A2, r[u], w2[u]); }
+                for (int u = 0; u < U4; ++u)
+#pragma unroll
+                    for (int f = 0; f < KF; ++f) l2_term(A[f], r[u], w[f][u]);
             }
             for (; ap < a; ++ap) {
                 const int d = i + ap, mm = ub - (a - ap);
                 const R12 r = ldr12(G, cbb - s_tet[mm] + (((d - 1) * (2 * mm + 2 - d)) >> 1) + kc);
-                l2_term(A, r, __ldg(&W3[(ap - 1) * n1 + i]));
-                l2_term(A2, r, __ldg(&W3[ap * n1 + i - 1]));
+#pragma unroll
+                for (int f = 0; f < KF; ++f) l2_term(A[f], r, __ldg(&W3[(ap - 1 + f) * n1 + i - f]));
             }
         }
-        SAVE(Q_PfL1, A.PfL); SAVE(Q_PfO1, A.PfO); SAVE(Q_PLm00b, A.PLm00); SAVE(Q_PLm10b, A.PLm10); SAVE(Q_PMm10a, A.PMm10);
-        SAVE(Q_POm00a, A.POm00); SAVE(Q_POm10a, A.POm10);
-        if (two) {
-            sc2 += (int64_t)(a + 1) * ncell2 + ROW2(i - 1) + kk;
-            SAVE2(Q_PfL1, A2.PfL); SAVE2(Q_PfO1, A2.PfO); SAVE2(Q_PLm00b, A2.PLm00); SAVE2(Q_PLm10b, A2.PLm10);
-            SAVE2(Q_PMm10a, A2.PMm10); SAVE2(Q_POm00a, A2.POm00); SAVE2(Q_POm10a, A2.POm10);
-        }
+#pragma unroll
+        for (int f = 0; f < KF; ++f)
+            if (m - f >= 1 && i - f >= 1) {   // partner (i-f,j,k,l)
+                int16_t *sc = slot(f, a + f, i - f, kk);
+                SAVE(Q_PfL1, A[f].PfL); SAVE(Q_PfO1, A[f].PfO); SAVE(Q_PLm00b, A[f].PLm00); SAVE(Q_PLm10b, A[f].PLm10);
+                SAVE(Q_PMm10a, A[f].PMm10); SAVE(Q_POm00a, A[f].POm00); SAVE(Q_POm10a, A[f].POm10);
+            }
     } else if (role == ROLE_R3) {
-        AccR3 A = {INF, INF, INF, INF, INF, INF}, A2 = A;
-        const bool two = m2 >= 1 && kk >= 1;   // partner (i,j,k-1,l)
+        AccR3 A[KF];
+#pragma unroll
+        for (int f = 0; f < KF; ++f) A[f] = {INF, INF, INF, INF, INF, INF};
         if (b >= 1) {
             const int *__restrict__ G = reinterpret_cast<const int *>(q.g3);
-            {  // d=l
+            {  // d=l, 2D interval (k-f, l-1)
                 const R12 r = ldr12(G, OFF(a, 0, i, l));
-                r3_first(A, r, __ldg(&W3[(b - 1) * n1 + k]));
-                r3_first(A2, r, __ldg(&W3[b * n1 + k - 1]));
+#pragma unroll
+                for (int f = 0; f < KF; ++f) r3_first(A[f], r, __ldg(&W3[(b - 1 + f) * n1 + k - f]));
             }
             const int ua = n - a - 2, ri = i - 1, kc = k - j - 2;
             int bq = 1;
             for (; bq + U4 <= b; bq += U4) {
                 R12 r[U4];
-                int4 w[U4], w2[U4];
+                int4 w[KF][U4];
 #pragma unroll
                 for (int u = 0; u < U4; ++u) {
                     const int b3 = b - bq - u, m3 = ua - b3;
                     r[u] = ldr12(G, s_cb[b3] - s_tet[m3] + ((ri * (2 * m3 + 2 - i)) >> 1) + (kc + bq + u));
-                    w[u] = __ldg(&W3[(bq + u - 1) * n1 + k]);       // (k, d-1)
-                    w2[u] = __ldg(&W3[(bq + u) * n1 + k - 1]);      // (k-1, d-1)
+#pragma unroll
+                    for (int f = 0; f < KF; ++f) w[f][u] = __ldg(&W3[(bq + u - 1 + f) * n1 + k - f]);   // (k-f, d-1)
                 }
 #pragma unroll
-                for (int u = 0; u < U4; ++u) { r3_term(A, r[u], w[u]); r3_term(A2, r[u], w2[u]); }
+                for (int u = 0; u < U4; ++u)
+#pragma unroll
+                    for (int f = 0; f < KF; ++f) r3_term(A[f], r[u], w[f][u]);
             }
             for (; bq < b; ++bq) {
                 const int b3 = b - bq, m3 = ua - b3;
                 const R12 r = ldr12(G, s_cb[b3] - s_tet[m3] + ((ri * (2 * m3 + 2 - i)) >> 1) + (kc + bq));
-                r3_term(A, r, __ldg(&W3[(bq - 1) * n1 + k]));
-                r3_term(A2, r, __ldg(&W3[bq * n1 + k - 1]));
+#pragma unroll
+                for (int f = 0; f < KF; ++f) r3_term(A[f], r, __ldg(&W3[(bq - 1 + f) * n1 + k - f]));
             }
         }
-        SAVE(Q_PK3, A.PK); SAVE(Q_PfR1, A.PfR); SAVE(Q_PfMp, A.PfMp); SAVE(Q_PRm00a, A.PRm00); SAVE(Q_PRm10, A.PRm10);
-        SAVE(Q_PMm00b, A.PMm00);
-        if (two) {
-            sc2 += (int64_t)a * ncell2 + ROW2(i) + kk - 1;
-            SAVE2(Q_PK3, A2.PK); SAVE2(Q_PfR1, A2.PfR); SAVE2(Q_PfMp, A2.PfMp); SAVE2(Q_PRm00a, A2.PRm00);
-            SAVE2(Q_PRm10, A2.PRm10); SAVE2(Q_PMm00b, A2.PMm00);
-        }
+#pragma unroll
+        for (int f = 0; f < KF; ++f)
+            if (m - f >= 1 && kk >= f) {   // partner (i,j,k-f,l)
+                int16_t *sc = slot(f, a, i, kk - f);
+                SAVE(Q_PK3, A[f].PK); SAVE(Q_PfR1, A[f].PfR); SAVE(Q_PfMp, A[f].PfMp); SAVE(Q_PRm00a, A[f].PRm00);
+                SAVE(Q_PRm10, A[f].PRm10); SAVE(Q_PMm00b, A[f].PMm00);
+            }
     } else {
-        AccR4 A = {INF, INF, INF, INF, INF, INF, INF, INF, INF}, A2 = A;
-        const bool two = m2 >= 1 && l + 1 <= n;   // partner (i,j,k,l+1)
+        AccR4 A[KF];
+#pragma unroll
+        for (int f = 0; f < KF; ++f) A[f] = {INF, INF, INF, INF, INF, INF, INF, INF, INF};
         if (b >= 1) {
             const int4 *__restrict__ G = reinterpret_cast<const int4 *>(q.g4);
-            {  // d=k
+            {  // d=k, 2D interval (k+1, l+f)
                 const int4 r = __ldg(&G[OFF(a, 0, i, k)]);
-                r4_first(A, r, __ldg(&W3[(b - 1) * n1 + k + 1]));
-                r4_first(A2, r, __ldg(&W3[b * n1 + k + 1]));
+#pragma unroll
+                for (int f = 0; f < KF; ++f) r4_first(A[f], r, __ldg(&W3[(b - 1 + f) * n1 + k + 1]));
             }
             const int ua = n - a - 2, ri = i - 1, kc = k - j - 2;
             int bq = 1;
             for (; bq + U4 <= b; bq += U4) {
-                int4 r[U4], w[U4], w2[U4];
+                int4 r[U4], w[KF][U4];
 #pragma unroll
                 for (int u = 0; u < U4; ++u) {
                     const int b4 = bq + u, m4 = ua - b4;
                     r[u] = __ldg(&G[s_cb[b4] - s_tet[m4] + ((ri * (2 * m4 + 2 - i)) >> 1) + kc]);
-                    w[u] = __ldg(&W3[(b - b4 - 1) * n1 + k + b4 + 1]);   // (d+1, l)
-                    w2[u] = __ldg(&W3[(b - b4) * n1 + k + b4 + 1]);      // (d+1, l+1)
+#pragma unroll
+                    for (int f = 0; f < KF; ++f) w[f][u] = __ldg(&W3[(b - b4 - 1 + f) * n1 + k + b4 + 1]);   // (d+1, l+f)
                 }
 #pragma unroll
-                for (int u = 0; u < U4; ++u) { r4_term(A, r[u], w[u]); r4_term(A2, r[u], w2[u]); }
+                for (int u = 0; u < U4; ++u)
+#pragma unroll
+                    for (int f = 0; f < KF; ++f) r4_term(A[f], r[u], w[f][u]);
             }
             for (; bq < b; ++bq) {
                 const int m4 = ua - bq;
                 const int4 r = __ldg(&G[s_cb[bq] - s_tet[m4] + ((ri * (2 * m4 + 2 - i)) >> 1) + kc]);
-                r4_term(A, r, __ldg(&W3[(b - bq - 1) * n1 + k + bq + 1]));
-                r4_term(A2, r, __ldg(&W3[(b - bq) * n1 + k + bq + 1]));
+#pragma unroll
+                for (int f = 0; f < KF; ++f) r4_term(A[f], r, __ldg(&W3[(b - bq - 1 + f) * n1 + k + bq + 1]));
             }
         }
-        SAVE(Q_PfR2, A.PfR); SAVE(Q_PfO2, A.PfO); SAVE(Q_PRm00b, A.PRm00); SAVE(Q_PRm01, A.PRm01); SAVE(Q_PMm01, A.PMm01);
-        SAVE(Q_PMm10b, A.PMm10); SAVE(Q_POm00b, A.POm00); SAVE(Q_POm01, A.POm01); SAVE(Q_POm10b, A.POm10);
-        if (two) {
-            sc2 += (int64_t)a * ncell2 + ROW2(i) + kk;
-            SAVE2(Q_PfR2, A2.PfR); SAVE2(Q_PfO2, A2.PfO); SAVE2(Q_PRm00b, A2.PRm00); SAVE2(Q_PRm01, A2.PRm01);
-            SAVE2(Q_PMm01, A2.PMm01); SAVE2(Q_PMm10b, A2.PMm10); SAVE2(Q_POm00b, A2.POm00); SAVE2(Q_POm01, A2.POm01);
-            SAVE2(Q_POm10b, A2.POm10);
-        }
+#pragma unroll
+        for (int f = 0; f < KF; ++f)
+            if (m - f >= 1 && l + f <= n) {   // partner (i,j,k,l+f)
+                int16_t *sc = slot(f, a, i, kk);
+                SAVE(Q_PfR2, A[f].PfR); SAVE(Q_PfO2, A[f].PfO); SAVE(Q_PRm00b, A[f].PRm00); SAVE(Q_PRm01, A[f].PRm01);
+                SAVE(Q_PMm01, A[f].PMm01); SAVE(Q_PMm10b, A[f].PMm10); SAVE(Q_POm00b, A[f].POm00); SAVE(Q_POm01, A[f].POm01);
+                SAVE(Q_POm10b, A[f].POm10);
+            }
     }
 #undef SAVE
-#undef SAVE2
-#undef ROW2
 }
 
 #define WB 8      // window candidates in flight per lane (FENCE8 assumes 8)
@@ -866,41 +879,42 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_final(const ccj_model *__rest
     auto H4 = [](int x) { return ((x >> 2) + 1) * (2 * (x >> 2) + (x & 3)); };
     const int bp = M->bp_penalty, cp = M->cp_penalty, PB = M->PB_penalty, apbp = M->ap_penalty + M->bp_penalty;
     const int64_t ss = q.scratch_stride;
-    const int16_t *__restrict__ sc = q.scratch + (int64_t)(t & 1) * Q_COUNT * ss + C.c;
+    const int16_t *__restrict__ sc = q.scratch + (int64_t)(t % KF) * Q_COUNT * ss + C.c;
 #define GET(id) ((int)__ldg(sc + (int64_t)(id) * ss))
     const int off0 = OFF(a, b, i, k);
-    // partial minima of the four split-point roles.  tail (odd levels): k_roles(t-1) left them for the sources of
-    // levels <= t-2 (nothing for a role without split points); the one split point per role whose source is a
-    // level-(t-1) cell is added here.
+    // partial minima of the four split-point roles.  tail = t mod KF: k_roles(t-tail) left them for the sources
+    // of levels <= t-tail-1 (nothing for a role whose arm is shorter than tail: no partner there); the last `tail`
+    // split points of each role, whose sources are cells of levels t-tail..t-1, are added here.
     AccL1 L1 = {INF, INF, INF, INF, INF, INF, INF};
     AccL2 L2 = {INF, INF, INF, INF, INF, INF, INF};
     AccR3 R3 = {INF, INF, INF, INF, INF, INF};
     AccR4 R4 = {INF, INF, INF, INF, INF, INF, INF, INF, INF};
-    if (!tail || a >= 1) {
+    if (a >= tail) {
         L1 = {GET(Q_PK1), GET(Q_PfL2), GET(Q_PfM), GET(Q_PLm00a), GET(Q_PLm01), GET(Q_PLm10a), GET(Q_PMm00a)};
         L2 = {GET(Q_PfL1), GET(Q_PfO1), GET(Q_PLm00b), GET(Q_PLm10b), GET(Q_PMm10a), GET(Q_POm00a), GET(Q_POm10a)};
     }
-    if (!tail || b >= 1) {
+    if (b >= tail) {
         R3 = {GET(Q_PK3), GET(Q_PfR1), GET(Q_PfMp), GET(Q_PRm00a), GET(Q_PRm10), GET(Q_PMm00b)};
         R4 = {GET(Q_PfR2), GET(Q_PfO2), GET(Q_PRm00b), GET(Q_PRm01), GET(Q_PMm01), GET(Q_PMm10b), GET(Q_POm00b), GET(Q_POm01), GET(Q_POm10b)};
     }
     if (tail) {
         const int4 *__restrict__ W3 = reinterpret_cast<const int4 *>(q.w3);
-        if (a >= 1) {
-            const R12 r1 = ldr12(reinterpret_cast<const int *>(q.g1), OFF(a - 1, b, i, k));      // X(i,j-1,k,l) with (j,j)
-            const int4 w1 = __ldg(&W3[j]);
-            if (a == 1) l1_first(L1, r1, w1); else l1_term(L1, r1, w1);
-            const R12 r2 = ldr12(reinterpret_cast<const int *>(q.g2), OFF(a - 1, b, i + 1, k));  // X(i+1,j,k,l) with (i,i)
-            const int4 w2 = __ldg(&W3[i]);
-            if (a == 1) l2_first(L2, r2, w2); else l2_term(L2, r2, w2);
+        // x = arm of the source cell (0 = the boundary split point of the role, its *_first form)
+        for (int x = max(0, a - tail); x < a; ++x) {
+            const int4 wl = __ldg(&W3[(a - x - 1) * n1 + i + x + 1]);                                   // (d+1, j), d=i+x
+            const R12 r1 = ldr12(reinterpret_cast<const int *>(q.g1), OFF(x, b, i, k));              // X(i,i+x,k,l)
+            if (x == 0) l1_first(L1, r1, wl); else l1_term(L1, r1, wl);
+            const int4 wr = __ldg(&W3[(a - x - 1) * n1 + i]);                                           // (i, d-1), d=j-x
+            const R12 r2 = ldr12(reinterpret_cast<const int *>(q.g2), OFF(x, b, j - x, k));          // X(j-x,j,k,l)
+            if (x == 0) l2_first(L2, r2, wr); else l2_term(L2, r2, wr);
         }
-        if (b >= 1) {
-            const R12 r3 = ldr12(reinterpret_cast<const int *>(q.g3), OFF(a, b - 1, i, k + 1));  // X(i,j,k+1,l) with (k,k)
-            const int4 w3 = __ldg(&W3[k]);
-            if (b == 1) r3_first(R3, r3, w3); else r3_term(R3, r3, w3);
-            const int4 r4 = __ldg(reinterpret_cast<const int4 *>(q.g4) + OFF(a, b - 1, i, k));   // X(i,j,k,l-1) with (l,l)
-            const int4 w4 = __ldg(&W3[l]);
-            if (b == 1) r4_first(R4, r4, w4); else r4_term(R4, r4, w4);
+        for (int x = max(0, b - tail); x < b; ++x) {
+            const int4 wl = __ldg(&W3[(b - x - 1) * n1 + k]);                                           // (k, d-1), d=l-x
+            const R12 r3 = ldr12(reinterpret_cast<const int *>(q.g3), OFF(a, x, i, l - x));          // X(i,j,l-x,l)
+            if (x == 0) r3_first(R3, r3, wl); else r3_term(R3, r3, wl);
+            const int4 wr = __ldg(&W3[(b - x - 1) * n1 + k + x + 1]);                                   // (d+1, l), d=k+x
+            const int4 r4 = __ldg(reinterpret_cast<const int4 *>(q.g4) + OFF(a, x, i, k));           // X(i,j,k,k+x)
+            if (x == 0) r4_first(R4, r4, wr); else r4_term(R4, r4, wr);
         }
     }
     int16_t *w4 = q.t4;
@@ -1127,7 +1141,7 @@ static bool level_dims(LaunchDims d, int t, int &bx) {
 }
 void launch_4d_roles(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st) {
     int bx;
-    if ((t & 1) == 0 && level_dims(d, t, bx)) k_roles<<<dim3(bx, t + 1, d.nseq * 4), K4_THREADS, 0, st>>>(M, seqs, t);  // levels t and t+1
+    if (t % KF == 0 && level_dims(d, t, bx)) k_roles<<<dim3(bx, t + 1, d.nseq * 4), K4_THREADS, 0, st>>>(M, seqs, t);  // levels t..t+KF-1
 }
 void launch_4d_windows(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st) {
     const int nm = d.nmax, m = nm - t - 2;
@@ -1153,7 +1167,7 @@ void launch_4d_windows(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, in
 }
 void launch_4d_final(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st) {
     int bx;
-    if (level_dims(d, t, bx)) k_final<<<dim3(bx, t + 1, d.nseq), K4_THREADS, 0, st>>>(M, seqs, t, t & 1);
+    if (level_dims(d, t, bx)) k_final<<<dim3(bx, t + 1, d.nseq), K4_THREADS, 0, st>>>(M, seqs, t, t % KF);
 }
 void launch_4d_tuned(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st) {
     launch_4d_roles(M, seqs, d, t, st);
@@ -1161,7 +1175,8 @@ void launch_4d_tuned(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int 
     launch_4d_final(M, seqs, d, t, st);
 }
 
-int fill4_partials() { return 2 * Q_COUNT; }  // two levels of partial minima (k_roles works on levels t and t+1)
+int fill4_partials() { return KF * Q_COUNT; }  // KF levels of partial minima (k_roles works on levels t..t+KF-1)
+int fill4_fused_levels() { return KF; }
 
 void launch_P_tuned(const ccj_model *, const ccj_seq *seqs, LaunchDims d, int s, cudaStream_t st) {
     if (s < 3 || s > d.nmax - 1) return;

@@ -154,8 +154,8 @@ int fill_launch_count(int nmax, bool tuned) {
     for (int s = 0; s < nmax; ++s) {
         if (s >= 3 && s <= nmax - 1) ++c;           // K_P
         ++c;                                        // K_2D
-        // level: split roles (even levels; they cover two), PL/PR windows, PM window (if any pair is short enough), assembly
-        if (nmax - s - 2 >= 1) c += tuned ? 2 + ((s & 1) == 0 ? 1 : 0) + (nmax - 1 - s > CCJ_TURN ? 1 : 0) : 1;
+        // level: split roles (every KF-th level; they cover KF), PL/PR windows, PM window (if any pair is short enough), assembly
+        if (nmax - s - 2 >= 1) c += tuned ? 2 + (s % fill4_fused_levels() == 0 ? 1 : 0) + (nmax - 1 - s > CCJ_TURN ? 1 : 0) : 1;
     }
     return c;
 }

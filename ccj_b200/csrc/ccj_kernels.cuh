@@ -31,6 +31,7 @@ void launch_4d_final(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int 
 void launch_P_tuned(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int s, cudaStream_t st);
 bool fill4_tuned_supported(int nmax);
 int fill4_partials();  // int16 partial minima per cell in the per-level scratch
+int fill4_fused_levels();  // KF: k_roles(t), t = 0 mod KF, covers levels t..t+KF-1 and needs the 2D tables up to span t+KF-2
 // exterior W (src/W_final.cc:68-77)
 void launch_W(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cudaStream_t st);
 // traceback, one warp per sequence
