@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(128) k_prep(const ccj_model *M, const ccj_seq 
         const int ij = ccj_idx2(n, i, j);
         if (lane == 0) c.q.estP[ij] = (j - i >= 2) ? ccj_e_stP(M, S, i, j) : CCJ_INF;
         const int slot = ccj_tri(i, j);
-        int nin = 0, nout = 0;
+        int nin = 0, nout = 0, nneg = 0;
         if (ccj_can_pair(c, i, j)) {
             uint32_t *il = c.q.inlist + (int64_t)slot * CCJ_WIN_IN;
             uint2 *ol = reinterpret_cast<uint2 *>(c.q.outlist) + (int64_t)slot * CCJ_WIN_OUT;
@@ -138,22 +138,34 @@ __global__ void __launch_bounds__(128) k_prep(const ccj_model *M, const ccj_seq 
                     if (x <= j - i - 1 && dp >= d + 4 && ccj_can_pair(c, d, dp))
                         ok = pack_entry(ccj_e_intP(M, S, i, d, dp, j), x, y, ent, c.q.status);
                 }
-                unsigned bal = __ballot_sync(0xffffffffu, ok);
+                const unsigned bal = __ballot_sync(0xffffffffu, ok);
                 if (ok) il[nin + __popc(bal & ((1u << lane) - 1))] = ent;
                 nin += __popc(bal);
-                // outside (i,j) as inner pair (j,k):=(i,j): d=i-x, dp=j+y  (get_PMiloop window)
-                ok = false;
-                int pm4 = 0;
-                if (s < CCJ_WIN) {
-                    const int d = i - x, dp = j + y;
-                    if (d >= 1 && dp <= n && ccj_can_pair(c, d, dp)) {
-                        ok = pack_entry(ccj_e_intP(M, S, d, i, j, dp), x, y, ent, c.q.status);
-                        if (n <= K4_MAXN) pm4 = c.q.pmlev4[d * n1 + dp];
+            }
+            // outside (i,j) as inner pair (j,k):=(i,j): d=i-x, dp=j+y  (get_PMiloop window).  Two sweeps: the
+            // candidates with a negative energy first (k_winM needs the mask halves of PMW only for those)
+            for (int sweep = 0; sweep < 2; ++sweep) {
+                for (int s0 = 0; s0 < CCJ_WIN; s0 += 32) {
+                    const int s = s0 + lane;
+                    const int x = s / 29 + 1, y = s % 29 + 1;
+                    uint32_t ent = 0;
+                    bool ok = false;
+                    int pm4 = 0;
+                    if (s < CCJ_WIN) {
+                        const int d = i - x, dp = j + y;
+                        if (d >= 1 && dp <= n && ccj_can_pair(c, d, dp)) {
+                            const int e = ccj_e_intP(M, S, d, i, j, dp);
+                            if ((e < 0) == (sweep == 0)) {
+                                ok = pack_entry(e, x, y, ent, c.q.status);
+                                if (n <= K4_MAXN) pm4 = c.q.pmlev4[d * n1 + dp];
+                            }
+                        }
                     }
+                    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+                    if (ok) ol[nout + __popc(bal & ((1u << lane) - 1))] = make_uint2(ent, (uint32_t)pm4);
+                    nout += __popc(bal);
                 }
-                bal = __ballot_sync(0xffffffffu, ok);
-                if (ok) ol[nout + __popc(bal & ((1u << lane) - 1))] = make_uint2(ent, (uint32_t)pm4);
-                nout += __popc(bal);
+                if (sweep == 0) nneg = nout;
             }
             // zero entries up to the next multiple of 8: the window kernels read whole 8-entry batches
             if (lane < 8) {
@@ -163,7 +175,7 @@ __global__ void __launch_bounds__(128) k_prep(const ccj_model *M, const ccj_seq 
         }
         if (lane == 0) {
             c.q.incnt[slot] = nin;
-            c.q.outcnt[slot] = nout;
+            c.q.outcnt[slot] = nout | (nneg << 16);   // all candidates | those with a negative energy (listed first)
         }
     }
 }
@@ -743,28 +755,30 @@ __global__ void __launch_bounds__(K4_THREADS, PIPE ? 4 : 10) k_winM(const ccj_mo
     const int own = t * wtot4 + __ldg(&q.pmlev4[j * n1 + k]) - qlo;   // the row's own (not yet written) quads
     int acc0 = WIN_INF2, acc1 = WIN_INF2;
     if (gact && t >= 2 && j >= 2 && k < n) {
-        // PM(i,j-1,k+1,l) + e_stP(j-1,k+1) for a>=1, b>=1: unlike the list candidates this one may read the end
-        // cells of its source row (a'=0, b'=0), so it is masked by position, once per lane, in 32 bits
-        const int lo1 = max(j - t + 1, ilo) - 1, cnt1 = min(j - 1, ihi) - 1 - lo1 + 1;
-        if (cnt1 > 0 && p0 + 3 >= lo1 && p0 < lo1 + cnt1) {
-            const int qls = (max(j - t + 1, 1) - 1) >> 2;
-            const int4 w = ldq4(src, (t - 2) * wtot4 + __ldg(&q.pmlev4[(j - 1) * n1 + k + 1]) - qls);
-            const int e = __ldg(&q.estP[(k - j + 2) * n1 + (j - 1)]);
-            const int dl = p0 - lo1;
-            const int m0 = lo16(w.x) + ((unsigned)dl < (unsigned)cnt1 ? e : INF);
-            const int m1 = hi16(w.x) + ((unsigned)(dl + 1) < (unsigned)cnt1 ? e : INF);
-            const int m2 = lo16(w.z) + ((unsigned)(dl + 2) < (unsigned)cnt1 ? e : INF);
-            const int m3 = hi16(w.z) + ((unsigned)(dl + 3) < (unsigned)cnt1 ? e : INF);
-            acc0 = pack_sat(m0, m1);
-            acc1 = pack_sat(m2, m3);
+        // PM(i,j-1,k+1,l) + e_stP(j-1,k+1) for a>=1, b>=1.  Unlike the list candidates this one may read the end cells
+        // of its source row (a'=0, b'=0), which PMW blanks out: read the main PM table, once per lane, in 32 bits
+        const int e = __ldg(&q.estP[(k - j + 2) * n1 + (j - 1)]);
+        const int16_t *__restrict__ pPM = q.t4 + (int64_t)T_PM * q.stride4;
+        const int *__restrict__ lay = q.lay;
+        int v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = p0 + 1 + u, a = j - i, b = t - a;
+            v[u] = INF;
+            if (i >= ilo && i <= ihi && a >= 1 && b >= 1) {   // source (i, j-1, k+1, l): slab (a-1, b-1), m' = m+2
+                const int mm = m + 2;
+                v[u] = ld16(pPM, __ldg(&lay[n1 + b - 1]) - __ldg(&lay[mm]) + (((i - 1) * (2 * mm + 2 - i)) >> 1) + (k - j)) + e;
+            }
         }
+        acc0 = pack_sat(v[0], v[1]);
+        acc1 = pack_sat(v[2], v[3]);
     }
     const int slot = ccj_tri(j, k);
     const uint2 *__restrict__ lst = reinterpret_cast<const uint2 *>(q.outlist) + (int64_t)slot * CCJ_WIN_OUT;
-    const int cnt = gact ? __ldg(&q.outcnt[slot]) : 0;
-    const int nb = (__reduce_max_sync(0xffffffffu, cnt) + WGRP - 1) / WGRP;   // batches of 8 candidates, warp-uniform
-    // lane gl fetches / decodes entry 8b+gl of its group's list
-    auto fetch = [&](int bb) -> uint2 { return bb * WGRP + gl < cnt ? __ldg(&lst[bb * WGRP + gl]) : make_uint2(0u, 0xffffffffu); };
+    const int cnts = gact ? __ldg(&q.outcnt[slot]) : 0;
+    const int cnt = cnts & 0xffff, nneg = cnts >> 16;   // the first nneg candidates have a negative energy
+    // lane gl fetches / decodes entry e of its group's list (entries [lo,hi) belong to the current loop)
+    auto fetch = [&](int e, int hi) -> uint2 { return e < hi ? __ldg(&lst[e]) : make_uint2(0u, 0xffffffffu); };
     auto decode = [&](uint2 L) -> int4 {
         if (L.y != 0xffffffffu) {
             const int x = (L.x >> 16) & 0xff, y = L.x >> 24, e = (int)(int16_t)(L.x & 0xffff);
@@ -777,35 +791,59 @@ __global__ void __launch_bounds__(K4_THREADS, PIPE ? 4 : 10) k_winM(const ccj_mo
         }
         return make_int4(own, 0x7fff0000, 0x7fffffff, 0);  // no candidate: no quad is inside its (empty) source row
     };
-    // one LDS.128 per candidate: (source row start, energy | clamp << 16, first quad, quads - 1)
+    // one LDS.128 per candidate: (source row start, energy | clamp << 16, first quad, quads - 1).
+    // Quads outside the source row belong to other rows: no load, value 32767.
+    // (1) candidates with a negative energy: value + energy of a blanked cell (32767) would look finite, so the mask
+    //     halves are loaded too (16 bytes per lane) and the candidate is max(value+energy, mask)
+    {
+        const int nbn = (__reduce_max_sync(0xffffffffu, nneg) + WGRP - 1) / WGRP;
+        for (int bb = 0; bb < nbn; ++bb) {
+            const int4 d = decode(fetch(bb * WGRP + gl, nneg));
+            __syncwarp();
+            tile[0][grp][gl] = d;
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < WB; ++u) {
+                const int4 d2 = tile[0][grp][u];
+                const bool ok = (unsigned)(qd - d2.z) <= (unsigned)d2.w;
+                const int4 w = ok ? ldq4(src, d2.x) : make_int4(WIN_INF2, WIN_INF2, WIN_INF2, WIN_INF2);
+                const int ee = (int)__byte_perm((unsigned)d2.y, 0u, 0x1010), cc = (int)__byte_perm((unsigned)d2.y, 0u, 0x3232);
+                acc0 = min2(acc0, addmax2(min2(w.x, cc), ee, w.z));
+                acc1 = min2(acc1, addmax2(min2(w.y, cc), ee, w.w));
+            }
+        }
+    }
+    // (2) all other candidates (energy >= 0, the bulk): 32767 + energy saturates to 32767 by itself, so only the value
+    //     halves are loaded (8 bytes per lane) and a candidate is two packed instructions per word
+    const int nb = (__reduce_max_sync(0xffffffffu, cnt - nneg) + WGRP - 1) / WGRP;   // batches of 8, warp-uniform
+    const int2 *srcv = reinterpret_cast<const int2 *>(src);
 #define ISSUE(W_, EC_, buf)                                                                       \
     _Pragma("unroll") for (int u = 0; u < WB; ++u) {                                              \
         const int4 d2 = tile[buf][grp][u];                                                        \
-        /* quads outside the source row belong to other rows: no load, "not a source" masks */    \
         const bool ok = (unsigned)(qd - d2.z) <= (unsigned)d2.w;                                  \
-        W_[u] = ok ? ldq4(src, d2.x) : make_int4(WIN_INF2, WIN_INF2, WIN_INF2, WIN_INF2);         \
+        W_[u] = ok ? ldq(srcv, 2 * d2.x) : make_int2(WIN_INF2, WIN_INF2);                         \
         EC_[u] = d2.y;                                                                            \
     }
 #define CONSUME(W_, EC_)                                                                          \
     _Pragma("unroll") for (int u = 0; u < WB; ++u) {                                              \
         const int ee = (int)__byte_perm((unsigned)EC_[u], 0u, 0x1010), cc = (int)__byte_perm((unsigned)EC_[u], 0u, 0x3232); \
-        acc0 = min2(acc0, addmax2(min2(W_[u].x, cc), ee, W_[u].y));                               \
-        acc1 = min2(acc1, addmax2(min2(W_[u].z, cc), ee, W_[u].w));                               \
+        acc0 = addmin2(min2(W_[u].x, cc), ee, acc0);                                              \
+        acc1 = addmin2(min2(W_[u].y, cc), ee, acc1);                                              \
     }
     if (PIPE) {  // see k_winLR
-        int4 wa[WB], wb[WB];
+        int2 wa[WB], wb[WB];
         int ea[WB], eb[WB];
         uint2 pre = make_uint2(0u, 0xffffffffu);
         if (nb > 0) {
-            tile[0][grp][gl] = decode(fetch(0));
-            pre = fetch(1);
+            tile[0][grp][gl] = decode(fetch(nneg + gl, cnt));
+            pre = fetch(nneg + WGRP + gl, cnt);
             __syncwarp();
             ISSUE(wa, ea, 0);
         }
         for (int bb = 0; bb < nb; bb += 2) {
             if (bb + 1 < nb) {
                 tile[1][grp][gl] = decode(pre);
-                pre = fetch(bb + 2);
+                pre = fetch(nneg + (bb + 2) * WGRP + gl, cnt);
                 __syncwarp();
                 ISSUE(wb, eb, 1);
             }
@@ -814,7 +852,7 @@ __global__ void __launch_bounds__(K4_THREADS, PIPE ? 4 : 10) k_winM(const ccj_mo
             if (bb + 1 < nb) {
                 if (bb + 2 < nb) {
                     tile[0][grp][gl] = decode(pre);
-                    pre = fetch(bb + 3);
+                    pre = fetch(nneg + (bb + 3) * WGRP + gl, cnt);
                     __syncwarp();
                     ISSUE(wa, ea, 0);
                 }
@@ -823,14 +861,14 @@ __global__ void __launch_bounds__(K4_THREADS, PIPE ? 4 : 10) k_winM(const ccj_mo
             }
         }
     } else {
-        uint2 pre = fetch(0);
+        uint2 pre = fetch(nneg + gl, cnt);
         for (int bb = 0; bb < nb; ++bb) {
             const int4 d = decode(pre);
-            pre = fetch(bb + 1);
+            pre = fetch(nneg + (bb + 1) * WGRP + gl, cnt);
             __syncwarp();
             tile[0][grp][gl] = d;
             __syncwarp();
-            int4 w[WB];
+            int2 w[WB];
             int ec[WB];
             ISSUE(w, ec, 0);
             CONSUME(w, ec);
@@ -1024,10 +1062,11 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_final(const ccj_model *__rest
         const int slab4 = s_cw[b] + s_hh[n - b - 2] - s_hh[mloc] + h4m;
         q.plw[4 * (int64_t)(slab4 - H4(mloc - i + 1)) + (n - b - k)] = (int16_t)vPL;
         q.prw[4 * (int64_t)(slab4 - H4(mloc - kr)) + (i - 1)] = (int16_t)vPR;
-        {   // value and, two halves further, the "is a window source" mask (a>=1 and b>=1)
-            int16_t *pq = q.pmw + 8 * ((int64_t)t * q.wtot4 + (pmrow >> 2)) + (pmrow & 1) + 2 * (pmrow & 2);
-            pq[0] = (int16_t)vPM;
-            pq[2] = (a >= 1 && b >= 1) ? (int16_t)-32768 : (int16_t)32767;
+        {   // value (blanked to 32767 where the PM window may not read it) and, four halves further, the mask
+            int16_t *pq = q.pmw + 8 * ((int64_t)t * q.wtot4 + (pmrow >> 2)) + (pmrow & 3);   // quad = v0 v1 v2 v3 m0 m1 m2 m3
+            const bool srcok = a >= 1 && b >= 1;
+            pq[0] = srcok ? (int16_t)vPM : (int16_t)32767;
+            pq[4] = srcok ? (int16_t)-32768 : (int16_t)32767;
         }
     }
     // read-group records (layout in ccj_types.h); consecutive cells -> consecutive records, coalesced

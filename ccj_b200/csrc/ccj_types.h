@@ -193,8 +193,10 @@ CCJ_HD int64_t ccj_pkg_idx(int n, int i, int j, int k, int l) {
 //        HH4(x) = sum_{m<=x} H4(m),  CbW4(b) = sum_{b'<b} HH4(n-b'-2)
 //   PMW: level-major; row (j,k) of level t holds i=j-a, position (i-1) - 4*((max(j-t,1)-1)>>2)
 //        (window keeps i,l; source row (j-x,k+y) of level t-x-y); row pitch W4(j,k) quads, see ccj_pmw_w4.
-//        A PMW quad is 16 bytes: v0 v1 m0 m1 v2 v3 m2 m3, m = -32768 for a cell the window may read (a>=1, b>=1)
-//        and 32767 otherwise (end cells, padding), so that max(value+energy, mask) masks two cells at once
+//        A PMW quad is 16 bytes: v0 v1 v2 v3 m0 m1 m2 m3.  For a cell the window may read (a>=1, b>=1) v = PM and
+//        m = -32768; for the end cells and the padding v = m = 32767.  Candidates with an energy >= 0 only load the
+//        value half (32767 + energy saturates by itself); for the few negative ones max(value+energy, mask) masks
+//        two cells per instruction.
 CCJ_HD int64_t ccj_h4(int64_t x) { const int64_t q = x >> 2, r = x & 3; return (q + 1) * (2 * q + r); }
 inline int64_t ccj_hh4(int x) { int64_t s = 0; for (int m = 1; m <= x; ++m) s += ccj_h4(m); return s; }
 inline int64_t ccj_winlr_quads(int n) { int64_t s = 0; for (int b = 0; b <= n - 3; ++b) s += ccj_hh4(n - b - 2); return s; }
