@@ -31,6 +31,18 @@ enum { TAB_T4 = 0, TAB_G1, TAB_G2, TAB_G3, TAB_G4, TAB_T2, TAB_W3, TAB_ESTP, TAB
        TAB_COUNT };
 size_t tab_bytes_uncached(int n, int which) {
     const size_t tri = (size_t)n * (n - 1) / 2 + 1;
+    // sequences beyond the tuned kernels' range run the generic level kernel, which only needs the 22 tables, the
+    // 2D tables and the traceback buffers: without the tuned copies such a sequence still fits one GPU up to n~530
+    if (!ccj::fill4_tuned_supported(n)) {
+        switch (which) {
+            case TAB_T4: return align_up((size_t)ccj_cells4(n) * CCJ_NT4 * sizeof(int16_t) + 16, 256);
+            case TAB_T2:
+            case TAB_W3:
+            case TAB_FTYPE:
+            case TAB_TBSTACK: break;
+            default: return 256;
+        }
+    }
     switch (which) {
         case TAB_T4: return align_up((size_t)ccj_cells4(n) * CCJ_NT4_STORE * sizeof(int16_t) + 16, 256);
         case TAB_G1:

@@ -17,6 +17,7 @@
 #include "ccj_cells4.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace ccj {
 
@@ -889,7 +890,10 @@ struct LayTab {
     const int *p;
     __device__ __forceinline__ int operator[](int x) const { return __ldg(p + x); }
 };
-__global__ void __launch_bounds__(K4_THREADS, 8) k_final(const ccj_model *__restrict__ M, const ccj_seq *__restrict__ seqs, int t, int tail) {
+#ifndef FINAL_MINB
+#define FINAL_MINB 8
+#endif
+__global__ void __launch_bounds__(K4_THREADS, FINAL_MINB) k_final(const ccj_model *__restrict__ M, const ccj_seq *__restrict__ seqs, int t, int tail) {
     const ccj_seq q = seqs[blockIdx.z];
     const int n = q.n;
     if (n - t - 2 < 1) return;
@@ -1092,7 +1096,9 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_final(const ccj_model *__rest
 // contiguous run; the first factor is contiguous per row (row i of slab (j-i, delta-1)).  A warp walks the
 // flattened triangle of its j, 8 consecutive terms per lane: no lane idles on a short row, and the row base of
 // the first factor is recomputed only when a lane's run crosses into the next row.
+#ifndef KP_RUN
 #define KP_RUN 8
+#endif
 __global__ void __launch_bounds__(256) k_P_tuned(const ccj_seq *__restrict__ seqs, int s, int nj) {
     __shared__ int s_tet[K4_MAXN + 4];
     __shared__ int s_cb[K4_MAXN + 4];
@@ -1170,7 +1176,15 @@ void launch_prep(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cudaStre
     k_prep<<<dim3(d.nmax - 1, d.nseq), 128, 0, st>>>(M, seqs);
 }
 
-bool fill4_tuned_supported(int nmax) { return nmax <= K4_MAXN; }
+// K4_MAXN, or less when CCJ_TUNED_MAXN is set (read once; lets the tests drive the beyond-the-range path cheaply)
+bool fill4_tuned_supported(int nmax) {
+    static const int limit = [] {
+        const char *e = getenv("CCJ_TUNED_MAXN");
+        const int v = e ? atoi(e) : K4_MAXN;
+        return v < K4_MAXN ? v : K4_MAXN;
+    }();
+    return nmax <= limit;
+}
 
 static bool level_dims(LaunchDims d, int t, int &bx) {
     const int m = d.nmax - t - 2;

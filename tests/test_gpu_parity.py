@@ -178,3 +178,25 @@ def test_cuda_matches_cpu_restatement(par, dangles, no_gu):
         for name, want in tables.items():
             got = ctx.table2_hash(0, name) if name in ccj_b200.TABLE2 else ctx.table4_hash(0, name)
             assert got == want, (name, seqs[0])
+
+
+def test_beyond_the_tuned_range(golden_folds):
+    """Sequences longer than the tuned kernels' limit get the slim buffer plan (22 tables only) and the generic
+    64-bit-index kernels.  CCJ_TUNED_MAXN lowers the limit (read once per process, hence the subprocess) so that
+    the path is exercised on golden 60-80-nt folds instead of a 450-nt one."""
+    import json
+    import os
+    import sys
+    recs = [r for r in golden_folds if len(r["seq"]) >= 60 and r["par"] == "rna_Turner04.par" and r["dangles"] == 2
+            and not r["extra"]][:6]
+    assert recs
+    code = (
+        "import json, sys; sys.path.insert(0, %r); import ccj_b200\n"
+        "seqs = json.loads(sys.stdin.read())\n"
+        "ctx = ccj_b200.Context(0, ccj_b200.default_par_file('rna_Turner04.par'), 2)\n"
+        "print(json.dumps([[f.returncode, f.stdout, f.stderr] for f in ctx.fold_batch(seqs)]))\n" % str(ROOT))
+    env = dict(os.environ, CCJ_TUNED_MAXN="50")
+    p = subprocess.run([sys.executable, "-c", code], input=json.dumps([r["seq"] for r in recs]), capture_output=True,
+                       text=True, env=env, check=True)
+    got = json.loads(p.stdout.strip().splitlines()[-1])
+    assert got == [[r["rc"], r["stdout"], r["stderr"]] for r in recs]
