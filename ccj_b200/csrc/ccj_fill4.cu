@@ -1,18 +1,20 @@
-// Tuned level-wavefront kernel for the 22 gap tables (sm_100a).
+// Tuned level-wavefront kernels for the 22 gap tables, compute_P and the tuned traceback scan (sm_100a).
 //
-// One launch = one DP level t=(j-i)+(l-k).  blockIdx.y -> a=j-i (b=t-a), blockIdx.z -> sequence,
-// threads walk the packed (i,k) triangle of slab (a,b), which is one contiguous run in every table
-// (layout in ccj_types.h) -> all 23 stores of a warp are full 64-byte lines.
+// A DP level is t=(j-i)+(l-k).  blockIdx.y -> a=j-i (b=t-a), threads walk the packed (i,k) triangle of slab (a,b),
+// which is one contiguous run in every table (layout in ccj_types.h) -> stores of a warp are full lines.
 //
-// The reference evaluates, per cell, 22 recurrences one after the other; each is a min over split
-// points d of  X(neighbour cell) + 2D-term  (src/pseudo_loop.cc:181-644).  Candidates only read cells of
-// LOWER levels, so their order is free.  We regroup them by the 4 access patterns
+// The reference evaluates, per cell, 22 recurrences one after the other; each is a min over split points d of
+// X(neighbour cell) + 2D-term  (src/pseudo_loop.cc:181-644).  Candidates only read cells of LOWER levels, so their
+// order is free.  They are regrouped by the 4 access patterns
 //     L1: X(i,d,k,l)   L2: X(d,j,k,l)   R3: X(i,j,d,l)   R4: X(i,j,k,d)
-// so that one offset computation and one 16-byte {WB,WP,WBP} load serve 5-7 tables, and apply the
-// same-cell terms afterwards in the reference's in-cell order (:85-127), which is what fixes the
-// "unset = 32767" reads.  The interior-loop windows (get_P{L,R,M}iloop, :682-773) walk per-pair lists of
-// pairable partners with pre-rounded energies instead of the 29x29 can_pair-gated scan.
-// Checked bit-for-bit against ccj_cell4d (generic version) and the reference's tables.
+// ("roles": one record load and one 16-byte {WB,WP,WBP} load serve 5-7 tables), evaluated for three levels per
+// launch (k_roles), and the same-cell terms are applied afterwards in the reference's in-cell order (:85-127),
+// which is what fixes the "unset = 32767" reads (k_final).  The interior-loop windows (get_P{L,R,M}iloop,
+// :682-773) walk per-pair lists of pairable partners with pre-rounded energies instead of the 29x29
+// can_pair-gated scan, over dedicated quad-aligned copies of PL/PR/PM with packed int16x2 arithmetic
+// (k_winLR, k_winM).  Kernels, in launch order per level: k_roles (every third level), k_winLR, k_winM, k_final;
+// per span: k_P_tuned, k_2d (ccj_kernels.cu); once per fill: k_prep_lay, k_fill_pmw, k_prep.
+// Checked bit-for-bit against ccj_cell4d (generic version), the reference's tables and the CPU restatement.
 #include "ccj_kernels.cuh"
 #include "ccj_cells4.cuh"
 
@@ -182,12 +184,12 @@ __global__ void __launch_bounds__(128) k_prep(const ccj_model *M, const ccj_seq 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Level kernels.  A cell's work is split over 7 independent "roles" (4 split-point groups, 3 interior
-// windows) that run as separate thread blocks of ONE launch and leave int16-saturated partial minima in a
-// per-level scratch; a second launch assembles the 22 tables in the reference's in-cell order.
-// Splitting keeps every role at <= 9 accumulators, so 4 split points can be in flight per thread (28-40
-// independent loads) at twice the occupancy of a monolithic cell kernel -- the monolithic version was
-// latency-bound (84 % long-scoreboard stalls, profiles/r1_notes.md).
+// Level kernels.  A cell's work is split over independent pieces -- 4 split-point "roles" (separate thread
+// blocks of k_roles) and the interior windows (k_winLR, k_winM, one level ahead on their own stream) -- that
+// leave int16-saturated partial minima in per-level scratch buffers; k_final assembles the 22 tables in the
+// reference's in-cell order.  Splitting keeps a role at <= 9 accumulators per level, which is what lets one
+// thread carry three levels at 7 blocks/SM -- a monolithic cell kernel was latency-bound (84 % long-scoreboard
+// stalls, profiles/r1_notes.md).
 // Saturating a partial at 32767 is exact: every later operation is +non-negative constant / min, and the
 // final store clamps at 32767 anyway (Matrix4D::set, src/matrices.hh:188-191).
 // ---------------------------------------------------------------------------------------------
@@ -198,7 +200,7 @@ enum {  // partial ids in the scratch
     Q_PfR2, Q_PfO2, Q_PRm00b, Q_PRm01, Q_PMm01, Q_PMm10b, Q_POm00b, Q_POm01, Q_POm10b,  // role R4
     Q_COUNT  // the window partials live in ccj_seq::wscr, in the window layouts
 };
-enum { ROLE_L1 = 0, ROLE_L2, ROLE_R3, ROLE_R4, ROLE_COUNT };
+enum { ROLE_L1 = 0, ROLE_L2, ROLE_R3, ROLE_R4 };
 
 // streaming read of a gap-table entry: read-only path, and ask L2 to fetch the whole 256-byte chunk -- the
 // neighbouring warps of the block need the adjacent 64-byte runs of the same slab row
@@ -521,9 +523,8 @@ __global__ void __launch_bounds__(K4_THREADS, ROLES_MINB) k_roles(const ccj_mode
 #undef SAVE
 }
 
-#define WB 8      // window candidates in flight per lane (FENCE8 assumes 8)
+#define WB 8      // window candidates in flight per lane (FENCE8X assumes 8)
 // keep the compiler from sinking the WB loads of a batch to their uses: all of them must be in flight together
-#define FENCE8(v) asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]))
 #define FENCE8X(v) asm volatile("" : "+r"(v[0].x), "+r"(v[1].x), "+r"(v[2].x), "+r"(v[3].x), "+r"(v[4].x), "+r"(v[5].x), "+r"(v[6].x), "+r"(v[7].x))
 #define WGRP 8    // lanes per run: one pass covers 8 quads = 32 cells
 #define WRUNS (K4_THREADS / WGRP)
