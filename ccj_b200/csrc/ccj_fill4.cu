@@ -1200,7 +1200,9 @@ void launch_4d_roles(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int 
 void launch_4d_windows(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st) {
     const int nm = d.nmax, m = nm - t - 2;
     if (m < 1) return;
-    const bool pipe = d.nseq < 4;  // few sequences: latency-bound, use the software-pipelined variants
+    // small waves are latency-bound: software-pipelined variants.  Measured break-even (B200): n^2 x sequences ~ 1.2e5
+    // (4 x 150 nt, 8 x 100 nt, 2 x 200 nt still gain; 8 x 150 nt, 16 x 100 nt lose)
+    const bool pipe = (long long)nm * nm * d.nseq < 120000;
     {   // PL / PR: at most m paired rows per slab, runs of up to m cells
         const int nchunk = (m + WRUNS - 1) / WRUNS, npass = (m + 4 * WGRP - 1) / (4 * WGRP);
         const dim3 grid(nchunk * npass, t + 1, d.nseq * 2);
