@@ -342,6 +342,8 @@ int ccj_model_load(ccj_ctx *ctx, const char *par_file, int dangles, int no_gu) {
         delete rp;
         return fail(ctx, CCJ_ERR_PARAMS, err);
     }
+    // the reference's reader prints its symmetry warnings while loading (vrna_message_warning, utils.c:180-196)
+    for (const std::string &w : rp->warnings) fprintf(stderr, "WARNING: %s\n", w.c_str());
     ccj::build_model(*rp, dangles, no_gu, *ctx->h_model);
     delete rp;
     CU(cudaSetDevice(ctx->device));
@@ -865,6 +867,7 @@ int ccj_model_text(const char *par_file, int dangles, int no_gu, const char *out
         delete rp;
         return CCJ_ERR_PARAMS;
     }
+    for (const std::string &w : rp->warnings) fprintf(stderr, "WARNING: %s\n", w.c_str());
     ccj_model *m = new ccj_model();
     ccj::build_model(*rp, dangles, no_gu, *m);
     FILE *f = fopen(out_path, "w");

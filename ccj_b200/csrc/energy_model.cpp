@@ -1,6 +1,8 @@
 // See energy_model.hpp for the reference locations this file replaces.
 #include "energy_model.hpp"
 
+#include <algorithm>
+
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -229,6 +231,8 @@ bool load_par_file(const char *path, RawParams &rp, std::string &err) {
     static const int d_dg[2] = {8, 5}, s_dg[2] = {1, 0};
 
     std::vector<int> scratch(8 * 8 * 5 * 5 * 5 * 5);
+    // enthalpy copies that check_symmetry looks at (start = INF everywhere, like row/column 0 of the defaults)
+    std::vector<int> stackdH, int11dH, int22dH;
     while (rd.next_line(line)) {
         char ident[256];
         if (sscanf(line.c_str(), "# %255s", ident) != 1) continue;
@@ -237,6 +241,7 @@ bool load_par_file(const char *path, RawParams &rp, std::string &err) {
         if (sec < 0) continue;  // "END" and unknown identifiers: nothing to read (io.c:484,664)
         bool ok = true;
         int *dst;
+        if (enth) std::fill(scratch.begin(), scratch.end(), CCJ_INF);
 #define TARGET(field) (enth ? scratch.data() : &rp.field)
         switch (sec) {
             case SEC_stack: dst = TARGET(stack[0][0]); ok = rd.read_slice(dst, d_stack, s_stack, p0, 2); break;
@@ -283,6 +288,61 @@ bool load_par_file(const char *path, RawParams &rp, std::string &err) {
             return false;
         }
         if (!enth) rp.present |= 1u << sec;
+        else if (sec == SEC_stack) stackdH.assign(scratch.begin(), scratch.begin() + 8 * 8);
+        else if (sec == SEC_int11) int11dH.assign(scratch.begin(), scratch.begin() + 8 * 8 * 5 * 5);
+        else if (sec == SEC_int22) int22dH.assign(scratch.begin(), scratch.begin() + 8 * 8 * 5 * 5 * 5 * 5);
+    }
+    // check_symmetry (io.c:1126-1178), same order and texts.  Sections the file does not hold keep the
+    // reference's built-in (symmetric) tables there; the int22 checks cover the entries a file provides
+    // (pairs 1..6, bases 1..4), the non-standard ones are derived maxima (update_nst).
+    char buf[160];
+    if (rp.present & (1u << SEC_stack))
+        for (int i = 0; i < 8; ++i)
+            for (int j = 0; j < 8; ++j)
+                if (rp.stack[i][j] != rp.stack[j][i]) rp.warnings.push_back("stacking energies not symmetric");
+    if (!stackdH.empty())
+        for (int i = 0; i < 8; ++i)
+            for (int j = 0; j < 8; ++j)
+                if (stackdH[i * 8 + j] != stackdH[j * 8 + i]) rp.warnings.push_back("stacking enthalpies not symmetric");
+    if (rp.present & (1u << SEC_int11))
+        for (int i = 0; i < 8; ++i)
+            for (int j = 0; j < 8; ++j)
+                for (int k = 0; k < 5; ++k)
+                    for (int l = 0; l < 5; ++l)
+                        if (rp.int11[i][j][k][l] != rp.int11[j][i][l][k]) {
+                            snprintf(buf, sizeof buf, "int11 energies not symmetric (%d,%d,%d,%d) (%d vs. %d)", i, j, k, l,
+                                     rp.int11[i][j][k][l], rp.int11[j][i][l][k]);
+                            rp.warnings.push_back(buf);
+                        }
+    if (!int11dH.empty()) {
+        auto at = [&](int i, int j, int k, int l) { return int11dH[((i * 8 + j) * 5 + k) * 5 + l]; };
+        for (int i = 0; i < 8; ++i)
+            for (int j = 0; j < 8; ++j)
+                for (int k = 0; k < 5; ++k)
+                    for (int l = 0; l < 5; ++l)
+                        if (at(i, j, k, l) != at(j, i, l, k)) rp.warnings.push_back("int11 enthalpies not symmetric");
+    }
+    if (rp.present & (1u << SEC_int22))
+        for (int i = 1; i < 7; ++i)
+            for (int j = 1; j < 7; ++j)
+                for (int k = 1; k < 5; ++k)
+                    for (int l = 1; l < 5; ++l)
+                        for (int m = 1; m < 5; ++m)
+                            for (int n = 1; n < 5; ++n)
+                                if (rp.int22[i][j][k][l][m][n] != rp.int22[j][i][m][n][k][l])
+                                    rp.warnings.push_back("int22 energies not symmetric");
+    if (!int22dH.empty()) {
+        auto at = [&](int i, int j, int k, int l, int m, int n) { return int22dH[((((i * 8 + j) * 5 + k) * 5 + l) * 5 + m) * 5 + n]; };
+        for (int i = 1; i < 7; ++i)
+            for (int j = 1; j < 7; ++j)
+                for (int k = 1; k < 5; ++k)
+                    for (int l = 1; l < 5; ++l)
+                        for (int m = 1; m < 5; ++m)
+                            for (int n = 1; n < 5; ++n)
+                                if (at(i, j, k, l, m, n) != at(j, i, m, n, k, l)) {
+                                    snprintf(buf, sizeof buf, "int22 enthalpies not symmetric: %d %d %d %d %d %d", i, j, k, l, m, n);
+                                    rp.warnings.push_back(buf);
+                                }
     }
     return true;
 }

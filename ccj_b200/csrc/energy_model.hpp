@@ -8,6 +8,7 @@
 //   src/ViennaRNA/pair_mat.h:80-155     make_pair_matrix (noGU)
 #pragma once
 #include <string>
+#include <vector>
 #include "ccj_types.h"
 
 namespace ccj {
@@ -29,11 +30,14 @@ struct RawParams {
     char Tetraloops[281], Triloops[241], Hexaloops[361];
     int Tetraloop_E[40], Triloop_E[40], Hexaloop_E[40];
     unsigned present;  // bit per section actually read
+    // check_symmetry() of the reference's reader (io.c:1126-1178): one line per asymmetric entry, in its order
+    std::vector<std::string> warnings;
     RawParams();
 };
 
 // Reads `path`. Returns false and sets `err` on I/O or syntax errors. Enthalpy sections are parsed
-// (to stay in sync with the line stream) and discarded: at 37 C the rescaling is the identity.
+// (to stay in sync with the line stream) and, except for the symmetry check, discarded: at 37 C the rescaling
+// is the identity.
 bool load_par_file(const char *path, RawParams &rp, std::string &err);
 
 // get_scaled_params at 37 C with the default model details (dangles=2 at scaling time, special_hp=1),

@@ -92,3 +92,22 @@ def test_bad_parameter_file(tmp_path, library):
     bad.write_text("## RNAfold parameter file v2.0\n# stack\n 1 2 three\n")
     with pytest.raises(ccj_b200.CCJError):
         ccj_b200.model_text(str(bad))
+
+
+def test_parameter_reader_symmetry_warnings(library, tmp_path):
+    """check_symmetry of the reference's reader (src/ViennaRNA/params/io.c:1126-1178): the Mathews-2004 DNA set makes
+    the reference print four "stacking enthalpies not symmetric" warnings on stderr, the RNA sets none."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); import ccj_b200; "
+            "ccj_b200.model_text(%r)") % (str(ROOT), "%s")
+    for par, want in [("dna_Matthews04.par", "WARNING: stacking enthalpies not symmetric\n" * 4),
+                      ("rna_Turner04.par", ""), ("rna_DirksPierce09.par", "")]:
+        p = subprocess.run([sys.executable, "-c", code % str(ROOT / "params" / par)], capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr
+        assert p.stderr == want, par
+        ref = ROOT / "oracle" / "_ref" / "CCJ"
+        if ref.exists() and par.startswith("dna"):
+            r = subprocess.run([str(ref), "--noConv", "-P", str(ROOT / "params" / par), "GCAACGATGACATACATCGCTAGTCGACGC"],
+                               capture_output=True, text=True)
+            assert r.stderr == want
