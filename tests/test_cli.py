@@ -68,8 +68,9 @@ def test_cli_input_conventions(cli):
     want = "GCAACGAUGACAUACAUCGCUAGUCGACGC\n....(((((.....)))))........... (-2.32)\n"  # DP09 default, SURVEY App. C
     assert run(cli, [], stdin="gcaacgatgacatacatcgctagtcgacgc\n") == (0, want, "")
     assert run(cli, ["GCAACGAUGACAUACAUCGCUAGUCGACGC", "ignored"]) == (0, want, "")
-    rc, out, _ = run(cli, ["--noConv", "GCAACGATGACATACATCGCTAGTCGACGC"])
+    rc, out, err = run(cli, ["--noConv", "GCAACGATGACATACATCGCTAGTCGACGC"])
     assert (rc, out) == (0, "GCAACGATGACATACATCGCTAGTCGACGC\n....(((((.....)))))........... (-4.4)\n")
+    assert err == "WARNING: stacking enthalpies not symmetric\n" * 4   # the reader's check_symmetry, like the reference
     # run from a directory without params/: the default file is cwd-relative, exactly like the reference
     assert run(cli, ["ACGU"], cwd="/tmp")[0] == 1
 
