@@ -294,7 +294,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="150-nt sequences per GPU per step")
+    ap.add_argument("--batch", type=int, default=48, help="150-nt sequences per GPU per step")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline sample")
     args = ap.parse_args()
     if args.impl == "reference":
