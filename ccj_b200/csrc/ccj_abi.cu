@@ -27,7 +27,7 @@ struct SeqPlan {
 
 // the per-sequence device buffers behind ccj_seq, in arena order
 enum { TAB_T4 = 0, TAB_G1, TAB_G2, TAB_G3, TAB_G4, TAB_T2, TAB_W3, TAB_ESTP, TAB_INLIST, TAB_OUTLIST, TAB_INCNT, TAB_OUTCNT, TAB_LAY, TAB_SCRATCH,
-       TAB_PLW, TAB_PRW, TAB_PMW, TAB_WSCR, TAB_PMLEV, TAB_PLIST, TAB_PCUM, TAB_PMLIST, TAB_PMSTART, TAB_FTYPE, TAB_TBSTACK,
+       TAB_PLW, TAB_PRW, TAB_PMW, TAB_PMM, TAB_WSCR, TAB_PMLEV, TAB_PLIST, TAB_PCUM, TAB_PMLIST, TAB_PMSTART, TAB_FTYPE, TAB_TBSTACK,
        TAB_COUNT };
 size_t tab_bytes_uncached(int n, int which) {
     const size_t tri = (size_t)n * (n - 1) / 2 + 1;
@@ -60,7 +60,8 @@ size_t tab_bytes_uncached(int n, int which) {
         case TAB_SCRATCH: return align_up((size_t)ccj_level_max(n) * ccj::fill4_partials() * sizeof(int16_t) + 64, 256);
         case TAB_PLW:
         case TAB_PRW: return align_up((size_t)ccj_winlr_quads(n) * 4 * sizeof(int16_t) + 64, 256);
-        case TAB_PMW: return align_up(((size_t)ccj_pmw_level_quads(n) * (size_t)(n > 2 ? n - 2 : 1) + 16) * 16, 256);  // 16 bytes per quad: 4 values + 4 masks
+        case TAB_PMW:
+        case TAB_PMM: return align_up(((size_t)ccj_pmw_level_quads(n) * (size_t)(n > 2 ? n - 2 : 1) + 16) * 8, 256);  // 8 bytes per quad: 4 values resp. 4 masks
         case TAB_WSCR: return align_up(((size_t)ccj_winlr_level_max(n) * 4 + (size_t)ccj_pmw_level_quads(n) * 8) * sizeof(int16_t) + 64, 256);
         case TAB_PMLEV: return align_up((size_t)(n + 1) * (n + 1) * sizeof(int32_t) + 64, 256);
         case TAB_PLIST: return align_up((size_t)(n + 1) * (n + 1) * sizeof(int32_t), 256);
@@ -443,6 +444,7 @@ int ccj_batch_prepare(ccj_ctx *ctx, const char *seqs, const int64_t *offsets, in
         q.plw = reinterpret_cast<int16_t *>(t + tab_offset(n, TAB_PLW));
         q.prw = reinterpret_cast<int16_t *>(t + tab_offset(n, TAB_PRW));
         q.pmw = reinterpret_cast<int16_t *>(t + tab_offset(n, TAB_PMW));
+        q.pmm = reinterpret_cast<int16_t *>(t + tab_offset(n, TAB_PMM));
         q.wscr = reinterpret_cast<int16_t *>(t + tab_offset(n, TAB_WSCR));
         q.wscr_lr = tab_sizes(n).wscr_lr;
         q.wtot4 = tab_sizes(n).wtot4;

@@ -711,14 +711,16 @@ __device__ __forceinline__ int4 ldq4(const int4 *p, int off) {
     return v;
 }
 
-// every entry of PMW starts as (32767, "not a source"): rows are padded and read past their ends
+// every entry of PMW / PMM starts as 32767 ("not a source"): rows are padded and read past their ends
 __global__ void __launch_bounds__(256) k_fill_pmw(const ccj_seq *seqs) {
     const ccj_seq q = seqs[blockIdx.y];
     if (q.n > K4_MAXN || q.n < 3) return;
-    const int64_t quads = (int64_t)q.wtot4 * (q.n - 2) + 16;
-    int4 *p = reinterpret_cast<int4 *>(q.pmw);
-    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < quads; x += (int64_t)gridDim.x * blockDim.x)
+    const int64_t pairs = ((int64_t)q.wtot4 * (q.n - 2) + 16) / 2;   // two 8-byte quads per int4
+    int4 *p = reinterpret_cast<int4 *>(q.pmw), *pm = reinterpret_cast<int4 *>(q.pmm);
+    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < pairs; x += (int64_t)gridDim.x * blockDim.x) {
         p[x] = make_int4(WIN_INF2, WIN_INF2, WIN_INF2, WIN_INF2);
+        pm[x] = make_int4(WIN_INF2, WIN_INF2, WIN_INF2, WIN_INF2);
+    }
 }
 
 // PM interior window (get_PMiloop, src/pseudo_loop.cc:752-773).  The partner list belongs to the INNER pair
@@ -751,8 +753,9 @@ __global__ void __launch_bounds__(K4_THREADS, PIPE ? 4 : 10) k_winM(const ccj_mo
     const bool gact = chunk * WRUNS + grp < nact && qlo + pass * WGRP <= qhi;  // the group has cells in this pass
     const int p0 = 4 * qd;                                     // i-1 of the lane's first cell
     const int wtot4 = q.wtot4;
-    const int4 *src = reinterpret_cast<const int4 *>(q.pmw) + qd;
-    asm volatile("" : "+l"(src));
+    const int2 *srcv = reinterpret_cast<const int2 *>(q.pmw) + qd;   // values
+    const int2 *srcm = reinterpret_cast<const int2 *>(q.pmm) + qd;   // mask halves, same index
+    asm volatile("" : "+l"(srcv));
     const int INF = CCJ_INF;
     const int own = t * wtot4 + __ldg(&q.pmlev4[j * n1 + k]) - qlo;   // the row's own (not yet written) quads
     int acc0 = WIN_INF2, acc1 = WIN_INF2;
@@ -808,22 +811,22 @@ __global__ void __launch_bounds__(K4_THREADS, PIPE ? 4 : 10) k_winM(const ccj_mo
             for (int u = 0; u < WB; ++u) {
                 const int4 d2 = tile[0][grp][u];
                 const bool ok = (unsigned)(qd - d2.z) <= (unsigned)d2.w;
-                const int4 w = ok ? ldq4(src, d2.x) : make_int4(WIN_INF2, WIN_INF2, WIN_INF2, WIN_INF2);
+                const int2 w = ok ? ldq(srcv, d2.x) : make_int2(WIN_INF2, WIN_INF2);
+                const int2 mk = ok ? ldq(srcm, d2.x) : make_int2(WIN_INF2, WIN_INF2);
                 const int ee = (int)__byte_perm((unsigned)d2.y, 0u, 0x1010), cc = (int)__byte_perm((unsigned)d2.y, 0u, 0x3232);
-                acc0 = min2(acc0, addmax2(min2(w.x, cc), ee, w.z));
-                acc1 = min2(acc1, addmax2(min2(w.y, cc), ee, w.w));
+                acc0 = min2(acc0, addmax2(min2(w.x, cc), ee, mk.x));
+                acc1 = min2(acc1, addmax2(min2(w.y, cc), ee, mk.y));
             }
         }
     }
     // (2) all other candidates (energy >= 0, the bulk): 32767 + energy saturates to 32767 by itself, so only the value
     //     halves are loaded (8 bytes per lane) and a candidate is two packed instructions per word
     const int nb = (__reduce_max_sync(0xffffffffu, cnt - nneg) + WGRP - 1) / WGRP;   // batches of 8, warp-uniform
-    const int2 *srcv = reinterpret_cast<const int2 *>(src);
 #define ISSUE(W_, EC_, buf)                                                                       \
     _Pragma("unroll") for (int u = 0; u < WB; ++u) {                                              \
         const int4 d2 = tile[buf][grp][u];                                                        \
         const bool ok = (unsigned)(qd - d2.z) <= (unsigned)d2.w;                                  \
-        W_[u] = ok ? ldq(srcv, 2 * d2.x) : make_int2(WIN_INF2, WIN_INF2);                         \
+        W_[u] = ok ? ldq(srcv, d2.x) : make_int2(WIN_INF2, WIN_INF2);                             \
         EC_[u] = d2.y;                                                                            \
     }
 #define CONSUME(W_, EC_)                                                                          \
@@ -1067,11 +1070,11 @@ __global__ void __launch_bounds__(K4_THREADS, FINAL_MINB) k_final(const ccj_mode
         const int slab4 = s_cw[b] + s_hh[n - b - 2] - s_hh[mloc] + h4m;
         q.plw[4 * (int64_t)(slab4 - H4(mloc - i + 1)) + (n - b - k)] = (int16_t)vPL;
         q.prw[4 * (int64_t)(slab4 - H4(mloc - kr)) + (i - 1)] = (int16_t)vPR;
-        {   // value (blanked to 32767 where the PM window may not read it) and, four halves further, the mask
-            int16_t *pq = q.pmw + 8 * ((int64_t)t * q.wtot4 + (pmrow >> 2)) + (pmrow & 3);   // quad = v0 v1 v2 v3 m0 m1 m2 m3
+        {   // value (blanked to 32767 where the PM window may not read it) and its mask half
+            const int64_t pe = 4 * (int64_t)t * q.wtot4 + pmrow;   // entry of this cell in PMW and PMM
             const bool srcok = a >= 1 && b >= 1;
-            pq[0] = srcok ? (int16_t)vPM : (int16_t)32767;
-            pq[4] = srcok ? (int16_t)-32768 : (int16_t)32767;
+            q.pmw[pe] = srcok ? (int16_t)vPM : (int16_t)32767;
+            q.pmm[pe] = srcok ? (int16_t)-32768 : (int16_t)32767;
         }
     }
     // read-group records (layout in ccj_types.h); consecutive cells -> consecutive records, coalesced

@@ -122,7 +122,7 @@ struct ccj_seq {
     int32_t *lay;        // layout tables, 5 arrays of n+1 ints: Tet(x), Cb(x), H4(x), HH4(x), CbW4(x)  (tuned path, n<=448)
     // copies of PL / PR / PM for the interior windows, rows padded to 4 entries so that a lane moves 4 cells
     // per 8-byte load ("window layouts" below); written by k_final, read by k_winLR / k_winM only
-    int16_t *plw, *prw, *pmw;
+    int16_t *plw, *prw, *pmw, *pmm;   // pmm: the mask halves of PMW (same quad index, separate array)
     int16_t *wscr;       // window partial minima in the same row layouts: [parity][PL,PR] x wscr_lr, then [parity] x 4*wtot4
     int64_t wscr_lr;     // entries of one PL/PR partial = largest padded level
     int32_t *pmlev4;     // (n+1)^2: quad offset of row (j,k) inside one PM level (ccj_pmw_quad)
@@ -193,10 +193,10 @@ CCJ_HD int64_t ccj_pkg_idx(int n, int i, int j, int k, int l) {
 //        HH4(x) = sum_{m<=x} H4(m),  CbW4(b) = sum_{b'<b} HH4(n-b'-2)
 //   PMW: level-major; row (j,k) of level t holds i=j-a, position (i-1) - 4*((max(j-t,1)-1)>>2)
 //        (window keeps i,l; source row (j-x,k+y) of level t-x-y); row pitch W4(j,k) quads, see ccj_pmw_w4.
-//        A PMW quad is 16 bytes: v0 v1 v2 v3 m0 m1 m2 m3.  For a cell the window may read (a>=1, b>=1) v = PM and
-//        m = -32768; for the end cells and the padding v = m = 32767.  Candidates with an energy >= 0 only load the
-//        value half (32767 + energy saturates by itself); for the few negative ones max(value+energy, mask) masks
-//        two cells per instruction.
+//        Every PMW quad (4 values, 8 bytes) has a quad of mask halves at the same index of a second array (PMM).
+//        For a cell the window may read (a>=1, b>=1) value = PM and mask = -32768; for the end cells and the padding
+//        both are 32767.  Candidates with an energy >= 0 only read PMW (32767 + energy saturates by itself); for the
+//        few negative ones max(value+energy, mask) masks two cells per instruction.
 CCJ_HD int64_t ccj_h4(int64_t x) { const int64_t q = x >> 2, r = x & 3; return (q + 1) * (2 * q + r); }
 inline int64_t ccj_hh4(int x) { int64_t s = 0; for (int m = 1; m <= x; ++m) s += ccj_h4(m); return s; }
 inline int64_t ccj_winlr_quads(int n) { int64_t s = 0; for (int b = 0; b <= n - 3; ++b) s += ccj_hh4(n - b - 2); return s; }
