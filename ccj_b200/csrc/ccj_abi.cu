@@ -27,7 +27,7 @@ struct SeqPlan {
 
 // the per-sequence device buffers behind ccj_seq, in arena order
 enum { TAB_T4 = 0, TAB_G1, TAB_G2, TAB_G3, TAB_G4, TAB_T2, TAB_W3, TAB_ESTP, TAB_INLIST, TAB_OUTLIST, TAB_INCNT, TAB_OUTCNT, TAB_LAY, TAB_SCRATCH,
-       TAB_PLW, TAB_PRW, TAB_PMW, TAB_PMM, TAB_WSCR, TAB_PMLEV, TAB_PLIST, TAB_PCUM, TAB_PMLIST, TAB_PMSTART, TAB_FTYPE, TAB_TBSTACK,
+       TAB_PLW, TAB_PRW, TAB_PMW, TAB_PMM, TAB_PKG, TAB_WSCR, TAB_PMLEV, TAB_PLIST, TAB_PCUM, TAB_PMLIST, TAB_PMSTART, TAB_FTYPE, TAB_TBSTACK,
        TAB_COUNT };
 size_t tab_bytes_uncached(int n, int which) {
     const size_t tri = (size_t)n * (n - 1) / 2 + 1;
@@ -56,7 +56,8 @@ size_t tab_bytes_uncached(int n, int which) {
         case TAB_OUTLIST: return align_up(tri * CCJ_WIN_OUT * 2 * sizeof(uint32_t), 256);
         case TAB_INCNT:
         case TAB_OUTCNT: return align_up(tri * sizeof(int32_t), 256);
-        case TAB_LAY: return align_up((size_t)(5 * (n + 1) + 8) * sizeof(int32_t), 256);
+        case TAB_LAY: return align_up((size_t)CCJ_LAY_INTS(n) * sizeof(int32_t), 256);
+        case TAB_PKG: return align_up((size_t)ccj_pkg_total(n) * sizeof(int16_t) + 64, 256);
         case TAB_SCRATCH: return align_up((size_t)ccj_level_max(n) * ccj::fill4_partials() * sizeof(int16_t) + 64, 256);
         case TAB_PLW:
         case TAB_PRW: return align_up((size_t)ccj_winlr_quads(n) * 4 * sizeof(int16_t) + 64, 256);
@@ -445,6 +446,7 @@ int ccj_batch_prepare(ccj_ctx *ctx, const char *seqs, const int64_t *offsets, in
         q.prw = reinterpret_cast<int16_t *>(t + tab_offset(n, TAB_PRW));
         q.pmw = reinterpret_cast<int16_t *>(t + tab_offset(n, TAB_PMW));
         q.pmm = reinterpret_cast<int16_t *>(t + tab_offset(n, TAB_PMM));
+        q.pkg = reinterpret_cast<int16_t *>(t + tab_offset(n, TAB_PKG));
         q.wscr = reinterpret_cast<int16_t *>(t + tab_offset(n, TAB_WSCR));
         q.wscr_lr = tab_sizes(n).wscr_lr;
         q.wtot4 = tab_sizes(n).wtot4;

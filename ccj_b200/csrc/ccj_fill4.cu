@@ -71,6 +71,14 @@ __global__ void __launch_bounds__(256) k_prep_lay(const ccj_model *M, const ccj_
         for (int b = 0; b <= n; ++b) { lay[4 * n1 + b] = acc; if (n - b - 2 >= 0) acc += lay[3 * n1 + n - b - 2]; }
         acc = 0;
         for (int j = 1; j <= n; ++j) { const int v = s_row[j]; s_row[j] = acc; acc += v; }
+        // block offsets of the second PK copy (ccj_types.h): S2[y] = sum_{y'<y} pad8(T(y')), EG[i] = sum_{i'<i} S2[n-i']
+        int *S2 = lay + CCJ_LAY_S2(n), *EG = lay + CCJ_LAY_EG(n);
+        S2[0] = S2[1] = 0;
+        for (int y = 1; y <= n; ++y) S2[y + 1] = S2[y] + (int)ccj_pad8(y * (y + 1) / 2);
+        acc = 0;
+        EG[0] = 0;
+        for (int i = 1; i <= n; ++i) { EG[i] = acc; acc += S2[n - i]; }
+        EG[n + 1] = acc;
     }
     __syncthreads();
     for (int j = threadIdx.x + 1; j <= n; j += blockDim.x) {
@@ -100,7 +108,7 @@ __global__ void __launch_bounds__(256) k_prep_lay(const ccj_model *M, const ccj_
         int acc = 0;
         for (int s = 0; s <= n; ++s) { q.pmstart[s] = acc; acc += s_row[s]; }
         q.pmstart[n + 1] = acc;
-        q.status[6] = 1;   // the tuned fill is running: layout tables and T_PKG will be valid for the traceback
+        q.status[6] = 1;   // the tuned fill is running: layout tables and the second PK copy will be valid for the traceback
     }
     __syncthreads();
     for (int s = wid; s <= n; s += nw) {
@@ -1061,10 +1069,9 @@ __global__ void __launch_bounds__(K4_THREADS, FINAL_MINB) k_final(const ccj_mode
     const int vPfO = PUT(T_PfromO, min(min(L2.PfO, R4.PfO), min(vPL + PB, vPR + PB)));
     const int vPK = PUT(T_PK, min(min(L1.PK, R3.PK), min(min(vPL + PB, vPM + PB), min(vPR + PB, vPO + PB))));
     w4[(int64_t)T_MPP * st4 + off0] = (int16_t)min(vPL, vPR);
-    {   // ccj_pkg_idx(n,i,j,k,l) through the layout tables: block (i,l) starts at Cb(i-2) + Tet(l-i-2)
+    {   // second PK copy (ccj_types.h): block (i,l), gap g=k-j, position j-i; scattered, one store per cell
         const int sp = l - i, g = k - j;
-        const int pkg = (i >= 2 ? s_cb[i - 2] : 0) + s_tet[sp - 2] + ((sp * (sp - 1) - (sp - g + 1) * (sp - g + 2)) >> 1) + (j - i);
-        w4[(int64_t)T_PKG * st4 + pkg] = (int16_t)vPK;  // scattered: one store per cell
+        q.pkg[__ldg(&q.lay[CCJ_LAY_EG(n) + i]) + __ldg(&q.lay[CCJ_LAY_S2(n) + sp - 1]) + ((sp * (sp - 1) - (sp - g + 1) * (sp - g + 2)) >> 1) + (j - i)] = (int16_t)vPK;
     }
     {   // window copies (layouts in ccj_types.h); PLW is coalesced, PRW / PMW are one scattered store per cell
         const int slab4 = s_cw[b] + s_hh[n - b - 2] - s_hh[mloc] + h4m;
@@ -1096,7 +1103,7 @@ __global__ void __launch_bounds__(K4_THREADS, FINAL_MINB) k_final(const ccj_mode
 
 // P(i,l) = min_{i<=j<d<k<l} PK(i,j,d+1,k) + PK(j+1,d,k+1,l)  (src/pseudo_loop.cc:166-179).
 // blockIdx.x -> i, warps (and blockIdx.y) -> j.  For fixed (i,j,l) the pairs (delta=k-d, d) form a triangle with
-// rows of length L, L-1, ..., 1 (L=l-j-2).  In the T_PKG copy the second factor of that whole triangle is ONE
+// rows of length L, L-1, ..., 1 (L=l-j-2).  In the second PK copy (ccj_seq::pkg) the second factor of that whole triangle is ONE
 // contiguous run; the first factor is contiguous per row (row i of slab (j-i, delta-1)).  A warp walks the
 // flattened triangle of its j, 8 consecutive terms per lane: no lane idles on a short row, and the row base of
 // the first factor is recomputed only when a lane's run crosses into the next row.
@@ -1119,7 +1126,8 @@ __global__ void __launch_bounds__(256) k_P_tuned(const ccj_seq *__restrict__ seq
     __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int16_t *__restrict__ F = q.t4 + (int64_t)T_PK * q.stride4;
-    const int16_t *__restrict__ Gt = q.t4 + (int64_t)T_PKG * q.stride4;
+    const int16_t *__restrict__ Gt = q.pkg;
+    const int *__restrict__ S2 = lay + CCJ_LAY_S2(n), *__restrict__ EG = lay + CCJ_LAY_EG(n);
     const int ri = i - 1;
     int mn = CCJ_INF;
     // Work items = (j, 256 consecutive terms of j's triangle), dealt round-robin to the warps: triangle sizes range
@@ -1137,8 +1145,8 @@ __global__ void __launch_bounds__(256) k_P_tuned(const ccj_seq *__restrict__ seq
             const int ua = n - (j - i) - 2;
             // row r: delta = r+1, first factor (i,j,d+1,d+delta) in slab (j-i, r), m1 = ua-r, row i, position d-j-1
             auto rowbase = [&](int r) { const int m1 = ua - r; return s_cb[r] - s_tet[m1] + ((ri * (2 * m1 + 2 - i)) >> 1); };
-            // second factor PK(j+1,d,d+delta+1,l): block (j+1,l) of the T_PKG copy starts at Cb(j-1) + Tet(l-j-3)  (ccj_pkg_idx)
-            const int16_t *__restrict__ G = Gt + (s_cb[j - 1] + s_tet[L - 1]);
+            // second factor PK(j+1,d,d+delta+1,l): block (j+1,l) of the second PK copy, 16-byte aligned (ccj_types.h)
+            const int16_t *__restrict__ G = Gt + (__ldg(&EG[j + 1]) + __ldg(&S2[L]));
             const int q0 = (p * 32 + lane) * KP_RUN;
             if (q0 >= T) continue;
             // invert q0 = r(2L+1-r)/2 + kk  (rows r=0..L-1 of length L-r)
@@ -1154,10 +1162,12 @@ __global__ void __launch_bounds__(256) k_P_tuned(const ccj_seq *__restrict__ seq
                 idx[e] = f0 + kk;
                 if (++kk == L - r) { ++r; kk = 0; f0 = rowbase(min(r, L - 1)); }
             }
+            // ... then all loads in flight together: the 8 second factors are one aligned 16-byte load
+            const int4 g4 = __ldg(reinterpret_cast<const int4 *>(G + q0));
+            const int gv[KP_RUN] = {lo16(g4.x), hi16(g4.x), lo16(g4.y), hi16(g4.y), lo16(g4.z), hi16(g4.z), lo16(g4.w), hi16(g4.w)};
             int v[KP_RUN];
 #pragma unroll
-            for (int e = 0; e < KP_RUN; ++e)   // ... then all 2*KP_RUN loads in flight together
-                v[e] = q0 + e < T ? (int)__ldg(F + idx[e]) + (int)__ldg(G + q0 + e) : CCJ_INF;
+            for (int e = 0; e < KP_RUN; ++e) v[e] = q0 + e < T ? (int)__ldg(F + idx[e]) + gv[e] : CCJ_INF;
 #pragma unroll
             for (int e = 0; e < KP_RUN; ++e) mn = min(mn, v[e]);
         }

@@ -315,16 +315,16 @@ CCJ_HD void ccj_tb_node(ccj_tb &T, const Par &par, int ni, int nj, int nk, int n
             const int s = l - i + 1;
             ccj_best b = {INF, -1};
             if (c.q.status[6] == 1) {
-                // the tuned fill left the layout tables and the second PK copy (T_PKG): walk, per j, the flattened
+                // the tuned fill left the layout tables and the second PK copy (ccj_seq::pkg): walk, per j, the flattened
                 // (delta=k-d, d) triangle like k_P_tuned -- the second factor is one contiguous run, the first one
                 // contiguous per row -- 8 consecutive terms per lane with all 16 loads in flight.  Same candidates,
                 // same (value, position) order as the loops below.
                 const int *lay = c.q.lay;
                 const int n1 = n + 1, ri = i - 1;
-                const int16_t *F = ccj_t4(c, T_PK), *Gt = ccj_t4(c, T_PKG);
+                const int16_t *F = ccj_t4(c, T_PK), *Gt = c.q.pkg;
                 for (int j = i; j <= l - 3; ++j) {
                     const int Lr = l - j - 2, T = Lr * (Lr + 1) / 2, ua = n - (j - i) - 2;
-                    const int16_t *G = Gt + (lay[n1 + j - 1] + lay[Lr - 1]);
+                    const int16_t *G = Gt + (lay[CCJ_LAY_EG(n) + j + 1] + lay[CCJ_LAY_S2(n) + Lr]);
                     for (int q0 = L * 8; q0 < T; q0 += NL * 8) {
                         int r = (int)(((2 * Lr + 1) - sqrtf((float)((2 * Lr + 1) * (2 * Lr + 1) - 8 * q0))) * 0.5f);
                         r = r < 0 ? 0 : (r > Lr - 1 ? Lr - 1 : r);

@@ -28,8 +28,7 @@ enum ccj_table4 {
     T_PMmloop00, T_PMmloop01, T_PMmloop10, T_POmloop00, T_POmloop01, T_POmloop10,
     CCJ_NT4 = 22,
     T_MPP = 22,       /* internal: min(PL,PR) of the cell = get_PfromMdoubleprime without PB (pseudo_loop.cc:675-678) */
-    T_PKG = 23,       /* internal: second copy of PK in the layout compute_P's 2nd factor walks (ccj_pkg_idx) */
-    CCJ_NT4_STORE = 24
+    CCJ_NT4_STORE = 23
 };
 
 // ---- 2D tables ----------------------------------------------------------------------------------
@@ -119,7 +118,9 @@ struct ccj_seq {
     //   g3 (12 B): PK PfromR min(PL,PR) PRmloop00 PMmloop00 -                   read as X(i,j,d,l)
     //   g4 (16 B): PfromR PfromO PRmloop00 PMmloop00 PMmloop10 POmloop00 POmloop10 -   read as X(i,j,k,d)
     int16_t *g1, *g2, *g3, *g4;
-    int32_t *lay;        // layout tables, 5 arrays of n+1 ints: Tet(x), Cb(x), H4(x), HH4(x), CbW4(x)  (tuned path, n<=448)
+    int32_t *lay;        // layout tables (tuned path, n<=448): Tet, Cb, H4, HH4, CbW4 with n+1 ints each, then S2, EG with
+                         // n+2 ints each (CCJ_LAY_S2 / CCJ_LAY_EG)
+    int16_t *pkg;        // second PK copy for compute_P ("PK copy for compute_P's second factor" below)
     // copies of PL / PR / PM for the interior windows, rows padded to 4 entries so that a lane moves 4 cells
     // per 8-byte load ("window layouts" below); written by k_final, read by k_winLR / k_winM only
     int16_t *plw, *prw, *pmw, *pmm;   // pmm: the mask halves of PMW (same quad index, separate array)
@@ -173,12 +174,25 @@ CCJ_HD int64_t ccj_level_max(int n) {
     return best;
 }
 
-// PK copy for compute_P's second factor PK(j+1,d,k+1,l) (src/pseudo_loop.cc:171): nesting [i][l][gap][j], j
-// fastest, so that for fixed (i,l,gap) consecutive j are consecutive in memory.
-//   block (i,l), s=l-i: gaps g=2..s, gap g holds j=i..l-g
-CCJ_HD int64_t ccj_pkg_idx(int n, int i, int j, int k, int l) {
-    const int64_t s = l - i, g = k - j;
-    return (ccj_pent(n - 2) - ccj_pent(n - i - 1)) + ccj_tet(s - 2) + (s * (s - 1) / 2 - (s - g + 1) * (s - g + 2) / 2) + (j - i);
+// PK copy for compute_P's second factor PK(j+1,d,k+1,l) (src/pseudo_loop.cc:171), ccj_seq::pkg: nesting [i][l][gap][j],
+// j fastest, so that for fixed (i,l,gap) consecutive j are consecutive in memory and the whole (gap,j) triangle of a
+// block (i,l) -- exactly the second factors of P(.,l) with j+1=i -- is one contiguous run.  A level writes whole rows
+// (the gap is fixed per level).  Blocks start on 8-entry boundaries (16-byte loads in k_P_tuned):
+//   block (i,l), y=l-i-1 >= 1, holds T(y) entries (T(x)=x(x+1)/2): gaps g=2..l-i, gap g holds j=i..l-g
+//   base(i,l) = EG[i] + S2[y],  S2[y] = sum_{y'<y} pad8(T(y')),  EG[i] = sum_{i'<i} S2[n-i']      (ccj_seq::lay)
+//   entry     = base + T(y) - T(l-i-g+1) + (j-i)
+CCJ_HD int64_t ccj_pad8(int64_t x) { return (x + 7) & ~(int64_t)7; }
+#define CCJ_LAY_S2(n) (5 * ((n) + 1))
+#define CCJ_LAY_EG(n) (5 * ((n) + 1) + ((n) + 2))
+#define CCJ_LAY_INTS(n) (5 * ((n) + 1) + 2 * ((n) + 2) + 8)
+inline int64_t ccj_pkg_total(int n) {   // EG[n+1]
+    int64_t tot = 0;
+    for (int i = 1; i <= n; ++i) {
+        int64_t s2 = 0;   // S2[n-i]
+        for (int y = 1; y < n - i; ++y) s2 += ccj_pad8((int64_t)y * (y + 1) / 2);
+        tot += s2;
+    }
+    return tot > 0 ? tot : 8;
 }
 
 // ---- window layouts ------------------------------------------------------------------------------------
