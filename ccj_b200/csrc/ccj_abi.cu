@@ -27,7 +27,7 @@ struct SeqPlan {
 
 // the per-sequence device buffers behind ccj_seq, in arena order
 enum { TAB_T4 = 0, TAB_G1, TAB_G2, TAB_G3, TAB_G4, TAB_T2, TAB_W3, TAB_ESTP, TAB_INLIST, TAB_OUTLIST, TAB_INCNT, TAB_OUTCNT, TAB_LAY, TAB_SCRATCH,
-       TAB_PLW, TAB_PRW, TAB_PMW, TAB_PMM, TAB_PKG, TAB_WSCR, TAB_PMLEV, TAB_PLIST, TAB_PCUM, TAB_PMLIST, TAB_PMSTART, TAB_FTYPE, TAB_TBSTACK,
+       TAB_PLW, TAB_PRW, TAB_PMW, TAB_PMM, TAB_PKF, TAB_PKG, TAB_WSCR, TAB_PMLEV, TAB_PLIST, TAB_PCUM, TAB_PMLIST, TAB_PMSTART, TAB_FTYPE, TAB_TBSTACK,
        TAB_COUNT };
 size_t tab_bytes_uncached(int n, int which) {
     const size_t tri = (size_t)n * (n - 1) / 2 + 1;
@@ -57,6 +57,7 @@ size_t tab_bytes_uncached(int n, int which) {
         case TAB_INCNT:
         case TAB_OUTCNT: return align_up(tri * sizeof(int32_t), 256);
         case TAB_LAY: return align_up((size_t)CCJ_LAY_INTS(n) * sizeof(int32_t), 256);
+        case TAB_PKF: return align_up((size_t)ccj_pkf_total(n) * sizeof(int16_t) + 64, 256);
         case TAB_PKG: return align_up((size_t)ccj_pkg_total(n) * sizeof(int16_t) + 64, 256);
         case TAB_SCRATCH: return align_up((size_t)ccj_level_max(n) * ccj::fill4_partials() * sizeof(int16_t) + 64, 256);
         case TAB_PLW:
@@ -446,6 +447,7 @@ int ccj_batch_prepare(ccj_ctx *ctx, const char *seqs, const int64_t *offsets, in
         q.prw = reinterpret_cast<int16_t *>(t + tab_offset(n, TAB_PRW));
         q.pmw = reinterpret_cast<int16_t *>(t + tab_offset(n, TAB_PMW));
         q.pmm = reinterpret_cast<int16_t *>(t + tab_offset(n, TAB_PMM));
+        q.pkf = reinterpret_cast<int16_t *>(t + tab_offset(n, TAB_PKF));
         q.pkg = reinterpret_cast<int16_t *>(t + tab_offset(n, TAB_PKG));
         q.wscr = reinterpret_cast<int16_t *>(t + tab_offset(n, TAB_WSCR));
         q.wscr_lr = tab_sizes(n).wscr_lr;

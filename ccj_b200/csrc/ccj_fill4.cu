@@ -71,10 +71,18 @@ __global__ void __launch_bounds__(256) k_prep_lay(const ccj_model *M, const ccj_
         for (int b = 0; b <= n; ++b) { lay[4 * n1 + b] = acc; if (n - b - 2 >= 0) acc += lay[3 * n1 + n - b - 2]; }
         acc = 0;
         for (int j = 1; j <= n; ++j) { const int v = s_row[j]; s_row[j] = acc; acc += v; }
-        // block offsets of the second PK copy (ccj_types.h): S2[y] = sum_{y'<y} pad8(T(y')), EG[i] = sum_{i'<i} S2[n-i']
-        int *S2 = lay + CCJ_LAY_S2(n), *EG = lay + CCJ_LAY_EG(n);
+        // block offsets of the two PK copies of compute_P (ccj_types.h, "PK copies for compute_P")
+        int *CF = lay + CCJ_LAY_CF(n), *DF = lay + CCJ_LAY_DF(n), *S2 = lay + CCJ_LAY_S2(n), *EG = lay + CCJ_LAY_EG(n);
+        acc = 0;
+        CF[0] = 0;
+        for (int j = 1; j <= n; ++j) { CF[j] = acc; acc += 8 * (int)ccj_q8(n - j - 1); }
+        CF[n + 1] = acc;
+        acc = 0;
+        DF[0] = 0;
+        for (int i = 1; i <= n; ++i) { DF[i] = acc; acc += CF[n + 1] - CF[i]; }
+        DF[n + 1] = acc;
         S2[0] = S2[1] = 0;
-        for (int y = 1; y <= n; ++y) S2[y + 1] = S2[y] + (int)ccj_pad8(y * (y + 1) / 2);
+        for (int y = 1; y <= n; ++y) S2[y + 1] = S2[y] + 8 * (int)ccj_q8(y);
         acc = 0;
         EG[0] = 0;
         for (int i = 1; i <= n; ++i) { EG[i] = acc; acc += S2[n - i]; }
@@ -1069,9 +1077,15 @@ __global__ void __launch_bounds__(K4_THREADS, FINAL_MINB) k_final(const ccj_mode
     const int vPfO = PUT(T_PfromO, min(min(L2.PfO, R4.PfO), min(vPL + PB, vPR + PB)));
     const int vPK = PUT(T_PK, min(min(L1.PK, R3.PK), min(min(vPL + PB, vPM + PB), min(vPR + PB, vPO + PB))));
     w4[(int64_t)T_MPP * st4 + off0] = (int16_t)min(vPL, vPR);
-    {   // second PK copy (ccj_types.h): block (i,l), gap g=k-j, position j-i; scattered, one store per cell
-        const int sp = l - i, g = k - j;
-        q.pkg[__ldg(&q.lay[CCJ_LAY_EG(n) + i]) + __ldg(&q.lay[CCJ_LAY_S2(n) + sp - 1]) + ((sp * (sp - 1) - (sp - g + 1) * (sp - g + 2)) >> 1) + (j - i)] = (int16_t)vPK;
+    {   // the two PK copies of compute_P (ccj_types.h).  As first factor PK(i,j,d+1,k') this cell is d=k-1, k'=l, i.e.
+        // row delta=l-k+1 of block (i,j), position k-j-2: coalesced.  As second factor PK(i2,d,k2,l) it is i2=i, d=j,
+        // k2=k: row delta=k-j-1 of block (i,l), position j-i: scattered, one store per cell.
+        const int *__restrict__ lay = q.lay;
+        const int Mf = n - j - 1, Mg = l - i - 1;
+        q.pkf[__ldg(&lay[CCJ_LAY_DF(n) + i]) + __ldg(&lay[CCJ_LAY_CF(n) + j]) - __ldg(&lay[CCJ_LAY_CF(n) + i]) +
+              8 * ((int)ccj_q8(Mf) - (int)ccj_q8(Mf + 1 - (b + 1))) + (k - j - 2)] = (int16_t)vPK;
+        q.pkg[__ldg(&lay[CCJ_LAY_EG(n) + i]) + __ldg(&lay[CCJ_LAY_S2(n) + Mg]) +
+              8 * ((int)ccj_q8(Mg) - (int)ccj_q8(Mg + 1 - (k - j - 1))) + (j - i)] = (int16_t)vPK;
     }
     {   // window copies (layouts in ccj_types.h); PLW is coalesced, PRW / PMW are one scattered store per cell
         const int slab4 = s_cw[b] + s_hh[n - b - 2] - s_hh[mloc] + h4m;
@@ -1102,74 +1116,61 @@ __global__ void __launch_bounds__(K4_THREADS, FINAL_MINB) k_final(const ccj_mode
 }
 
 // P(i,l) = min_{i<=j<d<k<l} PK(i,j,d+1,k) + PK(j+1,d,k+1,l)  (src/pseudo_loop.cc:166-179).
-// blockIdx.x -> i, warps (and blockIdx.y) -> j.  For fixed (i,j,l) the pairs (delta=k-d, d) form a triangle with
-// rows of length L, L-1, ..., 1 (L=l-j-2).  In the second PK copy (ccj_seq::pkg) the second factor of that whole triangle is ONE
-// contiguous run; the first factor is contiguous per row (row i of slab (j-i, delta-1)).  A warp walks the
-// flattened triangle of its j, 8 consecutive terms per lane: no lane idles on a short row, and the row base of
-// the first factor is recomputed only when a lane's run crosses into the next row.
-#ifndef KP_RUN
-#define KP_RUN 8
-#endif
+// For fixed (i,j,l), L=l-j-2, the terms are rows delta=1..L over d=j+1..l-delta-1: row delta of PKF block (i,j) and row
+// delta of PKG block (j+1,l), both starting on 16-byte boundaries (ccj_types.h) -- 8 consecutive terms are one
+// 16-byte load from each copy.  blockIdx.x -> i; work items = (j, 32 octets), dealt round-robin to the warps (the
+// term sets range from 1 to thousands of terms); a lane takes one octet of one row.
 __global__ void __launch_bounds__(256) k_P_tuned(const ccj_seq *__restrict__ seqs, int s, int nj) {
-    __shared__ int s_tet[K4_MAXN + 4];
-    __shared__ int s_cb[K4_MAXN + 4];
+    __shared__ int s_cf[K4_MAXN + 4], s_eg[K4_MAXN + 4], s_s2[K4_MAXN + 4];
     __shared__ int sm[8];
     const ccj_seq q = seqs[blockIdx.z];
-    const int n = q.n, n1 = n + 1;
+    const int n = q.n;
     const int i = 1 + blockIdx.x, l = i + s;
     if (l > n) return;
     const int *__restrict__ lay = q.lay;
-    for (int x = threadIdx.x; x <= n; x += 256) {
-        s_tet[x] = __ldg(&lay[x]);
-        s_cb[x] = __ldg(&lay[n1 + x]);
+    for (int x = threadIdx.x; x <= n + 1; x += 256) {
+        s_cf[x] = __ldg(&lay[CCJ_LAY_CF(n) + x]);
+        s_eg[x] = __ldg(&lay[CCJ_LAY_EG(n) + x]);
+        s_s2[x] = __ldg(&lay[CCJ_LAY_S2(n) + x]);
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int16_t *__restrict__ F = q.t4 + (int64_t)T_PK * q.stride4;
-    const int16_t *__restrict__ Gt = q.pkg;
-    const int *__restrict__ S2 = lay + CCJ_LAY_S2(n), *__restrict__ EG = lay + CCJ_LAY_EG(n);
-    const int ri = i - 1;
+    const int16_t *__restrict__ F0 = q.pkf + (__ldg(&lay[CCJ_LAY_DF(n) + i]) - s_cf[i]);   // + CF[j]: block (i,j)
+    const int16_t *__restrict__ G0 = q.pkg;                                               // + EG[j+1] + S2[L]: block (j+1,l)
+    auto Q8 = [](int x) { const int g = x >> 3, r = x & 7; return 4 * g * (g + 1) + r * (g + 1); };
     int mn = CCJ_INF;
-    // Work items = (j, 256 consecutive terms of j's triangle), dealt round-robin to the warps: triangle sizes range
-    // from 1 to L(L+1)/2 terms, so neither "a warp per j" nor "the block per j" keeps the lanes busy.  The j with
-    // more than 256*p terms are a prefix (the triangles shrink with j), which makes the item list a double loop.
-    const int Lmax = l - i - 2, Tmax = Lmax * (Lmax + 1) / 2;
-    for (int p = 0; p * (32 * KP_RUN) < Tmax; ++p) {
-        int Lmin = (int)((sqrtf(1.f + 8.f * (float)(p * 32 * KP_RUN)) - 1.f) * 0.5f);
-        Lmin = max(Lmin, 1);
-        while (Lmin * (Lmin + 1) / 2 <= p * 32 * KP_RUN) ++Lmin;
-        while (Lmin > 1 && (Lmin - 1) * Lmin / 2 > p * 32 * KP_RUN) --Lmin;
-        const int jmax = l - 2 - Lmin;   // L = l-j-2 >= Lmin
+    // the j with more than 32*p octets are a prefix (the term sets shrink with j), which makes the item list a double loop
+    const int Lmax = l - i - 2, Omax = Q8(Lmax);
+    int Lmin = 1;
+    for (int p = 0; p * 32 < Omax; ++p) {
+        while (Q8(Lmin) <= p * 32) ++Lmin;   // smallest L with more than 32*p octets
+        const int jmax = l - 2 - Lmin;       // L = l-j-2 >= Lmin
         for (int j = i + blockIdx.y + ((wid + p) & 7) * nj; j <= jmax; j += 8 * nj) {  // rotated: every warp gets large and small j
-            const int L = l - j - 2, T = L * (L + 1) / 2;
-            const int ua = n - (j - i) - 2;
-            // row r: delta = r+1, first factor (i,j,d+1,d+delta) in slab (j-i, r), m1 = ua-r, row i, position d-j-1
-            auto rowbase = [&](int r) { const int m1 = ua - r; return s_cb[r] - s_tet[m1] + ((ri * (2 * m1 + 2 - i)) >> 1); };
-            // second factor PK(j+1,d,d+delta+1,l): block (j+1,l) of the second PK copy, 16-byte aligned (ccj_types.h)
-            const int16_t *__restrict__ G = Gt + (__ldg(&EG[j + 1]) + __ldg(&S2[L]));
-            const int q0 = (p * 32 + lane) * KP_RUN;
-            if (q0 >= T) continue;
-            // invert q0 = r(2L+1-r)/2 + kk  (rows r=0..L-1 of length L-r)
-            int r = (int)(((2 * L + 1) - sqrtf((float)((2 * L + 1) * (2 * L + 1) - 8 * q0))) * 0.5f);
-            r = max(0, min(r, L - 1));
-            while (r > 0 && r * (2 * L + 1 - r) / 2 > q0) --r;
-            while ((r + 1) * (2 * L - r) / 2 <= q0) ++r;
-            int kk = q0 - r * (2 * L + 1 - r) / 2;
-            int f0 = rowbase(r);
-            int idx[KP_RUN];
-#pragma unroll
-            for (int e = 0; e < KP_RUN; ++e) {  // addresses first (pure index arithmetic) ...
-                idx[e] = f0 + kk;
-                if (++kk == L - r) { ++r; kk = 0; f0 = rowbase(min(r, L - 1)); }
+            const int L = l - j - 2, O = Q8(L);
+            const int o = p * 32 + lane;
+            if (o >= O) continue;
+            // octet o of the rows ordered by length: rows of 8g+1..8g+8 entries have g+1 octets each, 4g(g+1) octets before them
+            int g = (int)((sqrtf(1.f + (float)o) - 1.f) * 0.5f);
+            while (g > 0 && 4 * g * (g + 1) > o) --g;
+            while (4 * (g + 1) * (g + 2) <= o) ++g;
+            const int rem = o - 4 * g * (g + 1), r = rem / (g + 1), c = rem - r * (g + 1);
+            const int len = 8 * g + r + 1;           // entries of the row: delta = L+1-len
+            const int Mf = n - j - 1;                // PKF block (i,j): row delta starts at 8*(Q8(Mf) - Q8(Mf+1-delta))
+            const int4 f = __ldg(reinterpret_cast<const int4 *>(F0 + s_cf[j] + 8 * (Q8(Mf) - Q8(Mf - L + len) + c)));
+            const int4 gg = __ldg(reinterpret_cast<const int4 *>(G0 + s_eg[j + 1] + s_s2[L] + 8 * (O - Q8(len) + c)));
+            const int left = len - 8 * c;            // terms of this octet that exist (padding / later d follow)
+            int v0 = lo16(f.x) + lo16(gg.x), v1 = hi16(f.x) + hi16(gg.x), v2 = lo16(f.y) + lo16(gg.y), v3 = hi16(f.y) + hi16(gg.y);
+            int v4 = lo16(f.z) + lo16(gg.z), v5 = hi16(f.z) + hi16(gg.z), v6 = lo16(f.w) + lo16(gg.w), v7 = hi16(f.w) + hi16(gg.w);
+            if (left < 8) {
+                if (left < 2) v1 = CCJ_INF;
+                if (left < 3) v2 = CCJ_INF;
+                if (left < 4) v3 = CCJ_INF;
+                if (left < 5) v4 = CCJ_INF;
+                if (left < 6) v5 = CCJ_INF;
+                if (left < 7) v6 = CCJ_INF;
+                v7 = CCJ_INF;
             }
-            // ... then all loads in flight together: the 8 second factors are one aligned 16-byte load
-            const int4 g4 = __ldg(reinterpret_cast<const int4 *>(G + q0));
-            const int gv[KP_RUN] = {lo16(g4.x), hi16(g4.x), lo16(g4.y), hi16(g4.y), lo16(g4.z), hi16(g4.z), lo16(g4.w), hi16(g4.w)};
-            int v[KP_RUN];
-#pragma unroll
-            for (int e = 0; e < KP_RUN; ++e) v[e] = q0 + e < T ? (int)__ldg(F + idx[e]) + gv[e] : CCJ_INF;
-#pragma unroll
-            for (int e = 0; e < KP_RUN; ++e) mn = min(mn, v[e]);
+            mn = min(mn, min(min(min(v0, v1), min(v2, v3)), min(min(v4, v5), min(v6, v7))));
         }
     }
     mn = __reduce_min_sync(0xffffffffu, mn);

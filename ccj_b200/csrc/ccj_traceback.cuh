@@ -315,32 +315,22 @@ CCJ_HD void ccj_tb_node(ccj_tb &T, const Par &par, int ni, int nj, int nk, int n
             const int s = l - i + 1;
             ccj_best b = {INF, -1};
             if (c.q.status[6] == 1) {
-                // the tuned fill left the layout tables and the second PK copy (ccj_seq::pkg): walk, per j, the flattened
-                // (delta=k-d, d) triangle like k_P_tuned -- the second factor is one contiguous run, the first one
-                // contiguous per row -- 8 consecutive terms per lane with all 16 loads in flight.  Same candidates,
-                // same (value, position) order as the loops below.
+                // the tuned fill left the two PK copies of compute_P (ccj_types.h): per (j, delta) both factors are rows
+                // over d in PKF block (i,j) and PKG block (j+1,l).  Same candidates and the same (value, position)
+                // order as the loops below; lanes walk d.
                 const int *lay = c.q.lay;
-                const int n1 = n + 1, ri = i - 1;
-                const int16_t *F = ccj_t4(c, T_PK), *Gt = c.q.pkg;
+                const int *CF = lay + CCJ_LAY_CF(n), *S2 = lay + CCJ_LAY_S2(n), *EG = lay + CCJ_LAY_EG(n);
+                const int16_t *F0 = c.q.pkf + (lay[CCJ_LAY_DF(n) + i] - CF[i]);
                 for (int j = i; j <= l - 3; ++j) {
-                    const int Lr = l - j - 2, T = Lr * (Lr + 1) / 2, ua = n - (j - i) - 2;
-                    const int16_t *G = Gt + (lay[CCJ_LAY_EG(n) + j + 1] + lay[CCJ_LAY_S2(n) + Lr]);
-                    for (int q0 = L * 8; q0 < T; q0 += NL * 8) {
-                        int r = (int)(((2 * Lr + 1) - sqrtf((float)((2 * Lr + 1) * (2 * Lr + 1) - 8 * q0))) * 0.5f);
-                        r = r < 0 ? 0 : (r > Lr - 1 ? Lr - 1 : r);
-                        while (r > 0 && r * (2 * Lr + 1 - r) / 2 > q0) --r;
-                        while ((r + 1) * (2 * Lr - r) / 2 <= q0) ++r;
-                        int kk = q0 - r * (2 * Lr + 1 - r) / 2;
-                        int idx[8], ord[8], val[8];
-                        for (int e = 0; e < 8; ++e) {
-                            const int m1 = ua - r, d = j + 1 + kk, k = d + r + 1;
-                            idx[e] = lay[n1 + r] - lay[m1] + ((ri * (2 * m1 + 2 - i)) >> 1) + kk;
-                            ord[e] = ((j - i) * s + (d - i)) * s + (k - i);
-                            if (++kk == Lr - r) { kk = 0; if (r < Lr - 1) ++r; }
+                    const int Lr = l - j - 2, Mf = n - j - 1;
+                    const int16_t *Fb = F0 + CF[j], *Gb = c.q.pkg + EG[j + 1] + S2[Lr];
+                    for (int dl = 1; dl <= Lr; ++dl) {
+                        const int16_t *F = Fb + 8 * ((int)ccj_q8(Mf) - (int)ccj_q8(Mf + 1 - dl));
+                        const int16_t *G = Gb + 8 * ((int)ccj_q8(Lr) - (int)ccj_q8(Lr + 1 - dl));
+                        for (int x = L; x <= Lr - dl; x += NL) {   // d = j+1+x, k = d+dl
+                            const int d = j + 1 + x;
+                            ccj_cand(b, (int)F[x] + (int)G[x], ((j - i) * s + (d - i)) * s + (d + dl - i));
                         }
-                        for (int e = 0; e < 8; ++e) val[e] = q0 + e < T ? (int)F[idx[e]] + (int)G[q0 + e] : INF;
-                        for (int e = 0; e < 8; ++e)
-                            if (q0 + e < T) ccj_cand(b, val[e], ord[e]);
                     }
                 }
             } else {

@@ -118,9 +118,9 @@ struct ccj_seq {
     //   g3 (12 B): PK PfromR min(PL,PR) PRmloop00 PMmloop00 -                   read as X(i,j,d,l)
     //   g4 (16 B): PfromR PfromO PRmloop00 PMmloop00 PMmloop10 POmloop00 POmloop10 -   read as X(i,j,k,d)
     int16_t *g1, *g2, *g3, *g4;
-    int32_t *lay;        // layout tables (tuned path, n<=448): Tet, Cb, H4, HH4, CbW4 with n+1 ints each, then S2, EG with
-                         // n+2 ints each (CCJ_LAY_S2 / CCJ_LAY_EG)
-    int16_t *pkg;        // second PK copy for compute_P ("PK copy for compute_P's second factor" below)
+    int32_t *lay;        // layout tables (tuned path, n<=448): Tet, Cb, H4, HH4, CbW4 with n+1 ints each, then CF, DF, S2, EG
+                         // with n+2 ints each (CCJ_LAY_*)
+    int16_t *pkf, *pkg;  // first- and second-factor PK copies for compute_P ("PK copies for compute_P" below)
     // copies of PL / PR / PM for the interior windows, rows padded to 4 entries so that a lane moves 4 cells
     // per 8-byte load ("window layouts" below); written by k_final, read by k_winLR / k_winM only
     int16_t *plw, *prw, *pmw, *pmm;   // pmm: the mask halves of PMW (same quad index, separate array)
@@ -174,22 +174,33 @@ CCJ_HD int64_t ccj_level_max(int n) {
     return best;
 }
 
-// PK copy for compute_P's second factor PK(j+1,d,k+1,l) (src/pseudo_loop.cc:171), ccj_seq::pkg: nesting [i][l][gap][j],
-// j fastest, so that for fixed (i,l,gap) consecutive j are consecutive in memory and the whole (gap,j) triangle of a
-// block (i,l) -- exactly the second factors of P(.,l) with j+1=i -- is one contiguous run.  A level writes whole rows
-// (the gap is fixed per level).  Blocks start on 8-entry boundaries (16-byte loads in k_P_tuned):
-//   block (i,l), y=l-i-1 >= 1, holds T(y) entries (T(x)=x(x+1)/2): gaps g=2..l-i, gap g holds j=i..l-g
-//   base(i,l) = EG[i] + S2[y],  S2[y] = sum_{y'<y} pad8(T(y')),  EG[i] = sum_{i'<i} S2[n-i']      (ccj_seq::lay)
-//   entry     = base + T(y) - T(l-i-g+1) + (j-i)
-CCJ_HD int64_t ccj_pad8(int64_t x) { return (x + 7) & ~(int64_t)7; }
-#define CCJ_LAY_S2(n) (5 * ((n) + 1))
-#define CCJ_LAY_EG(n) (5 * ((n) + 1) + ((n) + 2))
-#define CCJ_LAY_INTS(n) (5 * ((n) + 1) + 2 * ((n) + 2) + 8)
+// ---- PK copies for compute_P (src/pseudo_loop.cc:166-179) -------------------------------------------------------
+// P(i,l) = min_{j,d,k} PK(i,j,d+1,k) + PK(j+1,d,k+1,l).  With delta=k-d, both factors of the terms of one (i,j,l) are
+// rows over d=j+1.. : row delta of block (i,j) of the first-factor copy PKF (nesting [i][j][delta][d], entries
+// d=j+1..n-delta) and row delta of block (j+1,l) of the second-factor copy PKG ([i2][l][delta][d], d=i2..l-delta-1).
+// Every row starts on an 8-entry boundary in both copies, so 8 consecutive terms are one 16-byte load from each.
+// A level writes whole rows (delta is fixed per level and block); PKF rows are written coalesced.
+//   Q8(x)  = sum_{u<=x} ceil(u/8)  (rows of 1..x entries, in octets);  a block with rows of M, M-1, .., 1 entries
+//            has 8*Q8(M) entries and its row delta starts at 8*(Q8(M) - Q8(M+1-delta))
+//   PKF: block (i,j), M=n-j-1:   base = DF[i] + CF[j] - CF[i],  CF[j] = sum_{j'<j} 8*Q8(n-j'-1), DF[i] = sum_{i'<i} (CF[n+1]-CF[i'])
+//   PKG: block (i2,l), M=l-i2-1: base = EG[i2] + S2[M],         S2[y] = sum_{y'<y} 8*Q8(y'),     EG[i] = sum_{i'<i} S2[n-i']
+CCJ_HD int64_t ccj_q8(int64_t x) { const int64_t g = x >> 3, r = x & 7; return x > 0 ? 4 * g * (g + 1) + r * (g + 1) : 0; }
+#define CCJ_LAY_CF(n) (5 * ((n) + 1))
+#define CCJ_LAY_DF(n) (5 * ((n) + 1) + ((n) + 2))
+#define CCJ_LAY_S2(n) (5 * ((n) + 1) + 2 * ((n) + 2))
+#define CCJ_LAY_EG(n) (5 * ((n) + 1) + 3 * ((n) + 2))
+#define CCJ_LAY_INTS(n) (5 * ((n) + 1) + 4 * ((n) + 2) + 8)
+inline int64_t ccj_pkf_total(int n) {   // DF[n+1]
+    int64_t cf_total = 0, tot = 0, cf = 0;
+    for (int j = 1; j <= n; ++j) cf_total += 8 * ccj_q8(n - j - 1);
+    for (int i = 1; i <= n; ++i) { tot += cf_total - cf; cf += 8 * ccj_q8(n - i - 1); }
+    return tot > 0 ? tot : 8;
+}
 inline int64_t ccj_pkg_total(int n) {   // EG[n+1]
     int64_t tot = 0;
     for (int i = 1; i <= n; ++i) {
         int64_t s2 = 0;   // S2[n-i]
-        for (int y = 1; y < n - i; ++y) s2 += ccj_pad8((int64_t)y * (y + 1) / 2);
+        for (int y = 1; y < n - i; ++y) s2 += 8 * ccj_q8(y);
         tot += s2;
     }
     return tot > 0 ? tot : 8;
