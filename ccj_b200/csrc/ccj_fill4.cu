@@ -1091,11 +1091,12 @@ __global__ void __launch_bounds__(K4_THREADS, FINAL_MINB) k_final(const ccj_mode
         const int slab4 = s_cw[b] + s_hh[n - b - 2] - s_hh[mloc] + h4m;
         q.plw[4 * (int64_t)(slab4 - H4(mloc - i + 1)) + (n - b - k)] = (int16_t)vPL;
         q.prw[4 * (int64_t)(slab4 - H4(mloc - kr)) + (i - 1)] = (int16_t)vPR;
-        {   // value (blanked to 32767 where the PM window may not read it) and its mask half
+        // PMW / PMM: the PM window only reads cells with a>=1, b>=1 whose (j,k) is in some partner list, i.e. can pair;
+        // everything else keeps the (32767, "not a source") that k_fill_pmw wrote
+        if (a >= 1 && b >= 1 && k - j > CCJ_TURN && ptype(j, k) > 0) {
             const int64_t pe = 4 * (int64_t)t * q.wtot4 + pmrow;   // entry of this cell in PMW and PMM
-            const bool srcok = a >= 1 && b >= 1;
-            q.pmw[pe] = srcok ? (int16_t)vPM : (int16_t)32767;
-            q.pmm[pe] = srcok ? (int16_t)-32768 : (int16_t)32767;
+            q.pmw[pe] = (int16_t)vPM;
+            q.pmm[pe] = (int16_t)-32768;
         }
     }
     // read-group records (layout in ccj_types.h); consecutive cells -> consecutive records, coalesced
