@@ -93,6 +93,7 @@ def load_library(path: Optional[os.PathLike] = None) -> C.CDLL:
     lib.ccj_table2_len.restype = C.c_int64
     lib.ccj_batch_fill_profiled.argtypes = [vp, C.POINTER(C.c_float)]
     lib.ccj_count_terms.argtypes = [C.c_char_p, i32, i32, i64p]
+    lib.ccj_measure_addmin_peak.argtypes = [vp, i32, C.POINTER(C.c_double)]
     i32p = C.POINTER(C.c_int32)
     lib.ccj_table4_get.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32p]
     lib.ccj_table2_get.argtypes = [vp, i32, i32, i32, i32, i32p]
@@ -279,6 +280,20 @@ class Context:
     @property
     def last_fill_launches(self) -> int:
         return int(self._lib.ccj_last_fill_launches(self._h))
+
+    def addmin_peak(self) -> dict:
+        """Measured integer ceiling of this GPU in min-plus candidates per second (include/ccj_b200.h)."""
+        out = {}
+        for variant, name in enumerate(["int32_viaddmnmx", "int16_unpack_viaddmnmx", "int16x2_viaddmnmx"]):
+            v = C.c_double()
+            self._check(self._lib.ccj_measure_addmin_peak(self._h, variant, C.byref(v)))
+            out[name] = v.value
+        return out
+
+    @property
+    def stream_ptr(self) -> int:
+        """The cudaStream_t the context launches on (for callers that time with their own CUDA events)."""
+        return int(self._lib.ccj_stream(self._h))
 
     def wave_capacity(self, n: int) -> int:
         return int(self._lib.ccj_wave_capacity(self._h, n))

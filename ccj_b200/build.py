@@ -41,7 +41,8 @@ def _run(cmd, **kw):
 
 
 def build_library(force: bool = False, verbose_ptxas: bool = False) -> Path:
-    sources = [CSRC / "ccj_abi.cu", CSRC / "ccj_kernels.cu", CSRC / "ccj_fill4.cu", CSRC / "energy_model.cpp"]
+    sources = [CSRC / "ccj_abi.cu", CSRC / "ccj_kernels.cu", CSRC / "ccj_fill4.cu", CSRC / "ccj_peak.cu",
+               CSRC / "energy_model.cpp"]
     sources = [s for s in sources if s.exists()]
     deps = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + list(CSRC.glob("*.hpp")) + sources + [
         ROOT / "include" / "ccj_b200.h"]

@@ -1,8 +1,12 @@
 """Independent-sequence partitioning across the GPUs of one box.
 
-Sequences do not interact, so there is no data-path collective: rank r folds a contiguous, cost-balanced
-slice and the (small) results are gathered on the host with `all_gather_object`.  Cost model: a fold is
-O(n^5) time, so slices are balanced on sum(n^5) rather than on count.
+Sequences do not interact, so there is no data-path collective.  Two ways to spread them:
+  * `fold_sharded`: rank r folds a contiguous, cost-balanced slice (static; cost model: a fold is O(n^5) time, so
+    slices are balanced on sum(n^5) rather than on count);
+  * `fold_dealt`: ranks draw chunks of consecutive indices from one shared counter until the job is empty
+    (dynamic dealing: a GPU that is slower -- power capping -- simply draws fewer chunks).  The counter is the
+    process group's TCP store (atomic add) under torchrun, a lock-protected integer inside one process.
+The (small) results are gathered on the host with `all_gather_object`.
 """
 from __future__ import annotations
 
@@ -44,3 +48,41 @@ def fold_sharded(seqs: Sequence[str], fold_batch: Callable[[List[str]], list], r
             return out
     parts = gather(mine)
     return [x for part in parts for x in part]
+
+
+class LocalCounter:
+    """Shared counter inside one process (threads, or a single rank)."""
+
+    def __init__(self):
+        import threading
+        self._v, self._lock = 0, threading.Lock()
+
+    def take(self, count: int) -> int:
+        with self._lock:
+            v = self._v
+            self._v += count
+            return v
+
+
+class StoreCounter:
+    """Shared counter across ranks: `add` on the torch.distributed key-value store is an atomic fetch-and-add."""
+
+    def __init__(self, store, key: str = "ccj_next"):
+        self._store, self._key = store, key
+
+    def take(self, count: int) -> int:
+        return int(self._store.add(self._key, count)) - count
+
+
+def fold_dealt(total: int, chunk: int, counter, fold_range: Callable[[int, int], list]) -> List[Tuple[int, object]]:
+    """Draws [lo, lo+chunk) index ranges from `counter` until `total` is exhausted and folds each with
+    `fold_range(lo, hi)` (which returns one result per index).  Returns this rank's [(index, result)]."""
+    out: List[Tuple[int, object]] = []
+    chunk = max(1, int(chunk))
+    while True:
+        lo = counter.take(chunk)
+        if lo >= total:
+            return out
+        hi = min(lo + chunk, total)
+        res = fold_range(lo, hi)
+        out.extend(zip(range(lo, hi), res))

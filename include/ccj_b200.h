@@ -114,6 +114,11 @@ int64_t ccj_layout_index(int n, int i, int j, int k, int l);
  * sequence evaluates (can_pair-gated), all exact. */
 int ccj_batch_fill_profiled(ccj_ctx *ctx, float *kernel_ms);
 int ccj_count_terms(const char *seq, int n, int no_gu, int64_t *out);
+/* ccj_measure_addmin_peak: the integer ceiling SURVEY.md 8d asks to be measured on the box.  Runs a register-only
+ * micro-kernel on every SM and returns min-plus candidates ("add-min pairs") per second for the instruction form
+ * variant 0: int32 VIADDMNMX; 1: sign-extension of a packed int16 + VIADDMNMX (the form the split-point kernel
+ * applies to a record); 2: VIADDMNMX.S16x2, two int16 cells per instruction (the window kernels' form). */
+int ccj_measure_addmin_peak(ccj_ctx *ctx, int variant, double *pairs_per_s);
 
 /* library / build identification */
 const char *ccj_version(void);

@@ -5,6 +5,10 @@ oracle/Makefile (oracle/_ref/CCJ, oracle/_ref/ccj_ref_dump).  Run in the build c
     python tests/golden/make_golden.py hashes     # per-table FNV hashes               -> table_hashes.json
     python tests/golden/make_golden.py long       # n=100/150/200 benchmark inputs     -> folds_long.json
     python tests/golden/make_golden.py params     # scaled vrna_param_t dump           -> params_*.txt.gz
+    python tests/golden/make_golden.py config4    # first 16 config-4 sequences (150 nt) -> folds_config4.json
+    python tests/golden/make_golden.py config2    # first 64 config-2 sequences (100 nt) -> folds_config2.json
+    python tests/golden/make_golden.py big        # n>213: oracle/_ref/ccj_oracle hashes -> table_hashes_big.json
+                                                  # (the reference aborts there; ~1 h per sequence on one core)
 
 Sequence generators are the ones BASELINE.json / SURVEY.md 8d name for each config.
 """
@@ -110,6 +114,30 @@ def main():
             out = list(ex.map(lambda j: run_ref(j[0], j[1], j[2], j[3]), jobs))
         (HERE / "folds_long.json").write_text(json.dumps(out[::-1], indent=0))
         print(len(out), "long folds")
+    elif what in ("config4", "config2"):
+        # parity on the first 16 config-4 and the first 64 config-2 sequences
+        workers = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+        if what == "config4":
+            jobs = [(rand_seq(20000 + x, 150), "rna_Turner04.par", 2, ()) for x in range(16)]
+        else:
+            jobs = [(rand_seq(1000 + x, 100), "rna_Turner04.par", 2, ()) for x in range(64)]
+        with ThreadPoolExecutor(workers) as ex:
+            out = list(ex.map(lambda j: run_ref(j[0], j[1], j[2], j[3]), jobs))
+        (HERE / f"folds_{what}.json").write_text(json.dumps(out, indent=0))
+        print(len(out), what, "folds;", sum(r["rc"] != 0 for r in out), "with rc!=0")
+    elif what == "big":
+        # n > 213: the reference asserts (src/matrices.hh:159-160), so the pinned CPU restatement is the checker
+        sys.path.insert(0, str(ROOT))
+        from oracle import oracle as orc
+        seqs = [rand_seq(216, 216), designed(214)]
+        def one(seq):
+            tabs, w = orc.oracle_hashes(seq, "rna_Turner04.par", 2)
+            return {"seq": seq, "par": "rna_Turner04.par", "dangles": 2, "tables": tabs, "W": w,
+                    "source": "oracle/ccj_oracle.cc (CPU restatement; reference aborts for n >= 214)"}
+        with ThreadPoolExecutor(2) as ex:
+            out = list(ex.map(one, seqs))
+        (HERE / "table_hashes_big.json").write_text(json.dumps(out, indent=0))
+        print(len(out), "big hash sets")
     elif what == "params":
         for par in ["rna_Turner04.par", "rna_DirksPierce09.par"]:
             p = subprocess.run([str(DUMP), "params", str(PARAMS / par), "2"], capture_output=True, text=True)
