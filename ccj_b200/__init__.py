@@ -71,6 +71,7 @@ def load_library(path: Optional[os.PathLike] = None) -> C.CDLL:
     lib.ccj_last_error.argtypes = [vp]
     lib.ccj_last_error.restype = C.c_char_p
     lib.ccj_model_load.argtypes = [vp, C.c_char_p, i32, i32]
+    lib.ccj_model_load_embedded.argtypes = [vp, C.c_char_p, i32, i32]
     lib.ccj_fold_batch.argtypes = [vp, vp, i64p, i32, vp, vp, vp]
     lib.ccj_batch_prepare.argtypes = [vp, vp, i64p, i32]
     lib.ccj_batch_fill.argtypes = [vp]
@@ -205,7 +206,12 @@ class Context:
 
     # -- model ----------------------------------------------------------------------------------
     def load_model(self, par_file: str, dangles: int = 2, no_gu: bool = False) -> None:
-        self._check(self._lib.ccj_model_load(self._h, str(par_file).encode(), int(dangles), int(bool(no_gu))))
+        """`par_file` is a path, or "@dna_mathews2004" / "@rna_turner2004" for a set linked into the library."""
+        if str(par_file).startswith("@"):
+            self._check(self._lib.ccj_model_load_embedded(self._h, str(par_file)[1:].encode(), int(dangles),
+                                                          int(bool(no_gu))))
+        else:
+            self._check(self._lib.ccj_model_load(self._h, str(par_file).encode(), int(dangles), int(bool(no_gu))))
         self.par_file, self.dangles, self.no_gu = str(par_file), dangles, no_gu
 
     # -- folding --------------------------------------------------------------------------------

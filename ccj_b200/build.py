@@ -40,15 +40,21 @@ def _run(cmd, **kw):
     subprocess.run([str(c) for c in cmd], check=True, **kw)
 
 
+def embedded_par_defines():
+    """-D flags that tell embedded_params.cpp where the reference's parameter data files are (.incbin)."""
+    par = ROOT / "params"
+    return [f'-DCCJ_PAR_TURNER04="{par / "rna_Turner04.par"}"', f'-DCCJ_PAR_DNA_MATHEWS04="{par / "dna_Matthews04.par"}"']
+
+
 def build_library(force: bool = False, verbose_ptxas: bool = False) -> Path:
     sources = [CSRC / "ccj_abi.cu", CSRC / "ccj_kernels.cu", CSRC / "ccj_fill4.cu", CSRC / "ccj_peak.cu",
-               CSRC / "energy_model.cpp"]
+               CSRC / "energy_model.cpp", CSRC / "embedded_params.cpp"]
     sources = [s for s in sources if s.exists()]
     deps = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + list(CSRC.glob("*.hpp")) + sources + [
-        ROOT / "include" / "ccj_b200.h"]
+        ROOT / "include" / "ccj_b200.h", ROOT / "params" / "rna_Turner04.par", ROOT / "params" / "dna_Matthews04.par"]
     if not force and not _newer(LIB, deps):
         return LIB
-    flags = list(NVCC_FLAGS)
+    flags = list(NVCC_FLAGS) + embedded_par_defines()
     if verbose_ptxas:
         flags += ["-Xptxas", "-v"]
     _run([_nvcc(), *flags, "-shared", "-o", LIB, *sources, "-I", ROOT / "include", "-lcudart"])

@@ -77,7 +77,7 @@ static int fold_batch_file(const args_info &args) {
     }
     std::string file;
     if (args.paramFile_given) file = args.paramFile_arg;
-    else if (dna) { noGU = 1; file = "params/dna_Matthews04.par"; }
+    else if (dna) { noGU = 1; file = "@dna_mathews2004"; }   // vrna_params_load_DNA_Mathews2004 (src/CCJ.cc:88-90)
     else file = "params/rna_DirksPierce09.par";
     ccj_ctx *ctx = nullptr;
     const char *dev = getenv("CCJ_DEVICE");
@@ -85,7 +85,9 @@ static int fold_batch_file(const args_info &args) {
         std::cerr << "ccj_b200: no CUDA device available (this build has no CPU path)" << std::endl;
         return EXIT_FAILURE;
     }
-    if (!exists(file) || ccj_model_load(ctx, file.c_str(), args.dangles_arg, noGU) != 0) {
+    const int mrc = file[0] == '@' ? ccj_model_load_embedded(ctx, file.c_str() + 1, args.dangles_arg, noGU)
+                                   : (exists(file) ? ccj_model_load(ctx, file.c_str(), args.dangles_arg, noGU) : -1);
+    if (mrc != 0) {
         std::cerr << "Not a valid parameter file!" << std::endl;
         return EXIT_FAILURE;
     }
@@ -161,14 +163,14 @@ int main(int argc, char *argv[]) {
     if (args.paramFile_given) {
         file = args.paramFile_arg;
     } else if (seq.find('T') != std::string::npos) {
-        // the reference switches to its embedded Mathews-2004 DNA set here (vrna_params_load_DNA_Mathews2004);
-        // that hex-encoded set is not bundled -- the equivalent file is params/dna_Matthews04.par
+        // the reference switches to its embedded Mathews-2004 DNA set here (src/CCJ.cc:88-90); the same set is linked
+        // into libccj_b200.so, so this works from any directory like the reference does
         noGU = 1;
-        file = "params/dna_Matthews04.par";
+        ccj_params_load_DNA_Mathews2004();
     } else {
         file = "params/rna_DirksPierce09.par";  // cwd-relative, as in the reference (src/CCJ.cc:92)
     }
-    if (!exists(file) || !ccj_params_load(file.c_str())) {
+    if (!file.empty() && (!exists(file) || !ccj_params_load(file.c_str()))) {
         std::cerr << "Not a valid parameter file!" << std::endl;
         exit(EXIT_FAILURE);
     }

@@ -19,6 +19,8 @@ int ccj_params_load(const char *par_file) {
     return 1;
 }
 
+void ccj_params_load_DNA_Mathews2004() { g_param_file = "@dna_mathews2004"; }
+
 namespace {
 // one context per process and device (CCJ_DEVICE selects the GPU); the reference is equally process-global
 ccj_ctx *shared_ctx() {
@@ -39,7 +41,10 @@ W_final::W_final(std::string seq, int dangle) : params_(new ccj_params_view{g_pa
     seq_ = seq;
     n = (cand_pos_t)seq.length();
     ctx_ = shared_ctx();
-    if (ccj_model_load(ctx_, g_param_file.c_str(), dangle, noGU) != 0) {
+    const int mrc = !g_param_file.empty() && g_param_file[0] == '@'
+                        ? ccj_model_load_embedded(ctx_, g_param_file.c_str() + 1, dangle, noGU)
+                        : ccj_model_load(ctx_, g_param_file.c_str(), dangle, noGU);
+    if (mrc != 0) {
         std::cerr << "Not a valid parameter file!" << std::endl;  // src/CCJ.cc:84,95
         exit(EXIT_FAILURE);
     }

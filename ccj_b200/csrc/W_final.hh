@@ -14,6 +14,7 @@
 // W_final uses (src/CCJ.cc:80-99), `noGU` is the ViennaRNA global read by make_pair_matrix (src/CCJ.cc:77).
 extern int noGU;
 int ccj_params_load(const char *par_file);  // 1 on success (like vrna_params_load), 0 if unreadable
+void ccj_params_load_DNA_Mathews2004();     // vrna_params_load_DNA_Mathews2004: the set linked into the library
 
 struct ccj_params_view {   // what W_final::params_ exposes of the loaded model
     std::string param_file;

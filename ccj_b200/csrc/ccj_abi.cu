@@ -202,6 +202,9 @@ size_t budget_bytes(ccj_ctx *ctx) {
     return fr > reserve ? fr - reserve : 0;
 }
 
+// the level kernels put the sequence index (times up to 4 roles) into gridDim.y/z, which CUDA limits to 65535
+const int kMaxWave = 65535 / 4;
+
 int validate(ccj_ctx *ctx, const char *s, int64_t len) {
     if (len <= 0) return fail(ctx, CCJ_ERR_SEQUENCE, "sequence is missing");
     if (len > CCJ_HAIRPIN_TAB - 2) return fail(ctx, CCJ_ERR_TOO_LARGE, "sequence longer than supported");
@@ -222,74 +225,98 @@ bool use_tuned(int nmax) {
     return !(g && g[0] == '1') && ccj::fill4_tuned_supported(nmax);
 }
 
-// Tuned path, three streams (all inside the captured graph):
-//   main : k_roles(t, even t: levels t and t+1) -> k_final(t)   (needs 2D spans <= t)
-//   s_win: k_windows(t)                                   (reads 4D levels <= t-2 only -> runs one level ahead)
-//   s_2d : k_P(s) -> k_2d(s)                              (needs PK of levels <= s-3 -> runs beside roles(s-2..s))
-void enqueue_fill(ccj_ctx *ctx, ccj::LaunchDims d) {
+// Tuned path, three streams (all inside the captured graph); KF = ccj::fill4_fused_levels() = 3, lead = KF-2 = 1:
+//   main : k_roles(t) for t = 0 mod KF -- the split points of levels t..t+KF-1 whose sources lie on levels <= t-1;
+//          its partner cells on level t+KF-1 read {WB,WP,WBP} of spans <= t+KF-2, hence the wait on evD[t+lead].
+//          k_final(t) for every t -- same-cell assembly plus the <= (t mod KF) late split points; reads levels <= t-1
+//          (main-stream order), 2D spans <= t (covered by the evD wait of its k_roles) and the window partials (evW[t]).
+//   s_win: k_winLR(t), k_winM(t).  A window candidate shortens an arm by x >= 1 on one side and y >= 1 on the other, so
+//          level t only reads the window copies of levels <= t-2; it writes the partials of level t into wscr[t & 1],
+//          whose previous content k_final(t-2) consumed.  One wait on evF[t-2] covers both -> the windows run one
+//          level ahead of the main stream.
+//   s_2d : k_P(s) -> k_2d(s) for span s, `lead` spans ahead of the levels.  P(i,i+s) reads PK of levels <= s-3: wait on
+//          evF[s-3].
+// Every CUDA call is checked; the first error ends the sequence and is returned (a failed launch inside a capture
+// is reported by cudaGetLastError, not by the launch statement).
+#define EQ(call)                                   \
+    do {                                           \
+        const cudaError_t e_ = (call);             \
+        if (e_ != cudaSuccess) return e_;          \
+    } while (0)
+#define EQL(launch)                                \
+    do {                                           \
+        launch;                                    \
+        const cudaError_t e_ = cudaGetLastError(); \
+        if (e_ != cudaSuccess) return e_;          \
+    } while (0)
+cudaError_t enqueue_fill(ccj_ctx *ctx, ccj::LaunchDims d) {
     const ccj_model *M = ctx->d_model;
     const ccj_seq *Q = ctx->d_seqs;
     cudaStream_t s0 = ctx->stream;
     if (!use_tuned(d.nmax)) {
-        ccj::launch_init(M, Q, d, s0);
+        EQL(ccj::launch_init(M, Q, d, s0));
         for (int s = 0; s < d.nmax; ++s) {
-            ccj::launch_P(M, Q, d, s, s0);
-            ccj::launch_2d(M, Q, d, s, s0);
-            ccj::launch_4d(M, Q, d, s, s0);
+            EQL(ccj::launch_P(M, Q, d, s, s0));
+            EQL(ccj::launch_2d(M, Q, d, s, s0));
+            EQL(ccj::launch_4d(M, Q, d, s, s0));
         }
-        ccj::launch_W(M, Q, d, s0);
-        return;
+        EQL(ccj::launch_W(M, Q, d, s0));
+        return cudaSuccess;
     }
     const int nm = d.nmax;
     while ((int)ctx->dep.size() < 3 * nm + 2) {
-        cudaEvent_t e;
-        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        cudaEvent_t e = nullptr;
+        EQ(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ctx->dep.push_back(e);
     }
     cudaEvent_t *evF = ctx->dep.data(), *evD = evF + nm, *evW = evD + nm, evPrep = ctx->dep[3 * nm];
     cudaStream_t sw = ctx->s_win, s2 = ctx->s_2d;
-    ccj::launch_init(M, Q, d, s0);
-    ccj::launch_prep(M, Q, d, s0);
-    cudaEventRecord(evPrep, s0);
+    EQL(ccj::launch_init(M, Q, d, s0));
+    EQL(ccj::launch_prep(M, Q, d, s0));
+    EQ(cudaEventRecord(evPrep, s0));
     const int last_level = nm - 3;
-    if (last_level >= 0) cudaStreamWaitEvent(sw, evPrep, 0);
-    cudaStreamWaitEvent(s2, evPrep, 0);
-    // k_roles(s) works on levels s..s+KF-1 and needs the 2D tables up to span s+KF-2: the 2D stream runs `lead`
-    // spans ahead of the levels (P(s') only needs PK of levels <= s'-3, so there is room)
+    if (last_level >= 0) EQ(cudaStreamWaitEvent(sw, evPrep, 0));
+    EQ(cudaStreamWaitEvent(s2, evPrep, 0));
     const int KFL = ccj::fill4_fused_levels(), lead = KFL - 2 > 0 ? KFL - 2 : 0;
-    auto span_step = [&](int sp) {
-        if (sp >= nm) return;
-        if (sp >= 3 && sp - 3 <= last_level) cudaStreamWaitEvent(s2, evF[sp - 3], 0);
-        ccj::launch_P_tuned(M, Q, d, sp, s2);
-        ccj::launch_2d(M, Q, d, sp, s2);
-        cudaEventRecord(evD[sp], s2);
+    auto span_step = [&](int sp) -> cudaError_t {
+        if (sp >= nm) return cudaSuccess;
+        if (sp >= 3 && sp - 3 <= last_level) EQ(cudaStreamWaitEvent(s2, evF[sp - 3], 0));
+        EQL(ccj::launch_P_tuned(M, Q, d, sp, s2));
+        EQL(ccj::launch_2d(M, Q, d, sp, s2));
+        EQ(cudaEventRecord(evD[sp], s2));
+        return cudaSuccess;
     };
-    for (int sp = 0; sp < lead; ++sp) span_step(sp);
+    for (int sp = 0; sp < lead; ++sp) EQ(span_step(sp));
     for (int s = 0; s < nm; ++s) {
-        span_step(s + lead);
+        EQ(span_step(s + lead));
         if (s <= last_level) {
-            if (s >= 2) cudaStreamWaitEvent(sw, evF[s - 2], 0);
-            ccj::launch_4d_windows(M, Q, d, s, sw);
-            cudaEventRecord(evW[s], sw);
+            if (s >= 2) EQ(cudaStreamWaitEvent(sw, evF[s - 2], 0));
+            EQL(ccj::launch_4d_windows(M, Q, d, s, sw));
+            EQ(cudaEventRecord(evW[s], sw));
             if (s % KFL == 0) {
-                cudaStreamWaitEvent(s0, evD[std::min(s + lead, nm - 1)], 0);
-                ccj::launch_4d_roles(M, Q, d, s, s0);
+                EQ(cudaStreamWaitEvent(s0, evD[std::min(s + lead, nm - 1)], 0));
+                EQL(ccj::launch_4d_roles(M, Q, d, s, s0));
             }
-            cudaStreamWaitEvent(s0, evW[s], 0);
-            ccj::launch_4d_final(M, Q, d, s, s0);
-            cudaEventRecord(evF[s], s0);
+            EQ(cudaStreamWaitEvent(s0, evW[s], 0));
+            EQL(ccj::launch_4d_final(M, Q, d, s, s0));
+            EQ(cudaEventRecord(evF[s], s0));
         }
     }
-    cudaStreamWaitEvent(s0, evD[nm - 1], 0);
-    if (last_level >= 0) cudaStreamWaitEvent(s0, evW[last_level], 0);
-    ccj::launch_W(M, Q, d, s0);
+    EQ(cudaStreamWaitEvent(s0, evD[nm - 1], 0));
+    if (last_level >= 0) EQ(cudaStreamWaitEvent(s0, evW[last_level], 0));
+    EQL(ccj::launch_W(M, Q, d, s0));
+    return cudaSuccess;
 }
+#undef EQ
+#undef EQL
 
 }  // namespace
 
 extern "C" {
 
 const char *ccj_version(void) { return "ccj_b200 0.1 (sm_100a)"; }
+
+void ccj_ctx_destroy(ccj_ctx *ctx);
 
 int ccj_ctx_create(int device, ccj_ctx **out) {
     if (!out) return CCJ_ERR_ARG;
@@ -309,7 +336,7 @@ int ccj_ctx_create(int device, ccj_ctx **out) {
         cudaStreamCreateWithPriority(&ctx->s_2d, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
         cudaMalloc((void **)&ctx->d_model, sizeof(ccj_model)) != cudaSuccess) {
-        delete ctx;
+        ccj_ctx_destroy(ctx);   // null-checks every handle it releases
         return CCJ_ERR_CUDA;
     }
     ctx->h_model = new ccj_model();
@@ -337,11 +364,25 @@ void ccj_ctx_destroy(ccj_ctx *ctx) {
 
 const char *ccj_last_error(const ccj_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context"; }
 
-int ccj_model_load(ccj_ctx *ctx, const char *par_file, int dangles, int no_gu) {
-    if (!ctx || !par_file) return CCJ_ERR_ARG;
+// defaults (the reference's compiled-in Turner-2004 tables), then the file or embedded set on top of them
+static bool read_params(const char *par_file, const char *embedded, ccj::RawParams &rp, std::string &err) {
+    if (!ccj::load_defaults(rp, err)) return false;
+    if (embedded) {
+        size_t len = 0;
+        const char *text = ccj::embedded_par(embedded, &len);
+        if (!text) {
+            err = std::string("unknown embedded parameter set ") + embedded;
+            return false;
+        }
+        return ccj::load_par_text(text, len, rp, err);
+    }
+    return ccj::load_par_file(par_file, rp, err);
+}
+
+static int model_load_common(ccj_ctx *ctx, const char *par_file, const char *embedded, int dangles, int no_gu) {
     ccj::RawParams *rp = new ccj::RawParams();
     std::string err;
-    if (!ccj::load_par_file(par_file, *rp, err)) {
+    if (!read_params(par_file, embedded, *rp, err)) {
         delete rp;
         return fail(ctx, CCJ_ERR_PARAMS, err);
     }
@@ -356,13 +397,23 @@ int ccj_model_load(ccj_ctx *ctx, const char *par_file, int dangles, int no_gu) {
     return 0;
 }
 
+int ccj_model_load(ccj_ctx *ctx, const char *par_file, int dangles, int no_gu) {
+    if (!ctx || !par_file) return CCJ_ERR_ARG;
+    return model_load_common(ctx, par_file, nullptr, dangles, no_gu);
+}
+
+int ccj_model_load_embedded(ccj_ctx *ctx, const char *name, int dangles, int no_gu) {
+    if (!ctx || !name) return CCJ_ERR_ARG;
+    return model_load_common(ctx, nullptr, name, dangles, no_gu);
+}
+
 int64_t ccj_wave_capacity(ccj_ctx *ctx, int n) {
     if (!ctx || n < 1) return 0;
     cudaSetDevice(ctx->device);
     SeqPlan p;
     plan_seq(n, p);
     const size_t per = p.in_bytes + p.out_bytes + p.tab_bytes + 512;
-    return (int64_t)(budget_bytes(ctx) / per);
+    return std::min<int64_t>((int64_t)(budget_bytes(ctx) / per), kMaxWave);
 }
 
 void *ccj_stream(ccj_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
@@ -370,6 +421,7 @@ void *ccj_stream(ccj_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 int ccj_batch_prepare(ccj_ctx *ctx, const char *seqs, const int64_t *offsets, int nseq) {
     if (!ctx || !seqs || !offsets || nseq < 1) return CCJ_ERR_ARG;
     if (!ctx->model_ok) return fail(ctx, CCJ_ERR_STATE, "no energy model loaded");
+    if (nseq > kMaxWave) return fail(ctx, CCJ_ERR_TOO_LARGE, "more than 16383 sequences in one wave; use ccj_fold_batch");
     CU(cudaSetDevice(ctx->device));
     ctx->prepared = ctx->filled = ctx->traced = false;
     ctx->plan.assign(nseq, SeqPlan());
@@ -485,19 +537,33 @@ int ccj_batch_fill(ccj_ctx *ctx) {
         // capture the per-level launch sequence once per wave shape
         cudaGraph_t g = nullptr;
         CU(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-        enqueue_fill(ctx, d);
-        CU(cudaStreamEndCapture(ctx->stream, &g));
+        const cudaError_t qe = enqueue_fill(ctx, d);
+        // always end the capture (also joins the side streams back), never keep a partial graph
+        const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
+        if (qe != cudaSuccess || ce != cudaSuccess) {
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            return fail(ctx, CCJ_ERR_CUDA, std::string("fill launch sequence: ") + cudaGetErrorString(qe != cudaSuccess ? qe : ce));
+        }
         cudaGraphExec_t ge = nullptr;
-        CU(cudaGraphInstantiate(&ge, g, 0));
-        CU(cudaGraphDestroy(g));
+        const cudaError_t ie = cudaGraphInstantiate(&ge, g, 0);
+        cudaGraphDestroy(g);
+        if (ie != cudaSuccess) return fail(ctx, CCJ_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie));
         if (ctx->graphs.size() > 32) drop_graphs(ctx);
         it = ctx->graphs.emplace(key, ge).first;
     }
-    CU(cudaEventRecord(ctx->ev0, ctx->stream));
-    CU(cudaGraphLaunch(it->second, ctx->stream));
-    CU(cudaEventRecord(ctx->ev1, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    CU(cudaGetLastError());
+    {   // a graph whose launch fails is not kept: the next call captures afresh
+        cudaError_t le = cudaEventRecord(ctx->ev0, ctx->stream);
+        if (le == cudaSuccess) le = cudaGraphLaunch(it->second, ctx->stream);
+        if (le == cudaSuccess) le = cudaEventRecord(ctx->ev1, ctx->stream);
+        if (le == cudaSuccess) le = cudaStreamSynchronize(ctx->stream);
+        if (le == cudaSuccess) le = cudaGetLastError();
+        if (le != cudaSuccess) {
+            cudaGraphExecDestroy(it->second);
+            ctx->graphs.erase(it);
+            return fail(ctx, CCJ_ERR_CUDA, std::string("fill graph launch: ") + cudaGetErrorString(le));
+        }
+    }
     CU(cudaEventElapsedTime(&ctx->fill_ms, ctx->ev0, ctx->ev1));
     ctx->fill_launches = ccj::fill_launch_count(d.nmax, use_tuned(d.nmax));
     ctx->filled = true;
@@ -513,13 +579,23 @@ int ccj_batch_fill_profiled(ccj_ctx *ctx, float *kernel_ms) {
     d.nseq = (int)ctx->plan.size();
     d.nmax = ctx->nmax;
     const int nlaunch = ccj::fill_launch_count(d.nmax, true) + 8;
-    std::vector<cudaEvent_t> ev((size_t)nlaunch + 1);
+    struct EventSet {   // destroyed on every return path
+        std::vector<cudaEvent_t> v;
+        ~EventSet() { for (cudaEvent_t e : v) if (e) cudaEventDestroy(e); }
+    } evs;
+    evs.v.assign((size_t)nlaunch + 1, nullptr);
+    std::vector<cudaEvent_t> &ev = evs.v;
     std::vector<int> kind;
     for (auto &e : ev) CU(cudaEventCreate(&e));
     size_t x = 0;
     cudaStream_t st = ctx->stream;
     CU(cudaEventRecord(ev[x++], st));
-    auto mark = [&](int k) { cudaEventRecord(ev[x++], st); kind.push_back(k); };
+    cudaError_t mark_err = cudaSuccess;
+    auto mark = [&](int k) {
+        const cudaError_t e = cudaEventRecord(ev[x++], st);
+        if (e != cudaSuccess && mark_err == cudaSuccess) mark_err = e;
+        kind.push_back(k);
+    };
     const bool tuned = use_tuned(d.nmax);
     ccj::launch_init(ctx->d_model, ctx->d_seqs, d, st); mark(3);
     if (tuned) { ccj::launch_prep(ctx->d_model, ctx->d_seqs, d, st); mark(3); }
@@ -550,6 +626,7 @@ int ccj_batch_fill_profiled(ccj_ctx *ctx, float *kernel_ms) {
     ccj::launch_W(ctx->d_model, ctx->d_seqs, d, st); mark(3);
     CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
+    CU(mark_err);
     for (int k = 0; k < 6; ++k) kernel_ms[k] = 0.f;
     for (size_t y = 0; y < kind.size(); ++y) {
         float ms = 0.f;
@@ -557,7 +634,6 @@ int ccj_batch_fill_profiled(ccj_ctx *ctx, float *kernel_ms) {
         kernel_ms[kind[y]] += ms;
     }
     CU(cudaEventElapsedTime(&ctx->fill_ms, ev[0], ev[x - 1]));
-    for (auto &e : ev) cudaEventDestroy(e);
     ctx->fill_launches = (int)kind.size();
     ctx->filled = true;
     ctx->traced = false;
@@ -638,7 +714,7 @@ int ccj_fold_batch(ccj_ctx *ctx, const char *seqs, const int64_t *offsets, int n
             SeqPlan p;
             plan_seq((int)len, p);
             const size_t add = p.in_bytes + p.out_bytes + p.tab_bytes;
-            if (bytes + add > budget) break;
+            if (bytes + add > budget || s1 - s0 >= kMaxWave) break;
             bytes += add;
             ++s1;
         }
@@ -868,7 +944,8 @@ int ccj_model_text(const char *par_file, int dangles, int no_gu, const char *out
     if (!par_file || !out_path) return CCJ_ERR_ARG;
     ccj::RawParams *rp = new ccj::RawParams();
     std::string e;
-    if (!ccj::load_par_file(par_file, *rp, e)) {
+    // "@name" selects a parameter set linked into the library (ccj_model_load_embedded)
+    if (!read_params(par_file, par_file[0] == '@' ? par_file + 1 : nullptr, *rp, e)) {
         if (err && err_len) snprintf(err, err_len, "%s", e.c_str());
         delete rp;
         return CCJ_ERR_PARAMS;

@@ -66,7 +66,7 @@ extern "C" int ccj_measure_addmin_peak(ccj_ctx *ctx, int variant, double *pairs_
     }
     int h_in[256];
     for (int x = 0; x < 256; ++x) h_in[x] = variant == 2 ? ((x * 37 - 1000) & 0x7fff) | (((x * 53 - 900) & 0x7fff) << 16) : x * 7919 - 100000;
-    for (int x = 0; x < 32; ++x) h_in[x] = variant == 2 ? 0xffffffff : -1;  // w = -1: the chains keep moving
+    for (int x = 0; x < 32; ++x) h_in[x] = -1;   // int32: -1; int16x2: (-1, -1)  // w = -1: the chains keep moving
     cudaMemcpyAsync(d_in, h_in, sizeof h_in, cudaMemcpyHostToDevice, st);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);

@@ -167,10 +167,9 @@ template <class T> void fill_all(T &arr, int v) {
 
 }  // namespace
 
-// Start state = what the reference holds before any file is read, restricted to what a v2.0 file does
-// not overwrite: pair-type row/column 0 is INF everywhere (src/ViennaRNA/params/default.c), and the
-// scalar defaults of default.c:64-76.  Array sections a file omits keep INF and build_model() refuses
-// them (the Turner-2004 default tables are not bundled).
+// Blank state: pair-type row/column 0 is INF everywhere (src/ViennaRNA/params/default.c), scalar defaults of
+// default.c:64-76, arrays INF.  load_defaults() turns it into what the reference holds before any file is read
+// (its compiled-in Turner-2004 tables), so that sections a file omits keep those values like in the reference.
 RawParams::RawParams() {
     fill_all(stack, CCJ_INF);
     fill_all(hairpin, CCJ_INF);
@@ -205,14 +204,43 @@ RawParams::RawParams() {
 }
 
 bool load_par_file(const char *path, RawParams &rp, std::string &err) {
-    std::ifstream in(path);
+    std::ifstream in(path, std::ios::binary);
     if (!in) {
         err = std::string("cannot open parameter file ") + path;
         return false;
     }
+    std::stringstream ss;
+    ss << in.rdbuf();
+    const std::string text = ss.str();
+    return load_par_text(text.data(), text.size(), rp, err);
+}
+
+// The reference's compiled-in defaults (src/ViennaRNA/params/default.c) are the Turner-2004 set; its own
+// params/rna_Turner04.par holds the same numbers (checked against a dump of the compiled reference after loading
+// a file without sections, tests/test_layout_params.py).  The special-loop strings of the defaults lack the extra
+// blank entry the file reader appends (io.c:1027-1040).
+bool load_defaults(RawParams &rp, std::string &err) {
+    size_t len = 0;
+    const char *text = embedded_par("rna_turner2004", &len);
+    if (!text) {
+        err = "embedded default parameter set missing";
+        return false;
+    }
+    if (!load_par_text(text, len, rp, err)) return false;
+    for (char *names : {rp.Tetraloops, rp.Triloops, rp.Hexaloops}) {
+        const size_t l = strlen(names);
+        if (l >= 2 && names[l - 1] == ' ' && names[l - 2] == ' ') names[l - 1] = '\0';
+    }
+    rp.present = 0;
+    rp.warnings.clear();
+    return true;
+}
+
+bool load_par_text(const char *text, size_t len, RawParams &rp, std::string &err) {
     Reader rd;
     rd.lxc37 = rp.lxc;
     std::string line;
+    std::istringstream in(std::string(text, len));
     while (std::getline(in, line)) {
         if (!line.empty() && line.back() == '\r') line.pop_back();
         rd.lines.push_back(line);

@@ -39,6 +39,15 @@ struct RawParams {
 // (to stay in sync with the line stream) and, except for the symmetry check, discarded: at 37 C the rescaling
 // is the identity.
 bool load_par_file(const char *path, RawParams &rp, std::string &err);
+// the same reader on a text held in memory (set_parameters_from_string, io.c:454-674)
+bool load_par_text(const char *text, size_t len, RawParams &rp, std::string &err);
+// Brings `rp` to the state the reference starts from: its compiled-in Turner-2004 defaults
+// (src/ViennaRNA/params/default.c).  A file read afterwards only overrides the sections it holds.
+bool load_defaults(RawParams &rp, std::string &err);
+// Parameter sets linked into the library (embedded_params.cpp): "rna_turner2004" (the defaults) and
+// "dna_mathews2004" (vrna_params_load_DNA_Mathews2004, src/ViennaRNA/params/io.c; byte-identical to the
+// reference's static/misc/dna_mathews2004.hex).  Returns nullptr for an unknown name.
+const char *embedded_par(const char *name, size_t *len);
 
 // get_scaled_params at 37 C with the default model details (dangles=2 at scaling time, special_hp=1),
 // then model_details.dangles := dangles (src/W_final.cc:20-25), pair matrix with noGU, PK penalties.

@@ -55,6 +55,12 @@ const char *ccj_last_error(const ccj_ctx *ctx);
 /* vrna_params_load(file) + scale_parameters() + model_details.dangles = dangles + make_pair_matrix()
  * (src/CCJ.cc:80-99, src/W_final.cc:20-25).  noGU as src/CCJ.cc:77. */
 int ccj_model_load(ccj_ctx *ctx, const char *par_file, int dangles, int no_gu);
+/* The same for a parameter set linked into the library: "dna_mathews2004" replaces
+ * vrna_params_load_DNA_Mathews2004() (src/CCJ.cc:88-90, the set the reference embeds as
+ * src/ViennaRNA/static/misc/dna_mathews2004.hex), "rna_turner2004" is the reference's compiled-in default set
+ * (src/ViennaRNA/params/default.c).  Sections a parameter file omits keep the values of the latter, as in the
+ * reference. */
+int ccj_model_load_embedded(ccj_ctx *ctx, const char *name, int dangles, int no_gu);
 
 /* W_final::W_final + W_final::ccj for `nseq` independent sequences (src/CCJ.cc:44-49).
  *   seqs     : concatenated upper-case sequences over GCAU(T), no separators
@@ -100,7 +106,7 @@ int ccj_table2_hash(ccj_ctx *ctx, int seq_index, int table, uint64_t *hash, int6
 
 /* Host-only helpers (no GPU needed), used by the CPU test-suite:
  * ccj_model_text writes the scaled model in the "name idx... value" text form of
- * `oracle/_ref/ccj_ref_dump params` to `out_path`; ccj_layout_index is the storage offset of cell
+ * `oracle/_ref/ccj_ref_dump params` to `out_path` (par_file "@name" = an embedded set); ccj_layout_index is the storage offset of cell
  * (i,j,k,l) inside one 4D table (-1 for an invalid index). */
 int ccj_model_text(const char *par_file, int dangles, int no_gu, const char *out_path, char *err, size_t err_len);
 int64_t ccj_layout_index(int n, int i, int j, int k, int l);

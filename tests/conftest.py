@@ -31,11 +31,14 @@ def library():
 @pytest.fixture(scope="session")
 def emu_bin():
     """Host build of the product's cell functions (tests/emu/ccj_emu.cpp), g++ only."""
-    srcs = [ROOT / "tests" / "emu" / "ccj_emu.cpp", ROOT / "ccj_b200" / "csrc" / "energy_model.cpp"]
+    srcs = [ROOT / "tests" / "emu" / "ccj_emu.cpp", ROOT / "ccj_b200" / "csrc" / "energy_model.cpp",
+            ROOT / "ccj_b200" / "csrc" / "embedded_params.cpp"]
     deps = srcs + list((ROOT / "ccj_b200" / "csrc").glob("*.cuh")) + list((ROOT / "ccj_b200" / "csrc").glob("*.h*"))
     if not EMU_BIN.exists() or any(d.stat().st_mtime > EMU_BIN.stat().st_mtime for d in deps):
         EMU_BIN.parent.mkdir(exist_ok=True)
-        subprocess.run(["g++", "-std=c++17", "-O2", "-o", str(EMU_BIN)] + [str(s) for s in srcs], check=True)
+        from ccj_b200 import build
+        subprocess.run(["g++", "-std=c++17", "-O2", *build.embedded_par_defines(), "-o", str(EMU_BIN)] +
+                       [str(s) for s in srcs], check=True)
     return EMU_BIN
 
 

@@ -144,6 +144,19 @@ def main():
             assert p.returncode == 0
             with gzip.open(HERE / f"params_{par[:-4]}.txt.gz", "wt") as f:
                 f.write(p.stdout)
+        # what the reference holds for sections a file omits: a file with no section, and one with two sections only
+        import tempfile
+        sys.path.insert(0, str(ROOT))
+        sys.path.insert(0, str(ROOT / "tests"))
+        from test_layout_params import STUB_PAR, partial_par
+        for name, text in (("defaults", STUB_PAR), ("partial", partial_par())):
+            with tempfile.NamedTemporaryFile("w", suffix=".par") as tf:
+                tf.write(text)
+                tf.flush()
+                p = subprocess.run([str(DUMP), "params", tf.name, "2"], capture_output=True, text=True)
+                assert p.returncode == 0
+                with gzip.open(HERE / f"params_{name}.txt.gz", "wt") as f:
+                    f.write(p.stdout)
         print("params dumped")
 
 

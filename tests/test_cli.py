@@ -71,8 +71,13 @@ def test_cli_input_conventions(cli):
     rc, out, err = run(cli, ["--noConv", "GCAACGATGACATACATCGCTAGTCGACGC"])
     assert (rc, out) == (0, "GCAACGATGACATACATCGCTAGTCGACGC\n....(((((.....)))))........... (-4.4)\n")
     assert err == "WARNING: stacking enthalpies not symmetric\n" * 4   # the reader's check_symmetry, like the reference
-    # run from a directory without params/: the default file is cwd-relative, exactly like the reference
+    # run from a directory without params/: the default file is cwd-relative, exactly like the reference ...
     assert run(cli, ["ACGU"], cwd="/tmp")[0] == 1
+    # ... while the DNA set is linked into the binary / library (vrna_params_load_DNA_Mathews2004, src/CCJ.cc:88-90)
+    rc2, out2, err2 = run(cli, ["--noConv", "GCAACGATGACATACATCGCTAGTCGACGC"], cwd="/tmp")
+    assert (rc2, out2, err2) == (rc, out, err)
+    if REF.exists():
+        assert run(REF, ["--noConv", "GCAACGATGACATACATCGCTAGTCGACGC"], cwd="/tmp") == (rc, out, err)
 
 
 @pytest.mark.gpu

@@ -51,10 +51,23 @@ def _parse(text):
     return out
 
 
-@pytest.mark.parametrize("par", ["rna_Turner04.par", "rna_DirksPierce09.par"])
-def test_scaled_model_matches_reference_dump(library, par):
-    mine = _parse(ccj_b200.model_text(str(ROOT / "params" / par), 2))
-    with gzip.open(ROOT / "tests" / "golden" / f"params_{par[:-4]}.txt.gz", "rt") as f:
+STUB_PAR = "## RNAfold parameter file v2.0\n\n#END\n"   # no section: the reference keeps all its compiled-in defaults
+
+
+@pytest.mark.parametrize("par", ["rna_Turner04.par", "rna_DirksPierce09.par", "defaults", "partial"])
+def test_scaled_model_matches_reference_dump(library, par, tmp_path):
+    """"defaults": a file without sections; "partial": a file holding only # stack and # hairpin -- everything the
+    file omits must keep the reference's compiled-in Turner-2004 values (src/ViennaRNA/params/default.c)."""
+    if par == "defaults":
+        (tmp_path / "stub.par").write_text(STUB_PAR)
+        mine = _parse(ccj_b200.model_text(str(tmp_path / "stub.par"), 2))
+    elif par == "partial":
+        (tmp_path / "partial.par").write_text(partial_par())
+        mine = _parse(ccj_b200.model_text(str(tmp_path / "partial.par"), 2))
+    else:
+        mine = _parse(ccj_b200.model_text(str(ROOT / "params" / par), 2))
+    stem = par[:-4] if par.endswith(".par") else par
+    with gzip.open(ROOT / "tests" / "golden" / f"params_{stem}.txt.gz", "rt") as f:
         ref = _parse(f.read())
     checked = 0
     for key, val in mine.items():
@@ -75,6 +88,27 @@ def test_scaled_model_matches_reference_dump(library, par):
         names = ref_names(ref, kind + "s", width)
         for pos, nm in enumerate(names):
             assert mine[(kind + "_E", nm)] == ref[(kind + "_E", str(pos))]
+
+
+def partial_par():
+    """The # stack and # hairpin sections of the DP09 file only (make_golden.py writes the same file for the reference)."""
+    lines = (ROOT / "params" / "rna_DirksPierce09.par").read_text().splitlines()
+    out, keep = [lines[0], ""], False
+    for ln in lines[1:]:
+        if ln.startswith("#"):
+            keep = ln.strip() in ("# stack", "# hairpin")
+        if keep:
+            out.append(ln)
+    return "\n".join(out) + "\n\n#END\n"
+
+
+def test_embedded_dna_set_equals_the_par_file(library):
+    """vrna_params_load_DNA_Mathews2004 (src/CCJ.cc:88-90): the set linked into the library is the reference's
+    params/dna_Matthews04.par, which is byte-identical to its static/misc/dna_mathews2004.hex."""
+    assert ccj_b200.model_text("@dna_mathews2004") == ccj_b200.model_text(str(ROOT / "params" / "dna_Matthews04.par"))
+    assert ccj_b200.model_text("@rna_turner2004") == ccj_b200.model_text(str(ROOT / "params" / "rna_Turner04.par"))
+    with pytest.raises(ccj_b200.CCJError):
+        ccj_b200.model_text("@no_such_set")
 
 
 def ref_names(ref, key, width):
