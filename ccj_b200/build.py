@@ -15,6 +15,9 @@ CSRC = ROOT / "ccj_b200" / "csrc"
 LIB = ROOT / "ccj_b200" / "libccj_b200.so"
 CLI = ROOT / "ccj_b200" / "bin" / "CCJ"
 
+# the C++ class shells (W_final / pseudo_loop / s_energy_matrix on top of the C ABI); host code, g++
+SHELL_SOURCES = [CSRC / "W_final.cc", CSRC / "ccj_classes.cc", CSRC / "ccj_shell.cc"]
+
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--expt-relaxed-constexpr", "-diag-suppress", "20012",
@@ -62,10 +65,10 @@ def build_library(force: bool = False, verbose_ptxas: bool = False) -> Path:
 
 
 def build_cli(force: bool = False) -> Path:
-    sources = [CSRC / "CCJ.cc", CSRC / "cmdline.cc", CSRC / "W_final.cc"]
+    sources = [CSRC / "CCJ.cc", CSRC / "cmdline.cc", *SHELL_SOURCES]
     if not all(s.exists() for s in sources):
         return CLI
-    deps = sources + list(CSRC.glob("*.hh")) + list(CSRC.glob("*.hpp")) + [LIB]
+    deps = sources + list(CSRC.glob("*.hh")) + list(CSRC.glob("*.hpp")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [LIB]
     if not force and not _newer(CLI, deps):
         return CLI
     CLI.parent.mkdir(parents=True, exist_ok=True)

@@ -7,70 +7,47 @@
 #include <iostream>
 
 #include "ccj_render.hpp"
+#include "ccj_shell.hpp"
 
-int noGU = 0;
-static std::string g_param_file;
+int ccj_params_load(const char *par_file) { return vrna_params_load(par_file, VRNA_PARAMETER_FORMAT_DEFAULT); }
+void ccj_params_load_DNA_Mathews2004() { vrna_params_load_DNA_Mathews2004(); }
 
-int ccj_params_load(const char *par_file) {
-    FILE *f = fopen(par_file, "r");
-    if (!f) return 0;
-    fclose(f);
-    g_param_file = par_file;
-    return 1;
-}
-
-void ccj_params_load_DNA_Mathews2004() { g_param_file = "@dna_mathews2004"; }
-
-namespace {
-// one context per process and device (CCJ_DEVICE selects the GPU); the reference is equally process-global
-ccj_ctx *shared_ctx() {
-    static ccj_ctx *ctx = nullptr;
-    if (!ctx) {
-        const char *d = getenv("CCJ_DEVICE");
-        const int rc = ccj_ctx_create(d ? atoi(d) : 0, &ctx);
-        if (rc != 0) {
-            std::cerr << "ccj_b200: no CUDA device available (this build has no CPU path)" << std::endl;
-            exit(EXIT_FAILURE);
-        }
-    }
-    return ctx;
-}
-}  // namespace
-
-W_final::W_final(std::string seq, int dangle) : params_(new ccj_params_view{g_param_file, dangle}), P(nullptr), V(nullptr) {
-    seq_ = seq;
-    n = (cand_pos_t)seq.length();
-    ctx_ = shared_ctx();
-    const int mrc = !g_param_file.empty() && g_param_file[0] == '@'
-                        ? ccj_model_load_embedded(ctx_, g_param_file.c_str() + 1, dangle, noGU)
-                        : ccj_model_load(ctx_, g_param_file.c_str(), dangle, noGU);
-    if (mrc != 0) {
+// src/W_final.cc:20-30,45-56
+W_final::W_final(std::string seq, int dangle) : params_(scale_parameters()), P(nullptr), V(nullptr) {
+    if (!params_) {
         std::cerr << "Not a valid parameter file!" << std::endl;  // src/CCJ.cc:84,95
         exit(EXIT_FAILURE);
     }
+    seq_ = seq;
+    n = (cand_pos_t)seq.length();
+    make_pair_matrix();
+    params_->model_details.dangles = dangle;
+    S_ = encode_sequence(seq.c_str(), 0);
+    S1_ = encode_sequence(seq.c_str(), 1);
     W.resize(n + 1, 0);
     structure = std::string(n + 1, '.');
-    V = new s_energy_matrix(seq_, n, ctx_);
-    P = new pseudo_loop(seq_, V, ctx_);
+    V = new s_energy_matrix(seq_, n, S_, S1_, params_);
+    P = new pseudo_loop(seq_, V, S_, S1_, params_);
 }
 
 W_final::~W_final() {
     delete P;
     delete V;
-    delete params_;
+    free(params_);
+    free(S_);
+    free(S1_);
 }
 
 double W_final::ccj() {
-    const int64_t offsets[2] = {0, (int64_t)n};
+    ccj_ctx *ctx = ccj::shell_ctx();
     ccj_result res;
     pairs.assign(n, -1);
     std::string dots(n, '.');
-    int rc = ccj_batch_prepare(ctx_, seq_.data(), offsets, 1);
-    if (!rc) rc = ccj_batch_fill(ctx_);
-    if (!rc) rc = ccj_batch_traceback(ctx_);
-    if (!rc) rc = ccj_batch_fetch(ctx_, &res, pairs.data(), &dots[0]);
+    V->fold()->ensure_resident();   // the bulk fill (V, P, the 22 gap tables, W), src/W_final.cc:60-77
+    int rc = ccj_batch_traceback(ctx);
+    if (!rc) rc = ccj_batch_fetch(ctx, &res, pairs.data(), &dots[0]);
     if (rc != 0) {
-        std::cerr << "ccj_b200: " << ccj_last_error(ctx_) << std::endl;
+        std::cerr << "ccj_b200: " << ccj_last_error(ctx) << std::endl;
         exit(EXIT_FAILURE);
     }
     // the reference prints these from inside the traceback, before main() prints the result

@@ -1,7 +1,7 @@
 // W_final -- the reference's fold orchestrator (src/W_final.hh:18-71) with the same public surface:
-//     W_final(std::string seq, int dangle);   double ccj();   std::string structure;   params_
+//     W_final(std::string seq, int dangle);   double ccj();   vrna_param_t *params_;   std::string structure;
 // Internally everything is one call sequence into the C ABI of include/ccj_b200.h; the tables stay in HBM
-// for the life of the object and are reachable through P / V getters.
+// for the life of the object and are reachable through P / V (protected in the reference, public here).
 #ifndef CCJ_B200_W_FINAL_HH
 #define CCJ_B200_W_FINAL_HH
 #include <string>
@@ -10,16 +10,9 @@
 #include "pseudo_loop.hh"
 #include "s_energy_matrix.hh"
 
-// Process-global configuration, as in the reference: vrna_params_load() stores the parameter set the next
-// W_final uses (src/CCJ.cc:80-99), `noGU` is the ViennaRNA global read by make_pair_matrix (src/CCJ.cc:77).
-extern int noGU;
-int ccj_params_load(const char *par_file);  // 1 on success (like vrna_params_load), 0 if unreadable
+// kept from round 1 for callers of the C++ shell: 1 on success (like vrna_params_load), 0 if unreadable
+int ccj_params_load(const char *par_file);
 void ccj_params_load_DNA_Mathews2004();     // vrna_params_load_DNA_Mathews2004: the set linked into the library
-
-struct ccj_params_view {   // what W_final::params_ exposes of the loaded model
-    std::string param_file;
-    int dangles;
-};
 
 class W_final {
 public:
@@ -27,7 +20,7 @@ public:
     ~W_final();
     double ccj();  // fold: returns the MFE in kcal/mol, leaves the dot-bracket in `structure`
 
-    ccj_params_view *params_;
+    vrna_param_t *params_;
     std::string structure;
 
     // tables of the finished fold
@@ -39,6 +32,7 @@ public:
 protected:
     cand_pos_t n;
     std::string seq_;
-    ccj_ctx *ctx_;
+    short *S_;
+    short *S1_;
 };
 #endif

@@ -935,6 +935,107 @@ int ccj_count_terms(const char *seq, int n, int no_gu, int64_t *out) {
     return 0;
 }
 
+// ---- what the C++ class shells (ccj_b200/csrc/{W_final,pseudo_loop,s_energy_matrix}.hh) need beyond a whole fold ----
+int ccj_model_build(const char *par_file, int dangles, int no_gu, void *model_out, size_t model_bytes, char *err, size_t err_len) {
+    if (!par_file || !model_out || model_bytes != sizeof(ccj_model)) return CCJ_ERR_ARG;
+    ccj::RawParams *rp = new ccj::RawParams();
+    std::string e;
+    if (!read_params(par_file, par_file[0] == '@' ? par_file + 1 : nullptr, *rp, e)) {
+        if (err && err_len) snprintf(err, err_len, "%s", e.c_str());
+        delete rp;
+        return CCJ_ERR_PARAMS;
+    }
+    for (const std::string &w : rp->warnings) fprintf(stderr, "WARNING: %s\n", w.c_str());
+    ccj::build_model(*rp, dangles, no_gu, *static_cast<ccj_model *>(model_out));
+    delete rp;
+    return 0;
+}
+
+int ccj_model_upload(ccj_ctx *ctx, const void *model, size_t model_bytes) {
+    if (!ctx || !model || model_bytes != sizeof(ccj_model)) return CCJ_ERR_ARG;
+    memcpy(ctx->h_model, model, sizeof(ccj_model));
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(ctx->d_model, ctx->h_model, sizeof(ccj_model), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->model_ok = true;
+    return 0;
+}
+
+size_t ccj_model_bytes(void) { return sizeof(ccj_model); }
+
+int ccj_copy_table4_raw(ccj_ctx *ctx, int seq_index, int table, int16_t *out, int64_t out_len) {
+    if (!ctx || !out || table < 0 || table >= CCJ_NT4) return CCJ_ERR_ARG;
+    if (!ctx->filled || seq_index < 0 || seq_index >= (int)ctx->plan.size())
+        return fail(ctx, CCJ_ERR_STATE, "no filled wave / bad sequence index");
+    const SeqPlan &p = ctx->plan[seq_index];
+    const int64_t cells = ccj_cells4(p.n);
+    if (out_len < cells) return fail(ctx, CCJ_ERR_ARG, "output buffer too small");
+    CU(cudaSetDevice(ctx->device));
+    const char *d_tab = ctx->d_arena + ctx->in_total + ctx->out_total + p.tab_off;
+    CU(cudaMemcpy(out, d_tab + (size_t)table * cells * sizeof(int16_t), (size_t)cells * sizeof(int16_t), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int ccj_copy_tables2_raw(ccj_ctx *ctx, int seq_index, int32_t *out, int64_t out_len) {
+    if (!ctx || !out) return CCJ_ERR_ARG;
+    if (!ctx->filled || seq_index < 0 || seq_index >= (int)ctx->plan.size())
+        return fail(ctx, CCJ_ERR_STATE, "no filled wave / bad sequence index");
+    const SeqPlan &p = ctx->plan[seq_index];
+    const int64_t len = ccj_stride2(p.n) * CCJ_NT2;
+    if (out_len < len) return fail(ctx, CCJ_ERR_ARG, "output buffer too small");
+    CU(cudaSetDevice(ctx->device));
+    const char *d_tab = ctx->d_arena + ctx->in_total + ctx->out_total + p.tab_off + tab_offset(p.n, TAB_T2);
+    CU(cudaMemcpy(out, d_tab, (size_t)len * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int ccj_traceback_step(ccj_ctx *ctx, int seq_index, const int32_t *node, int32_t *pushed, int32_t cap, int32_t *n_pushed,
+                       int32_t *status3) {
+    if (!ctx || !node || !pushed || !n_pushed || cap < 0) return CCJ_ERR_ARG;
+    if (!ctx->filled || seq_index < 0 || seq_index >= (int)ctx->plan.size())
+        return fail(ctx, CCJ_ERR_STATE, "no filled wave / bad sequence index");
+    CU(cudaSetDevice(ctx->device));
+    const SeqPlan &p = ctx->plan[seq_index];
+    int *d_top = nullptr;
+    CU(cudaMalloc((void **)&d_top, sizeof(int)));
+    ccj::launch_tb_step(ctx->d_model, ctx->d_seqs, seq_index, node, d_top, ctx->stream);
+    int top = 0;
+    cudaError_t e = cudaMemcpyAsync(&top, d_top, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaFree(d_top);
+    CU(e);
+    if (top > cap) return fail(ctx, CCJ_ERR_ARG, "pushed-node buffer too small");
+    const char *d_tab = ctx->d_arena + ctx->in_total + ctx->out_total + p.tab_off;
+    if (top > 0)
+        CU(cudaMemcpy(pushed, d_tab + tab_offset(p.n, TAB_TBSTACK), (size_t)top * 5 * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    *n_pushed = top;
+    if (status3) {
+        int32_t st[CCJ_STATUS_INTS];
+        CU(cudaMemcpy(st, ctx->d_arena + ctx->in_total + p.out_off, sizeof st, cudaMemcpyDeviceToHost));
+        status3[0] = st[0];
+        status3[1] = st[2];
+        status3[2] = st[1];
+    }
+    return 0;
+}
+
+int ccj_fetch_fold_state(ccj_ctx *ctx, int seq_index, int32_t *pair, int8_t *type) {
+    if (!ctx || !pair) return CCJ_ERR_ARG;
+    if (!ctx->filled || seq_index < 0 || seq_index >= (int)ctx->plan.size())
+        return fail(ctx, CCJ_ERR_STATE, "no filled wave / bad sequence index");
+    CU(cudaSetDevice(ctx->device));
+    const SeqPlan &p = ctx->plan[seq_index];
+    const int n = p.n;
+    const char *o = ctx->d_arena + ctx->in_total + p.out_off;
+    CU(cudaMemcpy(pair, o + sizeof(int32_t) * (CCJ_STATUS_INTS + (size_t)(n + 1)), sizeof(int32_t) * (size_t)(n + 1), cudaMemcpyDeviceToHost));
+    if (type) {
+        const char *d_tab = ctx->d_arena + ctx->in_total + ctx->out_total + p.tab_off;
+        CU(cudaMemcpy(type, d_tab + tab_offset(n, TAB_FTYPE), (size_t)(n + 1), cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
 int64_t ccj_layout_index(int n, int i, int j, int k, int l) {
     if (n < 1 || i < 1 || l > n || !ccj_valid4(i, j, k, l)) return -1;
     return ccj_idx4(n, i, j, k, l);

@@ -115,7 +115,24 @@ __global__ void k_traceback(const ccj_model *M, const ccj_seq *seqs) {
     ccj_traceback(c, par);
 }
 
+// one node of the traceback (pseudo_loop::backtrack / W_final::backtrack process one interval per call): the
+// nodes it pushes are left in the sequence's traceback stack [0, *out_top), pair/type updates in pair_out/ftype_out
+__global__ void k_tb_step(const ccj_model *M, const ccj_seq *seqs, int seq, int a0, int a1, int a2, int a3, int ty, int *out_top) {
+    ccj_cx c;
+    c.M = M;
+    c.q = seqs[seq];
+    WarpPar par;
+    ccj_tb T(c);
+    ccj_tb_node(T, par, a0, a1, a2, a3, ty);
+    par.sync();
+    if (par.lane() == 0) *out_top = T.top;
+}
+
 // ---------------------------------------------------------------------------------------------
+void launch_tb_step(const ccj_model *M, const ccj_seq *seqs, int seq, const int *node, int *out_top, cudaStream_t st) {
+    k_tb_step<<<1, 32, 0, st>>>(M, seqs, seq, node[0], node[1], node[2], node[3], node[4], out_top);
+}
+
 void launch_init(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cudaStream_t st) {
     const int64_t s2 = ccj_stride2(d.nmax);
     int bx = (int)((s2 + 255) / 256);

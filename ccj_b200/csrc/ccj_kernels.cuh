@@ -37,6 +37,10 @@ void launch_W(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cudaStream_
 // traceback, one warp per sequence
 void launch_traceback(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cudaStream_t st);
 
+// one traceback node of sequence `seq` (node = i, j, k, l, type as stored on the traceback stack); *out_top = number of
+// nodes it pushed (left in that sequence's tb_stack)
+void launch_tb_step(const ccj_model *M, const ccj_seq *seqs, int seq, const int *node, int *out_top, cudaStream_t st);
+
 // number of kernel launches the fill of a wave with longest sequence nmax issues (for gpu_launches)
 int fill_launch_count(int nmax, bool tuned);
 

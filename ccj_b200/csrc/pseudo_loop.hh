@@ -1,58 +1,74 @@
 // pseudo_loop -- the reference's pseudoknot-table class surface (src/pseudo_loop.hh:13-56) on top of the
-// device-resident tables: getters with Matrix4D::get / TriangleMatrix::get semantics; the fill and the
-// traceback themselves run on the GPU (W_final::ccj()).
+// device-resident tables: same constructor, same public methods, public TriangleMatrix P.  The fill is one bulk GPU
+// sweep (started on first use, see s_energy_matrix.hh); getters have Matrix4D::get / TriangleMatrix::get semantics
+// on a host mirror; backtrack() processes ONE interval like the reference, by running that node of the traceback
+// on the GPU (ccj_traceback_step) and prepending the nodes it pushes to stack_interval in the same order.
 #ifndef CCJ_B200_PSEUDO_LOOP_HH
 #define CCJ_B200_PSEUDO_LOOP_HH
+#include <memory>
 #include <string>
 
 #include "s_energy_matrix.hh"
 
 class pseudo_loop {
 public:
-    pseudo_loop(std::string seq, s_energy_matrix *V, ccj_ctx *ctx) : n((cand_pos_t)seq.length()), V_(V), ctx_(ctx) {}
+    pseudo_loop(std::string seq, s_energy_matrix *V, short *S, short *S1, vrna_param_t *params);   // src/pseudo_loop.hh:17
+    ~pseudo_loop();
 
-    // bulk-filled on the GPU; kept for source compatibility (src/pseudo_loop.cc:69-132)
-    void compute_energies(cand_pos_t, cand_pos_t) {}
+    void compute_energies(cand_pos_t, cand_pos_t) {}   // src/pseudo_loop.cc:69-132, bulk on the GPU
 
-    // P(i,j): TriangleMatrix::get with return value INF (src/pseudo_loop.hh:32, src/matrices.hh:37-40)
-    energy_t get_energy(cand_pos_t i, cand_pos_t j) { return (i > j) ? INF : raw2(T2_P, i, j); }
-    // src/pseudo_loop.cc:647-661
-    energy_t get_WB(cand_pos_t i, cand_pos_t j) { return wbwp(T2_WB, i, j); }
+    void backtrack(minimum_fold *f, seq_interval *cur_interval);   // src/pseudo_loop.cc:861-2820, one node
+    void set_stack_interval(seq_interval *stack_interval) { this->stack_interval = stack_interval; }
+    seq_interval *get_stack_interval() { return stack_interval; }
+    std::string get_structure() { return structure; }
+    minimum_fold *get_minimum_fold() { return f; }
+
+    energy_t get_WB(cand_pos_t i, cand_pos_t j) { return wbwp(T2_WB, i, j); }   // src/pseudo_loop.cc:647-661
     energy_t get_WP(cand_pos_t i, cand_pos_t j) { return wbwp(T2_WP, i, j); }
-    energy_t get_WBP(cand_pos_t i, cand_pos_t j) { return (i > j) ? INF : raw2(T2_WBP, i, j); }
-    energy_t get_WPP(cand_pos_t i, cand_pos_t j) { return (i > j) ? INF : raw2(T2_WPP, i, j); }
-    // any of the 22 gap tables (enum ccj_table4), Matrix4D::get semantics
-    energy_t get_gap(int table, cand_pos_t i, cand_pos_t j, cand_pos_t k, cand_pos_t l) {
-        int32_t v = INF;
-        ccj_table4_get(ctx_, 0, table, i, j, k, l, &v);
-        return v;
-    }
+    energy_t get_energy(cand_pos_t i, cand_pos_t j) { return P.get(i, j); }
+
+    // declared by the reference (src/pseudo_loop.hh:35-38); only the M variant is defined there (:663-679)
+    energy_t get_PfromLdoubleprime(cand_pos_t i, cand_pos_t j, cand_pos_t k, cand_pos_t l);
+    energy_t get_PfromRdoubleprime(cand_pos_t i, cand_pos_t j, cand_pos_t k, cand_pos_t l);
+    energy_t get_PfromMdoubleprime(cand_pos_t i, cand_pos_t j, cand_pos_t k, cand_pos_t l);
+    energy_t get_PfromOdoubleprime(cand_pos_t i, cand_pos_t j, cand_pos_t k, cand_pos_t l);
+
+    // src/pseudo_loop.cc:682-820
+    energy_t get_PLiloop(cand_pos_t i, cand_pos_t j, cand_pos_t k, cand_pos_t l);
+    energy_t get_PLmloop(cand_pos_t i, cand_pos_t j, cand_pos_t k, cand_pos_t l);
+    energy_t get_PRiloop(cand_pos_t i, cand_pos_t j, cand_pos_t k, cand_pos_t l);
+    energy_t get_PRmloop(cand_pos_t i, cand_pos_t j, cand_pos_t k, cand_pos_t l);
+    energy_t get_PMiloop(cand_pos_t i, cand_pos_t j, cand_pos_t k, cand_pos_t l);
+    energy_t get_PMmloop(cand_pos_t i, cand_pos_t j, cand_pos_t k, cand_pos_t l);
+    energy_t get_POiloop(cand_pos_t i, cand_pos_t j, cand_pos_t k, cand_pos_t l);
+    energy_t get_POmloop(cand_pos_t i, cand_pos_t j, cand_pos_t k, cand_pos_t l);
+
+    TriangleMatrix P;   // src/pseudo_loop.hh:56
+
+    // extensions (the reference keeps these tables private): any of the 22 gap tables (enum ccj_table4) with
+    // Matrix4D::get semantics, and WBP / WPP
+    energy_t get_gap(int table, cand_pos_t i, cand_pos_t j, cand_pos_t k, cand_pos_t l);
     energy_t get_PK(cand_pos_t i, cand_pos_t j, cand_pos_t k, cand_pos_t l) { return get_gap(T_PK, i, j, k, l); }
     energy_t get_PL(cand_pos_t i, cand_pos_t j, cand_pos_t k, cand_pos_t l) { return get_gap(T_PL, i, j, k, l); }
     energy_t get_PR(cand_pos_t i, cand_pos_t j, cand_pos_t k, cand_pos_t l) { return get_gap(T_PR, i, j, k, l); }
     energy_t get_PM(cand_pos_t i, cand_pos_t j, cand_pos_t k, cand_pos_t l) { return get_gap(T_PM, i, j, k, l); }
     energy_t get_PO(cand_pos_t i, cand_pos_t j, cand_pos_t k, cand_pos_t l) { return get_gap(T_PO, i, j, k, l); }
-    // get_PfromMdoubleprime (src/pseudo_loop.cc:663-679); PB_penalty = 246 (src/h_globals.hh:11)
-    energy_t get_PfromMdoubleprime(cand_pos_t i, cand_pos_t j, cand_pos_t k, cand_pos_t l, bool il_can_pair) {
-        if (!(i <= j && j < k - 1 && k <= l)) return INF;
-        if (i == j && k == l) return il_can_pair ? 0 : INF;
-        const energy_t b1 = get_PL(i, j, k, l) + 246, b2 = get_PR(i, j, k, l) + 246;
-        return b1 < b2 ? b1 : b2;
-    }
+    energy_t get_WBP(cand_pos_t i, cand_pos_t j) { return WBP.get(i, j); }
+    energy_t get_WPP(cand_pos_t i, cand_pos_t j) { return WPP.get(i, j); }
 
 private:
-    energy_t raw2(int table, cand_pos_t i, cand_pos_t j) {
-        int32_t v = 0;
-        if (i < 1 || j > n || ccj_table2_get(ctx_, 0, table, i, j, &v) != 0) return INF;
-        return v;
-    }
-    energy_t wbwp(int table, cand_pos_t i, cand_pos_t j) {
-        if (i <= 0 || j <= 0 || i > n || j > n) return INF;
-        if (i > j) return 0;
-        return raw2(table, i, j);
-    }
+    void insert_node(int i, int j, int k, int l, char type);   // src/pseudo_loop.cc:2823-2846
+    energy_t wbwp(int table, cand_pos_t i, cand_pos_t j);
     cand_pos_t n;
-    s_energy_matrix *V_;
-    ccj_ctx *ctx_;
+    std::string seq;
+    s_energy_matrix *V;
+    seq_interval *stack_interval;
+    std::string structure;
+    minimum_fold *f;
+    vrna_param_t *params_;
+    short *S_;
+    short *S1_;
+    TriangleMatrix WPP, WBP;
+    std::shared_ptr<ccj::ShellFold> fold_;
 };
 #endif

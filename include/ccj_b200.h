@@ -104,6 +104,29 @@ int ccj_table2_get(ccj_ctx *ctx, int seq_index, int table, int i, int j, int32_t
 int ccj_table4_hash(ccj_ctx *ctx, int seq_index, int table, uint64_t *hash, int64_t *finite, int32_t *min_value);
 int ccj_table2_hash(ccj_ctx *ctx, int seq_index, int table, uint64_t *hash, int64_t *finite, int64_t *sum);
 
+/* What the C++ class shells need beyond whole folds (ccj_b200/csrc/{W_final,pseudo_loop,s_energy_matrix}.hh; reference
+ * surface src/pseudo_loop.hh:13-56, src/s_energy_matrix.hh:16-68):
+ *   ccj_model_build   host only: scale_parameters() of the loaded set as the library's model blob (model_bytes must equal
+ *                     ccj_model_bytes(); layout = struct ccj_model of ccj_b200/csrc/ccj_types.h); par_file "@name" =
+ *                     an embedded set
+ *   ccj_model_upload  use a (possibly caller-edited) model blob for the following folds (vrna_param_t* argument of the
+ *                     reference's constructors)
+ *   ccj_copy_table4_raw / ccj_copy_tables2_raw   one gap table (storage order ccj_layout_index) / all 2D tables
+ *                     (CCJ_NT2 x ccj_stride2(n) int32, diagonal-major) of the filled wave, for host-side getters
+ *   ccj_traceback_step   ONE node of the traceback, i.e. one call of pseudo_loop::backtrack / W_final::backtrack
+ *                     (src/pseudo_loop.cc:861, src/W_final.cc:175): node = {i, j, k, l, type} as in seq_interval
+ *                     (src/h_struct.hh:65-92); the nodes it pushes, in push order, 5 ints each; status3 = {status,
+ *                     msg_id, "Should not be here!" count} of the sequence so far
+ *   ccj_fetch_fold_state minimum_fold::pair / ::type of positions 0..n as the traceback steps left them */
+int ccj_model_build(const char *par_file, int dangles, int no_gu, void *model_out, size_t model_bytes, char *err, size_t err_len);
+int ccj_model_upload(ccj_ctx *ctx, const void *model, size_t model_bytes);
+size_t ccj_model_bytes(void);
+int ccj_copy_table4_raw(ccj_ctx *ctx, int seq_index, int table, int16_t *out, int64_t out_len);
+int ccj_copy_tables2_raw(ccj_ctx *ctx, int seq_index, int32_t *out, int64_t out_len);
+int ccj_traceback_step(ccj_ctx *ctx, int seq_index, const int32_t *node, int32_t *pushed, int32_t cap, int32_t *n_pushed,
+                       int32_t *status3);
+int ccj_fetch_fold_state(ccj_ctx *ctx, int seq_index, int32_t *pair, int8_t *type);
+
 /* Host-only helpers (no GPU needed), used by the CPU test-suite:
  * ccj_model_text writes the scaled model in the "name idx... value" text form of
  * `oracle/_ref/ccj_ref_dump params` to `out_path` (par_file "@name" = an embedded set); ccj_layout_index is the storage offset of cell

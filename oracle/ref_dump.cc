@@ -8,6 +8,7 @@
 //   ccj_ref_dump hash   <parfile|-> <dangles> <seq>      per-table summary + FNV-1a hash (text)
 //   ccj_ref_dump bin    <parfile|-> <dangles> <seq> <out> raw tables (layout below)
 //   ccj_ref_dump fold   <parfile|-> <dangles> <seq>      same stdout as the CCJ binary's last two lines
+//   ccj_ref_dump probe  <parfile|-> <dangles> <seq>      public class surface probe (tests/shell/probe_body.inc)
 //
 // The reference keeps its tables private; this TU only flips the access specifiers while including
 // the reference headers (no reference source is modified or copied).
@@ -98,6 +99,8 @@ static int32_t get2d(W_final &w, int t, int i, int j) {
 }
 static const char *k2dNames[8] = {"V", "Vtype", "WM", "WMv", "WMp", "P", "WBP", "WPP"};
 
+#include "../tests/shell/probe_body.inc"
+
 #define DUMP1(name, len) for (int a = 0; a < (len); ++a) printf(#name " %d %d\n", a, p->name[a]);
 #define DUMP2(name, l0, l1) for (int a = 0; a < (l0); ++a) for (int b = 0; b < (l1); ++b) printf(#name " %d %d %d\n", a, b, p->name[a][b]);
 #define DUMP3(name, l0, l1, l2) for (int a = 0; a < (l0); ++a) for (int b = 0; b < (l1); ++b) for (int c = 0; c < (l2); ++c) printf(#name " %d %d %d %d\n", a, b, c, p->name[a][b][c]);
@@ -152,6 +155,10 @@ int main(int argc, char **argv) {
 
     if (argc < 5) return 2;
     std::string seq = argv[4];
+    if (mode == "probe") {
+        run_probe(seq, dangles);
+        return 0;
+    }
     W_final w(seq, dangles);
     int n = w.n;
 

@@ -7,6 +7,8 @@ oracle/Makefile (oracle/_ref/CCJ, oracle/_ref/ccj_ref_dump).  Run in the build c
     python tests/golden/make_golden.py params     # scaled vrna_param_t dump           -> params_*.txt.gz
     python tests/golden/make_golden.py config4    # first 16 config-4 sequences (150 nt) -> folds_config4.json
     python tests/golden/make_golden.py config2    # first 64 config-2 sequences (100 nt) -> folds_config2.json
+    python tests/golden/make_golden.py probe      # public class surface probe + struct layouts -> probe_*.txt.gz, vrna_layout.txt
+    python tests/golden/make_golden.py wrap       # int16 negative wrap (src/matrices.hh:188-191) at n=213 -> wrap213.json
     python tests/golden/make_golden.py big        # n>213: oracle/_ref/ccj_oracle hashes -> table_hashes_big.json
                                                   # (the reference aborts there; ~1 h per sequence on one core)
 
@@ -30,6 +32,12 @@ H60 = "AAUAGGCGCAGCAUACACGGUCGAGCUGCGCCAAUAACAAUACGACCGUGAUAAAUAAAA"
 K60 = "AUAGGACGCAAGGCUCGAAGCGUCCAAUAAUCCGUGCAACGAGCCAAGCACGGAUAAAAA"
 
 
+# (name, parameter file, dangles, sequence) of the class-surface probes
+PROBES = [("k60_t04_d2", "rna_Turner04.par", 2, K60),
+          ("r38_dp09_d1", "rna_DirksPierce09.par", 1, "GGGAAACGCUCUAGCGUUUCCCAAAGAGCAAAUCGAUCA"),
+          ("h44_t04_d0", "rna_Turner04.par", 0, H60[:44])]
+
+
 def designed(n):
     unit = H60 + "AAUAAUAAUA" + K60 + "AAUAAUAAUA"
     return (unit * (n // len(unit) + 1))[:n]
@@ -38,6 +46,13 @@ def designed(n):
 def rand_seq(seed, n):
     rng = random.Random(seed)
     return "".join(rng.choice("ACGU") for _ in range(n))
+
+
+def wrap213():
+    """A 103-bp poly-G/poly-C hairpin inside the left arm of a gapped region: PK(1,211,213,213) = PK(1,1,213,213) +
+    WP(2,211) falls below -32768 dcal/mol, which Matrix4D::set narrows to a positive int16 (src/matrices.hh:188-191).
+    213 nt is the longest input the reference accepts, and the shortest that reaches the wrap."""
+    return "G" + "G" * 103 + "GAAA" + "C" * 103 + "A" + "C"
 
 
 def seed200():
@@ -125,6 +140,25 @@ def main():
             out = list(ex.map(lambda j: run_ref(j[0], j[1], j[2], j[3]), jobs))
         (HERE / f"folds_{what}.json").write_text(json.dumps(out, indent=0))
         print(len(out), what, "folds;", sum(r["rc"] != 0 for r in out), "with rc!=0")
+    elif what == "probe":
+        # tests/shell/probe_body.inc run against the UNMODIFIED reference classes (ccj_ref_dump probe)
+        for name, par, d, seq in PROBES:
+            p = subprocess.run([str(DUMP), "probe", str(PARAMS / par), str(d), seq], capture_output=True, text=True)
+            assert p.returncode == 0, p.stderr
+            with gzip.open(HERE / f"probe_{name}.txt.gz", "wt") as f:
+                f.write(p.stdout)
+        p = subprocess.run([str(ROOT / "oracle" / "_ref" / "layout_probe_ref")], capture_output=True, text=True)
+        assert p.returncode == 0
+        (HERE / "vrna_layout.txt").write_text(p.stdout)
+        print("probes dumped")
+    elif what == "wrap":
+        seq = wrap213()
+        with ThreadPoolExecutor(2) as ex:
+            fa = ex.submit(run_ref, seq)
+            fb = ex.submit(run_hash, seq)
+            out = {"fold": fa.result(), "hashes": fb.result()}
+        (HERE / "wrap213.json").write_text(json.dumps(out, indent=0))
+        print("wrap213:", out["fold"]["rc"], out["fold"]["stdout"][-40:], out["hashes"]["tables"]["PK"])
     elif what == "big":
         # n > 213: the reference asserts (src/matrices.hh:159-160), so the pinned CPU restatement is the checker
         sys.path.insert(0, str(ROOT))
