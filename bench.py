@@ -231,10 +231,13 @@ def dist_setup():
     return world, rank, local
 
 
-def per_kernel_roofline(prof, terms, peak_gbs, addmin):
+def per_kernel_roofline(prof, terms, peak_gbs, addmin, traffic_json=None):
     """Every kernel group against both roofs.  Algorithmic bytes / candidates per group: split-point
     roles 2 B per split term; windows 2 B per evaluated window term; assembly 44 B per cell (the 22 stores);
-    compute_P 4 B (two reads) per term.  One candidate = one add + one min = one VIADDMNMX."""
+    compute_P 4 B (two reads) per term.  One candidate = one add + one min = one VIADDMNMX.
+    `hbm_frac` is the survey's algorithmic-byte figure (it exceeds 1 where one fetched record serves several levels);
+    `dram_frac` uses the DRAM bytes ncu measured for that kernel (profiles/r2_traffic.json, scaled by algorithmic
+    bytes to this step); `bound` = the larger of dram_frac and int32_frac, i.e. the roof that is actually closest."""
     split = sum(x["split"] for x in terms)
     iloop = sum(x["iloop"] for x in terms)
     pterm = sum(x["pterms"] for x in terms)
@@ -246,6 +249,12 @@ def per_kernel_roofline(prof, terms, peak_gbs, addmin):
         "k_P_tuned": (4 * pterm, pterm, prof["kP_ms"], "int32_viaddmnmx"),
     }
     out = {}
+    ncu_names = {"k_roles": ["k_roles"], "k_winLR+k_winM": ["k_winLR<0>", "k_winM<0>", "k_winLR<1>", "k_winM<1>"],
+                 "k_final": ["k_final"], "k_P_tuned": ["k_P_tuned"]}
+    scale = None
+    if traffic_json:
+        alg_all = sum(x["bytes_4d"] for x in terms)
+        scale = alg_all / traffic_json["algorithmic_bytes"]
     for name, (nbytes, cands, ms, form) in groups.items():
         if ms <= 0:
             continue
@@ -253,9 +262,15 @@ def per_kernel_roofline(prof, terms, peak_gbs, addmin):
         cps = cands / (ms / 1e3)
         hbm_frac = gbs / peak_gbs
         int_frac = cps / addmin[form] if addmin.get(form) else None
+        dram = None
+        if scale is not None:
+            pk = traffic_json.get("per_kernel", {})
+            dram = sum((pk[k]["dram_read_GB"] + pk[k]["dram_write_GB"]) * 1e9 for k in ncu_names[name] if k in pk) * scale
+        dram_frac = dram / (ms / 1e3) / 1e9 / peak_gbs if dram else None
+        roofs = {"hbm": dram_frac if dram_frac is not None else hbm_frac, "int32": int_frac or 0.0}
         out[name] = {"ms": ms, "algorithmic_bytes": nbytes, "candidates": cands, "achieved_gbs": gbs,
-                     "hbm_frac": hbm_frac, "candidates_per_s": cps, "int32_frac": int_frac, "int32_form": form,
-                     "bound": "int32" if (int_frac or 0) > hbm_frac else "hbm"}
+                     "hbm_frac": hbm_frac, "dram_bytes_ncu": dram, "dram_frac": dram_frac, "candidates_per_s": cps,
+                     "int32_frac": int_frac, "int32_form": form, "bound": max(roofs, key=roofs.get)}
     return out
 
 
@@ -312,8 +327,13 @@ def gpu_arm(args):
     cells_step = B * cells(N_NT)
     total_steps = args.warmup + args.steps
 
-    def batch_of(step):   # every step folds new workload sequences
-        return workload((step * world + rank) * B, B)
+    # every step folds new workload sequences: timed step x of rank r takes batch x*world + r (so the timed region starts
+    # at workload index 0, where the golden vectors are), the warm-up steps take the batches after the timed ones
+    order = list(range(args.steps, total_steps)) + list(range(args.steps))
+    batches = [workload((x * world + rank) * B, B) for x in order]
+
+    def batch_of(step):
+        return batches[step]
 
     def barrier():
         if world > 1:
@@ -380,7 +400,7 @@ def gpu_arm(args):
     # measured DRAM traffic: ncu dram__bytes_{read,write}.sum summed over every gap-table launch of one fold of this
     # workload (profiles/*_traffic.json, written by profiles/measure_traffic.py from the committed ncu launch list),
     # scaled from its algorithmic bytes to this step's
-    traffic, traffic_src = None, None
+    traffic, traffic_src, tj = None, None, None
     for name in ("r2_traffic.json", "r1_traffic.json"):
         tpath = ROOT / "profiles" / name
         if tpath.exists():
@@ -388,7 +408,7 @@ def gpu_arm(args):
             traffic = tj["dram_bytes"] / tj["algorithmic_bytes"] * bytes_4d
             traffic_src = tj.get("source")
             break
-    per_kernel = per_kernel_roofline(prof, terms, peak, addmin)
+    per_kernel = per_kernel_roofline(prof, terms, peak, addmin, tj)
     cand_4d = sum(x["split"] + x["iloop"] for x in terms)
     int_frac = cand_4d / (prof["k4d_ms"] / 1e3) / addmin["int32_viaddmnmx"]
     roofline = {"bound": "int32" if int_frac > achieved / peak else "hbm", "achieved": achieved, "peak": peak,

@@ -50,7 +50,7 @@ def embedded_par_defines():
 
 
 def build_library(force: bool = False, verbose_ptxas: bool = False) -> Path:
-    sources = [CSRC / "ccj_abi.cu", CSRC / "ccj_kernels.cu", CSRC / "ccj_fill4.cu", CSRC / "ccj_peak.cu",
+    sources = [CSRC / "ccj_abi.cu", CSRC / "ccj_kernels.cu", CSRC / "ccj_fill4.cu", CSRC / "ccj_peak.cu", CSRC / "ccj_shard.cu",
                CSRC / "energy_model.cpp", CSRC / "embedded_params.cpp"]
     sources = [s for s in sources if s.exists()]
     deps = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + list(CSRC.glob("*.hpp")) + sources + [
@@ -60,7 +60,7 @@ def build_library(force: bool = False, verbose_ptxas: bool = False) -> Path:
     flags = list(NVCC_FLAGS) + embedded_par_defines()
     if verbose_ptxas:
         flags += ["-Xptxas", "-v"]
-    _run([_nvcc(), *flags, "-shared", "-o", LIB, *sources, "-I", ROOT / "include", "-lcudart"])
+    _run([_nvcc(), *flags, "-shared", "-o", LIB, *sources, "-I", ROOT / "include", "-lcudart", "-ldl"])
     return LIB
 
 

@@ -126,6 +126,9 @@ struct ccj_ctx {
     size_t arena_bytes = 0;
     ccj_seq *d_seqs = nullptr;
     size_t d_seqs_cap = 0;
+    ccj_seq *d_seqs2 = nullptr;    // descriptors of the sequences a fill has to repeat with the generic kernels
+    size_t d_seqs2_cap = 0;
+    std::vector<ccj_seq> h_seqs;   // host copy of the wave's descriptors
     char *h_stage = nullptr;  // pinned staging for inputs/outputs
     size_t h_stage_bytes = 0;
 
@@ -310,6 +313,59 @@ cudaError_t enqueue_fill(ccj_ctx *ctx, ccj::LaunchDims d) {
 #undef EQ
 #undef EQL
 
+// Sequences whose tables reached the range where the reference's int16 narrowing wraps (flag status[7] of k_final,
+// ccj_fill4.cu): the tuned kernels saturate there, so those sequences are filled again by the generic kernels, which
+// evaluate every candidate in 32 bits and narrow exactly like Matrix4D::set.  Only designed inputs get here.
+int refill_wrapped(ccj_ctx *ctx, ccj::LaunchDims d) {
+    CU(cudaMemcpyAsync(ctx->h_stage, ctx->d_arena + ctx->in_total, ctx->out_total, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    std::vector<ccj_seq> redo;
+    int nmax = 0;
+    for (size_t s = 0; s < ctx->plan.size(); ++s) {
+        const int32_t *st = reinterpret_cast<const int32_t *>(ctx->h_stage + ctx->plan[s].out_off);
+        if (st[7] != 0) {
+            redo.push_back(ctx->h_seqs[s]);
+            nmax = std::max(nmax, ctx->plan[s].n);
+        }
+    }
+    if (redo.empty()) return 0;
+    if (redo.size() > ctx->d_seqs2_cap) {
+        if (ctx->d_seqs2) CU(cudaFree(ctx->d_seqs2));
+        ctx->d_seqs2 = nullptr;
+        ctx->d_seqs2_cap = 0;
+        CU(cudaMalloc((void **)&ctx->d_seqs2, redo.size() * sizeof(ccj_seq)));
+        ctx->d_seqs2_cap = redo.size();
+    }
+    CU(cudaMemcpyAsync(ctx->d_seqs2, redo.data(), redo.size() * sizeof(ccj_seq), cudaMemcpyHostToDevice, ctx->stream));
+    ccj::LaunchDims d2;
+    d2.nseq = (int)redo.size();
+    d2.nmax = nmax;
+    const ccj_model *M = ctx->d_model;
+    cudaStream_t s0 = ctx->stream;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    cudaEventRecord(e0, s0);
+    ccj::launch_init(M, ctx->d_seqs2, d2, s0);   // also clears status[6]: the traceback reads these sequences generically
+    for (int s = 0; s < d2.nmax; ++s) {
+        ccj::launch_P(M, ctx->d_seqs2, d2, s, s0);
+        ccj::launch_2d(M, ctx->d_seqs2, d2, s, s0);
+        ccj::launch_4d(M, ctx->d_seqs2, d2, s, s0);
+    }
+    ccj::launch_W(M, ctx->d_seqs2, d2, s0);
+    cudaEventRecord(e1, s0);
+    cudaError_t e = cudaStreamSynchronize(s0);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    float ms = 0.f;
+    if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    CU(e);
+    ctx->fill_ms += ms;
+    ctx->fill_launches += ccj::fill_launch_count(d2.nmax, false);
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -350,6 +406,7 @@ void ccj_ctx_destroy(ccj_ctx *ctx) {
     drop_graphs(ctx);
     if (ctx->d_arena) cudaFree(ctx->d_arena);
     if (ctx->d_seqs) cudaFree(ctx->d_seqs);
+    if (ctx->d_seqs2) cudaFree(ctx->d_seqs2);
     if (ctx->d_model) cudaFree(ctx->d_model);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -417,6 +474,8 @@ int64_t ccj_wave_capacity(ccj_ctx *ctx, int n) {
 }
 
 void *ccj_stream(ccj_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+// library-internal (ccj_shard.cu): the model blob in device memory
+const void *ccj_internal_device_model(ccj_ctx *ctx) { return ctx && ctx->model_ok ? ctx->d_model : nullptr; }
 
 int ccj_batch_prepare(ccj_ctx *ctx, const char *seqs, const int64_t *offsets, int nseq) {
     if (!ctx || !seqs || !offsets || nseq < 1) return CCJ_ERR_ARG;
@@ -513,6 +572,7 @@ int ccj_batch_prepare(ccj_ctx *ctx, const char *seqs, const int64_t *offsets, in
         q.tb_stack = reinterpret_cast<int32_t *>(t + tab_offset(n, TAB_TBSTACK));
         q.tb_cap = 16 * n + 64;
     }
+    ctx->h_seqs.assign(hd, hd + nseq);
     CU(cudaMemcpyAsync(d_in, ctx->h_stage, in_total, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_seqs, hd, (size_t)nseq * sizeof(ccj_seq), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -566,6 +626,10 @@ int ccj_batch_fill(ccj_ctx *ctx) {
     }
     CU(cudaEventElapsedTime(&ctx->fill_ms, ctx->ev0, ctx->ev1));
     ctx->fill_launches = ccj::fill_launch_count(d.nmax, use_tuned(d.nmax));
+    if (use_tuned(d.nmax)) {
+        const int rc = refill_wrapped(ctx, d);
+        if (rc) return rc;
+    }
     ctx->filled = true;
     ctx->traced = false;
     return 0;

@@ -23,27 +23,60 @@ struct ccj_cx {
 CCJ_HD int16_t *ccj_t4(const ccj_cx &c, int tbl) { return c.q.t4 + (int64_t)tbl * c.q.stride4; }
 CCJ_HD int32_t *ccj_t2(const ccj_cx &c, int tbl) { return c.q.t2 + (int64_t)tbl * c.q.stride2; }
 
+// Where a cell's 22 entries live: one index per layout.  Ordinary waves: table `tbl` at t4[tbl*stride4 + off].
+// Sharded folds (ccj_types.h, "sharded layout"): a column-read table at shard_rep[off + kind*C], a row-local one at
+// shard_loc[owner][aux + (kind-12)*C].
+struct ccj_pos4 {
+    int64_t off, aux, C;
+    int32_t owner;
+};
+CCJ_HD ccj_pos4 ccj_pos_of(const ccj_seq &q, int i, int j, int k, int l) {
+    ccj_pos4 p;
+    if (q.shard_G == 0) {
+        p.off = ccj_idx4(q.n, i, j, k, l);
+        p.aux = 0;
+        p.C = q.stride4;
+        p.owner = 0;
+        return p;
+    }
+    const int G = q.shard_G, t = (j - i) + (l - k);
+    const int64_t L = q.shard_lev[t], C = q.shard_lev[t + 1] - L;
+    const int64_t inner = ccj_shard_inner(q.n, G, i, j, k, l);
+    p.owner = (i - 1) % G;
+    p.C = C;
+    p.off = L * G * CCJ_SHARD_NREP + (int64_t)p.owner * CCJ_SHARD_NREP * C + inner;
+    p.aux = L * CCJ_SHARD_NLOC + inner;
+    return p;
+}
+CCJ_HD int16_t *ccj_addr4(const ccj_seq &q, int tbl, const ccj_pos4 &p) {
+    if (q.shard_G == 0) return q.t4 + (int64_t)tbl * p.C + p.off;
+    const int kd = q.shard_kind[tbl];
+    return kd < CCJ_SHARD_NREP ? q.shard_rep + p.off + (int64_t)kd * p.C
+                               : q.shard_loc[p.owner] + p.aux + (int64_t)(kd - CCJ_SHARD_NREP) * p.C;
+}
+
 // Matrix4D::get (src/matrices.hh:177-182)
 CCJ_HD int ccj_get4(const ccj_cx &c, int tbl, int i, int j, int k, int l) {
     if (!ccj_valid4(i, j, k, l)) return CCJ_INF;
-    return (int)ccj_t4(c, tbl)[ccj_idx4(c.q.n, i, j, k, l)];
+    if (c.q.shard_G == 0) return (int)ccj_t4(c, tbl)[ccj_idx4(c.q.n, i, j, k, l)];
+    return (int)*ccj_addr4(c.q, tbl, ccj_pos_of(c.q, i, j, k, l));
 }
 // unchecked read of a cell known to be valid
 CCJ_HD int ccj_get4u(const ccj_cx &c, int tbl, int i, int j, int k, int l) {
-    return (int)ccj_t4(c, tbl)[ccj_idx4(c.q.n, i, j, k, l)];
+    if (c.q.shard_G == 0) return (int)ccj_t4(c, tbl)[ccj_idx4(c.q.n, i, j, k, l)];
+    return (int)*ccj_addr4(c.q, tbl, ccj_pos_of(c.q, i, j, k, l));
 }
 // "if (min < INF/2) X.set(...)" + Matrix4D::set clamp + int16 narrowing; returns what a later get of
 // this cell yields.  Every valid cell is written exactly once, so no table initialisation is needed.
-CCJ_HD int ccj_put4(const ccj_cx &c, int tbl, int64_t idx, int mn) {
+CCJ_HD int ccj_put4(const ccj_cx &c, int tbl, const ccj_pos4 &pos, int mn) {
     int v = CCJ_INTERN_INF;
     if (mn < CCJ_INF / 2) {
         if (mn >= CCJ_INTERN_INF) mn = CCJ_INTERN_INF;
         v = (int)(int16_t)mn;
     }
-    ccj_t4(c, tbl)[idx] = (int16_t)v;
+    *ccj_addr4(c.q, tbl, pos) = (int16_t)v;
     return v;
 }
-
 CCJ_HD int ccj_raw2(const ccj_cx &c, int tbl, int i, int j) { return ccj_t2(c, tbl)[ccj_idx2(c.q.n, i, j)]; }
 // TriangleMatrix::get with return_val INF (P, WBP, WPP)
 CCJ_HD int ccj_tri_get(const ccj_cx &c, int tbl, int i, int j) {

@@ -67,8 +67,7 @@ CCJ_HD int ccj_PXmloop(const ccj_cx &c, int t10, int t01, int i, int j, int k, i
 
 CCJ_HD void ccj_cell4d(const ccj_cx &c, int i, int j, int k, int l) {
     const ccj_model *M = c.M;
-    const int n = c.q.n;
-    const int64_t idx = ccj_idx4(n, i, j, k, l);
+    const ccj_pos4 idx = ccj_pos_of(c.q, i, j, k, l);
     const int INF = CCJ_INF;
     const int bp = M->bp_penalty, cp = M->cp_penalty, PB = M->PB_penalty;
     int mn, tmp;

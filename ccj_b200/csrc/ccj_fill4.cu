@@ -27,6 +27,7 @@ namespace ccj {
 #define K4_THREADS 128
 #endif
 #define K4_MAXN 448  // int32 offsets and the shared layout tables
+#define CCJ_WRAP_GUARD (-31000)   // see k_final: entries below this make the sequence take the generic kernels
 
 // ---------------------------------------------------------------------------------------------
 // per-sequence precomputation: e_stP table and window partner lists
@@ -984,10 +985,17 @@ __global__ void __launch_bounds__(K4_THREADS, FINAL_MINB) k_final(const ccj_mode
     const int h4m = H4(mloc);
     // entry of (j,k)'s row of level t that holds this cell (ccj_types.h, PMW)
     const int pmrow = 4 * (__ldg(&q.pmlev4[j * n1 + k]) - ((max(j - t, 1) - 1) >> 2)) + (i - 1);
-    auto put16 = [](int16_t *dst, int mn) -> int {
+    // Matrix4D::set narrows int32 -> int16 without a lower clamp (src/matrices.hh:188-191): an entry below -32768
+    // wraps.  The partial minima and the packed window arithmetic of this path saturate there instead, so a
+    // sequence that comes near that range (only designed inputs can: -310 kcal/mol inside one gapped region) is
+    // flagged and re-filled by the generic kernels, whose every candidate is evaluated in 32 bits (ccj_batch_fill).
+    // The guard band covers the largest single step of the packed paths (a window energy, the PB penalty).
+    int32_t *const wrap_flag = q.status + 7;
+    auto put16 = [wrap_flag](int16_t *dst, int mn) -> int {
         int v = CCJ_INTERN_INF;
         if (mn < CCJ_INF / 2) {
             if (mn >= CCJ_INTERN_INF) mn = CCJ_INTERN_INF;
+            if (mn < CCJ_WRAP_GUARD) *wrap_flag = 1;
             v = (int)(int16_t)mn;
         }
         *dst = (int16_t)v;

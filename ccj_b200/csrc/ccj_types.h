@@ -138,6 +138,14 @@ struct ccj_seq {
     int32_t *tb_stack;   // traceback stack, 5 ints per node
     int32_t tb_cap;      // capacity in nodes
     int32_t pad2_;
+    // row-sharded fold of ONE oversized sequence ("sharded layout" below; all zero for ordinary waves)
+    int32_t shard_G;             // ranks the rows i are dealt to (row i belongs to rank (i-1) mod G); 0 = not sharded
+    int32_t shard_rank;          // this rank
+    const int64_t *shard_lev;    // lev[t] = sum_{t'<t} C(t'), t = 0..n (device)
+    int16_t *shard_rep;          // the 12 column-read tables, every rank's rows (filled by the allgather per level)
+    int16_t *const *shard_loc;   // [G] base of each rank's 10 row-local tables; only [shard_rank] is set unless the peers'
+                                 // memory was opened (the traceback rank)
+    int8_t shard_kind[24];       // table id -> 0..11 (column-read) or 12..21 (row-local)
 };
 #define CCJ_STATUS_INTS 8
 #define CCJ_WIN 841      /* 29*29 window slots of get_P{L,R,M}iloop (src/pseudo_loop.cc:694-700) */
@@ -238,6 +246,41 @@ inline int64_t ccj_pmw_level_quads(int n) {
 }
 
 CCJ_HD bool ccj_valid4(int i, int j, int k, int l) { return i <= j && j < k - 1 && k <= l; }
+
+// ---- sharded layout (one sequence whose gap tables exceed one GPU; SURVEY.md 8e, src/pseudo_loop.cc:69-132) ---------
+// Rows i are dealt cyclically: row i belongs to rank r=(i-1) mod G as its row q=(i-1) div G.  Storage is level-major
+// (level t=(j-i)+(l-k), m=n-t-2 rows of m+1-i cells per slab a=j-i): rank r's part of one slab is its rows
+// q=0..Q-1, Q=ceil((m-r)/G), row q holding m-r-qG cells, S_r(m) = Q(m-r) - G Q(Q-1)/2 cells in all.  A level reserves
+// C(t) = (t+1) S_0(m) cells per table and rank (rank 0 owns the most rows).
+//   column-read tables (12: PK PL PO PfromL PfromO PLmloop00/01/10 PMmloop00 POmloop00/01/10 -- read at rows d > i):
+//       every rank holds all ranks' rows:   rep[ 12 G lev[t] + (12 r + kind) C(t) + inner ]
+//       -> the 12 tables of rank r's rows of one level are ONE contiguous block, and the G blocks of a level are
+//          adjacent: the per-level exchange is a single in-place ncclAllGather
+//   row-local tables (10: PR PM PfromR PfromM PfromMprime PRmloop00/01/10 PMmloop01/10 -- read along row i only):
+//       only the owner holds them:          loc_r[ 10 lev[t] + (kind-12) C(t) + inner ]
+//   inner = a S_r(m) + q (m-r) - G q(q-1)/2 + (k-j-2)
+#define CCJ_SHARD_NREP 12
+#define CCJ_SHARD_NLOC 10
+CCJ_HD int64_t ccj_shard_rows(int m, int r, int G) { return m > r ? (m - r + G - 1) / G : 0; }
+CCJ_HD int64_t ccj_shard_slab(int m, int r, int G) {
+    const int64_t Q = ccj_shard_rows(m, r, G);
+    return Q * (m - r) - (int64_t)G * Q * (Q - 1) / 2;
+}
+CCJ_HD int64_t ccj_shard_level_cells(int n, int t, int G) { return n - t - 2 >= 1 ? (int64_t)(t + 1) * ccj_shard_slab(n - t - 2, 0, G) : 0; }
+CCJ_HD int64_t ccj_shard_inner(int n, int G, int i, int j, int k, int l) {
+    const int a = j - i, m = n - a - (l - k) - 2, r = (i - 1) % G;
+    const int64_t q = (i - 1) / G, mr = m - r;
+    return (int64_t)a * ccj_shard_slab(m, r, G) + q * mr - (int64_t)G * q * (q - 1) / 2 + (k - j - 2);
+}
+inline void ccj_shard_kinds(int8_t *kind24) {
+    static const int rep[CCJ_SHARD_NREP] = {T_PK, T_PL, T_PO, T_PfromL, T_PfromO, T_PLmloop00, T_PLmloop01, T_PLmloop10,
+                                            T_PMmloop00, T_POmloop00, T_POmloop01, T_POmloop10};
+    for (int t = 0; t < 24; ++t) kind24[t] = -1;
+    for (int x = 0; x < CCJ_SHARD_NREP; ++x) kind24[rep[x]] = (int8_t)x;
+    int nl = 0;
+    for (int t = 0; t < CCJ_NT4; ++t)
+        if (kind24[t] < 0) kind24[t] = (int8_t)(CCJ_SHARD_NREP + nl++);
+}
 
 // ---- 2D layout: diagonal-major, idx = (j-i)*(n+1) + i, 1<=i<=j<=n ----------------------------------
 CCJ_HD int64_t ccj_stride2(int n) { return (int64_t)n * (n + 1) + (n + 1); }

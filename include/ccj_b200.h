@@ -127,6 +127,39 @@ int ccj_traceback_step(ccj_ctx *ctx, int seq_index, const int32_t *node, int32_t
                        int32_t *status3);
 int ccj_fetch_fold_state(ccj_ctx *ctx, int seq_index, int32_t *pair, int8_t *type);
 
+/* ---- One sequence whose gap tables exceed one GPU (BASELINE config 5) ------------------------------------------------------
+ * The reference has no counterpart (it aborts for n >= 214, src/matrices.hh:159-160); what is sharded are the loops of
+ * pseudo_loop::compute_energies (src/pseudo_loop.cc:69-132) driven by W_final::ccj (src/W_final.cc:58-77): row i of
+ * every gap table belongs to rank (i-1) mod world, the 12 tables that are read across rows are exchanged with one
+ * in-place ncclAllGather per finished level, P(i,l) with an ncclAllReduce(min) per span (ccj_b200/csrc/ccj_shard.cu).
+ * One process per GPU: rank 0 calls ccj_shard_unique_id and hands the id to the others (e.g. torch.distributed
+ * broadcast); every rank then creates its shard on its own ccj_ctx (whose energy model is used), prepares the same
+ * sequence and calls ccj_shard_fill(&shard, 1, ms).  The traceback runs on one rank, which first opens the other
+ * ranks' memory (CUDA IPC handles from ccj_shard_ipc_handle, gathered by the caller) to read their row-local tables
+ * over NVLink.  An in-process group (count == world shards on one ccj_ctx, no unique id) runs the same loop with
+ * device copies as collectives: the single-GPU test of the multi-rank logic.
+ * ms4 = {whole fill, compute kernels, allgather, allreduce} device ms. */
+typedef struct ccj_shard ccj_shard;
+size_t ccj_shard_unique_id_bytes(void);
+int ccj_shard_unique_id(void *id, size_t bytes);
+int ccj_shard_create(ccj_ctx *ctx, int rank, int world, const void *unique_id, ccj_shard **out);
+void ccj_shard_destroy(ccj_shard *shard);
+const char *ccj_shard_last_error(const ccj_shard *shard);
+int64_t ccj_shard_bytes(int n, int world);   /* host only: one rank's device memory for a length-n sequence */
+int ccj_shard_prepare(ccj_shard *shard, const char *seq, int n);
+int ccj_shard_fill(ccj_shard **shards, int count, float *ms4);
+size_t ccj_shard_ipc_bytes(void);
+int ccj_shard_ipc_handle(ccj_shard *shard, void *handle, size_t bytes);
+int ccj_shard_open_peers(ccj_shard *shard, const void *handles, size_t bytes);
+int ccj_shard_link_local(ccj_shard *shard, ccj_shard **all, int count);
+int ccj_shard_traceback(ccj_shard *shard, ccj_result *result, int32_t *pairs, char *structs, float *ms);
+int ccj_shard_energy(ccj_shard *shard, int32_t *energy_dcal);
+int ccj_shard_table4_hash(ccj_shard *shard, int table, uint64_t *hash, int64_t *finite, int32_t *min_value);
+int ccj_shard_table2_hash(ccj_shard *shard, int table, uint64_t *hash, int64_t *finite, int64_t *sum);
+/* host only: position of cell (i,j,k,l) in the sharded layout (ccj_b200/csrc/ccj_types.h) */
+int64_t ccj_shard_layout(int n, int world, int i, int j, int k, int l, int32_t *owner, int32_t *level, int64_t *level_cells,
+                         int64_t *level_base);
+
 /* Host-only helpers (no GPU needed), used by the CPU test-suite:
  * ccj_model_text writes the scaled model in the "name idx... value" text form of
  * `oracle/_ref/ccj_ref_dump params` to `out_path` (par_file "@name" = an embedded set); ccj_layout_index is the storage offset of cell

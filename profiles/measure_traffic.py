@@ -1,6 +1,6 @@
 """Sums the DRAM traffic ncu measured for every gap-table launch of traffic_workload.py and sets it against the
-algorithmic bytes of the same fold:  python profiles/measure_traffic.py gpurun_out/traffic.csv [count]
-Writes profiles/r1_traffic.json (read by bench.py for roofline.traffic) and a per-kernel summary."""
+algorithmic bytes of the same fold:  python profiles/measure_traffic.py gpurun_out/traffic.csv [count] [out.json]
+Writes profiles/r2_traffic.json (read by bench.py for roofline.traffic) and a per-kernel summary."""
 import csv
 import json
 import sys
@@ -36,5 +36,6 @@ out = {"dram_bytes": dram, "algorithmic_bytes": alg, "ratio": dram / alg,
        "per_kernel": {k: {"launches": launches[k], "dram_read_GB": v["dram__bytes_read.sum"] / 1e9,
                           "dram_write_GB": v["dram__bytes_write.sum"] / 1e9,
                           "time_ms_under_ncu": v["gpu__time_duration.sum"] * 1e3} for k, v in per.items()}}
-(ROOT / "profiles" / "r1_traffic.json").write_text(json.dumps(out, indent=1))
+out_name = sys.argv[3] if len(sys.argv) > 3 else "r2_traffic.json"
+(ROOT / "profiles" / out_name).write_text(json.dumps(out, indent=1))
 print(json.dumps(out, indent=1))

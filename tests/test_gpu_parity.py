@@ -55,6 +55,60 @@ def test_golden_long(ctx_factory, golden_long):
     assert any("Should not be here!" in r["stdout"] for r in golden_long)
 
 
+@pytest.mark.parametrize("name,count", [("folds_config4.json", 16), ("folds_config2.json", 64)])
+def test_golden_benchmark_workloads(ctx_factory, name, count):
+    """the first 16 config-4 sequences (150 nt, seeds 20000+idx) and the first 64 config-2
+    sequences (100 nt, seeds 1000+idx), folded by the unmodified reference (make_golden.py config4 / config2)."""
+    import json
+    p = ROOT / "tests" / "golden" / name
+    if not p.exists():
+        pytest.skip(f"{name} not generated")
+    recs = json.loads(p.read_text())
+    assert len(recs) == count
+    ctx = ctx_factory()
+    check(ctx.fold_batch([r["seq"] for r in recs]), recs)
+
+
+def test_beyond_the_reference_limit_against_the_cpu_restatement(ctx_factory):
+    """n > 213: the reference aborts (src/matrices.hh:159-160), so the checker is oracle/ccj_oracle.cc -- itself
+    pinned to the reference for n <= 213 -- run once on a 216-nt random and a 214-nt designed sequence
+    (make_golden.py big, ~1 h per sequence on one core).  All 22+8 table hashes and W[n] of the tuned GPU path."""
+    import json
+    p = ROOT / "tests" / "golden" / "table_hashes_big.json"
+    if not p.exists():
+        pytest.skip("table_hashes_big.json not generated")
+    ctx = ctx_factory()
+    for r in json.loads(p.read_text()):
+        assert len(r["seq"]) > 213
+        ctx.prepare([r["seq"]])
+        ctx.fill()
+        for name, want in r["tables"].items():
+            got = ctx.table4_hash(0, name) if name in ccj_b200.TABLE4 else ctx.table2_hash(0, name)
+            assert got == want, (len(r["seq"]), name)
+        ctx.traceback()
+        assert ctx.fetch()[0].energy_dcal == r["W"]
+
+
+def test_int16_negative_wrap_at_n213(ctx_factory):
+    """Matrix4D::set clamps only the upper side and narrows int32 -> int16 (src/matrices.hh:188-191): an entry below
+    -32768 dcal/mol wraps to a positive value.  The designed 213-mer (a 103-bp poly-G/poly-C hairpin inside one arm)
+    is the shortest input that gets there and the longest the reference accepts; fold and every table hash must equal
+    the unmodified reference's (make_golden.py wrap)."""
+    import json
+    p = ROOT / "tests" / "golden" / "wrap213.json"
+    if not p.exists():
+        pytest.skip("wrap213.json not generated")
+    g = json.loads(p.read_text())
+    ctx = ctx_factory()
+    seq = g["fold"]["seq"]
+    ctx.prepare([seq])
+    ctx.fill()
+    for name, want in g["hashes"]["tables"].items():
+        got = ctx.table4_hash(0, name) if name in ccj_b200.TABLE4 else ctx.table2_hash(0, name)
+        assert got == want, name
+    check(ctx.fold_batch([seq]), [g["fold"]])
+
+
 def test_against_reference_binary_on_the_box(ctx_factory):
     if not REF.exists():
         pytest.skip("oracle/_ref did not travel")
