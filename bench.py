@@ -548,6 +548,7 @@ def main():
     ap.add_argument("--full-chunk", type=int, default=64)
     ap.add_argument("--config5", action="store_true", help="one oversized sequence, gap tables sharded by outer index")
     ap.add_argument("--n5", type=int, default=600)
+    ap.add_argument("--hash5", action="store_true", help="config5: also hash every table on rank 0 (small n only)")
     ap.add_argument("--no-ref-full-length", dest="ref_full_length", action="store_false",
                     help="reference arm: skip the single full-length 150-nt wave (about 6 minutes)")
     ap.add_argument("--ref-full-timeout", type=float, default=720.0)

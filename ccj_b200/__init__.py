@@ -73,6 +73,7 @@ def load_library(path: Optional[os.PathLike] = None) -> C.CDLL:
     lib.ccj_model_load.argtypes = [vp, C.c_char_p, i32, i32]
     lib.ccj_model_load_embedded.argtypes = [vp, C.c_char_p, i32, i32]
     lib.ccj_fold_batch.argtypes = [vp, vp, i64p, i32, vp, vp, vp]
+    lib.ccj_fold_batch_multi.argtypes = [C.POINTER(vp), i32, vp, i64p, i32, vp, vp, vp]
     lib.ccj_batch_prepare.argtypes = [vp, vp, i64p, i32]
     lib.ccj_batch_fill.argtypes = [vp]
     lib.ccj_batch_traceback.argtypes = [vp]
@@ -331,6 +332,23 @@ class Context:
         out = np.empty(self._lib.ccj_table2_len(n), dtype=np.int32)
         self._check(self._lib.ccj_export_table2(self._h, seq_index, t, out.ctypes.data, out.size))
         return out
+
+
+def fold_batch_multi(contexts: Sequence["Context"], seqs: Iterable[str]) -> List[Fold]:
+    """`Context.fold_batch` over several GPUs from one process: one host thread per context inside the library,
+    sequences dealt dynamically (ccj_fold_batch_multi)."""
+    seqs = list(seqs)
+    if not seqs:
+        return []
+    ctx0 = contexts[0]
+    blob, offs = Context._pack(seqs)
+    res = np.zeros(len(seqs), dtype=RESULT_DTYPE)
+    structs = np.zeros(len(blob), dtype=np.uint8)
+    arr = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
+    rc = ctx0._lib.ccj_fold_batch_multi(arr, len(contexts), blob, offs.ctypes.data_as(C.POINTER(C.c_int64)), len(seqs),
+                                        res.ctypes.data, None, structs.ctypes.data)
+    ctx0._check(rc)
+    return ctx0._unpack(seqs, offs, res, structs)
 
 
 def model_text(par_file: str, dangles: int = 2, no_gu: bool = False) -> str:

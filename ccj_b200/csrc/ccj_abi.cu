@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -799,6 +801,60 @@ int ccj_fold_batch(ccj_ctx *ctx, const char *seqs, const int64_t *offsets, int n
     ctx->fill_ms = fill_ms;
     ctx->tb_ms = tb_ms;
     ctx->fill_launches = launches;
+    return 0;
+}
+
+// The same over several GPUs of one box inside one process: one host thread per context, sequences dealt dynamically
+// in chunks from a shared counter (a GPU that runs slower simply draws fewer chunks).  No collective: sequences are
+// independent.  Results land in the caller's arrays at the sequences' own positions.
+int ccj_fold_batch_multi(ccj_ctx **ctxs, int nctx, const char *seqs, const int64_t *offsets, int nseq, ccj_result *results,
+                         int32_t *pairs, char *structs) {
+    if (!ctxs || nctx < 1 || !seqs || !offsets || nseq < 1 || !results) return CCJ_ERR_ARG;
+    for (int c = 0; c < nctx; ++c)
+        if (!ctxs[c]) return CCJ_ERR_ARG;
+    if (nctx == 1) return ccj_fold_batch(ctxs[0], seqs, offsets, nseq, results, pairs, structs);
+    int nmax = 1;
+    for (int s = 0; s < nseq; ++s) nmax = std::max<int64_t>(nmax, offsets[s + 1] - offsets[s]);
+    // chunk: at most one wave of the longest sequence, and small enough that every GPU draws several times
+    int64_t chunk = std::max<int64_t>(1, (nseq + 4 * nctx - 1) / (4 * nctx));
+    for (int c = 0; c < nctx; ++c) chunk = std::max<int64_t>(1, std::min<int64_t>(chunk, ccj_wave_capacity(ctxs[c], nmax)));
+    std::atomic<int64_t> next(0);
+    std::vector<int> rcs(nctx, 0);
+    std::vector<float> fill(nctx, 0.f), tb(nctx, 0.f);
+    std::vector<int> launches(nctx, 0);
+    std::vector<std::thread> th;
+    for (int c = 0; c < nctx; ++c)
+        th.emplace_back([&, c] {
+            ccj_ctx *ctx = ctxs[c];
+            for (;;) {
+                const int64_t lo = next.fetch_add(chunk);
+                if (lo >= nseq) break;
+                const int64_t hi = std::min<int64_t>(lo + chunk, nseq);
+                const int64_t base = offsets[lo];
+                std::vector<int64_t> off(hi - lo + 1);
+                for (int64_t s = lo; s <= hi; ++s) off[s - lo] = offsets[s] - base;
+                const int rc = ccj_fold_batch(ctx, seqs + base, off.data(), (int)(hi - lo), results + lo,
+                                              pairs ? pairs + base : nullptr, structs ? structs + base : nullptr);
+                if (rc) {
+                    rcs[c] = rc;
+                    next.store(nseq);   // stop the other threads at their next draw
+                    break;
+                }
+                fill[c] += ctx->fill_ms;
+                tb[c] += ctx->tb_ms;
+                launches[c] += ctx->fill_launches;
+            }
+        });
+    for (auto &t : th) t.join();
+    for (int c = 0; c < nctx; ++c) {
+        ctxs[c]->fill_ms = fill[c];
+        ctxs[c]->tb_ms = tb[c];
+        ctxs[c]->fill_launches = launches[c];
+        if (rcs[c]) {
+            if (c != 0) ctxs[0]->err = ctxs[c]->err;
+            return rcs[c];
+        }
+    }
     return 0;
 }
 

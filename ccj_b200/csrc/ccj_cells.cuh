@@ -41,8 +41,7 @@ CCJ_HD ccj_pos4 ccj_pos_of(const ccj_seq &q, int i, int j, int k, int l) {
     }
     const int G = q.shard_G, t = (j - i) + (l - k);
     const int64_t L = q.shard_lev[t], C = q.shard_lev[t + 1] - L;
-    const int64_t inner = ccj_shard_inner(q.n, G, i, j, k, l);
-    p.owner = (i - 1) % G;
+    const int64_t inner = ccj_shard_inner_fast(q.n, G, q.shard_shift, i, j, k, l, p.owner);
     p.C = C;
     p.off = L * G * CCJ_SHARD_NREP + (int64_t)p.owner * CCJ_SHARD_NREP * C + inner;
     p.aux = L * CCJ_SHARD_NLOC + inner;

@@ -20,6 +20,7 @@
 #include <nccl.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -49,9 +50,13 @@ struct Nccl {
 Nccl &nccl() {
     static Nccl n;
     if (n.lib || !n.err.empty()) return n;
+    // a process that already holds a libnccl (torch bundles its own) must keep using THAT one: loading a second copy
+    // under the same soname would shadow it for later imports
+    n.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!n.lib && getenv("CCJ_NCCL_LIB")) n.lib = dlopen(getenv("CCJ_NCCL_LIB"), RTLD_NOW | RTLD_LOCAL);
     for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
-        n.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
         if (n.lib) break;
+        n.lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
     }
     if (!n.lib) {
         n.err = "libnccl.so.2 not found";
@@ -87,6 +92,7 @@ struct ccj_shard {
     std::vector<int16_t *> h_locptr;     // [world]
     bool prepared = false, filled = false, peers = false;
     float ms[4] = {0, 0, 0, 0};          // total, compute, allgather, allreduce
+    std::vector<float> level_ms;         // per step s: P kernel, allreduce, 2D + gap-table kernels, allgather
 };
 
 namespace {
@@ -212,6 +218,16 @@ int ccj_shard_create(ccj_ctx *ctx, int rank, int world, const void *unique_id, c
             delete sh;
             return CCJ_ERR_CUDA;
         }
+        // NCCL connects its channels lazily inside the first collective of each kind (hundreds of ms): do that here,
+        // not inside the first level of a fill
+        int32_t *warm = nullptr;
+        if (cudaMalloc((void **)&warm, sizeof(int32_t) * 64 * (size_t)world) == cudaSuccess) {
+            cudaMemsetAsync(warm, 0, sizeof(int32_t) * 64 * (size_t)world, sh->stream);
+            N.AllReduce(warm, warm, 64, ncclInt32, ncclMin, sh->comm, sh->stream);
+            N.AllGather(reinterpret_cast<char *>(warm) + 256 * (size_t)rank, warm, 256, ncclInt8, sh->comm, sh->stream);
+            cudaStreamSynchronize(sh->stream);
+            cudaFree(warm);
+        }
     }
     *out = sh;
     return 0;
@@ -322,6 +338,9 @@ int ccj_shard_prepare(ccj_shard *sh, const char *seq, int n) {
     q.tb_cap = 16 * n + 64;
     q.shard_G = G;
     q.shard_rank = sh->rank;
+    q.shard_shift = -1;
+    for (int b = 0; b < 16; ++b)
+        if ((1 << b) == G) q.shard_shift = b;
     q.shard_lev = reinterpret_cast<const int64_t *>(sh->arena + sh->off_lev);
     q.shard_rep = reinterpret_cast<int16_t *>(sh->arena + sh->off_rep);
     q.shard_loc = reinterpret_cast<int16_t *const *>(sh->arena + sh->off_locptr);
@@ -378,7 +397,8 @@ int ccj_shard_fill(ccj_shard **shards, int count, float *ms4) {
         if (!shards[x] || !shards[x]->prepared || shards[x]->n != n || shards[x]->world != G || shards[x]->seq != sh->seq)
             return sfail(sh, CCJ_ERR_STATE, "every shard must be prepared with the same sequence");
     cudaStream_t st = sh->stream;
-    Nccl &N = nccl();
+    static Nccl none;
+    Nccl &N = (!group && G > 1) ? nccl() : none;   // in-process groups and single ranks never touch libnccl
     const ccj_model *M = static_cast<const ccj_model *>(ccj_internal_device_model(sh->ctx));
     ccj::LaunchDims d;
     d.nseq = 1;
@@ -457,6 +477,7 @@ int ccj_shard_fill(ccj_shard **shards, int count, float *ms4) {
     ck(cudaStreamSynchronize(st), "sync");
     ck(cudaGetLastError(), "fill");
     float total = 0.f, tp = 0.f, tr = 0.f, tc = 0.f, tg = 0.f;
+    std::vector<float> lvl((size_t)4 * n, 0.f);
     if (rc == 0) {
         cudaEventElapsedTime(&total, ev[0], ev[4 * n + 1]);
         for (int s = 0; s < n; ++s) {
@@ -466,6 +487,7 @@ int ccj_shard_fill(ccj_shard **shards, int count, float *ms4) {
             cudaEventElapsedTime(&c2, ev[4 * s + 2], ev[4 * s + 3]);
             cudaEventElapsedTime(&g2, ev[4 * s + 3], ev[4 * s + 4]);
             tp += a; tr += b; tc += c2; tg += g2;
+            lvl[4 * s] = a; lvl[4 * s + 1] = b; lvl[4 * s + 2] = c2; lvl[4 * s + 3] = g2;
         }
     }
     for (auto &e : ev) cudaEventDestroy(e);
@@ -473,9 +495,22 @@ int ccj_shard_fill(ccj_shard **shards, int count, float *ms4) {
     for (int x = 0; x < count; ++x) {
         shards[x]->filled = true;
         shards[x]->ms[0] = total; shards[x]->ms[1] = tp + tc; shards[x]->ms[2] = tg; shards[x]->ms[3] = tr;
+        shards[x]->level_ms = lvl;
     }
     if (ms4) { ms4[0] = total; ms4[1] = tp + tc; ms4[2] = tg; ms4[3] = tr; }
     return 0;
+}
+
+// per-step device times of the last fill: 4 floats per step s = 0..n-1 (P kernel, allreduce, 2D + gap-table kernels,
+// allgather), and the bytes this rank contributes to the allgather of level s
+int ccj_shard_level_ms(ccj_shard *sh, float *out, int64_t out_len) {
+    if (!sh || !out) return CCJ_ERR_ARG;
+    if (!sh->filled || out_len < (int64_t)sh->level_ms.size()) return sfail(sh, CCJ_ERR_STATE, "no fill / buffer too small");
+    memcpy(out, sh->level_ms.data(), sh->level_ms.size() * sizeof(float));
+    return 0;
+}
+int64_t ccj_shard_level_bytes(int n, int world, int level) {
+    return ccj_shard_level_cells(n, level, world) * CCJ_SHARD_NREP * (int64_t)sizeof(int16_t);
 }
 
 // in-process groups: give shard `sh` direct pointers to the other shards' row-local tables (same process, same device

@@ -141,6 +141,8 @@ struct ccj_seq {
     // row-sharded fold of ONE oversized sequence ("sharded layout" below; all zero for ordinary waves)
     int32_t shard_G;             // ranks the rows i are dealt to (row i belongs to rank (i-1) mod G); 0 = not sharded
     int32_t shard_rank;          // this rank
+    int32_t shard_shift;         // log2(G) if G is a power of two, else -1
+    int32_t shard_pad_;
     const int64_t *shard_lev;    // lev[t] = sum_{t'<t} C(t'), t = 0..n (device)
     int16_t *shard_rep;          // the 12 column-read tables, every rank's rows (filled by the allgather per level)
     int16_t *const *shard_loc;   // [G] base of each rank's 10 row-local tables; only [shard_rank] is set unless the peers'
@@ -261,16 +263,34 @@ CCJ_HD bool ccj_valid4(int i, int j, int k, int l) { return i <= j && j < k - 1 
 //   inner = a S_r(m) + q (m-r) - G q(q-1)/2 + (k-j-2)
 #define CCJ_SHARD_NREP 12
 #define CCJ_SHARD_NLOC 10
-CCJ_HD int64_t ccj_shard_rows(int m, int r, int G) { return m > r ? (m - r + G - 1) / G : 0; }
+// (all of this fits 32 bits for n < 1600: a S_r(m) < n^3/2; only the level bases need 64 bits)
+CCJ_HD int ccj_shard_rows(int m, int r, int G) { return m > r ? (m - r + G - 1) / G : 0; }
 CCJ_HD int64_t ccj_shard_slab(int m, int r, int G) {
-    const int64_t Q = ccj_shard_rows(m, r, G);
-    return Q * (m - r) - (int64_t)G * Q * (Q - 1) / 2;
+    const int Q = ccj_shard_rows(m, r, G);
+    return Q * (m - r) - G * (Q * (Q - 1) / 2);
 }
 CCJ_HD int64_t ccj_shard_level_cells(int n, int t, int G) { return n - t - 2 >= 1 ? (int64_t)(t + 1) * ccj_shard_slab(n - t - 2, 0, G) : 0; }
+// sh = log2(G) when G is a power of two (the usual 1/2/4/8 ranks: no integer division on the device), else -1
+CCJ_HD int ccj_shard_inner_fast(int n, int G, int sh, int i, int j, int k, int l, int &owner) {
+    const int a = j - i, m = n - a - (l - k) - 2;
+    int r, q, Q;
+    if (sh >= 0) {
+        r = (i - 1) & (G - 1);
+        q = (i - 1) >> sh;
+        Q = (m - r + G - 1) >> sh;
+    } else {
+        r = (i - 1) % G;
+        q = (i - 1) / G;
+        Q = (m - r + G - 1) / G;
+    }
+    owner = r;
+    const int mr = m - r;
+    const int slab = Q * mr - G * (Q * (Q - 1) / 2);
+    return a * slab + q * mr - G * (q * (q - 1) / 2) + (k - j - 2);
+}
 CCJ_HD int64_t ccj_shard_inner(int n, int G, int i, int j, int k, int l) {
-    const int a = j - i, m = n - a - (l - k) - 2, r = (i - 1) % G;
-    const int64_t q = (i - 1) / G, mr = m - r;
-    return (int64_t)a * ccj_shard_slab(m, r, G) + q * mr - (int64_t)G * q * (q - 1) / 2 + (k - j - 2);
+    int owner;
+    return ccj_shard_inner_fast(n, G, -1, i, j, k, l, owner);
 }
 inline void ccj_shard_kinds(int8_t *kind24) {
     static const int rep[CCJ_SHARD_NREP] = {T_PK, T_PL, T_PO, T_PfromL, T_PfromO, T_PLmloop00, T_PLmloop01, T_PLmloop10,

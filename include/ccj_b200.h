@@ -73,6 +73,13 @@ int ccj_model_load_embedded(ccj_ctx *ctx, const char *name, int dangles, int no_
 int ccj_fold_batch(ccj_ctx *ctx, const char *seqs, const int64_t *offsets, int nseq, ccj_result *results,
                    int32_t *pairs, char *structs);
 
+/* ccj_fold_batch over several GPUs of one box from ONE process: nctx contexts (one per device, each with the same
+ * model loaded), one host thread each, sequences dealt dynamically in chunks; no collective, sequences are independent
+ * ("one host thread + context per GPU; results gathered on host").  Per-context times of the call are
+ * left in ccj_last_fill_ms / ccj_last_traceback_ms of each context. */
+int ccj_fold_batch_multi(ccj_ctx **ctxs, int nctx, const char *seqs, const int64_t *offsets, int nseq, ccj_result *results,
+                         int32_t *pairs, char *structs);
+
 /* The same work split for measurement: prepare (H2D + table allocation, one wave only), fill
  * (W_final::ccj's loops, src/W_final.cc:60-77), traceback (:84-103), fetch (D2H). */
 int ccj_batch_prepare(ccj_ctx *ctx, const char *seqs, const int64_t *offsets, int nseq);
@@ -148,6 +155,10 @@ const char *ccj_shard_last_error(const ccj_shard *shard);
 int64_t ccj_shard_bytes(int n, int world);   /* host only: one rank's device memory for a length-n sequence */
 int ccj_shard_prepare(ccj_shard *shard, const char *seq, int n);
 int ccj_shard_fill(ccj_shard **shards, int count, float *ms4);
+/* per step s of the last fill, 4 floats: P kernel, allreduce, 2D + gap-table kernels, allgather (device ms); and the
+ * bytes one rank contributes to the allgather of a level (host only) */
+int ccj_shard_level_ms(ccj_shard *shard, float *out, int64_t out_len);
+int64_t ccj_shard_level_bytes(int n, int world, int level);
 size_t ccj_shard_ipc_bytes(void);
 int ccj_shard_ipc_handle(ccj_shard *shard, void *handle, size_t bytes);
 int ccj_shard_open_peers(ccj_shard *shard, const void *handles, size_t bytes);

@@ -6,6 +6,8 @@
 //
 //   ccj_emu hash <parfile> <dangles> <seq>   -> same text as `ccj_ref_dump hash`
 //   ccj_emu fold <parfile> <dangles> <seq>   -> same stdout/stderr/exit code as the CCJ binary
+//   ... [noGU] [G]: with G > 0 the gap tables live in the ROW-SHARDED layout of ccj_types.h (G ranks; the ranks'
+//   replicated region is shared here, which is what the per-level allgather establishes on the GPUs)
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -38,6 +40,7 @@ int main(int argc, char **argv) {
     std::string mode = argv[1], seq = argv[4], err;
     int dangles = atoi(argv[3]);
     int noGU = argc > 5 ? atoi(argv[5]) : 0;
+    const int shardG = argc > 6 ? atoi(argv[6]) : 0;
     ccj::RawParams rp;
     if (!ccj::load_par_file(argv[2], rp, err)) {
         fprintf(stderr, "%s\n", err.c_str());
@@ -77,6 +80,25 @@ int main(int argc, char **argv) {
     c.q.status = st.data();
     c.q.tb_stack = tbs.data();
     c.q.tb_cap = 16 * n + 64;
+    std::vector<int64_t> lev(n + 2, 0);
+    std::vector<int16_t> rep;
+    std::vector<std::vector<int16_t>> loc;
+    std::vector<int16_t *> locptr;
+    if (shardG > 0) {
+        for (int t = 0; t <= n; ++t) lev[t + 1] = lev[t] + ccj_shard_level_cells(n, t, shardG);
+        rep.assign((size_t)(lev[n + 1] * CCJ_SHARD_NREP * shardG) + 8, (int16_t)0x5555);
+        loc.assign(shardG, std::vector<int16_t>((size_t)(lev[n + 1] * CCJ_SHARD_NLOC) + 8, (int16_t)0x5555));
+        for (auto &v : loc) locptr.push_back(v.data());
+        c.q.t4 = nullptr;   // nothing may touch the ordinary layout
+        c.q.shard_G = shardG;
+        c.q.shard_shift = -1;
+        for (int b = 0; b < 16; ++b)
+            if ((1 << b) == shardG) c.q.shard_shift = b;
+        c.q.shard_lev = lev.data();
+        c.q.shard_rep = rep.data();
+        c.q.shard_loc = locptr.data();
+        ccj_shard_kinds(c.q.shard_kind);
+    }
 
     ccj_serial par;
     for (int s = 0; s < n; ++s) {
