@@ -86,6 +86,8 @@ def build_oracle() -> None:
         targets.append("_ref/ccj_oracle")
     if Path(os.environ.get("CCJ_REFERENCE", "/root/reference")).exists():
         targets.append("ref")
+        if LIB.exists():
+            targets.append("refmain")   # the reference's own main() against the B200 shells (test tool)
     if targets:
         _run(["make", "-C", odir, "-j8", *targets], stdout=subprocess.DEVNULL)
 

@@ -12,6 +12,7 @@
 #include "W_final.hh"
 #include "ccj_render.hpp"
 #include "cmdline.hh"
+#include "h_globals.hh"
 
 static bool exists(const std::string &path) {
     struct stat buffer;

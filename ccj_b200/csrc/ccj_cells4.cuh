@@ -1,6 +1,5 @@
-// The 22 four-dimensional gap tables of one cell (i,j,k,l), evaluated in the reference's in-cell
-// order (src/pseudo_loop.cc:85-127).  Generic-index version: every read goes through ccj_get4 /
-// ccj_idx4.  The tuned kernels in ccj_fill4.cu walk the same candidates with strided pointers and are
+// The 22 four-dimensional gap tables of one cell (i,j,k,l) (src/pseudo_loop.cc:85-127).  Generic-index version: every
+// read goes through ccj_pos_of / ccj_addr4 (ordinary or sharded layout).  The tuned kernels in ccj_fill4.cu walk the same candidates with strided pointers and are
 // checked against this function table-for-table.
 #pragma once
 #include "ccj_cells.cuh"
@@ -65,77 +64,112 @@ CCJ_HD int ccj_PXmloop(const ccj_cx &c, int t10, int t01, int i, int j, int k, i
     return ccj_min(ccj_get4(c, t10, i, j, k, l) + add, ccj_get4(c, t01, i, j, k, l) + add);
 }
 
+// All 22 tables of one cell.  Every split-point candidate of the 22 recurrences (src/pseudo_loop.cc:181-644) reads a
+// cell of a LOWER level, so their order inside the cell is free: they are walked by the four access patterns
+//     L1: X(i,d,k,l) with the 2D interval (d+1,j)     L2: X(d,j,k,l) with (i,d-1)
+//     R3: X(i,j,d,l) with (k,d-1)                     R4: X(i,j,k,d) with (d+1,l)
+// -- one position computation per split point serves every table read there (the dominant cost of this generic
+// version, in the ordinary and even more in the sharded layout) --, and the same-cell terms are then applied in the
+// reference's in-cell order (:85-127), which is what fixes the "PX(cell) is still unset = 32767" reads of P?mloop00.
 CCJ_HD void ccj_cell4d(const ccj_cx &c, int i, int j, int k, int l) {
     const ccj_model *M = c.M;
-    const ccj_pos4 idx = ccj_pos_of(c.q, i, j, k, l);
+    const ccj_seq &q = c.q;
+    const ccj_pos4 idx = ccj_pos_of(q, i, j, k, l);
     const int INF = CCJ_INF;
     const int bp = M->bp_penalty, cp = M->cp_penalty, PB = M->PB_penalty;
-    int mn, tmp;
+#define RD(tbl, pos) ((int)*ccj_addr4(q, (tbl), (pos)))
+    // partial minima per recurrence, by pattern
+    int PLm00 = CCJ_INTERN_INF + bp, PLm01 = INF, PLm10 = INF;   // PL(i,j,k,l) is still unset where PLmloop00 reads it
+    int PRm00 = CCJ_INTERN_INF + bp, PRm01, PRm10;
+    int PMm00 = CCJ_INTERN_INF + bp, PMm01, PMm10;
+    int POm00 = CCJ_INTERN_INF + bp, POm01 = INF, POm10 = INF;
+    int PfL = INF, PfR = INF, PfM = INF, PfMp = INF, PfO = INF, PK = INF;
+    PRm01 = ccj_get4(c, T_PRmloop01, i, j, k, l - 1) + cp;   // :517-519
+    PRm10 = ccj_get4(c, T_PRmloop10, i, j, k + 1, l) + cp;   // :531-533
+    PMm01 = ccj_get4(c, T_PMmloop01, i, j, k + 1, l) + cp;   // :564-566
+    PMm10 = ccj_get4(c, T_PMmloop10, i, j - 1, k, l) + cp;   // :578-580
 
-    // ---- PLmloop00 / 01 / 10 (src/pseudo_loop.cc:445-493) ----
-    mn = CCJ_INTERN_INF + bp;  // PL(i,j,k,l) is still unset here
-    for (int d = i; d <= j; ++d) {
-        if (d > i) mn = ccj_min(mn, ccj_WB(c, i, d - 1) + ccj_get4u(c, T_PLmloop00, d, j, k, l));
-        if (d < j) mn = ccj_min(mn, ccj_get4u(c, T_PLmloop00, i, d, k, l) + ccj_WB(c, d + 1, j));
+    // ---- L1: X(i,d,k,l), d = i .. j-1 ----
+    for (int d = i; d < j; ++d) {
+        const ccj_pos4 p = ccj_pos_of(q, i, d, k, l);
+        const int wb = ccj_WB(c, d + 1, j), wbp = ccj_tri_get(c, T2_WBP, d + 1, j);
+        const int x00 = RD(T_PLmloop00, p);
+        PLm00 = ccj_min(PLm00, x00 + wb);                       // :455-458
+        PLm01 = ccj_min(PLm01, x00 + wbp);                      // :468-471
+        PMm00 = ccj_min(PMm00, RD(T_PMmloop00, p) + wb);        // :548-551
+        if (d > i) {
+            const int wp = ccj_WP(c, d + 1, j);
+            PLm10 = ccj_min(PLm10, RD(T_PLmloop10, p) + wb);    // :484-487
+            PfL = ccj_min(PfL, RD(T_PfromL, p) + wp);           // :360-361
+            PfM = ccj_min(PfM, RD(T_PfromMprime, p) + wp);      // :399-402
+            PK = ccj_min(PK, RD(T_PK, p) + wp);                 // :184-187
+        }
     }
-    ccj_put4(c, T_PLmloop00, idx, mn);
-    mn = INF;
-    for (int d = i; d < j; ++d)
-        mn = ccj_min(mn, ccj_get4u(c, T_PLmloop00, i, d, k, l) + ccj_tri_get(c, T2_WBP, d + 1, j));
-    ccj_put4(c, T_PLmloop01, idx, mn);
-    mn = INF;
+    // ---- L2: X(d,j,k,l), d = i+1 .. j ----
     for (int d = i + 1; d <= j; ++d) {
-        mn = ccj_min(mn, ccj_tri_get(c, T2_WBP, i, d - 1) + ccj_get4u(c, T_PLmloop00, d, j, k, l));
-        if (d < j) mn = ccj_min(mn, ccj_get4u(c, T_PLmloop10, i, d, k, l) + ccj_WB(c, d + 1, j));
+        const ccj_pos4 p = ccj_pos_of(q, d, j, k, l);
+        const int wb = ccj_WB(c, i, d - 1), wbp = ccj_tri_get(c, T2_WBP, i, d - 1);
+        const int x00 = RD(T_PLmloop00, p), o00 = RD(T_POmloop00, p);
+        PLm00 = ccj_min(PLm00, wb + x00);                       // :450-453
+        PLm10 = ccj_min(PLm10, wbp + x00);                      // :481-483
+        PMm10 = ccj_min(PMm10, wbp + RD(T_PMmloop00, p));       // :581-584
+        POm00 = ccj_min(POm00, wb + o00);                       // :599-602
+        POm10 = ccj_min(POm10, wbp + o00);                      // :632-635
+        if (d < j) {
+            const int wp = ccj_WP(c, i, d - 1);
+            PfL = ccj_min(PfL, RD(T_PfromL, p) + wp);           // :357-359
+            PfO = ccj_min(PfO, RD(T_PfromO, p) + wp);           // :425-428
+        }
     }
-    ccj_put4(c, T_PLmloop10, idx, mn);
-
-    // ---- PRmloop00 / 01 / 10 (src/pseudo_loop.cc:495-542) ----
-    mn = CCJ_INTERN_INF + bp;
-    for (int d = k; d <= l; ++d) {
-        if (d > k) mn = ccj_min(mn, ccj_WB(c, k, d - 1) + ccj_get4u(c, T_PRmloop00, i, j, d, l));
-        if (d < l) mn = ccj_min(mn, ccj_get4u(c, T_PRmloop00, i, j, k, d) + ccj_WB(c, d + 1, l));
+    // ---- R3: X(i,j,d,l), d = k+1 .. l ----
+    for (int d = k + 1; d <= l; ++d) {
+        const ccj_pos4 p = ccj_pos_of(q, i, j, d, l);
+        const int wb = ccj_WB(c, k, d - 1), wbp = ccj_tri_get(c, T2_WBP, k, d - 1);
+        const int r00 = RD(T_PRmloop00, p);
+        PRm00 = ccj_min(PRm00, wb + r00);                       // :499-503
+        PRm10 = ccj_min(PRm10, wbp + r00);                      // :534-537
+        PMm00 = ccj_min(PMm00, RD(T_PMmloop00, p) + wb);        // :552-555
+        if (d < l) {
+            const int wp = ccj_WP(c, k, d - 1);
+            PfR = ccj_min(PfR, RD(T_PfromR, p) + wp);           // :379-381
+            // get_PfromMdoubleprime (:663-679); d<l, so its i==j&&k==l base case cannot occur
+            PfMp = ccj_min(PfMp, ccj_min(RD(T_PL, p) + PB, RD(T_PR, p) + PB) + wp);   // :412-415
+            PK = ccj_min(PK, RD(T_PK, p) + wp);                 // :189-192
+        }
     }
-    ccj_put4(c, T_PRmloop00, idx, mn);
-    mn = ccj_get4(c, T_PRmloop01, i, j, k, l - 1) + cp;
-    for (int d = k; d < l; ++d)
-        mn = ccj_min(mn, ccj_get4u(c, T_PRmloop00, i, j, k, d) + ccj_tri_get(c, T2_WBP, d + 1, l));
-    ccj_put4(c, T_PRmloop01, idx, mn);
-    mn = ccj_get4(c, T_PRmloop10, i, j, k + 1, l) + cp;
-    for (int d = k + 1; d <= l; ++d)
-        mn = ccj_min(mn, ccj_tri_get(c, T2_WBP, k, d - 1) + ccj_get4u(c, T_PRmloop00, i, j, d, l));
-    ccj_put4(c, T_PRmloop10, idx, mn);
-
-    // ---- PMmloop00 / 01 / 10 (src/pseudo_loop.cc:544-593) ----
-    mn = CCJ_INTERN_INF + bp;
-    for (int d = i; d < j; ++d) mn = ccj_min(mn, ccj_get4u(c, T_PMmloop00, i, d, k, l) + ccj_WB(c, d + 1, j));
-    for (int d = k + 1; d <= l; ++d) mn = ccj_min(mn, ccj_get4u(c, T_PMmloop00, i, j, d, l) + ccj_WB(c, k, d - 1));
-    ccj_put4(c, T_PMmloop00, idx, mn);
-    mn = ccj_get4(c, T_PMmloop01, i, j, k + 1, l) + cp;
-    for (int d = k; d < l; ++d)
-        mn = ccj_min(mn, ccj_get4u(c, T_PMmloop00, i, j, k, d) + ccj_tri_get(c, T2_WBP, d + 1, l));
-    ccj_put4(c, T_PMmloop01, idx, mn);
-    mn = ccj_get4(c, T_PMmloop10, i, j - 1, k, l) + cp;
-    for (int d = i + 1; d <= j; ++d)
-        mn = ccj_min(mn, ccj_tri_get(c, T2_WBP, i, d - 1) + ccj_get4u(c, T_PMmloop00, d, j, k, l));
-    for (int d = k + 1; d < l; ++d) mn = ccj_min(mn, ccj_get4u(c, T_PMmloop10, i, j, k, d) + ccj_WB(c, d + 1, l));
-    ccj_put4(c, T_PMmloop10, idx, mn);
-
-    // ---- POmloop00 / 01 / 10 (src/pseudo_loop.cc:595-644) ----
-    mn = CCJ_INTERN_INF + bp;
-    for (int d = i + 1; d <= j; ++d) mn = ccj_min(mn, ccj_WB(c, i, d - 1) + ccj_get4u(c, T_POmloop00, d, j, k, l));
-    for (int d = k; d < l; ++d) mn = ccj_min(mn, ccj_get4u(c, T_POmloop00, i, j, k, d) + ccj_WB(c, d + 1, l));
-    ccj_put4(c, T_POmloop00, idx, mn);
-    mn = INF;
-    for (int d = k; d < l; ++d)
-        mn = ccj_min(mn, ccj_get4u(c, T_POmloop00, i, j, k, d) + ccj_tri_get(c, T2_WBP, d + 1, l));
-    ccj_put4(c, T_POmloop01, idx, mn);
-    mn = INF;
-    for (int d = i + 1; d <= j; ++d)
-        mn = ccj_min(mn, ccj_tri_get(c, T2_WBP, i, d - 1) + ccj_get4u(c, T_POmloop00, d, j, k, l));
-    for (int d = k + 1; d < l; ++d) mn = ccj_min(mn, ccj_get4u(c, T_POmloop10, i, j, k, d) + ccj_WB(c, d + 1, l));
-    ccj_put4(c, T_POmloop10, idx, mn);
-
+    // ---- R4: X(i,j,k,d), d = k .. l-1 ----
+    for (int d = k; d < l; ++d) {
+        const ccj_pos4 p = ccj_pos_of(q, i, j, k, d);
+        const int wb = ccj_WB(c, d + 1, l), wbp = ccj_tri_get(c, T2_WBP, d + 1, l);
+        const int r00 = RD(T_PRmloop00, p), o00 = RD(T_POmloop00, p);
+        PRm00 = ccj_min(PRm00, r00 + wb);                       // :504-507
+        PRm01 = ccj_min(PRm01, r00 + wbp);                      // :520-523
+        PMm01 = ccj_min(PMm01, RD(T_PMmloop00, p) + wbp);       // :567-570
+        POm00 = ccj_min(POm00, o00 + wb);                       // :603-606
+        POm01 = ccj_min(POm01, o00 + wbp);                      // :618-621
+        if (d > k) {
+            const int wp = ccj_WP(c, d + 1, l);
+            PMm10 = ccj_min(PMm10, RD(T_PMmloop10, p) + wb);    // :585-588
+            POm10 = ccj_min(POm10, RD(T_POmloop10, p) + wb);    // :636-639
+            PfR = ccj_min(PfR, RD(T_PfromR, p) + wp);           // :382-383
+            PfO = ccj_min(PfO, RD(T_PfromO, p) + wp);           // :429-432
+        }
+    }
+#undef RD
+    // ---- stores, in the reference's in-cell order (:85-127) ----
+    ccj_put4(c, T_PLmloop00, idx, PLm00);
+    ccj_put4(c, T_PLmloop01, idx, PLm01);
+    ccj_put4(c, T_PLmloop10, idx, PLm10);
+    ccj_put4(c, T_PRmloop00, idx, PRm00);
+    ccj_put4(c, T_PRmloop01, idx, PRm01);
+    ccj_put4(c, T_PRmloop10, idx, PRm10);
+    ccj_put4(c, T_PMmloop00, idx, PMm00);
+    ccj_put4(c, T_PMmloop01, idx, PMm01);
+    ccj_put4(c, T_PMmloop10, idx, PMm10);
+    ccj_put4(c, T_POmloop00, idx, POm00);
+    ccj_put4(c, T_POmloop01, idx, POm01);
+    ccj_put4(c, T_POmloop10, idx, POm10);
+    int mn;
     // ---- PL (src/pseudo_loop.cc:232-253) ----
     mn = INF;
     if (ccj_pt(c, i, j) > 0) {
@@ -169,47 +203,13 @@ CCJ_HD void ccj_cell4d(const ccj_cx &c, int i, int j, int k, int l) {
         if (l >= i + CCJ_TURN + 1) mn = ccj_min(mn, ccj_get4(c, T_PfromO, i + 1, j, k, l - 1));
     }
     const int vPO = ccj_put4(c, T_PO, idx, mn);
-
-    // ---- PfromL (src/pseudo_loop.cc:354-374) ----
-    mn = INF;
-    for (int d = i + 1; d < j; ++d) {
-        mn = ccj_min(mn, ccj_get4u(c, T_PfromL, d, j, k, l) + ccj_WP(c, i, d - 1));
-        mn = ccj_min(mn, ccj_get4u(c, T_PfromL, i, d, k, l) + ccj_WP(c, d + 1, j));
-    }
-    mn = ccj_min(mn, ccj_min(vPR + PB, ccj_min(vPM + PB, vPO + PB)));
-    ccj_put4(c, T_PfromL, idx, mn);
-    // ---- PfromR (src/pseudo_loop.cc:376-394) ----
-    mn = INF;
-    for (int d = k + 1; d < l; ++d) {
-        mn = ccj_min(mn, ccj_get4u(c, T_PfromR, i, j, d, l) + ccj_WP(c, k, d - 1));
-        mn = ccj_min(mn, ccj_get4u(c, T_PfromR, i, j, k, d) + ccj_WP(c, d + 1, l));
-    }
-    mn = ccj_min(mn, ccj_min(vPM + PB, vPO + PB));
-    ccj_put4(c, T_PfromR, idx, mn);
-    // ---- PfromM (src/pseudo_loop.cc:396-407) ----
-    mn = INF;
-    for (int d = i + 1; d < j; ++d) mn = ccj_min(mn, ccj_get4u(c, T_PfromMprime, i, d, k, l) + ccj_WP(c, d + 1, j));
-    ccj_put4(c, T_PfromM, idx, mn);
-    // ---- PfromMprime (src/pseudo_loop.cc:409-420) with get_PfromMdoubleprime (:663-679); inside the
-    //      loop d<l so the i==j&&k==l base case of M'' cannot occur ----
-    mn = INF;
-    for (int d = k + 1; d < l; ++d) {
-        tmp = ccj_min(ccj_get4u(c, T_PL, i, j, d, l) + PB, ccj_get4u(c, T_PR, i, j, d, l) + PB);
-        mn = ccj_min(mn, tmp + ccj_WP(c, k, d - 1));
-    }
-    ccj_put4(c, T_PfromMprime, idx, mn);
-    // ---- PfromO (src/pseudo_loop.cc:422-443) ----
-    mn = INF;
-    for (int d = i + 1; d < j; ++d) mn = ccj_min(mn, ccj_get4u(c, T_PfromO, d, j, k, l) + ccj_WP(c, i, d - 1));
-    for (int d = k + 1; d < l; ++d) mn = ccj_min(mn, ccj_get4u(c, T_PfromO, i, j, k, d) + ccj_WP(c, d + 1, l));
-    mn = ccj_min(mn, ccj_min(vPL + PB, vPR + PB));
-    ccj_put4(c, T_PfromO, idx, mn);
-    // ---- PK (src/pseudo_loop.cc:181-202) ----
-    mn = INF;
-    for (int d = i + 1; d < j; ++d) mn = ccj_min(mn, ccj_get4u(c, T_PK, i, d, k, l) + ccj_WP(c, d + 1, j));
-    for (int d = k + 1; d < l; ++d) mn = ccj_min(mn, ccj_get4u(c, T_PK, i, j, d, l) + ccj_WP(c, k, d - 1));
-    mn = ccj_min(mn, ccj_min(ccj_min(vPL + PB, vPM + PB), ccj_min(vPR + PB, vPO + PB)));
-    ccj_put4(c, T_PK, idx, mn);
+    // ---- PfromL / PfromR / PfromM / PfromMprime / PfromO / PK: the same-cell terms (:354-443, :181-202) ----
+    ccj_put4(c, T_PfromL, idx, ccj_min(PfL, ccj_min(vPR + PB, ccj_min(vPM + PB, vPO + PB))));
+    ccj_put4(c, T_PfromR, idx, ccj_min(PfR, ccj_min(vPM + PB, vPO + PB)));
+    ccj_put4(c, T_PfromM, idx, PfM);
+    ccj_put4(c, T_PfromMprime, idx, PfMp);
+    ccj_put4(c, T_PfromO, idx, ccj_min(PfO, ccj_min(vPL + PB, vPR + PB)));
+    ccj_put4(c, T_PK, idx, ccj_min(PK, ccj_min(ccj_min(vPL + PB, vPM + PB), ccj_min(vPR + PB, vPO + PB))));
 }
 
 // one (j,d,k) candidate of compute_P (src/pseudo_loop.cc:166-179)

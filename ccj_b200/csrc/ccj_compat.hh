@@ -240,16 +240,16 @@ static inline void make_pair_matrix(void) {
 
 // ---- TriangleMatrix: the public face of src/matrices.hh:14-79 over a device-resident 2D table ------------------------
 // (pseudo_loop::P is a public member of the reference and W_final::ccj passes it to compute_energy_WM)
-namespace ccj { struct ShellFold; }
+struct ccj_shell_fold;   // the shared bulk fold behind the shell objects (ccj_shell.hpp)
 class TriangleMatrix {
 public:
     TriangleMatrix() : fold_(nullptr), table_(0), return_val_(INF) {}
-    void bind(ccj::ShellFold *fold, int table, energy_t return_val = INF) { fold_ = fold; table_ = table; return_val_ = return_val; }
+    void bind(ccj_shell_fold *fold, int table, energy_t return_val = INF) { fold_ = fold; table_ = table; return_val_ = return_val; }
     energy_t get_uc(cand_pos_t i, cand_pos_t j) const;
     energy_t get(cand_pos_t i, cand_pos_t j) const { return i > j ? return_val_ : get_uc(i, j); }
 
 private:
-    ccj::ShellFold *fold_;
+    ccj_shell_fold *fold_;
     int table_;
     energy_t return_val_;
 };

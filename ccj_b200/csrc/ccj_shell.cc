@@ -1,5 +1,6 @@
 // See ccj_shell.hpp / ccj_compat.hh.  Host glue only: the fill and the traceback run on the GPU.
 #include "ccj_shell.hpp"
+#include "h_externs.hh"
 
 #include <cmath>
 #include <cstdio>
@@ -131,10 +132,12 @@ void model_from_vrna(const vrna_param_t &p, int no_gu, ccj_model &m) {
     if (no_gu) m.pair[3][4] = m.pair[4][3] = 0;
     static const int rt[8] = {0, 2, 1, 4, 3, 6, 5, 7};
     for (int t = 0; t < 8; ++t) m.rtype[t] = rt[t];
-    // the reference's recurrences read the penalty GLOBALS of src/h_globals.hh:7-25, not the struct fields
-    m.PS_penalty = -138; m.PSM_penalty = 1007; m.PSP_penalty = 1500; m.PB_penalty = 246; m.PUP_penalty = 6;
-    m.PPS_penalty = 96; m.e_stP_penalty = 0.89; m.e_intP_penalty = 0.74;
-    m.a_penalty = 339; m.b_penalty = 3; m.c_penalty = 2; m.ap_penalty = 341; m.bp_penalty = 56; m.cp_penalty = 12;
+    // the reference's recurrences read the penalty GLOBALS (src/h_externs.hh), not the struct fields: whatever the
+    // program has set them to by now is what the GPU uses
+    m.PS_penalty = ::PS_penalty; m.PSM_penalty = ::PSM_penalty; m.PSP_penalty = ::PSP_penalty; m.PB_penalty = ::PB_penalty;
+    m.PUP_penalty = ::PUP_penalty; m.PPS_penalty = ::PPS_penalty; m.e_stP_penalty = ::e_stP_penalty;
+    m.e_intP_penalty = ::e_intP_penalty; m.a_penalty = ::a_penalty; m.b_penalty = ::b_penalty; m.c_penalty = ::c_penalty;
+    m.ap_penalty = ::ap_penalty; m.bp_penalty = ::bp_penalty; m.cp_penalty = ::cp_penalty;
 }
 
 void vrna_from_model(const ccj_model &m, vrna_param_t &p) {
@@ -206,12 +209,15 @@ void vrna_from_model(const ccj_model &m, vrna_param_t &p) {
     }
 }
 
-ShellFold::~ShellFold() {
+}  // namespace ccj
+
+ccj_shell_fold::~ccj_shell_fold() {
     free(t4);
     if (g_resident == this) g_resident = nullptr;
 }
 
-void ShellFold::ensure_resident() {
+void ccj_shell_fold::ensure_resident() {
+    using ccj::shell_ctx;
     if (g_resident == this && filled) return;
     ccj_ctx *ctx = shell_ctx();
     if (ccj_model_upload(ctx, &model, sizeof model) != 0) die_abi(ctx, "model upload");
@@ -227,11 +233,12 @@ void ShellFold::ensure_resident() {
     }
 }
 
-void ShellFold::ensure_filled() {
+void ccj_shell_fold::ensure_filled() {
     if (!filled) ensure_resident();
 }
 
-void ShellFold::need4(int table) {
+void ccj_shell_fold::need4(int table) {
+    using ccj::shell_ctx;
     if (have4[table]) return;
     ensure_resident();
     const int64_t cells = ccj_cells4(n);
@@ -247,7 +254,7 @@ void ShellFold::need4(int table) {
     have4[table] = true;
 }
 
-ccj_cx ShellFold::cx() {
+ccj_cx ccj_shell_fold::cx() {
     ensure_filled();
     ccj_cx c;
     memset(&c.q, 0, sizeof c.q);
@@ -262,11 +269,13 @@ ccj_cx ShellFold::cx() {
     return c;
 }
 
-energy_t ShellFold::get4(int table, int i, int j, int k, int l) {
+energy_t ccj_shell_fold::get4(int table, int i, int j, int k, int l) {
     if (!ccj_valid4(i, j, k, l) || i < 1 || l > n) return INF;
     need4(table);
     return t4[(size_t)table * ccj_cells4(n) + ccj_idx4(n, i, j, k, l)];
 }
+
+namespace ccj {
 
 std::shared_ptr<ShellFold> shell_fold(const std::string &seq, const vrna_param_t *params) {
     ccj_model m;

@@ -24,7 +24,9 @@ ccj_ctx *shell_ctx();   // one context per process and device (CCJ_DEVICE select
 void model_from_vrna(const vrna_param_t &p, int no_gu, ccj_model &m);
 void vrna_from_model(const ccj_model &m, vrna_param_t &p);
 
-struct ShellFold {
+}  // namespace ccj
+
+struct ccj_shell_fold {
     std::string seq;
     int n = 0;
     ccj_model model;
@@ -34,7 +36,7 @@ struct ShellFold {
     int16_t *t4 = nullptr;        // CCJ_NT4 x C(n+1,4), lazily committed; a table is copied on first use
     bool have4[CCJ_NT4] = {false};
 
-    ~ShellFold();
+    ~ccj_shell_fold();
     void ensure_filled();         // bulk fill on the GPU (once) and make this fold the context's resident wave
     void ensure_resident();       // tables of THIS fold on the device (re-fills if another fold took the context)
     void need4(int table);
@@ -42,6 +44,9 @@ struct ShellFold {
     energy_t raw2(int table, int i, int j) { ensure_filled(); return t2[(size_t)table * ccj_stride2(n) + ccj_idx2(n, i, j)]; }
     energy_t get4(int table, int i, int j, int k, int l);   // Matrix4D::get semantics
 };
+
+namespace ccj {
+using ShellFold = ::ccj_shell_fold;
 
 // the fold shared by all shell objects constructed for the same sequence and parameters
 std::shared_ptr<ShellFold> shell_fold(const std::string &seq, const vrna_param_t *params);

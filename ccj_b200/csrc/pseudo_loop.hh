@@ -69,6 +69,6 @@ private:
     short *S_;
     short *S1_;
     TriangleMatrix WPP, WBP;
-    std::shared_ptr<ccj::ShellFold> fold_;
+    std::shared_ptr<ccj_shell_fold> fold_;
 };
 #endif

@@ -12,7 +12,7 @@
 
 #include "ccj_compat.hh"
 
-namespace ccj { struct ShellFold; }
+struct ccj_shell_fold;   // the shared bulk fold behind the shell objects (ccj_shell.hpp)
 
 class s_energy_matrix {
 public:
@@ -48,14 +48,14 @@ public:
     energy_t E_MbLoop(const energy_t WM2ij, const energy_t WM2ip1j, const energy_t WM2ijm1, const energy_t WM2ip1jm1,
                       const short *S, paramT *params, cand_pos_t i, cand_pos_t j);
 
-    ccj::ShellFold *fold() { return fold_.get(); }   // extension: the shared bulk fold behind this object
+    ccj_shell_fold *fold() { return fold_.get(); }   // extension: the shared bulk fold behind this object
 
 protected:
     energy_t raw(int table, cand_pos_t i, cand_pos_t j);
     const ccj_model *model_for(const paramT *params);   // the object's model, or a conversion of a different `params`
     std::string seq_;
     cand_pos_t n;
-    std::shared_ptr<ccj::ShellFold> fold_;
+    std::shared_ptr<ccj_shell_fold> fold_;
     std::vector<free_energy_node> nodes_;   // get_node() hands out stable pointers like the reference
     std::unique_ptr<ccj_model> other_model_;
     const paramT *other_params_ = nullptr;

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "W_final.hh"
+#include "h_globals.hh"
 
 #include "probe_body.inc"
 

@@ -106,3 +106,31 @@ def test_cli_batch_file(cli, golden_folds, tmp_path):
     plain.write_text("\n".join(r["seq"] for r in ok) + "\n")
     rc, out, err = run(cli, ["-P", str(ROOT / "params" / "rna_Turner04.par"), "--batch-file", str(plain)])
     assert (rc, out, err) == (0, "".join(r["stdout"] for r in ok), "")
+
+
+REFMAIN = ROOT / "oracle" / "_ref" / "CCJ_refmain_b200"
+
+
+def test_reference_main_compiles_against_the_shells():
+    """The reference's own src/CCJ.cc, unchanged, compiled against ccj_b200/csrc/*.hh and linked to libccj_b200.so
+    (oracle/Makefile target refmain; only where /root/reference exists -- the binary travels to the GPU box)."""
+    if not Path("/root/reference/src/CCJ.cc").exists():
+        pytest.skip("no reference sources here")
+    from ccj_b200 import build
+    build.build_library()
+    subprocess.run(["make", "-C", str(ROOT / "oracle"), "refmain"], check=True, stdout=subprocess.DEVNULL)
+    assert REFMAIN.exists()
+    assert run(REFMAIN, ["-V"]) == (0, "CCJ 1.0\n", "")
+
+
+@pytest.mark.gpu
+def test_reference_main_on_the_gpu_library(golden_folds):
+    """That binary folds on the GPU and prints what the reference prints."""
+    if not REFMAIN.exists():
+        pytest.skip("oracle/_ref/CCJ_refmain_b200 did not travel")
+    recs = [r for r in golden_folds if 20 <= len(r["seq"]) <= 60][:16] + [r for r in golden_folds if r["rc"] != 0][:3]
+    for r in recs:
+        args = ["-P", str(ROOT / "params" / r["par"]), "-d", str(r["dangles"])] + r["extra"] + [r["seq"]]
+        assert run(REFMAIN, args) == (r["rc"], r["stdout"], r["stderr"]), r["seq"]
+    rc, out, err = run(REFMAIN, ["--noConv", "GCAACGATGACATACATCGCTAGTCGACGC"], cwd="/tmp")
+    assert (rc, out) == (0, "GCAACGATGACATACATCGCTAGTCGACGC\n....(((((.....)))))........... (-4.4)\n")

@@ -157,6 +157,27 @@ def test_batch_invariance_and_ragged_batches(ctx_factory):
     assert ctx.fold_batch(seqs[::-1]) == together[::-1]
 
 
+def test_in_process_multi_context_dealing(ctx_factory, golden_folds):
+    """ccj_fold_batch_multi: one host thread per context, chunks dealt dynamically; results in input order and equal to
+    the single-context call.  Contexts may sit on different GPUs (one per device) or, as here when only one GPU is
+    visible, on the same one."""
+    import torch
+    ndev = max(1, torch.cuda.device_count())
+    par = str(ROOT / "params" / "rna_Turner04.par")
+    ctxs = [ccj_b200.Context(d % ndev, par, 2) for d in range(3)]
+    try:
+        recs = [r for r in golden_folds if r["par"] == "rna_Turner04.par" and r["dangles"] == 2 and not r["extra"]]
+        recs = recs[:97]
+        folds = ccj_b200.fold_batch_multi(ctxs, [r["seq"] for r in recs])
+        check(folds, recs)
+        assert folds == ctx_factory().fold_batch([r["seq"] for r in recs])
+        with pytest.raises(ccj_b200.CCJError):
+            ccj_b200.fold_batch_multi(ctxs, ["ACGU", "ACGN"])
+    finally:
+        for c in ctxs:
+            c.close()
+
+
 def test_edge_inputs(ctx_factory):
     ctx = ctx_factory()
     assert ctx.fold("A").stdout == "A\n. (0)\n"
