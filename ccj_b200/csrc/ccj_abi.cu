@@ -1042,9 +1042,10 @@ int ccj_count_terms(const char *seq, int n, int no_gu, int64_t *out) {
                     }
                     pre[x][y] = v;
                 }
-            for (int i = 1; i <= j; ++i)
-                for (int l = k; l <= n; ++l) {
-                    const int x = std::min(j - i, 29), y = std::min(l - k, 29);
+            // d > max(i, j-30) and dp < min(l, k+30) (:763-766): x = j-d <= min(j-i-1, 29), y = dp-k <= min(l-k-1, 29)
+            for (int i = 1; i < j; ++i)
+                for (int l = k + 1; l <= n; ++l) {
+                    const int x = std::min(j - i - 1, 29), y = std::min(l - k - 1, 29);
                     iloop += pre[x][y];
                 }
         }

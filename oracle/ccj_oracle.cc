@@ -19,6 +19,7 @@
 //
 //   ccj_oracle hash   <params.txt> <dangles> <noGU 0|1> <sequence>   table hashes, format of `ccj_ref_dump hash`, + "W <dcal>"
 //   ccj_oracle energy <params.txt> <dangles> <noGU 0|1> <sequence>   W[n] in dcal/mol
+//   ccj_oracle count  <params.txt> <dangles> <noGU 0|1> <sequence>   interior-window candidates the fill evaluates
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -499,6 +500,9 @@ static void compute_P(int i, int l) {
     if (mn < INF / 2) Pm.at(i, l) = mn;
 }
 // interior windows, src/pseudo_loop.cc:682-703, 717-738, 752-773, 787-808
+// g_win[x]: window candidates that pass can_pair and are evaluated (one 4D read each), per window: PL, PR, PM, and the
+// PO window, whose reads are all invalid indices (no memory access; "dead").  Reported by the `count` mode.
+static long long g_win[4] = {0, 0, 0, 0};
 static int get_PLiloop(int i, int j, int k, int l) {
     if (!valid4(i, j, k, l)) return INF;
     if (!can_pair(i, j)) return INF;
@@ -509,6 +513,7 @@ static int get_PLiloop(int i, int j, int k, int l) {
         const int min_dp = std::max(d + TURN, j - MAXLOOP);
         for (int dp = j - 1; dp > min_dp; --dp) {
             if (!can_pair(d, dp)) continue;
+            ++g_win[0];
             mn = std::min(mn, get_e_intP(i, d, dp, j) + PL.get(d, dp, k, l));
         }
     }
@@ -524,6 +529,7 @@ static int get_PRiloop(int i, int j, int k, int l) {
         const int min_dp = std::max(d + TURN, l - MAXLOOP);
         for (int dp = l - 1; dp > min_dp; --dp) {
             if (!can_pair(d, dp)) continue;
+            ++g_win[1];
             mn = std::min(mn, get_e_intP(k, d, dp, l) + PR.get(i, j, d, dp));
         }
     }
@@ -539,6 +545,7 @@ static int get_PMiloop(int i, int j, int k, int l) {
         const int min_dp = std::min(l, k + MAXLOOP);
         for (int dp = k + 1; dp < min_dp; ++dp) {
             if (!can_pair(d, dp)) continue;
+            ++g_win[2];
             mn = std::min(mn, get_e_intP(d, j, k, dp) + PM.get(i, d, dp, l));
         }
     }
@@ -554,6 +561,7 @@ static int get_POiloop(int i, int j, int k, int l) {
         const int min_dp = std::max(l - MAXLOOP, k);
         for (int dp = l - 1; dp > min_dp; --dp) {
             if (!can_pair(d, dp)) continue;
+            ++g_win[3];
             mn = std::min(mn, get_e_intP(i, d, dp, l) + PO.get(d, j, dp, k));   // (d,j,dp,k) as written at :803
         }
     }
@@ -864,6 +872,11 @@ int main(int argc, char **argv) {
     fold();
     if (mode == "energy") {
         printf("%d\n", W[n]);
+        return 0;
+    }
+    if (mode == "count") {   // evaluated interior-window candidates of the fill ("iloop terms")
+        printf("iloop %lld PL %lld PR %lld PM %lld PO_dead %lld\n", g_win[0] + g_win[1] + g_win[2], g_win[0], g_win[1], g_win[2],
+               g_win[3]);
         return 0;
     }
     static const char *names4[22] = {"PK", "PL", "PR", "PM", "PO", "PfromL", "PfromR", "PfromM", "PfromMprime", "PfromO",

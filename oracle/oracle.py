@@ -74,3 +74,9 @@ def reference_fold(seq: str, par_file: str, extra: Optional[List[str]] = None):
         return None
     p = subprocess.run([str(REF_BIN), "-P", par_file, *(extra or []), seq], capture_output=True, text=True)
     return p.returncode, p.stdout, p.stderr
+
+
+def oracle_window_terms(seq: str, par_name: str = "rna_Turner04.par", dangles: int = 2, no_gu: bool = False) -> dict:
+    """Interior-window candidates the restated fill evaluates: {"iloop": PL+PR+PM, "PL", "PR", "PM", "PO_dead"}."""
+    f = _run("count", seq, par_name, dangles, no_gu).split()
+    return {f[x]: int(f[x + 1]) for x in range(0, len(f), 2)}

@@ -54,3 +54,16 @@ def test_oracle_matches_live_reference(par, dangles):
         got = subprocess.run([str(orc.build_oracle()), "hash", orc.params_dump(par), str(dangles), "0", seq],
                              capture_output=True, text=True, check=True).stdout
         assert [l for l in got.splitlines() if not l.startswith("W ")] == want.splitlines(), seq
+
+
+def test_window_term_count_matches_the_restated_fill(library):
+    """the interior-window candidates the fill evaluates (the `iloop` part of the algorithmic bytes
+    bench.py reports).  ccj_count_terms derives it from the pair table in closed form; the restatement counts the
+    candidates while it evaluates them.  H60: 8.59e6, the figure SURVEY measured with an instrumented reference."""
+    import random
+    import ccj_b200
+    H60 = "AAUAGGCGCAGCAUACACGGUCGAGCUGCGCCAAUAACAAUACGACCGUGAUAAAUAAAA"
+    assert ccj_b200.count_terms(H60)["iloop"] == 8592675
+    rng = random.Random(3)
+    for seq in (H60, "".join(rng.choice("ACGU") for _ in range(47)), "".join(rng.choice("ACGU") for _ in range(23)), "ACGU"):
+        assert ccj_b200.count_terms(seq)["iloop"] == orc.oracle_window_terms(seq)["iloop"], seq
