@@ -63,7 +63,7 @@ size_t tab_bytes_uncached(int n, int which) {
         case TAB_PKG: return align_up((size_t)ccj_pkg_total(n) * sizeof(int16_t) + 64, 256);
         case TAB_SCRATCH: return align_up((size_t)ccj_level_max(n) * ccj::fill4_partials() * sizeof(int16_t) + 64, 256);
         case TAB_PLW:
-        case TAB_PRW: return align_up((size_t)ccj_winlr_quads(n) * 4 * sizeof(int16_t) + 64, 256);
+        case TAB_PRW: return align_up((size_t)ccj_winlr_quads(n) * 4 * sizeof(int16_t) + 256, 256);   // lanes read up to 60 cells past a run
         case TAB_PMW:
         case TAB_PMM: return align_up(((size_t)ccj_pmw_level_quads(n) * (size_t)(n > 2 ? n - 2 : 1) + 16) * 8, 256);  // 8 bytes per quad: 4 values resp. 4 masks
         case TAB_WSCR: return align_up(((size_t)ccj_winlr_level_max(n) * 4 + (size_t)ccj_pmw_level_quads(n) * 8) * sizeof(int16_t) + 64, 256);

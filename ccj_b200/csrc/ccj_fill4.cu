@@ -587,11 +587,13 @@ __device__ __forceinline__ int splat16(int e) { return (int)__byte_perm((unsigne
 // energy, clamp) in shared memory; every candidate is then one 8-byte load and four packed int16x2
 // instructions per lane (4 cells).  Results go to the wscr partial in the same layout, 8 bytes per lane.
 //   blockIdx.x -> (pass, chunk of 16 paired rows), blockIdx.y -> a, blockIdx.z -> (sequence, PL|PR)
-template <bool PIPE>
+// G = lanes per run (8: one pass covers 32 cells of a run, four runs per warp; 16: 64 cells, two runs per warp -- half
+// the distinct cache lines per warp request, for levels whose runs are long)
+template <bool PIPE, int G>
 __global__ void __launch_bounds__(K4_THREADS, PIPE ? 6 : 12) k_winLR(const ccj_model *__restrict__ M, const ccj_seq *__restrict__ seqs, int t, int nchunk) {
     __shared__ int s_T[64];              // quad offset of source slab (a-s,b) resp. (a,b-s), plus H4(m+s)
     __shared__ int s_h4[K4_MAXN + 4];
-    __shared__ int2 tile[2][WRUNS][WGRP];   // double-buffered: (source run start, energy | clamp << 16)
+    __shared__ int2 tile[2][K4_THREADS / G][G];   // double-buffered: (source run start, energy | clamp << 16)
     const int role = blockIdx.z & 1;     // 0: PL   1: PR
     const ccj_seq q = seqs[blockIdx.z >> 1];
     const int n = q.n, n1 = n + 1;
@@ -601,12 +603,12 @@ __global__ void __launch_bounds__(K4_THREADS, PIPE ? 6 : 12) k_winLR(const ccj_m
     const int arm = role == 0 ? a : b;   // length of the arm whose closing pair carries the window
     if (arm <= CCJ_TURN) return;
     const int chunk = blockIdx.x % nchunk, pass = blockIdx.x / nchunk;
-    if (pass * (4 * WGRP) >= m) return;
+    if (pass * (4 * G) >= m) return;
     const int *__restrict__ pc = q.pcum + arm * (n + 2);
     // paired 5' ends of this slab: PL i in 1..m, PR k in a+3..n-b
     const int first = role == 0 ? 0 : __ldg(&pc[a + 2]);
     const int last = role == 0 ? __ldg(&pc[m]) : __ldg(&pc[n - b]);
-    if (first + chunk * WRUNS >= last) return;
+    if (first + chunk * (K4_THREADS / G) >= last) return;
     const int *__restrict__ lay = q.lay;
     for (int x = threadIdx.x; x <= n; x += K4_THREADS) s_h4[x] = __ldg(&lay[2 * n1 + x]);
     if (threadIdx.x < 64) {
@@ -620,13 +622,13 @@ __global__ void __launch_bounds__(K4_THREADS, PIPE ? 6 : 12) k_winLR(const ccj_m
         s_T[s] = v;
     }
     __syncthreads();
-    const int grp = threadIdx.x / WGRP, gl = threadIdx.x & (WGRP - 1);
-    const int idx = first + chunk * WRUNS + grp;
+    const int grp = threadIdx.x / G, gl = threadIdx.x & (G - 1);
+    const int idx = first + chunk * (K4_THREADS / G) + grp;
     const int p5 = __ldg(&q.plist[arm * n1 + min(idx, last - 1)]);
     const int c = role == 0 ? p5 - 1 : n - b - p5;     // row of the run: i-1 resp. kr=n-b-k
     const int zc = m - c;                               // its length
-    const bool gact = idx < last && pass * (4 * WGRP) < zc;   // the group has cells in this pass
-    const int qd = pass * WGRP + gl;                    // this lane's quad of the run
+    const bool gact = idx < last && pass * (4 * G) < zc;   // the group has cells in this pass
+    const int qd = pass * G + gl;                    // this lane's quad of the run
     const int2 *src = reinterpret_cast<const int2 *>(role == 0 ? q.plw : q.prw) + qd;
     asm volatile("" : "+l"(src));  // per-lane base in a register pair: one IMAD.WIDE per candidate
     const int own = s_T[0] - s_h4[zc];                  // the run's own (not yet written) quads
@@ -642,11 +644,11 @@ __global__ void __launch_bounds__(K4_THREADS, PIPE ? 6 : 12) k_winLR(const ccj_m
     const int slot = ccj_tri(p5, p5 + arm);
     const uint32_t *__restrict__ lst = q.inlist + (int64_t)slot * CCJ_WIN_IN;
     const int cnt = gact ? __ldg(&q.incnt[slot]) : 0;
-    const int nb = (__reduce_max_sync(0xffffffffu, cnt) + WGRP - 1) / WGRP;   // batches of 8 candidates, warp-uniform
+    const int nb = (__reduce_max_sync(0xffffffffu, cnt) + G - 1) / G;   // batches of 8 candidates, warp-uniform
     // PIPE (small waves): software pipeline over the batches -- while batch b is consumed, the loads of batch b+1
     // are in flight and the list entry of batch b+2 is on its way.
     // lane gl fetches entry 8b+gl of its group's list; past the end the last entry again (min is idempotent)
-    auto fetch = [&](int bb) -> uint32_t { return cnt > 0 ? __ldg(&lst[min(bb * WGRP + gl, cnt - 1)]) : 0u; };
+    auto fetch = [&](int bb) -> uint32_t { return cnt > 0 ? __ldg(&lst[min(bb * G + gl, cnt - 1)]) : 0u; };
     auto decode = [&](uint32_t en) -> int2 {
         if (cnt == 0) return make_int2(own, 0x7fff0000);
         const int x = (en >> 16) & 0xff, y = en >> 24, e = (int)(int16_t)(en & 0xffff);
@@ -656,9 +658,10 @@ __global__ void __launch_bounds__(K4_THREADS, PIPE ? 6 : 12) k_winLR(const ccj_m
     };
     // one LDS.64 per candidate (shared memory / L1 is the busiest unit of this kernel): the energy and its clamp
     // travel as two halves of one word and are splatted with two PRMTs
-#define ISSUE(W_, EC_, buf)                                                   \
+#define ISSUE(W_, EC_, buf)  ISSUEH(W_, EC_, buf, 0)
+#define ISSUEH(W_, EC_, buf, h0)                                              \
     _Pragma("unroll") for (int u = 0; u < WB; ++u) {                         \
-        const int2 d2 = tile[buf][grp][u];                                   \
+        const int2 d2 = tile[buf][grp][(h0) + u];                            \
         W_[u] = ldq(src, d2.x);                                              \
         EC_[u] = d2.y;                                                       \
     }
@@ -706,14 +709,18 @@ __global__ void __launch_bounds__(K4_THREADS, PIPE ? 6 : 12) k_winLR(const ccj_m
             __syncwarp();
             tile[0][grp][gl] = d;
             __syncwarp();
-            int2 w[WB];
-            int ec[WB];
-            ISSUE(w, ec, 0);
-            FENCE8X(w);
-            CONSUME(w, ec);
+#pragma unroll
+            for (int h = 0; h < G; h += WB) {   // WB candidates in flight at a time
+                int2 w[WB];
+                int ec[WB];
+                ISSUEH(w, ec, 0, h);
+                FENCE8X(w);
+                CONSUME(w, ec);
+            }
         }
     }
 #undef ISSUE
+#undef ISSUEH
 #undef CONSUME
     if (gact && 4 * qd < zc) {
         if (cnt == 0) { acc0 = keep0; acc1 = keep1; }
@@ -1084,7 +1091,6 @@ __global__ void __launch_bounds__(K4_THREADS, FINAL_MINB) k_final(const ccj_mode
     const int vPfMp = PUT(T_PfromMprime, R3.PfMp + PB);
     const int vPfO = PUT(T_PfromO, min(min(L2.PfO, R4.PfO), min(vPL + PB, vPR + PB)));
     const int vPK = PUT(T_PK, min(min(L1.PK, R3.PK), min(min(vPL + PB, vPM + PB), min(vPR + PB, vPO + PB))));
-    w4[(int64_t)T_MPP * st4 + off0] = (int16_t)min(vPL, vPR);
     {   // the two PK copies of compute_P (ccj_types.h).  As first factor PK(i,j,d+1,k') this cell is d=k-1, k'=l, i.e.
         // row delta=l-k+1 of block (i,j), position k-j-2: coalesced.  As second factor PK(i2,d,k2,l) it is i2=i, d=j,
         // k2=k: row delta=k-j-1 of block (i,l), position j-i: scattered, one store per cell.
@@ -1227,10 +1233,19 @@ void launch_4d_windows(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, in
     // (4 x 150 nt, 8 x 100 nt, 2 x 200 nt still gain; 8 x 150 nt, 16 x 100 nt lose)
     const bool pipe = (long long)nm * nm * d.nseq < 120000;
     {   // PL / PR: at most m paired rows per slab, runs of up to m cells
-        const int nchunk = (m + WRUNS - 1) / WRUNS, npass = (m + 4 * WGRP - 1) / (4 * WGRP);
-        const dim3 grid(nchunk * npass, t + 1, d.nseq * 2);
-        if (pipe) k_winLR<true><<<grid, K4_THREADS, 0, st>>>(M, seqs, t, nchunk);
-        else k_winLR<false><<<grid, K4_THREADS, 0, st>>>(M, seqs, t, nchunk);
+        // wide groups (16 lanes = 64 cells per pass, two runs per warp request instead of four) for levels whose runs
+        // reach 32 cells: measured 76.9 -> 72.8 ms for the window kernels of a 32 x 150 nt fill, monotonic in the
+        // threshold (profiles/r2_notes.md); CCJ_WINLR_WIDE_FROM overrides the threshold for experiments
+        static const int wide_from = [] { const char *e = getenv("CCJ_WINLR_WIDE_FROM"); return e ? atoi(e) : 32; }();
+        if (!pipe && m >= wide_from) {
+            const int runs = K4_THREADS / 16, nchunk = (m + runs - 1) / runs, npass = (m + 63) / 64;
+            k_winLR<false, 16><<<dim3(nchunk * npass, t + 1, d.nseq * 2), K4_THREADS, 0, st>>>(M, seqs, t, nchunk);
+        } else {
+            const int nchunk = (m + WRUNS - 1) / WRUNS, npass = (m + 4 * WGRP - 1) / (4 * WGRP);
+            const dim3 grid(nchunk * npass, t + 1, d.nseq * 2);
+            if (pipe) k_winLR<true, 8><<<grid, K4_THREADS, 0, st>>>(M, seqs, t, nchunk);
+            else k_winLR<false, 8><<<grid, K4_THREADS, 0, st>>>(M, seqs, t, nchunk);
+        }
     }
     {   // PM: pairs (j,k) with TURN < k-j <= n-1-t; a row has at most min(t+1, n-4-t) cells at any quad phase
         long long rows = 0;

@@ -27,8 +27,7 @@ enum ccj_table4 {
     T_PLmloop00, T_PLmloop01, T_PLmloop10, T_PRmloop00, T_PRmloop01, T_PRmloop10,
     T_PMmloop00, T_PMmloop01, T_PMmloop10, T_POmloop00, T_POmloop01, T_POmloop10,
     CCJ_NT4 = 22,
-    T_MPP = 22,       /* internal: min(PL,PR) of the cell = get_PfromMdoubleprime without PB (pseudo_loop.cc:675-678) */
-    CCJ_NT4_STORE = 23
+    CCJ_NT4_STORE = 22   /* min(PL,PR) of a cell (get_PfromMdoubleprime without PB, pseudo_loop.cc:675-678) lives in record g3 only */
 };
 
 // ---- 2D tables ----------------------------------------------------------------------------------

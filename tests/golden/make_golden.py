@@ -8,6 +8,7 @@ oracle/Makefile (oracle/_ref/CCJ, oracle/_ref/ccj_ref_dump).  Run in the build c
     python tests/golden/make_golden.py config4    # first 16 config-4 sequences (150 nt) -> folds_config4.json
     python tests/golden/make_golden.py config2    # first 64 config-2 sequences (100 nt) -> folds_config2.json
     python tests/golden/make_golden.py probe      # public class surface probe + struct layouts -> probe_*.txt.gz, vrna_layout.txt
+    python tests/golden/make_golden.py wrap_real  # a real int16 wrap at n=87 with tripled stacking energies -> wrap_real.json
     python tests/golden/make_golden.py wrap       # int16 negative wrap (src/matrices.hh:188-191) at n=213 -> wrap213.json
     python tests/golden/make_golden.py big        # n>213: oracle/_ref/ccj_oracle hashes -> table_hashes_big.json
                                                   # (the reference aborts there; ~1 h per sequence on one core)
@@ -53,6 +54,26 @@ def wrap213():
     WP(2,211) falls below -32768 dcal/mol, which Matrix4D::set narrows to a positive int16 (src/matrices.hh:188-191).
     213 nt is the longest input the reference accepts, and the shortest that reaches the wrap."""
     return "G" + "G" * 103 + "GAAA" + "C" * 103 + "A" + "C"
+
+
+def strong_stack_par(path):
+    """rna_Turner04.par with the '# stack' free energies tripled: a 40-bp helix then reaches -39 000 dcal/mol, below
+    the int16 range of Matrix4D, at a length the reference folds in seconds.  Written to `path`, returns it."""
+    out, inside = [], False
+    for ln in (PARAMS / "rna_Turner04.par").read_text().splitlines():
+        if ln.startswith("#"):
+            inside = ln.strip() == "# stack"
+        elif inside and ln.strip() and not ln.lstrip().startswith("/*"):
+            ln = " ".join(str(3 * int(tok)) if tok.lstrip("-").isdigit() else tok for tok in ln.split())
+        out.append(ln)
+    Path(path).write_text("\n".join(out) + "\n")
+    return path
+
+
+def wrap87():
+    """40-bp poly-G/poly-C hairpin inside the left arm of a gapped region; with strong_stack_par PK(1,85,87,87) is about
+    -38 000 dcal/mol in exact arithmetic and wraps to a positive int16 in the reference (src/matrices.hh:188-191)."""
+    return "G" + "G" * 40 + "GAAA" + "C" * 40 + "A" + "C"
 
 
 def seed200():
@@ -159,6 +180,21 @@ def main():
             out = {"fold": fa.result(), "hashes": fb.result()}
         (HERE / "wrap213.json").write_text(json.dumps(out, indent=0))
         print("wrap213:", out["fold"]["rc"], out["fold"]["stdout"][-40:], out["hashes"]["tables"]["PK"])
+    elif what == "wrap_real":
+        # a REAL wrap at a length the reference folds in seconds: stacking energies tripled (custom -P file)
+        import tempfile
+        par = strong_stack_par(Path(tempfile.gettempdir()) / "ccj_strong_stack.par")
+        seq = wrap87()
+        p = subprocess.run([str(REF), "-P", str(par), seq], capture_output=True, text=True, cwd=str(ROOT))
+        h = subprocess.run([str(DUMP), "hash", str(par), "2", seq], capture_output=True, text=True, cwd=str(ROOT))
+        assert h.returncode == 0, h.stderr
+        tabs = {}
+        for line in h.stdout.splitlines()[1:]:
+            name, cnt, agg, hh = line.split()
+            tabs[name] = [int(cnt), int(agg), hh]
+        out = {"seq": seq, "rc": p.returncode, "stdout": p.stdout, "stderr": p.stderr, "tables": tabs}
+        (HERE / "wrap_real.json").write_text(json.dumps(out, indent=0))
+        print("wrap_real:", p.returncode, p.stdout[-60:], tabs["PK"], tabs["PfromL"])
     elif what == "big":
         # n > 213: the reference asserts (src/matrices.hh:159-160), so the pinned CPU restatement is the checker
         sys.path.insert(0, str(ROOT))

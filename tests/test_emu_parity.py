@@ -53,3 +53,23 @@ def test_emu_matches_reference_binary_when_present(emu_bin):
         a = subprocess.run([str(ref), "-P", par, seq], capture_output=True, text=True)
         b = subprocess.run([str(emu_bin), "fold", par, "2", seq], capture_output=True, text=True)
         assert (a.returncode, a.stdout, a.stderr) == (b.returncode, b.stdout, b.stderr), seq
+
+
+def test_real_int16_wrap(emu_bin, tmp_path):
+    """The generic cell path narrows like Matrix4D::set: entries below -32768 dcal/mol wrap (tests/golden/wrap_real.json,
+    the reference run with tripled stacking energies; see tests/test_gpu_parity.py)."""
+    import json
+    import sys
+    sys.path.insert(0, str(ROOT / "tests" / "golden"))
+    from make_golden import strong_stack_par, wrap87
+    g = json.loads((ROOT / "tests" / "golden" / "wrap_real.json").read_text())
+    par = strong_stack_par(tmp_path / "strong.par")
+    p = subprocess.run([str(emu_bin), "hash", str(par), "2", wrap87()], capture_output=True, text=True)
+    got = {}
+    for line in p.stdout.splitlines()[1:]:
+        name, cnt, agg, h = line.split()
+        got[name] = [int(cnt), int(agg), h]
+    assert got == g["tables"]
+    assert min(v[1] for k, v in got.items() if k in ("PK", "PfromL", "PfromR")) < -32700   # at the edge of the range
+    p = subprocess.run([str(emu_bin), "fold", str(par), "2", wrap87()], capture_output=True, text=True)
+    assert (p.returncode, p.stdout, p.stderr) == (g["rc"], g["stdout"], g["stderr"])

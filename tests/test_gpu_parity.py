@@ -89,11 +89,38 @@ def test_beyond_the_reference_limit_against_the_cpu_restatement(ctx_factory):
         assert ctx.fetch()[0].energy_dcal == r["W"]
 
 
+def test_real_int16_wrap_matches_the_reference(tmp_path):
+    """With the stacking energies tripled (custom -P file, tests/golden/make_golden.py strong_stack_par) a 40-bp helix
+    inside one gapped region drives entries below -32768 dcal/mol at n=87, and the reference's Matrix4D::set wraps them
+    (src/matrices.hh:188-191).  The tuned kernels saturate instead, detect that (k_final's guard) and hand the sequence to
+    the generic kernels, which narrow like the reference: every table hash and the fold must equal the reference's."""
+    import json
+    import sys
+    sys.path.insert(0, str(ROOT / "tests" / "golden"))
+    from make_golden import strong_stack_par, wrap87
+    g = json.loads((ROOT / "tests" / "golden" / "wrap_real.json").read_text())
+    assert g["seq"] == wrap87()
+    par = strong_stack_par(tmp_path / "strong.par")
+    with ccj_b200.Context(0, str(par), 2) as ctx:
+        # in a batch with ordinary neighbours: only the flagged sequence is repeated
+        other = "GCAACGAUGACAUACAUCGCUAGUCGACGC"
+        ctx.prepare([other, g["seq"], other])
+        ctx.fill()
+        for name, want in g["tables"].items():
+            got = ctx.table4_hash(1, name) if name in ccj_b200.TABLE4 else ctx.table2_hash(1, name)
+            assert got == want, name
+        ctx.traceback()
+        folds = ctx.fetch()
+        assert (folds[1].returncode, folds[1].stdout, folds[1].stderr) == (g["rc"], g["stdout"], g["stderr"])
+        assert folds[0] == folds[2] == ctx.fold(other)
+
+
 def test_int16_negative_wrap_at_n213(ctx_factory):
     """Matrix4D::set clamps only the upper side and narrows int32 -> int16 (src/matrices.hh:188-191): an entry below
-    -32768 dcal/mol wraps to a positive value.  The designed 213-mer (a 103-bp poly-G/poly-C hairpin inside one arm)
-    is the shortest input that gets there and the longest the reference accepts; fold and every table hash must equal
-    the unmodified reference's (make_golden.py wrap)."""
+    -32768 dcal/mol wraps to a positive value.  With the shipped parameter sets the most extreme input the reference
+    accepts -- a 103-bp poly-G/poly-C hairpin inside one arm of a gapped region at n=213, -335.1 kcal/mol -- comes within
+    126 dcal of that range (smallest entry -32642) without reaching it; the tuned path detects the proximity and takes
+    the generic kernels.  Fold and every table hash must equal the unmodified reference's (make_golden.py wrap)."""
     import json
     p = ROOT / "tests" / "golden" / "wrap213.json"
     if not p.exists():
@@ -176,6 +203,21 @@ def test_in_process_multi_context_dealing(ctx_factory, golden_folds):
     finally:
         for c in ctxs:
             c.close()
+
+
+def test_more_sequences_than_one_launch_can_index(ctx_factory):
+    """The level kernels put the sequence index (x up to 4 roles) into gridDim.y/z (limit 65535): waves are capped at
+    16383 sequences, a longer batch is split, a prepared wave beyond the cap is refused."""
+    ctx = ctx_factory()
+    seqs = ["GGGAAACCC", "ACGUACGU", "GGGGAAAACCCC", "A", "GCGCAAGC"] * 3400          # 17 000 short sequences
+    folds = ctx.fold_batch(seqs)
+    assert len(folds) == len(seqs)
+    want = ctx.fold_batch(seqs[:5])
+    for x in range(0, len(seqs), 5):
+        assert folds[x:x + 5] == want
+    assert ctx.wave_capacity(8) <= 16383
+    with pytest.raises(ccj_b200.CCJError):
+        ctx.prepare(seqs)
 
 
 def test_edge_inputs(ctx_factory):
