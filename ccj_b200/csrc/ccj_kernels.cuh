@@ -5,7 +5,17 @@
 
 #include "ccj_types.h"
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges cost nothing unless a profiler is attached
+
 namespace ccj {
+
+// NVTX range around a phase of the fold (tracing); shows up in Nsight timelines
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
 
 struct LaunchDims {
     int nseq;   // sequences in the wave (blockIdx.z / .y)

@@ -85,6 +85,7 @@ struct ccj_shard {
     std::string seq;
     char *arena = nullptr;
     size_t arena_bytes = 0;
+    size_t off_w3 = 0;
     size_t off_in = 0, off_out = 0, off_t2 = 0, off_ftype = 0, off_tb = 0, off_lev = 0, off_locptr = 0, off_rep = 0, off_loc = 0, off_desc = 0;
     std::vector<int64_t> lev;            // n+2 entries
     ccj_seq h_desc;
@@ -290,6 +291,7 @@ int ccj_shard_prepare(ccj_shard *sh, const char *seq, int n) {
     sh->off_in = take((size_t)(n + 2) + (size_t)n + 2);
     sh->off_out = take(sizeof(int32_t) * (CCJ_STATUS_INTS + (size_t)(n + 1) + (size_t)(n + 2)));
     sh->off_t2 = take((size_t)ccj_stride2(n) * CCJ_NT2 * sizeof(int32_t));
+    sh->off_w3 = take((size_t)ccj_stride2(n) * 4 * sizeof(int32_t));
     sh->off_ftype = take((size_t)n + 2);
     sh->off_tb = take(sizeof(int32_t) * 5 * (size_t)(16 * n + 64));
     sh->off_lev = take(sizeof(int64_t) * (size_t)(n + 2));
@@ -333,6 +335,7 @@ int ccj_shard_prepare(ccj_shard *sh, const char *seq, int n) {
     q.t2 = reinterpret_cast<int32_t *>(sh->arena + sh->off_t2);
     q.stride2 = ccj_stride2(n);
     q.stride4 = 0;
+    q.w3 = reinterpret_cast<int32_t *>(sh->arena + sh->off_w3);   // {WB,WP,WBP} packed per interval: one load per split point
     q.ftype_out = reinterpret_cast<int8_t *>(sh->arena + sh->off_ftype);
     q.tb_stack = reinterpret_cast<int32_t *>(sh->arena + sh->off_tb);
     q.tb_cap = 16 * n + 64;
@@ -415,8 +418,12 @@ int ccj_shard_fill(ccj_shard **shards, int count, float *ms4) {
     };
     for (int x = 0; x < count; ++x) ccj::launch_init(M, d_desc(shards[x]), d, st);
     ck(cudaEventRecord(ev[0], st), "event");
+    ccj::NvtxRange nvtx_fill("ccj_shard_fill");
     for (int s = 0; s < n && rc == 0; ++s) {
         const int m = n - s - 2;
+        char label[32];
+        snprintf(label, sizeof label, "level %d", s);
+        ccj::NvtxRange nvtx_level(label);
         // --- P(i,i+s) of the own rows, then the minimum over ranks of the span-s diagonal ---
         if (s >= 3 && s <= n - 1) {
             for (int x = 0; x < count; ++x) {

@@ -41,6 +41,7 @@ int main(int argc, char **argv) {
     int dangles = atoi(argv[3]);
     int noGU = argc > 5 ? atoi(argv[5]) : 0;
     const int shardG = argc > 6 ? atoi(argv[6]) : 0;
+    const int packed2d = argc > 7 ? atoi(argv[7]) : 0;   // keep {WB,WP,WBP} packed per interval (ccj_seq::w3) as the GPU folds do
     ccj::RawParams rp;
     if (!ccj::load_par_file(argv[2], rp, err)) {
         fprintf(stderr, "%s\n", err.c_str());
@@ -80,6 +81,11 @@ int main(int argc, char **argv) {
     c.q.status = st.data();
     c.q.tb_stack = tbs.data();
     c.q.tb_cap = 16 * n + 64;
+    std::vector<int32_t> w3v;
+    if (packed2d) {
+        w3v.assign((size_t)s2 * 4, 0x55555555);
+        c.q.w3 = w3v.data();
+    }
     std::vector<int64_t> lev(n + 2, 0);
     std::vector<int16_t> rep;
     std::vector<std::vector<int16_t>> loc;

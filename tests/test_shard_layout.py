@@ -69,8 +69,9 @@ def test_memory_model(library):
 
 
 def _emu(emu_bin, mode, rec, world):
+    # last argument: keep {WB,WP,WBP} packed per interval, as the sharded GPU fold does
     args = [str(emu_bin), mode, str(ROOT / "params" / rec["par"]), str(rec["dangles"]), rec["seq"],
-            "1" if "--noGU" in rec.get("extra", []) else "0", str(world)]
+            "1" if "--noGU" in rec.get("extra", []) else "0", str(world), "1" if world != 3 else "0"]
     return subprocess.run(args, capture_output=True, text=True)
 
 
