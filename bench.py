@@ -547,7 +547,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--full", action="store_true", help="fold the whole config-4 job once (dynamic dealing)")
     ap.add_argument("--full-count", type=int, default=8192)
-    ap.add_argument("--full-chunk", type=int, default=48)
+    ap.add_argument("--full-chunk", type=int, default=64)
     ap.add_argument("--config5", action="store_true", help="one oversized sequence, gap tables sharded by outer index")
     ap.add_argument("--n5", type=int, default=600)
     ap.add_argument("--hash5", action="store_true", help="config5: also hash every table on rank 0 (small n only)")

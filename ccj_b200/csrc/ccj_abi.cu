@@ -40,6 +40,11 @@ size_t tab_bytes_uncached(int n, int which) {
             case TAB_T4: return align_up((size_t)ccj_cells4(n) * CCJ_NT4 * sizeof(int16_t) + 16, 256);
             case TAB_T2:
             case TAB_W3:
+            case TAB_ESTP:      // the generic cell functions walk the partner lists of k_prep too
+            case TAB_INLIST:
+            case TAB_OUTLIST:
+            case TAB_INCNT:
+            case TAB_OUTCNT:
             case TAB_FTYPE:
             case TAB_TBSTACK: break;
             default: return 256;
@@ -224,6 +229,13 @@ int validate(ccj_ctx *ctx, const char *s, int64_t len) {
     return 0;
 }
 
+// CCJ_GENERIC_SCAN=1: the generic cell functions scan the 29 x 29 interior windows like the reference instead of
+// walking k_prep's partner lists (debugging aid; read once)
+bool generic_scan() {
+    static const bool v = [] { const char *e = getenv("CCJ_GENERIC_SCAN"); return e && e[0] == '1'; }();
+    return v;
+}
+
 // the fill's launch sequence: per span s  K_P(s) -> K_2D(s) -> K_4D(level s)   (DESIGN.md "schedule")
 bool use_tuned(int nmax) {
     const char *g = getenv("CCJ_FILL_GENERIC");  // debugging aid: force the generic-index level kernel
@@ -260,6 +272,7 @@ cudaError_t enqueue_fill(ccj_ctx *ctx, ccj::LaunchDims d) {
     cudaStream_t s0 = ctx->stream;
     if (!use_tuned(d.nmax)) {
         EQL(ccj::launch_init(M, Q, d, s0));
+        if (!generic_scan()) EQL(ccj::launch_prep_lists(M, Q, d, s0));
         for (int s = 0; s < d.nmax; ++s) {
             EQL(ccj::launch_P(M, Q, d, s, s0));
             EQL(ccj::launch_2d(M, Q, d, s, s0));
@@ -349,6 +362,7 @@ int refill_wrapped(ccj_ctx *ctx, ccj::LaunchDims d) {
     CU(cudaEventCreate(&e1));
     cudaEventRecord(e0, s0);
     ccj::launch_init(M, ctx->d_seqs2, d2, s0);   // also clears status[6]: the traceback reads these sequences generically
+    if (!generic_scan()) ccj::launch_prep_lists(M, ctx->d_seqs2, d2, s0);
     for (int s = 0; s < d2.nmax; ++s) {
         ccj::launch_P(M, ctx->d_seqs2, d2, s, s0);
         ccj::launch_2d(M, ctx->d_seqs2, d2, s, s0);
@@ -574,6 +588,13 @@ int ccj_batch_prepare(ccj_ctx *ctx, const char *seqs, const int64_t *offsets, in
         q.ftype_out = reinterpret_cast<int8_t *>(t + tab_offset(n, TAB_FTYPE));
         q.tb_stack = reinterpret_cast<int32_t *>(t + tab_offset(n, TAB_TBSTACK));
         q.tb_cap = 16 * n + 64;
+        q.use_lists = generic_scan() ? 0 : 1;
+        if (!ccj::fill4_tuned_supported(n)) {   // slim plan: the tuned-only buffers are 256-byte stubs -- nobody may follow them
+            q.g1 = q.g2 = q.g3 = q.g4 = nullptr;
+            q.lay = nullptr;
+            q.scratch = q.plw = q.prw = q.pmw = q.pmm = q.pkf = q.pkg = q.wscr = nullptr;
+            q.pmlev4 = q.plist = q.pcum = q.pmlist = q.pmstart = nullptr;
+        }
     }
     ctx->h_seqs.assign(hd, hd + nseq);
     CU(cudaMemcpyAsync(d_in, ctx->h_stage, in_total, cudaMemcpyHostToDevice, ctx->stream));
@@ -667,6 +688,7 @@ int ccj_batch_fill_profiled(ccj_ctx *ctx, float *kernel_ms) {
     const bool tuned = use_tuned(d.nmax);
     ccj::launch_init(ctx->d_model, ctx->d_seqs, d, st); mark(3);
     if (tuned) { ccj::launch_prep(ctx->d_model, ctx->d_seqs, d, st); mark(3); }
+    else if (!generic_scan()) { ccj::launch_prep_lists(ctx->d_model, ctx->d_seqs, d, st); mark(3); }
     // same order as enqueue_fill on one stream: the 2D tables run `lead` spans ahead of the levels
     const int lead = tuned ? std::max(ccj::fill4_fused_levels() - 2, 0) : 0;
     auto span_step = [&](int sp) {
@@ -740,7 +762,9 @@ int ccj_batch_fetch(ccj_ctx *ctx, ccj_result *results, int32_t *pairs, char *str
         const int32_t *st = reinterpret_cast<const int32_t *>(ctx->h_stage + p.out_off);
         const int32_t *W = st + CCJ_STATUS_INTS;
         const int32_t *pr = W + (n + 1);
-        if (st[5] != 0)  // k_prep met an interior-loop energy outside int16: the packed window lists cannot hold this model
+        // k_prep met an interior-loop energy outside int16: the packed window lists cannot hold this model (the generic
+        // cell functions notice the flag themselves and scan the windows instead)
+        if (st[5] != 0 && use_tuned(ctx->nmax))
             return fail(ctx, CCJ_ERR_STATE, "energy model outside the range of the tuned kernels (set CCJ_FILL_GENERIC=1)");
         ccj_result &r = results[s];
         r.energy_dcal = W[n];

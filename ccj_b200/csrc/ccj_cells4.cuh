@@ -4,11 +4,34 @@
 #pragma once
 #include "ccj_cells.cuh"
 
+// The interior windows (get_P{L,R,M}iloop, src/pseudo_loop.cc:682-773) in two equivalent forms: the reference's scan of
+// the 29 x 29 window with a can_pair test per slot, and -- where the fold has per-pair partner lists (ccj_seq::inlist /
+// outlist, written once per sequence by k_prep with the already rounded energies) -- a walk over the pairable partners
+// only.  Same candidates, same energies, same minimum; the scan touches ~7 slots per candidate it evaluates.
+//   inlist  of (p,q): partners INSIDE  the pair, entry = int16 energy | x << 16 | y << 24 for (p+x, q-y)
+//   outlist of (p,q): partners OUTSIDE the pair, entry.x the same for (p-x, q+y); candidates with a negative energy first
+// status[5]: k_prep met an interior-loop energy outside int16 -- the lists cannot hold this model, scan instead
+CCJ_HD bool ccj_lists_ok(const ccj_cx &c) { return c.q.use_lists != 0 && c.q.status[5] == 0; }
+CCJ_HD int ccj_win_inside(const ccj_cx &c, int tbl, int p, int q, int i, int j, int k, int l, bool left) {
+    const int slot = ccj_tri(p, q);
+    const uint32_t *lst = c.q.inlist + (int64_t)slot * CCJ_WIN_IN;
+    const int cnt = c.q.incnt[slot];
+    int mn = CCJ_INF;
+    for (int e = 0; e < cnt; ++e) {
+        const uint32_t en = lst[e];
+        const int x = (en >> 16) & 0xff, y = en >> 24, energy = (int)(int16_t)(en & 0xffff);
+        // PL: PL(i+x, j-y, k, l) closed by (i,j);  PR: PR(i, j, k+x, l-y) closed by (k,l)
+        mn = ccj_min(mn, energy + (left ? ccj_get4u(c, tbl, i + x, j - y, k, l) : ccj_get4u(c, tbl, i, j, k + x, l - y)));
+    }
+    return mn;
+}
+
 // get_PLiloop (src/pseudo_loop.cc:682-703)
 CCJ_HD int ccj_PLiloop(const ccj_cx &c, int i, int j, int k, int l) {
     if (!ccj_can_pair(c, i, j)) return CCJ_INF;
     int mn = CCJ_INF;
     if (i + CCJ_TURN + 2 < j) mn = ccj_get4(c, T_PL, i + 1, j - 1, k, l) + ccj_e_stP(c.M, c.q.S, i, j);
+    if (ccj_lists_ok(c)) return ccj_min(mn, ccj_win_inside(c, T_PL, i, j, i, j, k, l, true));
     const int max_d = ccj_min(j, i + CCJ_MAXLOOP);
     for (int d = i + 1; d < max_d; ++d) {
         const int min_dp = ccj_max(d + CCJ_TURN, j - CCJ_MAXLOOP);
@@ -24,6 +47,7 @@ CCJ_HD int ccj_PRiloop(const ccj_cx &c, int i, int j, int k, int l) {
     if (!ccj_can_pair(c, k, l)) return CCJ_INF;
     int mn = CCJ_INF;
     if (k + CCJ_TURN + 2 < l) mn = ccj_get4(c, T_PR, i, j, k + 1, l - 1) + ccj_e_stP(c.M, c.q.S, k, l);
+    if (ccj_lists_ok(c)) return ccj_min(mn, ccj_win_inside(c, T_PR, k, l, i, j, k, l, false));
     const int max_d = ccj_min(l, k + CCJ_MAXLOOP);
     for (int d = k + 1; d < max_d; ++d) {
         const int min_dp = ccj_max(d + CCJ_TURN, l - CCJ_MAXLOOP);
@@ -39,6 +63,19 @@ CCJ_HD int ccj_PMiloop(const ccj_cx &c, int i, int j, int k, int l) {
     if (!ccj_can_pair(c, j, k)) return CCJ_INF;
     int mn = CCJ_INF;
     if (i < j && k < l) mn = ccj_get4(c, T_PM, i, j - 1, k + 1, l) + ccj_e_stP(c.M, c.q.S, j - 1, k + 1);
+    if (ccj_lists_ok(c)) {
+        // partners (d,dp) = (j-x, k+y) of the inner pair (j,k); this cell admits d > max(i, j-30), dp < min(l, k+30),
+        // i.e. x < j-i and y < l-k (x, y <= 29 by construction of the list)
+        const int slot = ccj_tri(j, k), a = j - i, b = l - k;
+        const uint32_t *lst = c.q.outlist + (int64_t)slot * CCJ_WIN_OUT * 2;   // 8-byte entries: (packed term, PMW row offset)
+        const int cnt = c.q.outcnt[slot] & 0xffff;
+        for (int e = 0; e < cnt; ++e) {
+            const uint32_t en = lst[2 * e];
+            const int x = (en >> 16) & 0xff, y = en >> 24;
+            if (x < a && y < b) mn = ccj_min(mn, (int)(int16_t)(en & 0xffff) + ccj_get4u(c, T_PM, i, j - x, k + y, l));
+        }
+        return mn;
+    }
     const int max_d = ccj_max(i, j - CCJ_MAXLOOP);
     for (int d = j - 1; d > max_d; --d) {
         const int min_dp = ccj_min(l, k + CCJ_MAXLOOP);

@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(128) k_prep(const ccj_model *M, const ccj_seq 
                             const int e = ccj_e_intP(M, S, d, i, j, dp);
                             if ((e < 0) == (sweep == 0)) {
                                 ok = pack_entry(e, x, y, ent, c.q.status);
-                                if (n <= K4_MAXN) pm4 = c.q.pmlev4[d * n1 + dp];
+                                if (c.q.pmlev4 && n <= K4_MAXN) pm4 = c.q.pmlev4[d * n1 + dp];
                             }
                         }
                     }
@@ -1195,6 +1195,12 @@ __global__ void __launch_bounds__(256) k_P_tuned(const ccj_seq *__restrict__ seq
         for (int x = 1; x < 8; ++x) mn = min(mn, sm[x]);
         if (mn < CCJ_INF / 2) atomicMin(&q.t2[T2_P * q.stride2 + ccj_idx2(n, i, l)], mn);
     }
+}
+
+// partner lists + e_stP table only (folds that run the generic cell functions over lists: beyond the tuned range, sharded)
+void launch_prep_lists(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cudaStream_t st) {
+    if (d.nmax < 2) return;
+    k_prep<<<dim3(d.nmax - 1, d.nseq), 128, 0, st>>>(M, seqs);
 }
 
 void launch_prep(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cudaStream_t st) {

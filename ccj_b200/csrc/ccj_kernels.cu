@@ -167,7 +167,7 @@ void launch_traceback(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cud
 }
 
 int fill_launch_count(int nmax, bool tuned) {
-    int c = tuned ? 5 : 2;  // init (+ layout prep + PMW fill + list prep) + W
+    int c = tuned ? 5 : 3;  // init (+ layout prep + PMW fill) + list prep + W
     for (int s = 0; s < nmax; ++s) {
         if (s >= 3 && s <= nmax - 1) ++c;           // K_P
         ++c;                                        // K_2D

@@ -32,6 +32,7 @@ void launch_2d(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int s, cud
 void launch_4d(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st);
 // tuned level kernel (ccj_fill4.cu) + its per-sequence precomputation (e_stP table, window partner lists)
 void launch_prep(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cudaStream_t st);
+void launch_prep_lists(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cudaStream_t st);   // k_prep only
 void launch_4d_tuned(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st);
 // the three parts of launch_4d_tuned, for callers that overlap them on different streams:
 // windows(t) only reads levels <= t-2, roles(t) levels <= t-1, final(t) needs both

@@ -85,7 +85,7 @@ struct ccj_shard {
     std::string seq;
     char *arena = nullptr;
     size_t arena_bytes = 0;
-    size_t off_w3 = 0;
+    size_t off_w3 = 0, off_estp = 0, off_inlist = 0, off_outlist = 0, off_incnt = 0, off_outcnt = 0;
     size_t off_in = 0, off_out = 0, off_t2 = 0, off_ftype = 0, off_tb = 0, off_lev = 0, off_locptr = 0, off_rep = 0, off_loc = 0, off_desc = 0;
     std::vector<int64_t> lev;            // n+2 entries
     ccj_seq h_desc;
@@ -250,7 +250,8 @@ int64_t ccj_shard_bytes(int n, int world) {
     if (n < 1 || world < 1) return 0;
     int64_t cells = 0;
     for (int t = 0; t <= n - 3; ++t) cells += ccj_shard_level_cells(n, t, world);
-    const int64_t small = (int64_t)ccj_stride2(n) * CCJ_NT2 * 4 + 64 * (int64_t)n + (1 << 16);
+    const int64_t tri = (int64_t)n * (n - 1) / 2 + 1;
+    const int64_t small = (int64_t)ccj_stride2(n) * (CCJ_NT2 + 5) * 4 + tri * (CCJ_WIN_IN * 4 + CCJ_WIN_OUT * 8 + 8) + 64 * (int64_t)n + (1 << 16);
     return small + cells * 2 * ((int64_t)CCJ_SHARD_NREP * world + CCJ_SHARD_NLOC);
 }
 
@@ -292,6 +293,12 @@ int ccj_shard_prepare(ccj_shard *sh, const char *seq, int n) {
     sh->off_out = take(sizeof(int32_t) * (CCJ_STATUS_INTS + (size_t)(n + 1) + (size_t)(n + 2)));
     sh->off_t2 = take((size_t)ccj_stride2(n) * CCJ_NT2 * sizeof(int32_t));
     sh->off_w3 = take((size_t)ccj_stride2(n) * 4 * sizeof(int32_t));
+    const size_t tri = (size_t)n * (n - 1) / 2 + 1;   // per-pair partner lists of the interior windows (k_prep)
+    sh->off_estp = take((size_t)ccj_stride2(n) * sizeof(int32_t));
+    sh->off_inlist = take(tri * CCJ_WIN_IN * sizeof(uint32_t));
+    sh->off_outlist = take(tri * CCJ_WIN_OUT * 2 * sizeof(uint32_t));
+    sh->off_incnt = take(tri * sizeof(int32_t));
+    sh->off_outcnt = take(tri * sizeof(int32_t));
     sh->off_ftype = take((size_t)n + 2);
     sh->off_tb = take(sizeof(int32_t) * 5 * (size_t)(16 * n + 64));
     sh->off_lev = take(sizeof(int64_t) * (size_t)(n + 2));
@@ -336,6 +343,12 @@ int ccj_shard_prepare(ccj_shard *sh, const char *seq, int n) {
     q.stride2 = ccj_stride2(n);
     q.stride4 = 0;
     q.w3 = reinterpret_cast<int32_t *>(sh->arena + sh->off_w3);   // {WB,WP,WBP} packed per interval: one load per split point
+    q.estP = reinterpret_cast<int32_t *>(sh->arena + sh->off_estp);
+    q.inlist = reinterpret_cast<uint32_t *>(sh->arena + sh->off_inlist);
+    q.outlist = reinterpret_cast<uint32_t *>(sh->arena + sh->off_outlist);
+    q.incnt = reinterpret_cast<int32_t *>(sh->arena + sh->off_incnt);
+    q.outcnt = reinterpret_cast<int32_t *>(sh->arena + sh->off_outcnt);
+    { const char *e = getenv("CCJ_GENERIC_SCAN"); q.use_lists = (e && e[0] == '1') ? 0 : 1; }
     q.ftype_out = reinterpret_cast<int8_t *>(sh->arena + sh->off_ftype);
     q.tb_stack = reinterpret_cast<int32_t *>(sh->arena + sh->off_tb);
     q.tb_cap = 16 * n + 64;
@@ -416,7 +429,10 @@ int ccj_shard_fill(ccj_shard **shards, int count, float *ms4) {
     auto cn = [&](ncclResult_t r, const char *what) {
         if (r != ncclSuccess && rc == 0) { rc = CCJ_ERR_CUDA; why = std::string(what) + ": " + N.GetErrorString(r); }
     };
-    for (int x = 0; x < count; ++x) ccj::launch_init(M, d_desc(shards[x]), d, st);
+    for (int x = 0; x < count; ++x) {
+        ccj::launch_init(M, d_desc(shards[x]), d, st);
+        if (shards[x]->h_desc.use_lists) ccj::launch_prep_lists(M, d_desc(shards[x]), d, st);
+    }
     ck(cudaEventRecord(ev[0], st), "event");
     ccj::NvtxRange nvtx_fill("ccj_shard_fill");
     for (int s = 0; s < n && rc == 0; ++s) {

@@ -141,7 +141,8 @@ struct ccj_seq {
     int32_t shard_G;             // ranks the rows i are dealt to (row i belongs to rank (i-1) mod G); 0 = not sharded
     int32_t shard_rank;          // this rank
     int32_t shard_shift;         // log2(G) if G is a power of two, else -1
-    int32_t shard_pad_;
+    int32_t use_lists;           // the generic cell functions walk inlist / outlist (filled by k_prep) instead of scanning
+                                 // the 29 x 29 windows with can_pair tests
     const int64_t *shard_lev;    // lev[t] = sum_{t'<t} C(t'), t = 0..n (device)
     int16_t *shard_rep;          // the 12 column-read tables, every rank's rows (filled by the allgather per level)
     int16_t *const *shard_loc;   // [G] base of each rank's 10 row-local tables; only [shard_rank] is set unless the peers'

@@ -1,0 +1,13 @@
+"""One in-process sharded fold (world ranks on one GPU), for timing and ncu: python profiles/shard_one.py N [WORLD]"""
+import sys, time
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import ccj_b200
+from ccj_b200 import shard5
+n = int(sys.argv[1]); world = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+ctx = ccj_b200.Context(0, str(ROOT / "params" / "rna_Turner04.par"), 2)
+grp = shard5.LocalGroup(ctx, world)
+sh = grp.fold(shard5.config5_sequence(n))
+f = sh.traceback()
+print(n, world, grp.ms, f.energy)

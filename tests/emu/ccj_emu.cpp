@@ -42,6 +42,7 @@ int main(int argc, char **argv) {
     int noGU = argc > 5 ? atoi(argv[5]) : 0;
     const int shardG = argc > 6 ? atoi(argv[6]) : 0;
     const int packed2d = argc > 7 ? atoi(argv[7]) : 0;   // keep {WB,WP,WBP} packed per interval (ccj_seq::w3) as the GPU folds do
+    const int lists = argc > 8 ? atoi(argv[8]) : 0;      // walk per-pair partner lists in the interior windows (k_prep's rule)
     ccj::RawParams rp;
     if (!ccj::load_par_file(argv[2], rp, err)) {
         fprintf(stderr, "%s\n", err.c_str());
@@ -85,6 +86,51 @@ int main(int argc, char **argv) {
     if (packed2d) {
         w3v.assign((size_t)s2 * 4, 0x55555555);
         c.q.w3 = w3v.data();
+    }
+    // partner lists, built on the host by the rule of k_prep (ccj_fill4.cu): entry = int16 energy | x << 16 | y << 24
+    std::vector<uint32_t> inl, outl;
+    std::vector<int32_t> incnt, outcnt;
+    if (lists) {
+        const size_t tri = (size_t)n * (n - 1) / 2 + 1;
+        inl.assign(tri * CCJ_WIN_IN, 0);
+        outl.assign(tri * CCJ_WIN_OUT * 2, 0);
+        incnt.assign(tri, 0);
+        outcnt.assign(tri, 0);
+        auto pack = [&](int e, int x, int y, uint32_t &out) {
+            if (e >= CCJ_INF / 2 + 40000) return false;
+            if (e > 32767 || e < -32768) { st[5] = 1; return false; }
+            out = (uint32_t)(uint16_t)(int16_t)e | ((uint32_t)x << 16) | ((uint32_t)y << 24);
+            return true;
+        };
+        for (int j = 2; j <= n; ++j)
+            for (int i = 1; i < j; ++i) {
+                if (!ccj_can_pair(c, i, j)) continue;
+                const size_t slot = (size_t)ccj_tri(i, j);
+                int nin = 0, nout = 0, nneg = 0;
+                for (int sidx = 0; sidx < CCJ_WIN; ++sidx) {
+                    const int x = sidx / 29 + 1, y = sidx % 29 + 1, d = i + x, dp = j - y;
+                    uint32_t ent;
+                    if (x <= j - i - 1 && dp >= d + 4 && ccj_can_pair(c, d, dp) && pack(ccj_e_intP(&M, S.data(), i, d, dp, j), x, y, ent))
+                        inl[slot * CCJ_WIN_IN + nin++] = ent;
+                }
+                for (int sweep = 0; sweep < 2; ++sweep) {
+                    for (int sidx = 0; sidx < CCJ_WIN; ++sidx) {
+                        const int x = sidx / 29 + 1, y = sidx % 29 + 1, d = i - x, dp = j + y;
+                        if (!(d >= 1 && dp <= n && ccj_can_pair(c, d, dp))) continue;
+                        const int e = ccj_e_intP(&M, S.data(), d, i, j, dp);
+                        uint32_t ent;
+                        if ((e < 0) == (sweep == 0) && pack(e, x, y, ent)) outl[(slot * CCJ_WIN_OUT + nout++) * 2] = ent;
+                    }
+                    if (sweep == 0) nneg = nout;
+                }
+                incnt[slot] = nin;
+                outcnt[slot] = nout | (nneg << 16);
+            }
+        c.q.inlist = inl.data();
+        c.q.outlist = outl.data();
+        c.q.incnt = incnt.data();
+        c.q.outcnt = outcnt.data();
+        c.q.use_lists = 1;
     }
     std::vector<int64_t> lev(n + 2, 0);
     std::vector<int16_t> rep;
