@@ -73,3 +73,30 @@ def test_real_int16_wrap(emu_bin, tmp_path):
     assert min(v[1] for k, v in got.items() if k in ("PK", "PfromL", "PfromR")) < -32700   # at the edge of the range
     p = subprocess.run([str(emu_bin), "fold", str(par), "2", wrap87()], capture_output=True, text=True)
     assert (p.returncode, p.stdout, p.stderr) == (g["rc"], g["stdout"], g["stderr"])
+
+
+def test_cell_functions_under_asan_ubsan(tmp_path, golden_folds, golden_hashes):
+    """compute-sanitizer is closed on the GPU pool (profiles/r2_compute_sanitizer_closed.log), so the memory-safety check
+    runs where it can: the product's cell, window-list and traceback functions -- the same source the kernels compile --
+    built for the host with AddressSanitizer + UBSan (every table in an exactly sized heap buffer) and swept over the
+    ordinary and the row-sharded layout.  Any out-of-bounds or uninitialised-index access aborts the tool."""
+    from ccj_b200 import build
+    exe = tmp_path / "ccj_emu_asan"
+    srcs = [ROOT / "tests" / "emu" / "ccj_emu.cpp", ROOT / "ccj_b200" / "csrc" / "energy_model.cpp",
+            ROOT / "ccj_b200" / "csrc" / "embedded_params.cpp"]
+    subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all",
+                    *build.embedded_par_defines(), "-o", str(exe)] + [str(s) for s in srcs], check=True)
+    folds = [r for r in golden_folds if 18 <= len(r["seq"]) <= 30 and r["par"] == "rna_Turner04.par" and not r["extra"]][:4]
+    folds += [r for r in golden_folds if r["rc"] != 0 and len(r["seq"]) <= 34][:1]
+    assert len(folds) >= 4
+    for r in folds:
+        for extra in ([], ["0", "0", "1", "1"], ["0", "4", "1", "1"], ["0", "3", "0", "0"]):
+            args = [str(exe), "fold", str(ROOT / "params" / r["par"]), str(r["dangles"]), r["seq"]] + extra
+            p = subprocess.run(args, capture_output=True, text=True)
+            assert "Sanitizer" not in p.stderr and "runtime error" not in p.stderr, p.stderr[-2000:]
+            assert (p.returncode, p.stdout, p.stderr) == (r["rc"], r["stdout"], r["stderr"]), (extra, r["seq"])
+    h = [r for r in golden_hashes if len(r["seq"]) <= 26][:1]
+    for r in h:
+        p = subprocess.run([str(exe), "hash", str(ROOT / "params" / r["par"]), str(r["dangles"]), r["seq"], "0", "2", "1", "1"],
+                           capture_output=True, text=True)
+        assert p.returncode == 0 and "Sanitizer" not in p.stderr and "runtime error" not in p.stderr, p.stderr[-2000:]
