@@ -21,6 +21,35 @@ struct WarpPar {
     }
 };
 
+// block-cooperative candidate spreading for the traceback: TB_THREADS threads of one block work on one sequence.  Every
+// thread follows the same control flow (all decisions come from reductions or from memory every thread reads), so the
+// block-wide barriers inside red / argmin are reached uniformly.
+#define TB_THREADS 128
+struct BlockPar {
+    static constexpr int nlanes = TB_THREADS;
+    int *sm;   // 2 * (TB_THREADS / 32) ints of shared memory
+    __device__ __forceinline__ int lane() const { return threadIdx.x; }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+    __device__ __forceinline__ int red(int v) const {
+        v = __reduce_min_sync(0xffffffffu, v);
+        __syncthreads();   // the scratch may still be read by a slower warp of the previous reduction
+        if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+        __syncthreads();
+        int r = sm[0];
+#pragma unroll
+        for (int w = 1; w < TB_THREADS / 32; ++w) r = min(r, sm[w]);
+        return r;
+    }
+    __device__ __forceinline__ ccj_best argmin(ccj_best b) const {   // lexicographic (value, position)
+        const int m = red(b.val);
+        const int o = red(b.val == m ? b.ord : 0x7fffffff);
+        ccj_best r;
+        r.val = m;
+        r.ord = o;
+        return r;
+    }
+};
+
 __global__ void k_init(const ccj_model *M, const ccj_seq *seqs) {
     const ccj_seq q = seqs[blockIdx.y];
     const int64_t s2 = q.stride2;
@@ -107,11 +136,13 @@ __global__ void k_W(const ccj_model *M, const ccj_seq *seqs) {
     }
 }
 
-__global__ void k_traceback(const ccj_model *M, const ccj_seq *seqs) {
+__global__ void __launch_bounds__(TB_THREADS) k_traceback(const ccj_model *M, const ccj_seq *seqs) {
+    __shared__ int sm[2 * (TB_THREADS / 32)];
     ccj_cx c;
     c.M = M;
     c.q = seqs[blockIdx.x];
-    WarpPar par;
+    BlockPar par;
+    par.sm = sm;
     ccj_traceback(c, par);
 }
 
@@ -163,7 +194,7 @@ void launch_W(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cudaStream_
 }
 
 void launch_traceback(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cudaStream_t st) {
-    k_traceback<<<d.nseq, 32, 0, st>>>(M, seqs);
+    k_traceback<<<d.nseq, TB_THREADS, 0, st>>>(M, seqs);
 }
 
 int fill_launch_count(int nmax, bool tuned) {
