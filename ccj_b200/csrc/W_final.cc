@@ -43,12 +43,34 @@ double W_final::ccj() {
     ccj_result res;
     pairs.assign(n, -1);
     std::string dots(n, '.');
-    V->fold()->ensure_resident();   // the bulk fill (V, P, the 22 gap tables, W), src/W_final.cc:60-77
-    int rc = ccj_batch_traceback(ctx);
-    if (!rc) rc = ccj_batch_fetch(ctx, &res, pairs.data(), &dots[0]);
-    if (rc != 0) {
-        std::cerr << "ccj_b200: " << ccj_last_error(ctx) << std::endl;
-        exit(EXIT_FAILURE);
+    int rc;
+    if (n > 0 && ccj_wave_capacity(ctx, n) < 1 && ccj_device_count() > 1) {
+        // the tables of this sequence exceed one GPU: deal the rows of the gap tables to every GPU of the box
+        // (ccj_shard_fold; getters of P / V are not available for such a fold)
+        const int ndev = ccj_device_count();
+        std::vector<ccj_ctx *> ctxs;
+        for (int d = 0; d < ndev; ++d) {
+            ccj_ctx *c = nullptr;
+            if (ccj_ctx_create(d, &c) != 0 || ccj_model_upload(c, &V->fold()->model, sizeof(ccj_model)) != 0) {
+                std::cerr << "ccj_b200: cannot use GPU " << d << std::endl;
+                exit(EXIT_FAILURE);
+            }
+            ctxs.push_back(c);
+        }
+        rc = ccj_shard_fold(ctxs.data(), ndev, seq_.data(), n, &res, pairs.data(), &dots[0], nullptr);
+        for (ccj_ctx *c : ctxs) ccj_ctx_destroy(c);
+        if (rc != 0) {
+            std::cerr << "ccj_b200: the sequence does not fit the GPUs of this box" << std::endl;
+            exit(EXIT_FAILURE);
+        }
+    } else {
+        V->fold()->ensure_resident();   // the bulk fill (V, P, the 22 gap tables, W), src/W_final.cc:60-77
+        rc = ccj_batch_traceback(ctx);
+        if (!rc) rc = ccj_batch_fetch(ctx, &res, pairs.data(), &dots[0]);
+        if (rc != 0) {
+            std::cerr << "ccj_b200: " << ccj_last_error(ctx) << std::endl;
+            exit(EXIT_FAILURE);
+        }
     }
     // the reference prints these from inside the traceback, before main() prints the result
     for (int x = 0; x < res.n_should_not_be_here; ++x) printf("Should not be here!\n");

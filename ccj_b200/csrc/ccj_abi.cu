@@ -492,6 +492,12 @@ int64_t ccj_wave_capacity(ccj_ctx *ctx, int n) {
 void *ccj_stream(ccj_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 // library-internal (ccj_shard.cu): the model blob in device memory
 const void *ccj_internal_device_model(ccj_ctx *ctx) { return ctx && ctx->model_ok ? ctx->d_model : nullptr; }
+int ccj_internal_device(ccj_ctx *ctx) { return ctx ? ctx->device : -1; }
+const void *ccj_internal_host_model(ccj_ctx *ctx) { return ctx && ctx->model_ok ? ctx->h_model : nullptr; }
+int ccj_device_count(void) {
+    int count = 0;
+    return cudaGetDeviceCount(&count) == cudaSuccess ? count : 0;
+}
 
 int ccj_batch_prepare(ccj_ctx *ctx, const char *seqs, const int64_t *offsets, int nseq) {
     if (!ctx || !seqs || !offsets || nseq < 1) return CCJ_ERR_ARG;

@@ -32,6 +32,8 @@
 #include "energy_model.hpp"
 
 extern "C" const void *ccj_internal_device_model(ccj_ctx *ctx);   // ccj_abi.cu
+extern "C" const void *ccj_internal_host_model(ccj_ctx *ctx);
+extern "C" int ccj_internal_device(ccj_ctx *ctx);
 
 namespace {
 
@@ -44,6 +46,9 @@ struct Nccl {
     decltype(&ncclAllGather) AllGather = nullptr;
     decltype(&ncclAllReduce) AllReduce = nullptr;
     decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    decltype(&ncclCommInitAll) CommInitAll = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
     bool ok = false;
     std::string err;
 };
@@ -64,8 +69,10 @@ Nccl &nccl() {
     }
 #define SYM(f) n.f = reinterpret_cast<decltype(n.f)>(dlsym(n.lib, "nccl" #f))
     SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(AllGather); SYM(AllReduce); SYM(GetErrorString);
+    SYM(CommInitAll); SYM(GroupStart); SYM(GroupEnd);
 #undef SYM
-    n.ok = n.GetUniqueId && n.CommInitRank && n.CommDestroy && n.AllGather && n.AllReduce && n.GetErrorString;
+    n.ok = n.GetUniqueId && n.CommInitRank && n.CommDestroy && n.AllGather && n.AllReduce && n.GetErrorString &&
+           n.CommInitAll && n.GroupStart && n.GroupEnd;
     if (!n.ok) n.err = "libnccl lacks a required symbol";
     return n;
 }
@@ -77,6 +84,7 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 struct ccj_shard {
     ccj_ctx *ctx = nullptr;
     int rank = 0, world = 1;
+    int device = 0;
     ncclComm_t comm = nullptr;
     cudaStream_t stream = nullptr;
     std::string err;
@@ -205,6 +213,7 @@ int ccj_shard_create(ccj_ctx *ctx, int rank, int world, const void *unique_id, c
     sh->rank = rank;
     sh->world = world;
     sh->stream = (cudaStream_t)ccj_stream(ctx);
+    sh->device = ccj_internal_device(ctx);
     if (unique_id && world > 1) {
         Nccl &N = nccl();
         if (!N.ok) {
@@ -232,6 +241,83 @@ int ccj_shard_create(ccj_ctx *ctx, int rank, int world, const void *unique_id, c
     }
     *out = sh;
     return 0;
+}
+
+// All ranks inside ONE process, one GPU each (the command line / a host program without a launcher): `world` contexts on
+// distinct devices, one NCCL communicator per rank from ncclCommInitAll, peer access enabled between the devices so that
+// the traceback rank can read the other ranks' row-local tables directly.
+int ccj_shard_create_group(ccj_ctx **ctxs, int world, ccj_shard **out) {
+    if (!ctxs || !out || world < 1) return CCJ_ERR_ARG;
+    for (int r = 0; r < world; ++r) out[r] = nullptr;
+    std::vector<int> devs(world);
+    for (int r = 0; r < world; ++r) {
+        if (!ctxs[r]) return CCJ_ERR_ARG;
+        devs[r] = ccj_internal_device(ctxs[r]);
+        for (int q = 0; q < r; ++q)
+            if (devs[q] == devs[r]) return CCJ_ERR_ARG;   // one device per rank
+    }
+    std::vector<ncclComm_t> comms(world, nullptr);
+    if (world > 1) {
+        Nccl &N = nccl();
+        if (!N.ok) return CCJ_ERR_STATE;
+        const ncclResult_t r = N.CommInitAll(comms.data(), world, devs.data());
+        if (r != ncclSuccess) {
+            fprintf(stderr, "ccj_b200: ncclCommInitAll: %s\n", N.GetErrorString(r));
+            return CCJ_ERR_CUDA;
+        }
+        for (int a = 0; a < world; ++a)
+            for (int b = 0; b < world; ++b)
+                if (a != b) {
+                    cudaSetDevice(devs[a]);
+                    const cudaError_t e = cudaDeviceEnablePeerAccess(devs[b], 0);
+                    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                        fprintf(stderr, "ccj_b200: no peer access %d -> %d: %s\n", devs[a], devs[b], cudaGetErrorString(e));
+                        cudaGetLastError();
+                        for (ncclComm_t c : comms) if (c) N.CommDestroy(c);
+                        return CCJ_ERR_CUDA;
+                    }
+                    cudaGetLastError();
+                }
+    }
+    for (int r = 0; r < world; ++r) {
+        ccj_shard *sh = new ccj_shard();
+        sh->ctx = ctxs[r];
+        sh->rank = r;
+        sh->world = world;
+        sh->device = devs[r];
+        sh->stream = (cudaStream_t)ccj_stream(ctxs[r]);
+        sh->comm = comms[r];
+        out[r] = sh;
+    }
+    return 0;
+}
+
+// One sequence over every GPU the caller hands in: prepare, fill (ccj_shard_fill as an in-process NCCL group),
+// traceback on rank 0.  ms4 as ccj_shard_fill.  The contexts must hold the same energy model.
+int ccj_shard_fold(ccj_ctx **ctxs, int nctx, const char *seq, int n, ccj_result *result, int32_t *pairs, char *structs,
+                   float *ms4) {
+    if (!ctxs || nctx < 1 || !seq || n < 1 || !result) return CCJ_ERR_ARG;
+    std::vector<ccj_shard *> sh(nctx, nullptr);
+    int rc = ccj_shard_create_group(ctxs, nctx, sh.data());
+    if (rc) return rc;
+    for (int r = 0; r < nctx && !rc; ++r) {
+        cudaSetDevice(sh[r]->device);
+        rc = ccj_shard_prepare(sh[r], seq, n);
+        if (rc) fprintf(stderr, "ccj_b200: %s\n", sh[r]->err.c_str());
+    }
+    if (!rc) rc = ccj_shard_fill(sh.data(), nctx, ms4);
+    if (!rc) {
+        cudaSetDevice(sh[0]->device);
+        rc = ccj_shard_link_local(sh[0], sh.data(), nctx);
+    }
+    if (!rc) rc = ccj_shard_traceback(sh[0], result, pairs, structs, nullptr);
+    if (rc && sh[0] && !sh[0]->err.empty()) fprintf(stderr, "ccj_b200: %s\n", sh[0]->err.c_str());
+    for (ccj_shard *z : sh)
+        if (z) {
+            cudaSetDevice(z->device);
+            ccj_shard_destroy(z);
+        }
+    return rc;
 }
 
 void ccj_shard_destroy(ccj_shard *sh) {
@@ -412,13 +498,19 @@ int ccj_shard_fill(ccj_shard **shards, int count, float *ms4) {
     for (int x = 0; x < count; ++x)
         if (!shards[x] || !shards[x]->prepared || shards[x]->n != n || shards[x]->world != G || shards[x]->seq != sh->seq)
             return sfail(sh, CCJ_ERR_STATE, "every shard must be prepared with the same sequence");
-    cudaStream_t st = sh->stream;
+    // three backends behind one loop: (1) one rank of a multi-process NCCL communicator; (2) an in-process group with one
+    // GPU and one NCCL communicator per rank (ccj_shard_create_group): collectives inside ncclGroupStart/End;
+    // (3) an in-process group on ONE device without NCCL (tests): collectives are device copies on the shared stream
+    const bool nccl_group = group && sh->comm != nullptr;
+    const bool use_nccl = (!group && G > 1) || nccl_group;
     static Nccl none;
-    Nccl &N = (!group && G > 1) ? nccl() : none;   // in-process groups and single ranks never touch libnccl
-    const ccj_model *M = static_cast<const ccj_model *>(ccj_internal_device_model(sh->ctx));
+    Nccl &N = use_nccl ? nccl() : none;
+    auto on = [&](ccj_shard *z) { if (nccl_group) cudaSetDevice(z->device); return z->stream; };
+    auto model = [](ccj_shard *z) { return static_cast<const ccj_model *>(ccj_internal_device_model(z->ctx)); };
     ccj::LaunchDims d;
     d.nseq = 1;
     d.nmax = n;
+    cudaStream_t st0 = on(sh);
     std::vector<cudaEvent_t> ev((size_t)4 * n + 2, nullptr);
     for (auto &e : ev) SCU(cudaEventCreate(&e));
     int rc = 0;
@@ -429,11 +521,13 @@ int ccj_shard_fill(ccj_shard **shards, int count, float *ms4) {
     auto cn = [&](ncclResult_t r, const char *what) {
         if (r != ncclSuccess && rc == 0) { rc = CCJ_ERR_CUDA; why = std::string(what) + ": " + N.GetErrorString(r); }
     };
+    auto mark = [&](int e) { on(sh); ck(cudaEventRecord(ev[e], st0), "event"); };   // timing on rank 0, which owns the most rows
     for (int x = 0; x < count; ++x) {
-        ccj::launch_init(M, d_desc(shards[x]), d, st);
-        if (shards[x]->h_desc.use_lists) ccj::launch_prep_lists(M, d_desc(shards[x]), d, st);
+        cudaStream_t st = on(shards[x]);
+        ccj::launch_init(model(shards[x]), d_desc(shards[x]), d, st);
+        if (shards[x]->h_desc.use_lists) ccj::launch_prep_lists(model(shards[x]), d_desc(shards[x]), d, st);
     }
-    ck(cudaEventRecord(ev[0], st), "event");
+    mark(0);
     ccj::NvtxRange nvtx_fill("ccj_shard_fill");
     for (int s = 0; s < n && rc == 0; ++s) {
         const int m = n - s - 2;
@@ -445,60 +539,72 @@ int ccj_shard_fill(ccj_shard **shards, int count, float *ms4) {
             for (int x = 0; x < count; ++x) {
                 ccj_shard *z = shards[x];
                 const int rows = (int)ccj_shard_rows(n - s, z->rank, G);
-                if (rows > 0) k_P_shard<<<dim3(rows, s), 256, 0, st>>>(M, d_desc(z), s);
+                if (rows > 0) k_P_shard<<<dim3(rows, s), 256, 0, on(z)>>>(model(z), d_desc(z), s);
             }
         }
-        ck(cudaEventRecord(ev[4 * s + 1], st), "event");
+        mark(4 * s + 1);
         if (s >= 3 && s <= n - 1 && G > 1) {
             const size_t diag = (size_t)T2_P * ccj_stride2(n) + (size_t)s * (n + 1);
-            if (group) {
-                int32_t *d0 = shards[0]->h_desc.t2 + diag;
-                for (int x = 1; x < count; ++x) k_min_into<<<(n + 256) / 256, 256, 0, st>>>(d0, shards[x]->h_desc.t2 + diag, n + 1);
-                for (int x = 1; x < count; ++x)
-                    ck(cudaMemcpyAsync(shards[x]->h_desc.t2 + diag, d0, sizeof(int32_t) * (size_t)(n + 1), cudaMemcpyDeviceToDevice, st), "copy");
+            if (use_nccl) {
+                if (nccl_group) cn(N.GroupStart(), "ncclGroupStart");
+                for (int x = 0; x < count; ++x) {
+                    int32_t *dg = shards[x]->h_desc.t2 + diag;
+                    cn(N.AllReduce(dg, dg, (size_t)(n + 1), ncclInt32, ncclMin, shards[x]->comm, on(shards[x])), "ncclAllReduce");
+                }
+                if (nccl_group) cn(N.GroupEnd(), "ncclGroupEnd");
             } else {
-                int32_t *dg = sh->h_desc.t2 + diag;
-                cn(N.AllReduce(dg, dg, (size_t)(n + 1), ncclInt32, ncclMin, sh->comm, st), "ncclAllReduce");
+                int32_t *d0 = shards[0]->h_desc.t2 + diag;
+                for (int x = 1; x < count; ++x) k_min_into<<<(n + 256) / 256, 256, 0, st0>>>(d0, shards[x]->h_desc.t2 + diag, n + 1);
+                for (int x = 1; x < count; ++x)
+                    ck(cudaMemcpyAsync(shards[x]->h_desc.t2 + diag, d0, sizeof(int32_t) * (size_t)(n + 1), cudaMemcpyDeviceToDevice, st0), "copy");
             }
         }
-        ck(cudaEventRecord(ev[4 * s + 2], st), "event");
+        mark(4 * s + 2);
         // --- 2D tables of span s (replicated), gap tables of level s (own rows) ---
-        for (int x = 0; x < count; ++x) ccj::launch_2d(M, d_desc(shards[x]), d, s, st);
-        if (m >= 1) {
-            for (int x = 0; x < count; ++x) {
-                ccj_shard *z = shards[x];
-                const int rows = (int)ccj_shard_rows(m, z->rank, G);
-                if (rows < 1) continue;
-                const int itiles = (rows + 3) / 4, ktiles = (m + 31) / 32;
-                k_4d_shard<<<dim3(itiles * ktiles, s + 1), dim3(32, 4), 0, st>>>(M, d_desc(z), s, ktiles);
-            }
+        for (int x = 0; x < count; ++x) {
+            ccj_shard *z = shards[x];
+            cudaStream_t st = on(z);
+            ccj::launch_2d(model(z), d_desc(z), d, s, st);
+            const int rows = m >= 1 ? (int)ccj_shard_rows(m, z->rank, G) : 0;
+            if (rows < 1) continue;
+            const int itiles = (rows + 3) / 4, ktiles = (m + 31) / 32;
+            k_4d_shard<<<dim3(itiles * ktiles, s + 1), dim3(32, 4), 0, st>>>(model(z), d_desc(z), s, ktiles);
         }
-        ck(cudaEventRecord(ev[4 * s + 3], st), "event");
+        mark(4 * s + 3);
         // --- the 12 column-read tables of level s to every rank: G adjacent blocks, in place ---
         if (m >= 1 && G > 1) {
             const int64_t C = sh->lev[s + 1] - sh->lev[s];
             const size_t block = (size_t)C * CCJ_SHARD_NREP * sizeof(int16_t);     // bytes one rank contributes
             const size_t base = (size_t)sh->lev[s] * G * CCJ_SHARD_NREP * sizeof(int16_t);
-            if (group) {
+            if (use_nccl) {
+                if (nccl_group) cn(N.GroupStart(), "ncclGroupStart");
+                for (int x = 0; x < count; ++x) {
+                    ccj_shard *z = shards[x];
+                    char *recv = reinterpret_cast<char *>(z->h_desc.shard_rep) + base;
+                    cn(N.AllGather(recv + block * (size_t)z->rank, recv, block, ncclInt8, z->comm, on(z)), "ncclAllGather");
+                }
+                if (nccl_group) cn(N.GroupEnd(), "ncclGroupEnd");
+            } else {
                 for (int x = 0; x < count; ++x)       // rank x's block -> every other rank's copy
                     for (int y = 0; y < count; ++y)
                         if (y != x) {
                             const char *src = reinterpret_cast<const char *>(shards[x]->h_desc.shard_rep) + base + block * (size_t)shards[x]->rank;
                             char *dst = reinterpret_cast<char *>(shards[y]->h_desc.shard_rep) + base + block * (size_t)shards[x]->rank;
-                            ck(cudaMemcpyAsync(dst, src, block, cudaMemcpyDeviceToDevice, st), "copy");
+                            ck(cudaMemcpyAsync(dst, src, block, cudaMemcpyDeviceToDevice, st0), "copy");
                         }
-            } else {
-                char *recv = reinterpret_cast<char *>(sh->h_desc.shard_rep) + base;
-                cn(N.AllGather(recv + block * (size_t)sh->rank, recv, block, ncclInt8, sh->comm, st), "ncclAllGather");
             }
         }
-        ck(cudaEventRecord(ev[4 * s + 4], st), "event");
+        mark(4 * s + 4);
         ck(cudaGetLastError(), "launch");
     }
-    for (int x = 0; x < count; ++x) ccj::launch_W(M, d_desc(shards[x]), d, st);
-    ck(cudaEventRecord(ev[4 * n + 1], st), "event");
-    ck(cudaStreamSynchronize(st), "sync");
-    ck(cudaGetLastError(), "fill");
+    for (int x = 0; x < count; ++x) ccj::launch_W(model(shards[x]), d_desc(shards[x]), d, on(shards[x]));
+    mark(4 * n + 1);
+    for (int x = 0; x < count; ++x) {
+        cudaStream_t st = on(shards[x]);
+        ck(cudaStreamSynchronize(st), "sync");
+        ck(cudaGetLastError(), "fill");
+    }
+    on(sh);
     float total = 0.f, tp = 0.f, tr = 0.f, tc = 0.f, tg = 0.f;
     std::vector<float> lvl((size_t)4 * n, 0.f);
     if (rc == 0) {

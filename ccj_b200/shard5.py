@@ -48,6 +48,7 @@ def _lib():
         lib.ccj_shard_energy.argtypes = [vp, C.POINTER(C.c_int32)]
         lib.ccj_shard_table4_hash.argtypes = [vp, i32, C.POINTER(C.c_uint64), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
         lib.ccj_shard_table2_hash.argtypes = [vp, i32, C.POINTER(C.c_uint64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        lib.ccj_shard_fold.argtypes = [C.POINTER(vp), i32, C.c_char_p, i32, vp, vp, vp, C.POINTER(C.c_float)]
         lib.ccj_shard_layout.argtypes = [i32, i32, i32, i32, i32, i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                          C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         lib.ccj_shard_layout.restype = C.c_int64
@@ -166,6 +167,25 @@ class ShardedFold:
         out = {name: self.table4_hash(name) for name in TABLE4}
         out.update({name: self.table2_hash(name) for name in TABLE2[:8]})
         return out
+
+
+def fold_multi(contexts, seq: str):
+    """One sequence over the GPUs of `contexts` (one per device, same model) from ONE process: the in-process NCCL
+    group of ccj_shard_fold.  Returns (Fold, {"fill_ms", "compute_ms", "allgather_ms", "allreduce_ms"})."""
+    import torch  # noqa: F401  -- see unique_id()
+    lib = _lib()
+    n = len(seq)
+    arr = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
+    res = np.zeros(1, dtype=RESULT_DTYPE)
+    structs = np.zeros(n, dtype=np.uint8)
+    ms = (C.c_float * 4)()
+    rc = lib.ccj_shard_fold(arr, len(contexts), seq.encode("ascii"), n, res.ctypes.data, None, structs.ctypes.data, ms)
+    if rc != 0:
+        raise CCJError(rc, "ccj_shard_fold failed (see stderr)")
+    r = res[0]
+    fold = Fold(seq, structs.tobytes().decode("ascii"), int(r["energy_dcal"]), int(r["status"]), int(r["n_should_not_be_here"]),
+                int(r["msg_id"]), int(r["aux_i"]), int(r["aux_j"]))
+    return fold, {"fill_ms": ms[0], "compute_ms": ms[1], "allgather_ms": ms[2], "allreduce_ms": ms[3]}
 
 
 class LocalGroup:

@@ -150,6 +150,11 @@ typedef struct ccj_shard ccj_shard;
 size_t ccj_shard_unique_id_bytes(void);
 int ccj_shard_unique_id(void *id, size_t bytes);
 int ccj_shard_create(ccj_ctx *ctx, int rank, int world, const void *unique_id, ccj_shard **out);
+/* all ranks inside one process, one GPU each (ncclCommInitAll; peer access between the devices is enabled): out[world] */
+int ccj_shard_create_group(ccj_ctx **ctxs, int world, ccj_shard **out);
+/* the whole sharded fold of one sequence over the GPUs of `ctxs` from one process: group, prepare, fill, traceback */
+int ccj_shard_fold(ccj_ctx **ctxs, int nctx, const char *seq, int n, ccj_result *result, int32_t *pairs, char *structs,
+                   float *ms4);
 void ccj_shard_destroy(ccj_shard *shard);
 const char *ccj_shard_last_error(const ccj_shard *shard);
 int64_t ccj_shard_bytes(int n, int world);   /* host only: one rank's device memory for a length-n sequence */
@@ -192,6 +197,9 @@ int ccj_count_terms(const char *seq, int n, int no_gu, int64_t *out);
  * variant 0: int32 VIADDMNMX; 1: sign-extension of a packed int16 + VIADDMNMX (the form the split-point kernel
  * applies to a record); 2: VIADDMNMX.S16x2, two int16 cells per instruction (the window kernels' form). */
 int ccj_measure_addmin_peak(ccj_ctx *ctx, int variant, double *pairs_per_s);
+
+/* number of CUDA devices visible to the process (0 without a driver) */
+int ccj_device_count(void);
 
 /* library / build identification */
 const char *ccj_version(void);

@@ -149,6 +149,24 @@ def test_against_reference_binary_on_the_box(ctx_factory):
         assert (p.returncode, p.stdout, p.stderr) == (f.returncode, f.stdout, f.stderr), s
 
 
+@pytest.mark.parametrize("par,dangles,extra", [("rna_DirksPierce09.par", 2, []), ("rna_Turner04.par", 1, []),
+                                               ("rna_Turner04.par", 0, ["--noGU"]), ("rna_DirksPierce09.par", 0, []),
+                                               ("dna_Matthews04.par", 2, ["--noConv"])])
+def test_other_models_against_reference_binary_on_the_box(ctx_factory, par, dangles, extra):
+    """Live comparison with the unmodified reference for the other parameter sets, dangle models, --noGU and DNA."""
+    if not REF.exists():
+        pytest.skip("oracle/_ref did not travel")
+    rng = random.Random(sum(map(ord, par)) * 7 + dangles)
+    alphabet = "ACGT" if "--noConv" in extra else "ACGU"
+    seqs = ["".join(rng.choice(alphabet) for _ in range(rng.randint(8, 52))) for _ in range(14)]
+    ctx = ctx_factory(par, dangles, "--noGU" in extra)
+    folds = ctx.fold_batch(seqs)
+    for s, f in zip(seqs, folds):
+        p = subprocess.run([str(REF), "-P", str(ROOT / "params" / par), "-d", str(dangles), *extra, s], capture_output=True, text=True)
+        warn = "".join(l + "\n" for l in p.stderr.splitlines() if l.startswith("WARNING"))   # the reader's symmetry warnings
+        assert (p.returncode, p.stdout, p.stderr[len(warn):]) == (f.returncode, f.stdout, f.stderr), (par, dangles, extra, s)
+
+
 def test_full_tables_against_reference_dump(ctx_factory, tmp_path):
     """Every int16 of every table, not only hashes (n=48 random)."""
     if not DUMP.exists():

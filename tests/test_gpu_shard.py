@@ -64,3 +64,24 @@ def test_nccl_ranks_match_reference(golden_hashes):
     p = subprocess.run(cmd, capture_output=True, text=True, cwd=str(ROOT), timeout=900)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     assert "CONFIG5 GOLDEN OK" in p.stdout
+
+
+def test_in_process_nccl_group_over_all_gpus(golden_long, golden_folds):
+    """ccj_shard_fold: every rank in ONE process, one GPU each, ncclCommInitAll + grouped collectives (what the CCJ command
+    line uses for a sequence that exceeds one GPU).  Needs >= 2 GPUs."""
+    import torch
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs at least 2 GPUs")
+    par = str(ROOT / "params" / "rna_Turner04.par")
+    ctxs = [ccj_b200.Context(d, par, 2) for d in range(ngpu)]
+    try:
+        recs = [r for r in golden_folds if r["par"] == "rna_Turner04.par" and r["dangles"] == 2 and not r["extra"] and len(r["seq"]) >= 40][:6]
+        recs += [r for r in golden_long if len(r["seq"]) == 150][:1]
+        for r in recs:
+            f, ms = shard5.fold_multi(ctxs, r["seq"])
+            assert (f.returncode, f.stdout, f.stderr) == (r["rc"], r["stdout"], r["stderr"]), r["seq"]
+            assert ms["fill_ms"] > 0
+    finally:
+        for c in ctxs:
+            c.close()
