@@ -44,7 +44,8 @@ double W_final::ccj() {
     pairs.assign(n, -1);
     std::string dots(n, '.');
     int rc;
-    if (n > 0 && ccj_wave_capacity(ctx, n) < 1 && ccj_device_count() > 1) {
+    const char *force = getenv("CCJ_FORCE_SHARD");   // testing aid: take the multi-GPU path for any length
+    if (n > 0 && ccj_device_count() > 1 && (ccj_wave_capacity(ctx, n) < 1 || (force && force[0] == '1'))) {
         // the tables of this sequence exceed one GPU: deal the rows of the gap tables to every GPU of the box
         // (ccj_shard_fold; getters of P / V are not available for such a fold)
         const int ndev = ccj_device_count();

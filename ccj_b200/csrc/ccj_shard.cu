@@ -55,6 +55,9 @@ struct Nccl {
 Nccl &nccl() {
     static Nccl n;
     if (n.lib || !n.err.empty()) return n;
+    // NCCL writes its debug lines (NCCL_DEBUG=VERSION/INFO) to stdout by default; the stdout of a fold is the reference's
+    // output format and is parsed by callers, so they go to stderr unless the user chose a file
+    setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
     // a process that already holds a libnccl (torch bundles its own) must keep using THAT one: loading a second copy
     // under the same soname would shadow it for later imports
     n.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);

@@ -134,3 +134,20 @@ def test_reference_main_on_the_gpu_library(golden_folds):
         assert run(REFMAIN, args) == (r["rc"], r["stdout"], r["stderr"]), r["seq"]
     rc, out, err = run(REFMAIN, ["--noConv", "GCAACGATGACATACATCGCTAGTCGACGC"], cwd="/tmp")
     assert (rc, out) == (0, "GCAACGATGACATACATCGCTAGTCGACGC\n....(((((.....)))))........... (-4.4)\n")
+
+
+@pytest.mark.gpu
+def test_cli_takes_all_gpus_for_a_sequence_beyond_one_gpu(cli, golden_folds):
+    """W_final::ccj() deals the rows of the gap tables to every GPU of the box when a sequence does not fit one
+    (ccj_shard_fold); CCJ_FORCE_SHARD=1 takes that path for sequences of any length.  Needs >= 2 GPUs."""
+    import os
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    recs = [r for r in golden_folds if 30 <= len(r["seq"]) <= 60 and r["par"] == "rna_Turner04.par" and not r["extra"]][:5]
+    recs += [r for r in golden_folds if r["rc"] != 0][:1]
+    env = dict(os.environ, CCJ_FORCE_SHARD="1", NCCL_DEBUG="WARN")   # the box may export NCCL_DEBUG=VERSION
+    for r in recs:
+        args = [str(cli), "-P", str(ROOT / "params" / r["par"]), "-d", str(r["dangles"]), r["seq"]]
+        p = subprocess.run(args, capture_output=True, text=True, cwd=str(ROOT), env=env)
+        assert (p.returncode, p.stdout, p.stderr.replace(str(cli), "CCJ")) == (r["rc"], r["stdout"], r["stderr"]), r["seq"]
