@@ -146,7 +146,8 @@ def test_cli_takes_all_gpus_for_a_sequence_beyond_one_gpu(cli, golden_folds):
         pytest.skip("needs at least 2 GPUs")
     recs = [r for r in golden_folds if 30 <= len(r["seq"]) <= 60 and r["par"] == "rna_Turner04.par" and not r["extra"]][:5]
     recs += [r for r in golden_folds if r["rc"] != 0][:1]
-    env = dict(os.environ, CCJ_FORCE_SHARD="1", NCCL_DEBUG="WARN")   # the box may export NCCL_DEBUG=VERSION
+    env = dict(os.environ, CCJ_FORCE_SHARD="1")
+    env.pop("NCCL_DEBUG", None)   # the box may export NCCL_DEBUG=VERSION; NCCL's own lines go to stderr (never stdout)
     for r in recs:
         args = [str(cli), "-P", str(ROOT / "params" / r["par"]), "-d", str(r["dangles"]), r["seq"]]
         p = subprocess.run(args, capture_output=True, text=True, cwd=str(ROOT), env=env)
