@@ -106,21 +106,22 @@ __global__ void __launch_bounds__(128) k_2d(const ccj_model *M, const ccj_seq *s
     ccj_cell2d(c, i, j, par);
 }
 
-// level t: blockIdx.y -> a (b=t-a), blockIdx.z -> sequence, blockIdx.x -> (i-tile, k-tile), lanes walk k
-#define K4_TI 4
-__global__ void __launch_bounds__(32 * K4_TI) k_4d(const ccj_model *M, const ccj_seq *seqs, int t, int ktiles) {
+// level t: blockIdx.y -> a (b=t-a), blockIdx.z -> sequence, threads walk the packed (i,k) triangle of slab (a,b) in
+// storage order (every lane has a cell, a warp's stores are contiguous)
+__global__ void __launch_bounds__(128) k_4d(const ccj_model *M, const ccj_seq *seqs, int t) {
     ccj_cx c;
     c.M = M;
     c.q = seqs[blockIdx.z];
     const int n = c.q.n;
     const int m = n - t - 2;  // rows i = 1..m, row i has m+1-i cells
     if (m < 1) return;
+    const int ncell = m * (m + 1) / 2;
+    const int p = blockIdx.x * 128 + threadIdx.x;
+    if (p >= ncell) return;
+    int q, kk;
+    ccj_shard_cell_of(p, m, 1, m, q, kk);
     const int a = blockIdx.y, b = t - a;
-    const int ti = blockIdx.x / ktiles, tk = blockIdx.x % ktiles;
-    const int i = 1 + ti * K4_TI + threadIdx.y;
-    const int kk = tk * 32 + threadIdx.x;
-    if (i > m || kk > m - i) return;
-    const int k = i + a + 2 + kk;
+    const int i = 1 + q, k = i + a + 2 + kk;
     ccj_cell4d(c, i, i + a, k, k + b);
 }
 
@@ -185,8 +186,8 @@ void launch_2d(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int s, cud
 void launch_4d(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st) {
     const int m = d.nmax - t - 2;
     if (m < 1) return;
-    const int itiles = (m + K4_TI - 1) / K4_TI, ktiles = (m + 31) / 32;
-    k_4d<<<dim3(itiles * ktiles, t + 1, d.nseq), dim3(32, K4_TI), 0, st>>>(M, seqs, t, ktiles);
+    const int ncell = m * (m + 1) / 2;
+    k_4d<<<dim3((ncell + 127) / 128, t + 1, d.nseq), 128, 0, st>>>(M, seqs, t);
 }
 
 void launch_W(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cudaStream_t st) {

@@ -122,20 +122,23 @@ int sfail(ccj_shard *s, int code, const std::string &msg) {
 ccj_seq *d_desc(ccj_shard *sh) { return reinterpret_cast<ccj_seq *>(sh->arena + sh->off_desc); }
 
 // ---- kernels -------------------------------------------------------------------------------------------------------------
-// level t of the rank's rows: blockIdx.y -> a (b=t-a), blockIdx.x -> (tile of 4 own rows, tile of 32 k), lanes walk k
-__global__ void __launch_bounds__(128) k_4d_shard(const ccj_model *M, const ccj_seq *seqs, int t, int ktiles) {
+// level t of the rank's rows: blockIdx.y -> a (b=t-a), threads walk the rank's cells of slab (a,b) in storage order
+// (rows of decreasing length back to back, so every lane has a cell and a warp's stores are contiguous)
+__global__ void __launch_bounds__(128) k_4d_shard(const ccj_model *M, const ccj_seq *seqs, int t) {
     ccj_cx c;
     c.M = M;
     c.q = seqs[0];
-    const int n = c.q.n, G = c.q.shard_G;
+    const int n = c.q.n, G = c.q.shard_G, r = c.q.shard_rank;
     const int m = n - t - 2;
-    if (m < 1) return;
+    if (m <= r) return;
+    const int mr = m - r, Q = (mr + G - 1) / G;
+    const int ncell = Q * mr - G * (Q * (Q - 1) / 2);
+    const int p = blockIdx.x * 128 + threadIdx.x;
+    if (p >= ncell) return;
+    int q, kk;
+    ccj_shard_cell_of(p, mr, G, Q, q, kk);
     const int a = blockIdx.y, b = t - a;
-    const int ti = blockIdx.x / ktiles, tk = blockIdx.x % ktiles;
-    const int i = c.q.shard_rank + 1 + (ti * 4 + threadIdx.y) * G;
-    const int kk = tk * 32 + threadIdx.x;
-    if (i > m || kk > m - i) return;
-    const int k = i + a + 2 + kk;
+    const int i = r + 1 + q * G, k = i + a + 2 + kk;
     ccj_cell4d(c, i, i + a, k, k + b);
 }
 
@@ -568,10 +571,9 @@ int ccj_shard_fill(ccj_shard **shards, int count, float *ms4) {
             ccj_shard *z = shards[x];
             cudaStream_t st = on(z);
             ccj::launch_2d(model(z), d_desc(z), d, s, st);
-            const int rows = m >= 1 ? (int)ccj_shard_rows(m, z->rank, G) : 0;
-            if (rows < 1) continue;
-            const int itiles = (rows + 3) / 4, ktiles = (m + 31) / 32;
-            k_4d_shard<<<dim3(itiles * ktiles, s + 1), dim3(32, 4), 0, st>>>(model(z), d_desc(z), s, ktiles);
+            const int64_t ncell = m >= 1 ? ccj_shard_slab(m, z->rank, G) : 0;
+            if (ncell < 1) continue;
+            k_4d_shard<<<dim3((unsigned)((ncell + 127) / 128), s + 1), 128, 0, st>>>(model(z), d_desc(z), s);
         }
         mark(4 * s + 3);
         // --- the 12 column-read tables of level s to every rank: G adjacent blocks, in place ---

@@ -292,6 +292,22 @@ CCJ_HD int64_t ccj_shard_inner(int n, int G, int i, int j, int k, int l) {
     int owner;
     return ccj_shard_inner_fast(n, G, -1, i, j, k, l, owner);
 }
+// inverse of the row offsets of one rank's part of a slab: cell p (0 <= p < S_r(m)) -> own row q and position kk.
+// Row q holds mr - qG cells (mr = m - r) and starts at q mr - G q(q-1)/2.
+CCJ_HD void ccj_shard_cell_of(int p, int mr, int G, int Q, int &q, int &kk) {
+    const float A = 2.f * (float)mr + (float)G;
+#if defined(__CUDA_ARCH__)
+    int qq = (int)((A - sqrtf(A * A - 8.f * (float)G * (float)p)) / (2.f * (float)G));
+#else
+    int qq = (int)((A - __builtin_sqrtf(A * A - 8.f * (float)G * (float)p)) / (2.f * (float)G));
+#endif
+    if (qq < 0) qq = 0;
+    if (qq > Q - 1) qq = Q - 1;
+    while (qq > 0 && qq * mr - G * (qq * (qq - 1) / 2) > p) --qq;
+    while (qq + 1 < Q && (qq + 1) * mr - G * ((qq + 1) * qq / 2) <= p) ++qq;
+    q = qq;
+    kk = p - (qq * mr - G * (qq * (qq - 1) / 2));
+}
 inline void ccj_shard_kinds(int8_t *kind24) {
     static const int rep[CCJ_SHARD_NREP] = {T_PK, T_PL, T_PO, T_PfromL, T_PfromO, T_PLmloop00, T_PLmloop01, T_PLmloop10,
                                             T_PMmloop00, T_POmloop00, T_POmloop01, T_POmloop10};

@@ -93,3 +93,13 @@ def test_cell_functions_over_the_sharded_layout_match_the_reference(emu_bin, gol
     for r in folds:
         p = _emu(emu_bin, "fold", r, world)
         assert (p.returncode, p.stdout, p.stderr) == (r["rc"], r["stdout"], r["stderr"]), (world, r["seq"])
+
+
+def test_flat_thread_to_cell_mapping_is_the_exact_inverse(tmp_path):
+    """k_4d / k_4d_shard give thread p of a slab the p-th cell in storage order; the inverse of the row offsets uses a
+    float square root plus fix-ups -- checked exhaustively on the host (tests/shell/cell_of_test.cc)."""
+    exe = tmp_path / "cell_of_test"
+    subprocess.run(["g++", "-O2", "-I", str(ROOT / "ccj_b200" / "csrc"), "-o", str(exe), str(ROOT / "tests" / "shell" / "cell_of_test.cc")],
+                   check=True)
+    p = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert p.returncode == 0 and " 0 bad" in p.stdout, p.stdout
