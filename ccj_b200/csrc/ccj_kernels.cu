@@ -108,7 +108,8 @@ __global__ void __launch_bounds__(128) k_2d(const ccj_model *M, const ccj_seq *s
 
 // level t: blockIdx.y -> a (b=t-a), blockIdx.z -> sequence, threads walk the packed (i,k) triangle of slab (a,b) in
 // storage order (every lane has a cell, a warp's stores are contiguous)
-__global__ void __launch_bounds__(128) k_4d(const ccj_model *M, const ccj_seq *seqs, int t) {
+// 12 blocks/SM: see k_4d_shard (ccj_shard.cu) for the measurement behind the occupancy choice
+__global__ void __launch_bounds__(128, 12) k_4d(const ccj_model *M, const ccj_seq *seqs, int t) {
     ccj_cx c;
     c.M = M;
     c.q = seqs[blockIdx.z];

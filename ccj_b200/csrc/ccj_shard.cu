@@ -124,7 +124,10 @@ ccj_seq *d_desc(ccj_shard *sh) { return reinterpret_cast<ccj_seq *>(sh->arena + 
 // ---- kernels -------------------------------------------------------------------------------------------------------------
 // level t of the rank's rows: blockIdx.y -> a (b=t-a), threads walk the rank's cells of slab (a,b) in storage order
 // (rows of decreasing length back to back, so every lane has a cell and a warp's stores are contiguous)
-__global__ void __launch_bounds__(128) k_4d_shard(const ccj_model *M, const ccj_seq *seqs, int t) {
+// 12 blocks of 128 threads per SM (<= 42 registers, ~0.3 KB of spills per thread): the kernel is latency-bound -- a serial
+// chain of dependent loads per cell -- and occupancy buys more than the spills cost (300-nt fill: 3.23 s at 4 blocks/SM,
+// 2.90 / 2.54 / 2.21 / 2.04 / 1.95 / 1.97 s at 5 / 6 / 8 / 10 / 12 / 16)
+__global__ void __launch_bounds__(128, 12) k_4d_shard(const ccj_model *M, const ccj_seq *seqs, int t) {
     ccj_cx c;
     c.M = M;
     c.q = seqs[0];
@@ -573,7 +576,8 @@ int ccj_shard_fill(ccj_shard **shards, int count, float *ms4) {
             ccj::launch_2d(model(z), d_desc(z), d, s, st);
             const int64_t ncell = m >= 1 ? ccj_shard_slab(m, z->rank, G) : 0;
             if (ncell < 1) continue;
-            k_4d_shard<<<dim3((unsigned)((ncell + 127) / 128), s + 1), 128, 0, st>>>(model(z), d_desc(z), s);
+            const dim3 grid((unsigned)((ncell + 127) / 128), s + 1);
+            k_4d_shard<<<grid, 128, 0, st>>>(model(z), d_desc(z), s);
         }
         mark(4 * s + 3);
         // --- the 12 column-read tables of level s to every rank: G adjacent blocks, in place ---
