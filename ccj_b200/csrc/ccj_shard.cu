@@ -155,12 +155,10 @@ __global__ void __launch_bounds__(256) k_P_shard(const ccj_model *M, const ccj_s
     if (l > n) return;
     const int j = i + blockIdx.y;
     if (j >= l) return;
-    const int w = l - j - 1;
+    // d in [j+1, l-1], k in [d+1, l-1]: warps take d, lanes walk k (the second factor PK(j+1,d,k+1,l) is contiguous in k)
     int mn = CCJ_INF;
-    for (int p = threadIdx.x; p < w * w; p += blockDim.x) {
-        const int d = j + 1 + p / w, k = j + 1 + p % w;
-        if (k > d) mn = ccj_min(mn, ccj_P_term(c, i, l, j, d, k));
-    }
+    for (int d = j + 1 + (threadIdx.x >> 5); d < l; d += (int)(blockDim.x >> 5))
+        for (int k = d + 1 + (threadIdx.x & 31); k < l; k += 32) mn = ccj_min(mn, ccj_P_term(c, i, l, j, d, k));
     mn = __reduce_min_sync(0xffffffffu, mn);
     __shared__ int sm[8];
     if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mn;

@@ -11,3 +11,5 @@ grp = shard5.LocalGroup(ctx, world)
 sh = grp.fold(shard5.config5_sequence(n))
 f = sh.traceback()
 print(n, world, grp.ms, f.energy)
+lv = sh.level_ms()
+print("P kernel ms", float(lv[:, 0].sum()), "allreduce", float(lv[:, 1].sum()), "2D+4D", float(lv[:, 2].sum()), "allgather", float(lv[:, 3].sum()))
