@@ -124,6 +124,15 @@ CCJ_HD ccj_w3v ccj_w3_at(const ccj_cx &c, int i, int j) {
     return r;
 }
 
+// split-point loops: iterations are independent (only the running minima carry over), unrolling lets the loads of
+// several split points be in flight at once
+#ifndef CCJ_CELL_UNROLL_N
+#define CCJ_CELL_UNROLL_N 1
+#endif
+#define CCJ_PRAGMA(x) _Pragma(#x)
+#define CCJ_UNROLL_BY(n) CCJ_PRAGMA(unroll n)
+#define CCJ_CELL_UNROLL CCJ_UNROLL_BY(CCJ_CELL_UNROLL_N)
+
 // All 22 tables of one cell.  Every split-point candidate of the 22 recurrences (src/pseudo_loop.cc:181-644) reads a
 // cell of a LOWER level, so their order inside the cell is free: they are walked by the four access patterns
 //     L1: X(i,d,k,l) with the 2D interval (d+1,j)     L2: X(d,j,k,l) with (i,d-1)
@@ -150,6 +159,7 @@ CCJ_HD void ccj_cell4d(const ccj_cx &c, int i, int j, int k, int l) {
     PMm10 = ccj_get4(c, T_PMmloop10, i, j - 1, k, l) + cp;   // :578-580
 
     // ---- L1: X(i,d,k,l), d = i .. j-1 ----
+    CCJ_CELL_UNROLL
     for (int d = i; d < j; ++d) {
         const ccj_pos4 p = ccj_pos_of(q, i, d, k, l);
         const ccj_w3v w = ccj_w3_at(c, d + 1, j);
@@ -167,6 +177,7 @@ CCJ_HD void ccj_cell4d(const ccj_cx &c, int i, int j, int k, int l) {
         }
     }
     // ---- L2: X(d,j,k,l), d = i+1 .. j ----
+    CCJ_CELL_UNROLL
     for (int d = i + 1; d <= j; ++d) {
         const ccj_pos4 p = ccj_pos_of(q, d, j, k, l);
         const ccj_w3v w = ccj_w3_at(c, i, d - 1);
@@ -184,6 +195,7 @@ CCJ_HD void ccj_cell4d(const ccj_cx &c, int i, int j, int k, int l) {
         }
     }
     // ---- R3: X(i,j,d,l), d = k+1 .. l ----
+    CCJ_CELL_UNROLL
     for (int d = k + 1; d <= l; ++d) {
         const ccj_pos4 p = ccj_pos_of(q, i, j, d, l);
         const ccj_w3v w = ccj_w3_at(c, k, d - 1);
@@ -201,6 +213,7 @@ CCJ_HD void ccj_cell4d(const ccj_cx &c, int i, int j, int k, int l) {
         }
     }
     // ---- R4: X(i,j,k,d), d = k .. l-1 ----
+    CCJ_CELL_UNROLL
     for (int d = k; d < l; ++d) {
         const ccj_pos4 p = ccj_pos_of(q, i, j, k, d);
         const ccj_w3v w = ccj_w3_at(c, d + 1, l);
