@@ -58,7 +58,7 @@ def load_library(path: Optional[os.PathLike] = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = Path(path) if path else LIB_PATH
+    p = Path(path) if path else Path(os.environ.get("CCJ_B200_LIB", LIB_PATH))   # CCJ_B200_LIB: an alternative build (experiments)
     if not p.exists():
         raise CCJError(-1, f"{p} is missing: build it with `python -m ccj_b200.build` (nvcc, sm_100a); "
                            "there is no CPU fallback")
