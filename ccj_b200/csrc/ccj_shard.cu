@@ -517,8 +517,15 @@ int ccj_shard_fill(ccj_shard **shards, int count, float *ms4) {
     ccj::LaunchDims d;
     d.nseq = 1;
     d.nmax = n;
+    for (int x = 0; x < count; ++x)
+        if (!model(shards[x])) return sfail(sh, CCJ_ERR_STATE, "no energy model loaded in a rank's context");
     cudaStream_t st0 = on(sh);
-    std::vector<cudaEvent_t> ev((size_t)4 * n + 2, nullptr);
+    struct EventSet {   // destroyed on every return path
+        std::vector<cudaEvent_t> v;
+        ~EventSet() { for (cudaEvent_t e : v) if (e) cudaEventDestroy(e); }
+    } evs;
+    evs.v.assign((size_t)4 * n + 2, nullptr);
+    std::vector<cudaEvent_t> &ev = evs.v;
     for (auto &e : ev) SCU(cudaEventCreate(&e));
     int rc = 0;
     std::string why;
@@ -626,7 +633,6 @@ int ccj_shard_fill(ccj_shard **shards, int count, float *ms4) {
             lvl[4 * s] = a; lvl[4 * s + 1] = b; lvl[4 * s + 2] = c2; lvl[4 * s + 3] = g2;
         }
     }
-    for (auto &e : ev) cudaEventDestroy(e);
     if (rc) return sfail(sh, rc, why);
     for (int x = 0; x < count; ++x) {
         shards[x]->filled = true;
@@ -669,6 +675,7 @@ int ccj_shard_traceback(ccj_shard *sh, ccj_result *res, int32_t *pairs, char *st
     if (sh->world > 1 && !sh->peers) return sfail(sh, CCJ_ERR_STATE, "the traceback rank must open its peers' memory first");
     const int n = sh->n;
     const ccj_model *M = static_cast<const ccj_model *>(ccj_internal_device_model(sh->ctx));
+    if (!M) return sfail(sh, CCJ_ERR_STATE, "no energy model loaded");
     ccj::LaunchDims d;
     d.nseq = 1;
     d.nmax = n;
