@@ -249,8 +249,8 @@ def per_kernel_roofline(prof, terms, peak_gbs, addmin, traffic_json=None):
         "k_P_tuned": (4 * pterm, pterm, prof["kP_ms"], "int32_viaddmnmx"),
     }
     out = {}
-    ncu_names = {"k_roles": ["k_roles"], "k_winLR+k_winM": ["k_winLR<0>", "k_winM<0>", "k_winLR<1>", "k_winM<1>"],
-                 "k_final": ["k_final"], "k_P_tuned": ["k_P_tuned"]}
+    ncu_names = {"k_roles": ("k_roles",), "k_winLR+k_winM": ("k_winLR", "k_winM"), "k_final": ("k_final",),
+                 "k_P_tuned": ("k_P_tuned",)}   # prefixes of the kernel names in the ncu launch list
     scale = None
     if traffic_json:
         alg_all = sum(x["bytes_4d"] for x in terms)
@@ -265,7 +265,7 @@ def per_kernel_roofline(prof, terms, peak_gbs, addmin, traffic_json=None):
         dram = None
         if scale is not None:
             pk = traffic_json.get("per_kernel", {})
-            dram = sum((pk[k]["dram_read_GB"] + pk[k]["dram_write_GB"]) * 1e9 for k in ncu_names[name] if k in pk) * scale
+            dram = sum((v["dram_read_GB"] + v["dram_write_GB"]) * 1e9 for k, v in pk.items() if k.startswith(ncu_names[name])) * scale
         dram_frac = dram / (ms / 1e3) / 1e9 / peak_gbs if dram else None
         roofs = {"hbm": dram_frac if dram_frac is not None else hbm_frac, "int32": int_frac or 0.0}
         out[name] = {"ms": ms, "algorithmic_bytes": nbytes, "candidates": cands, "achieved_gbs": gbs,
