@@ -227,7 +227,11 @@ __device__ __forceinline__ int ld16(const int16_t *__restrict__ p, int off) {
     return v;
 }
 __device__ __forceinline__ int lo16(int w) { return (int)(int16_t)(w & 0xffff); }
+#ifdef HI16_PRMT   // experiment: sign-extend the high half with one PRMT that the three levels of k_roles share
+__device__ __forceinline__ int hi16(int w) { int r; asm("prmt.b32 %0, %1, 0, 0xbb32;" : "=r"(r) : "r"(w)); return r; }
+#else
 __device__ __forceinline__ int hi16(int w) { return w >> 16; }
+#endif
 struct R12 { int w0, w1, w2; };  // one 12-byte read-group record (6 int16)
 __device__ __forceinline__ R12 ldr12(const int *__restrict__ g, int off) {
     const int *p = g + (int64_t)off * 3;
@@ -921,6 +925,13 @@ struct LayTab {
 #ifndef FINAL_MINB
 #define FINAL_MINB 8
 #endif
+// CCJ_ABLATE: timing experiments only (profiles/exp_ablate.py) -- every bit removes one class of memory operations from
+// k_final, so the tables are WRONG when it is non-zero; the shipped library is built without it.
+//   1 scattered copies (PRW, PKG, PMW, PMM)   2 plain tables the fill never reads   4 read-group records
+//   8 scratch reads   16 late split points   32 lower-level plain-table reads   64 PLW/PKF   128 all plain tables
+#ifndef CCJ_ABLATE
+#define CCJ_ABLATE 0
+#endif
 __global__ void __launch_bounds__(K4_THREADS, FINAL_MINB) k_final(const ccj_model *__restrict__ M, const ccj_seq *__restrict__ seqs, int t, int tail) {
     const ccj_seq q = seqs[blockIdx.z];
     const int n = q.n;
@@ -950,8 +961,15 @@ __global__ void __launch_bounds__(K4_THREADS, FINAL_MINB) k_final(const ccj_mode
     const int bp = M->bp_penalty, cp = M->cp_penalty, PB = M->PB_penalty, apbp = M->ap_penalty + M->bp_penalty;
     const int64_t ss = q.scratch_stride;
     const int16_t *__restrict__ sc = q.scratch + (int64_t)(t % KF) * Q_COUNT * ss + C.c;
+#if CCJ_ABLATE & 8
+#define GET(id) (20000 + (id))
+#else
 #define GET(id) ((int)__ldg(sc + (int64_t)(id) * ss))
+#endif
     const int off0 = OFF(a, b, i, k);
+#if CCJ_ABLATE & 32
+#define ld16(p, o) (1000 + ((o) & 15))
+#endif
     // partial minima of the four split-point roles.  tail = t mod KF: k_roles(t-tail) left them for the sources
     // of levels <= t-tail-1 (nothing for a role whose arm is shorter than tail: no partner there); the last `tail`
     // split points of each role, whose sources are cells of levels t-tail..t-1, are added here.
@@ -967,7 +985,7 @@ __global__ void __launch_bounds__(K4_THREADS, FINAL_MINB) k_final(const ccj_mode
         R3 = {GET(Q_PK3), GET(Q_PfR1), GET(Q_PfMp), GET(Q_PRm00a), GET(Q_PRm10), GET(Q_PMm00b)};
         R4 = {GET(Q_PfR2), GET(Q_PfO2), GET(Q_PRm00b), GET(Q_PRm01), GET(Q_PMm01), GET(Q_PMm10b), GET(Q_POm00b), GET(Q_POm01), GET(Q_POm10b)};
     }
-    if (tail) {
+    if (tail && !(CCJ_ABLATE & 16)) {
         const int4 *__restrict__ W3 = reinterpret_cast<const int4 *>(q.w3);
         // x = arm of the source cell (0 = the boundary split point of the role, its *_first form)
         for (int x = max(0, a - tail); x < a; ++x) {
@@ -998,17 +1016,19 @@ __global__ void __launch_bounds__(K4_THREADS, FINAL_MINB) k_final(const ccj_mode
     // flagged and re-filled by the generic kernels, whose every candidate is evaluated in 32 bits (ccj_batch_fill).
     // The guard band covers the largest single step of the packed paths (a window energy, the PB penalty).
     int32_t *const wrap_flag = q.status + 7;
-    auto put16 = [wrap_flag](int16_t *dst, int mn) -> int {
+    auto put16 = [wrap_flag](int16_t *dst, int mn, bool store) -> int {
         int v = CCJ_INTERN_INF;
         if (mn < CCJ_INF / 2) {
             if (mn >= CCJ_INTERN_INF) mn = CCJ_INTERN_INF;
             if (mn < CCJ_WRAP_GUARD) *wrap_flag = 1;
             v = (int)(int16_t)mn;
         }
-        *dst = (int16_t)v;
+        if (store) *dst = (int16_t)v;
         return v;
     };
-#define PUT(tbl, val) put16(w4 + (int64_t)(tbl) * st4 + off0, (val))
+#define PUT_UNREAD(tbl) ((tbl) == T_PK || (tbl) == T_PfromMprime || (tbl) == T_PLmloop00 || (tbl) == T_PMmloop00 || \
+                         (tbl) == T_POmloop00 || (tbl) == T_PRmloop00 || (tbl) == T_PL || (tbl) == T_PR)
+#define PUT(tbl, val) put16(w4 + (int64_t)(tbl) * st4 + off0, (val), !((CCJ_ABLATE & 128) || ((CCJ_ABLATE & 2) && PUT_UNREAD(tbl))))
     const int vPLm00 = PUT(T_PLmloop00, min(II + bp, min(L1.PLm00, L2.PLm00)));
     PUT(T_PLmloop01, L1.PLm01);
     const int vPLm10 = PUT(T_PLmloop10, min(L1.PLm10, L2.PLm10));
@@ -1096,25 +1116,27 @@ __global__ void __launch_bounds__(K4_THREADS, FINAL_MINB) k_final(const ccj_mode
         // k2=k: row delta=k-j-1 of block (i,l), position j-i: scattered, one store per cell.
         const int *__restrict__ lay = q.lay;
         const int Mf = n - j - 1, Mg = l - i - 1;
+        if (!(CCJ_ABLATE & 64))
         q.pkf[__ldg(&lay[CCJ_LAY_DF(n) + i]) + __ldg(&lay[CCJ_LAY_CF(n) + j]) - __ldg(&lay[CCJ_LAY_CF(n) + i]) +
               8 * ((int)ccj_q8(Mf) - (int)ccj_q8(Mf + 1 - (b + 1))) + (k - j - 2)] = (int16_t)vPK;
+        if (!(CCJ_ABLATE & 1))
         q.pkg[__ldg(&lay[CCJ_LAY_EG(n) + i]) + __ldg(&lay[CCJ_LAY_S2(n) + Mg]) +
               8 * ((int)ccj_q8(Mg) - (int)ccj_q8(Mg + 1 - (k - j - 1))) + (j - i)] = (int16_t)vPK;
     }
     {   // window copies (layouts in ccj_types.h); PLW is coalesced, PRW / PMW are one scattered store per cell
         const int slab4 = s_cw[b] + s_hh[n - b - 2] - s_hh[mloc] + h4m;
-        q.plw[4 * (int64_t)(slab4 - H4(mloc - i + 1)) + (n - b - k)] = (int16_t)vPL;
-        q.prw[4 * (int64_t)(slab4 - H4(mloc - kr)) + (i - 1)] = (int16_t)vPR;
+        if (!(CCJ_ABLATE & 64)) q.plw[4 * (int64_t)(slab4 - H4(mloc - i + 1)) + (n - b - k)] = (int16_t)vPL;
+        if (!(CCJ_ABLATE & 1)) q.prw[4 * (int64_t)(slab4 - H4(mloc - kr)) + (i - 1)] = (int16_t)vPR;
         // PMW / PMM: the PM window only reads cells with a>=1, b>=1 whose (j,k) is in some partner list, i.e. can pair;
         // everything else keeps the (32767, "not a source") that k_fill_pmw wrote
-        if (a >= 1 && b >= 1 && k - j > CCJ_TURN && ptype(j, k) > 0) {
+        if (!(CCJ_ABLATE & 1) && a >= 1 && b >= 1 && k - j > CCJ_TURN && ptype(j, k) > 0) {
             const int64_t pe = 4 * (int64_t)t * q.wtot4 + pmrow;   // entry of this cell in PMW and PMM
             q.pmw[pe] = (int16_t)vPM;
             q.pmm[pe] = (int16_t)-32768;
         }
     }
     // read-group records (layout in ccj_types.h); consecutive cells -> consecutive records, coalesced
-    {
+    if (!(CCJ_ABLATE & 4)) {
         const int vMpp = min(vPL, vPR);
         auto pk2 = [](int lo, int hi) { return (int)((uint32_t)(uint16_t)(int16_t)lo | ((uint32_t)(uint16_t)(int16_t)hi << 16)); };
         int *r1 = reinterpret_cast<int *>(q.g1) + (int64_t)off0 * 3;
@@ -1128,6 +1150,9 @@ __global__ void __launch_bounds__(K4_THREADS, FINAL_MINB) k_final(const ccj_mode
     }
 #undef PUT
 #undef GET
+#if CCJ_ABLATE & 32
+#undef ld16
+#endif
 }
 
 // P(i,l) = min_{i<=j<d<k<l} PK(i,j,d+1,k) + PK(j+1,d,k+1,l)  (src/pseudo_loop.cc:166-179).
