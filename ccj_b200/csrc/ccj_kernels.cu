@@ -2,6 +2,9 @@
 // cell functions of ccj_cells*.cuh / ccj_traceback.cuh (which carry the reference citations).
 #include "ccj_kernels.cuh"
 #include "ccj_traceback.cuh"
+#include "ccj_cells4_lean.cuh"
+
+#include <cstdlib>
 
 namespace ccj {
 
@@ -93,6 +96,30 @@ __global__ void __launch_bounds__(256) k_P(const ccj_model *M, const ccj_seq *se
     }
 }
 
+// the same with ccj_P_lean (ccj_cells4_lean.cuh): warps take delta = k-d, lanes walk d (first factors consecutive in memory)
+__global__ void __launch_bounds__(256) k_P_lean(const ccj_model *M, const ccj_seq *seqs, int s) {
+    extern __shared__ int64_t s_tab[];
+    __shared__ int sm[8];
+    const ccj_seq &q = seqs[blockIdx.z];
+    const int n = q.n;
+    const int i = 1 + blockIdx.x, l = i + s;
+    if (l > n) return;
+    const int j = i + blockIdx.y;
+    if (j >= l) return;
+    ccj_lean_plain_tab(s_tab, n, threadIdx.x, 256);
+    __syncthreads();
+    ccj_lean_plain ly;
+    ly.t4 = q.t4; ly.st4 = q.stride4; ly.tab = s_tab; ly.n = n;
+    int mn = ccj_P_lean(ly, i, j, l, threadIdx.x >> 5, 8, threadIdx.x & 31, 32);
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mn;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int x = 1; x < 8; ++x) mn = ccj_min(mn, sm[x]);
+        if (mn < CCJ_INF / 2) atomicMin(&q.t2[T2_P * q.stride2 + ccj_idx2(n, i, l)], mn);
+    }
+}
+
 __global__ void __launch_bounds__(128) k_2d(const ccj_model *M, const ccj_seq *seqs, int s) {
     ccj_cx c;
     c.M = M;
@@ -122,6 +149,38 @@ __global__ void __launch_bounds__(128, 12) k_4d(const ccj_model *M, const ccj_se
     const int a = blockIdx.y, b = t - a;
     const int i = 1 + q, k = i + a + 2 + kk;
     ccj_cell4d(c, i, i + a, k, k + b);
+}
+
+// The same level with the lean cell function (ccj_cells4_lean.cuh): Cb / Tet of the ordinary layout from a table in
+// shared memory, one position per split point.  Sequences without partner lists (CCJ_GENERIC_SCAN) take k_4d.
+#ifndef K4D_LEAN_MINB
+#define K4D_LEAN_MINB 8
+#endif
+__global__ void __launch_bounds__(128, K4D_LEAN_MINB) k_4d_lean(const ccj_model *M, const ccj_seq *seqs, int t, int nmax) {
+    extern __shared__ int64_t s_tab[];   // per-block copy for the block's sequence: Cb(0..n), Tet(0..n)
+    ccj_cx c;
+    c.M = M;
+    c.q = seqs[blockIdx.z];
+    const int n = c.q.n;
+    const int m = n - t - 2;  // rows i = 1..m, row i has m+1-i cells
+    if (m < 1 || n > nmax) return;
+    const int ncell = m * (m + 1) / 2;
+    if ((int)(blockIdx.x * 128) >= ncell) return;
+    ccj_lean_plain_tab(s_tab, n, threadIdx.x, 128);
+    __syncthreads();
+    const int p = blockIdx.x * 128 + threadIdx.x;
+    if (p >= ncell) return;
+    int q, kk;
+    ccj_shard_cell_of(p, m, 1, m, q, kk);
+    const int a = blockIdx.y, b = t - a;
+    const int i = 1 + q, k = i + a + 2 + kk;
+    if (!ccj_lists_ok(c) || !c.q.w3) {   // uniform per sequence
+        ccj_cell4d(c, i, i + a, k, k + b);
+        return;
+    }
+    ccj_lean_plain ly;
+    ly.t4 = c.q.t4; ly.st4 = c.q.stride4; ly.tab = s_tab; ly.n = n;
+    ccj_cell4d_lean(c, ly, i, i + a, k, k + b);
 }
 
 __global__ void k_W(const ccj_model *M, const ccj_seq *seqs) {
@@ -164,6 +223,12 @@ void launch_tb_step(const ccj_model *M, const ccj_seq *seqs, int seq, const int 
     k_tb_step<<<1, 32, 0, st>>>(M, seqs, seq, node[0], node[1], node[2], node[3], node[4], out_top);
 }
 
+// CCJ_K4D_LEAN=0 selects the generic-index kernels (k_4d, k_P) for comparison
+static bool lean_enabled() {
+    static const bool lean = [] { const char *e = getenv("CCJ_K4D_LEAN"); return !(e && e[0] == '0'); }();
+    return lean;
+}
+
 void launch_init(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cudaStream_t st) {
     const int64_t s2 = ccj_stride2(d.nmax);
     int bx = (int)((s2 + 255) / 256);
@@ -173,7 +238,11 @@ void launch_init(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cudaStre
 
 void launch_P(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int s, cudaStream_t st) {
     if (s < 3 || s > d.nmax - 1) return;  // needs i<=j<d<k<l
-    k_P<<<dim3(d.nmax - s, s, d.nseq), 256, 0, st>>>(M, seqs, s);
+    const size_t smem = 2 * (size_t)(d.nmax + 1) * sizeof(int64_t);
+    if (lean_enabled() && smem <= 40000)
+        k_P_lean<<<dim3(d.nmax - s, s, d.nseq), 256, smem, st>>>(M, seqs, s);
+    else
+        k_P<<<dim3(d.nmax - s, s, d.nseq), 256, 0, st>>>(M, seqs, s);
 }
 
 void launch_2d(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int s, cudaStream_t st) {
@@ -186,7 +255,11 @@ void launch_4d(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cud
     const int m = d.nmax - t - 2;
     if (m < 1) return;
     const int ncell = m * (m + 1) / 2;
-    k_4d<<<dim3((ncell + 127) / 128, t + 1, d.nseq), 128, 0, st>>>(M, seqs, t);
+    const size_t smem = 2 * (size_t)(d.nmax + 1) * sizeof(int64_t);
+    if (lean_enabled() && smem <= 40000)
+        k_4d_lean<<<dim3((ncell + 127) / 128, t + 1, d.nseq), 128, smem, st>>>(M, seqs, t, d.nmax);
+    else
+        k_4d<<<dim3((ncell + 127) / 128, t + 1, d.nseq), 128, 0, st>>>(M, seqs, t);
 }
 
 void launch_W(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cudaStream_t st) {

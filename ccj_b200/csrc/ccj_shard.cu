@@ -19,6 +19,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -26,7 +27,7 @@
 #include <vector>
 
 #include "../../include/ccj_b200.h"
-#include "ccj_cells4.cuh"
+#include "ccj_cells4_lean.cuh"
 #include "ccj_kernels.cuh"
 #include "ccj_render.hpp"
 #include "energy_model.hpp"
@@ -145,6 +146,47 @@ __global__ void __launch_bounds__(128, 12) k_4d_shard(const ccj_model *M, const 
     ccj_cell4d(c, i, i + a, k, k + b);
 }
 
+// The same level with the lean cell function (ccj_cells4_lean.cuh): one position per split point from level bases kept
+// in shared memory, compile-time table kinds.  Needs the packed 2D records, the partner lists and 32-bit in-level
+// offsets (shard_lean_ok); CCJ_SHARD_LEAN=0 selects k_4d_shard for comparison.
+#ifndef SHARD_LEAN_MINB
+#define SHARD_LEAN_MINB 8
+#endif
+template <bool POW2>
+__global__ void __launch_bounds__(128, SHARD_LEAN_MINB) k_4d_shard_lean(const ccj_model *M, const ccj_seq *seqs, int t) {
+    extern __shared__ ccj_lean_lvl s_lvl[];
+    ccj_cx c;
+    c.M = M;
+    c.q = seqs[0];
+    const int n = c.q.n, G = c.q.shard_G, r = c.q.shard_rank;
+    ccj_lean_lvl_fill(s_lvl, c.q.shard_lev, t, G, threadIdx.x, 128);   // sources are cells of levels < t, the cell itself is on t
+    __syncthreads();
+    const int m = n - t - 2;
+    if (m <= r) return;
+    const int mr = m - r, Q = (mr + G - 1) / G;
+    const int ncell = Q * mr - G * (Q * (Q - 1) / 2);
+    const int p = blockIdx.x * 128 + threadIdx.x;
+    if (p >= ncell) return;
+    int q, kk;
+    ccj_shard_cell_of(p, mr, G, Q, q, kk);
+    const int a = blockIdx.y, b = t - a;
+    const int i = r + 1 + q * G, k = i + a + 2 + kk;
+    ccj_lean_shard<POW2> ly;
+    ly.rep = c.q.shard_rep;
+    ly.loc = c.q.shard_loc[r];
+    ly.lvl = s_lvl;
+    ly.n = n; ly.G = G; ly.sh = c.q.shard_shift;
+    ccj_cell4d_lean(c, ly, i, i + a, k, k + b);
+}
+// the lean kernel applies: lists + packed 2D records present, kinds as compiled in, in-level offsets fit 32 bits
+bool shard_lean_ok(const ccj_seq &q, const int64_t *lev_host, int n, int G) {
+    static const bool off = [] { const char *e = getenv("CCJ_SHARD_LEAN"); return e && e[0] == '0'; }();
+    if (off || !q.use_lists || !q.w3 || !ccj_lean_kinds_ok(q.shard_kind)) return false;
+    int64_t cmax = 0;
+    for (int t = 0; t <= n; ++t) cmax = std::max<int64_t>(cmax, lev_host[t + 1] - lev_host[t]);
+    return (int64_t)(CCJ_SHARD_NREP * G + 1) * cmax < (int64_t)0x7fffffff && (size_t)(n + 1) * sizeof(ccj_lean_lvl) <= 40000;
+}
+
 // P(i,l), l=i+s, for the rank's rows: blockIdx.x -> own row, blockIdx.y -> j (first split point), threads -> (d,k)
 __global__ void __launch_bounds__(256) k_P_shard(const ccj_model *M, const ccj_seq *seqs, int s) {
     ccj_cx c;
@@ -166,6 +208,35 @@ __global__ void __launch_bounds__(256) k_P_shard(const ccj_model *M, const ccj_s
     if (threadIdx.x == 0) {
         for (int x = 1; x < 8; ++x) mn = ccj_min(mn, sm[x]);
         if (mn < CCJ_INF / 2) atomicMin(&c.q.t2[T2_P * c.q.stride2 + ccj_idx2(n, i, l)], mn);
+    }
+}
+
+// the same with ccj_P_lean (ccj_cells4_lean.cuh): warps take delta = k-d, lanes walk d -- the first factors are consecutive
+// entries of one row, the second factors a constant stride apart on one level
+template <bool POW2>
+__global__ void __launch_bounds__(256) k_P_shard_lean(const ccj_model *M, const ccj_seq *seqs, int s) {
+    extern __shared__ ccj_lean_lvl s_lvl[];
+    __shared__ int sm[8];
+    const ccj_seq &q = seqs[0];
+    const int n = q.n, G = q.shard_G;
+    ccj_lean_lvl_fill(s_lvl, q.shard_lev, s, G, threadIdx.x, 256);   // both factors lie on levels <= s-3
+    __syncthreads();
+    const int i = q.shard_rank + 1 + blockIdx.x * G, l = i + s;
+    if (l > n) return;
+    const int j = i + blockIdx.y;
+    if (j >= l) return;
+    ccj_lean_shard<POW2> ly;
+    ly.rep = q.shard_rep;
+    ly.loc = nullptr;   // PK is a column-read table
+    ly.lvl = s_lvl;
+    ly.n = n; ly.G = G; ly.sh = q.shard_shift;
+    int mn = ccj_P_lean(ly, i, j, l, threadIdx.x >> 5, 8, threadIdx.x & 31, 32);
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mn;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int x = 1; x < 8; ++x) mn = ccj_min(mn, sm[x]);
+        if (mn < CCJ_INF / 2) atomicMin(&q.t2[T2_P * q.stride2 + ccj_idx2(n, i, l)], mn);
     }
 }
 
@@ -553,7 +624,13 @@ int ccj_shard_fill(ccj_shard **shards, int count, float *ms4) {
             for (int x = 0; x < count; ++x) {
                 ccj_shard *z = shards[x];
                 const int rows = (int)ccj_shard_rows(n - s, z->rank, G);
-                if (rows > 0) k_P_shard<<<dim3(rows, s), 256, 0, on(z)>>>(model(z), d_desc(z), s);
+                if (rows <= 0) continue;
+                if (!shard_lean_ok(z->h_desc, sh->lev.data(), n, G))
+                    k_P_shard<<<dim3(rows, s), 256, 0, on(z)>>>(model(z), d_desc(z), s);
+                else if (z->h_desc.shard_shift >= 0)
+                    k_P_shard_lean<true><<<dim3(rows, s), 256, (size_t)(s + 1) * sizeof(ccj_lean_lvl), on(z)>>>(model(z), d_desc(z), s);
+                else
+                    k_P_shard_lean<false><<<dim3(rows, s), 256, (size_t)(s + 1) * sizeof(ccj_lean_lvl), on(z)>>>(model(z), d_desc(z), s);
             }
         }
         mark(4 * s + 1);
@@ -582,7 +659,14 @@ int ccj_shard_fill(ccj_shard **shards, int count, float *ms4) {
             const int64_t ncell = m >= 1 ? ccj_shard_slab(m, z->rank, G) : 0;
             if (ncell < 1) continue;
             const dim3 grid((unsigned)((ncell + 127) / 128), s + 1);
-            k_4d_shard<<<grid, 128, 0, st>>>(model(z), d_desc(z), s);
+            if (shard_lean_ok(z->h_desc, sh->lev.data(), n, G)) {
+                if (z->h_desc.shard_shift >= 0)
+                    k_4d_shard_lean<true><<<grid, 128, (size_t)(s + 1) * sizeof(ccj_lean_lvl), st>>>(model(z), d_desc(z), s);
+                else
+                    k_4d_shard_lean<false><<<grid, 128, (size_t)(s + 1) * sizeof(ccj_lean_lvl), st>>>(model(z), d_desc(z), s);
+            } else {
+                k_4d_shard<<<grid, 128, 0, st>>>(model(z), d_desc(z), s);
+            }
         }
         mark(4 * s + 3);
         // --- the 12 column-read tables of level s to every rank: G adjacent blocks, in place ---

@@ -15,7 +15,7 @@
 #include <vector>
 
 #include "../../ccj_b200/csrc/energy_model.hpp"
-#include "../../ccj_b200/csrc/ccj_cells4.cuh"
+#include "../../ccj_b200/csrc/ccj_cells4_lean.cuh"
 #ifndef CCJ_EMU_NO_TB
 #include "../../ccj_b200/csrc/ccj_traceback.cuh"
 #include "../../ccj_b200/csrc/ccj_render.hpp"
@@ -43,6 +43,11 @@ int main(int argc, char **argv) {
     const int shardG = argc > 6 ? atoi(argv[6]) : 0;
     const int packed2d = argc > 7 ? atoi(argv[7]) : 0;   // keep {WB,WP,WBP} packed per interval (ccj_seq::w3) as the GPU folds do
     const int lists = argc > 8 ? atoi(argv[8]) : 0;      // walk per-pair partner lists in the interior windows (k_prep's rule)
+    const int lean = argc > 9 ? atoi(argv[9]) : 0;       // sweep ccj_cell4d_lean (the form k_4d / k_4d_shard run) instead of ccj_cell4d
+    if (lean && !(packed2d && lists)) {
+        fprintf(stderr, "lean needs the packed 2D records and the partner lists\n");
+        return 2;
+    }
     ccj::RawParams rp;
     if (!ccj::load_par_file(argv[2], rp, err)) {
         fprintf(stderr, "%s\n", err.c_str());
@@ -152,15 +157,38 @@ int main(int argc, char **argv) {
         ccj_shard_kinds(c.q.shard_kind);
     }
 
+    std::vector<int64_t> leantab(2 * (size_t)(n + 1) + 2, 0);
+    ccj_lean_plain_tab(leantab.data(), n, 0, 1);
+    std::vector<ccj_lean_lvl> leanlvl((size_t)n + 1);
+    if (shardG > 0) ccj_lean_lvl_fill(leanlvl.data(), lev.data(), n, shardG, 0, 1);
+    if (lean && shardG > 0 && !ccj_lean_kinds_ok(c.q.shard_kind)) {
+        fprintf(stderr, "ccj_lean_kind disagrees with ccj_shard_kinds\n");
+        return 2;
+    }
     ccj_serial par;
     for (int s = 0; s < n; ++s) {
         // K_P + K_2D of span s
         for (int i = 1; i + s <= n; ++i) {
             const int l = i + s;
             int mn = CCJ_INF;
-            for (int j = i; j < l; ++j)
-                for (int d = j + 1; d < l; ++d)
-                    for (int k = d + 1; k < l; ++k) mn = ccj_min(mn, ccj_P_term(c, i, l, j, d, k));
+            for (int j = i; j < l; ++j) {
+                if (lean && shardG > 0 && c.q.shard_shift >= 0) {
+                    ccj_lean_shard<true> ly;
+                    ly.rep = rep.data(); ly.loc = nullptr; ly.lvl = leanlvl.data(); ly.n = n; ly.G = shardG; ly.sh = c.q.shard_shift;
+                    mn = ccj_min(mn, ccj_min(ccj_P_lean(ly, i, j, l, 0, 2, 0, 1), ccj_P_lean(ly, i, j, l, 1, 2, 0, 1)));   // two "warps"
+                } else if (lean && shardG > 0) {
+                    ccj_lean_shard<false> ly;
+                    ly.rep = rep.data(); ly.loc = nullptr; ly.lvl = leanlvl.data(); ly.n = n; ly.G = shardG; ly.sh = -1;
+                    mn = ccj_min(mn, ccj_min(ccj_P_lean(ly, i, j, l, 0, 1, 0, 2), ccj_P_lean(ly, i, j, l, 0, 1, 1, 2)));   // two "lanes"
+                } else if (lean) {
+                    ccj_lean_plain ly;
+                    ly.t4 = c.q.t4; ly.st4 = c.q.stride4; ly.tab = leantab.data(); ly.n = n;
+                    mn = ccj_min(mn, ccj_P_lean(ly, i, j, l, 0, 1, 0, 1));
+                } else {
+                    for (int d = j + 1; d < l; ++d)
+                        for (int k = d + 1; k < l; ++k) mn = ccj_min(mn, ccj_P_term(c, i, l, j, d, k));
+                }
+            }
             if (mn < CCJ_INF / 2) t2[T2_P * s2 + ccj_idx2(n, i, l)] = mn;
             ccj_cell2d(c, i, l, par);
         }
@@ -170,7 +198,31 @@ int main(int argc, char **argv) {
             for (int a = 0; a <= t; ++a) {
                 const int b = t - a;
                 for (int i = 1; i <= n - t - 2; ++i)
-                    for (int k = i + a + 2; k <= n - b; ++k) ccj_cell4d(c, i, i + a, k, k + b);
+                    for (int k = i + a + 2; k <= n - b; ++k) {
+                        if (!lean) {
+                            ccj_cell4d(c, i, i + a, k, k + b);
+                        } else if (shardG > 0) {
+                            if (c.q.shard_shift >= 0) {
+                                ccj_lean_shard<true> ly;
+                                ly.rep = rep.data();
+                                ly.loc = locptr[(i - 1) % shardG];   // the rank that owns row i
+                                ly.lvl = leanlvl.data();
+                                ly.n = n; ly.G = shardG; ly.sh = c.q.shard_shift;
+                                ccj_cell4d_lean(c, ly, i, i + a, k, k + b);
+                            } else {
+                                ccj_lean_shard<false> ly;
+                                ly.rep = rep.data();
+                                ly.loc = locptr[(i - 1) % shardG];
+                                ly.lvl = leanlvl.data();
+                                ly.n = n; ly.G = shardG; ly.sh = -1;
+                                ccj_cell4d_lean(c, ly, i, i + a, k, k + b);
+                            }
+                        } else {
+                            ccj_lean_plain ly;
+                            ly.t4 = c.q.t4; ly.st4 = c.q.stride4; ly.tab = leantab.data(); ly.n = n;
+                            ccj_cell4d_lean(c, ly, i, i + a, k, k + b);
+                        }
+                    }
             }
     }
     for (int j = CCJ_TURN + 1; j <= n; ++j) W[j] = ccj_W_at(c, j, par);

@@ -95,6 +95,30 @@ def test_cell_functions_over_the_sharded_layout_match_the_reference(emu_bin, gol
         assert (p.returncode, p.stdout, p.stderr) == (r["rc"], r["stdout"], r["stderr"]), (world, r["seq"])
 
 
+@pytest.mark.parametrize("world", [0, 1, 2, 3, 4, 8])
+def test_lean_cell_functions_match_the_reference(emu_bin, golden_hashes, golden_folds, world):
+    """ccj_cells4_lean.cuh (what k_4d_lean / k_4d_shard_lean / k_P_*_lean run: one position per split point, compile-time
+    table kinds, strided second factors in compute_P) swept on the CPU over the ordinary layout (world 0) and the sharded
+    layout (power-of-two and other rank counts): table hashes and folds equal the reference's golden vectors."""
+    def run(mode, rec):
+        args = [str(emu_bin), mode, str(ROOT / "params" / rec["par"]), str(rec["dangles"]), rec["seq"],
+                "1" if "--noGU" in rec.get("extra", []) else "0", str(world), "1", "1", "1"]
+        return subprocess.run(args, capture_output=True, text=True)
+    recs = [r for r in golden_hashes if len(r["seq"]) <= 41]
+    assert len(recs) >= 6
+    for r in recs:
+        p = run("hash", r)
+        assert p.returncode == 0, p.stderr
+        got = {}
+        for line in p.stdout.splitlines()[1:]:
+            name, cnt, agg, h = line.split()
+            got[name] = [int(cnt), int(agg), h]
+        assert got == r["tables"], (world, r["seq"])
+    for r in [r for r in golden_folds if 20 <= len(r["seq"]) <= 34][:8]:
+        p = run("fold", r)
+        assert (p.returncode, p.stdout, p.stderr) == (r["rc"], r["stdout"], r["stderr"]), (world, r["seq"])
+
+
 def test_flat_thread_to_cell_mapping_is_the_exact_inverse(tmp_path):
     """k_4d / k_4d_shard give thread p of a slab the p-th cell in storage order; the inverse of the row offsets uses a
     float square root plus fix-ups -- checked exhaustively on the host (tests/shell/cell_of_test.cc)."""
