@@ -146,7 +146,7 @@ CCJ_HD ccj_w3v ccj_lean_w3(const int32_t *w3, int idx) {
 #define CCJ_LEAN_UNROLL_PRAGMA CCJ_UNROLL_BY(CCJ_LEAN_UNROLL)
 // the window loops are chains of two dependent loads per candidate (list entry -> source cell): several in flight
 #ifndef CCJ_LEAN_WIN_UNROLL
-#define CCJ_LEAN_WIN_UNROLL 4
+#define CCJ_LEAN_WIN_UNROLL 8
 #endif
 #define CCJ_LEAN_WIN_PRAGMA CCJ_UNROLL_BY(CCJ_LEAN_WIN_UNROLL)
 #ifndef CCJ_LEAN_ABLATE_WIN   // timing experiments only: 1 = skip the window lists (wrong tables)
