@@ -295,7 +295,9 @@ def bench_config5(args):
             "bytes_per_rank": shard_bytes(n, world), "cells": terms["cells"],
             "algorithmic_bytes": terms["bytes"], "achieved_gbs_all_ranks": terms["bytes"] / fill_s / 1e9,
             "roofline_frac_of_aggregate_hbm": terms["bytes"] / fill_s / 1e9 / (peak * world),
-            "kernel": "generic one-thread-per-cell level kernel over the sharded layout (k_4d_shard)",
+            "kernel": ("one-thread-per-cell level kernel over the sharded layout, lean addressing (k_4d_shard_lean, k_P_shard_lean)"
+                       if os.environ.get("CCJ_SHARD_LEAN", "1") != "0" else
+                       "one-thread-per-cell level kernel over the sharded layout, generic addressing (k_4d_shard)"),
             "energy": fold.energy, "status": fold.status, "should_not_be_here": fold.n_should_not_be_here,
             "structure": fold.structure, "hashes": hashes,
         }
