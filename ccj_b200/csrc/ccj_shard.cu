@@ -6,8 +6,9 @@
 //   k_P_shard(s)      P(i,i+s) for the rank's rows i, from PK of levels <= s-3            (every rank holds all of PK)
 //   allreduce-min     the span-s diagonal of P (n+1 int32, contiguous in the diagonal-major 2D layout)
 //   k_2d(s)           V / WBP / WPP / WB / WP / WMv / WMp / WM of span s, every rank        (replicated, cheap)
-//   k_4d_shard(s)     all 22 gap tables of the rank's cells of level s: the product's cell function ccj_cell4d, table
-//                     access through the sharded layout of ccj_types.h
+//   k_4d_shard(s)     all 22 gap tables of the rank's cells of level s: the product's cell function, table access through
+//                     the sharded layout of ccj_types.h (k_4d_shard_lean / k_P_shard_lean: the lean form of
+//                     ccj_cells4_lean.cuh, one position per split point; k_4d_shard / k_P_shard: ccj_cell4d as it stands)
 //   allgather         the 12 column-read tables of level s: one in-place ncclAllGather of G adjacent blocks
 // then k_W everywhere and the traceback on the rank that opened its peers' memory (the 10 row-local tables of the
 // other ranks are read over NVLink through CUDA IPC pointers; the traceback touches O(n) cells per node).
