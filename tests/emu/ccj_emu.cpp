@@ -175,15 +175,18 @@ int main(int argc, char **argv) {
                 if (lean && shardG > 0 && c.q.shard_shift >= 0) {
                     ccj_lean_shard<true> ly;
                     ly.rep = rep.data(); ly.loc = nullptr; ly.lvl = leanlvl.data(); ly.n = n; ly.G = shardG; ly.sh = c.q.shard_shift;
-                    mn = ccj_min(mn, ccj_min(ccj_P_lean(ly, i, j, l, 0, 2, 0, 1), ccj_P_lean(ly, i, j, l, 1, 2, 0, 1)));   // two "warps"
+                    for (int wid = 0; wid < 3; ++wid)       // the shares of 3 "warps" x 5 "lanes" together are all terms
+                        for (int lane = 0; lane < 5; ++lane) mn = ccj_min(mn, ccj_P_lean(ly, i, j, l, wid, 3, lane, 5));
                 } else if (lean && shardG > 0) {
                     ccj_lean_shard<false> ly;
                     ly.rep = rep.data(); ly.loc = nullptr; ly.lvl = leanlvl.data(); ly.n = n; ly.G = shardG; ly.sh = -1;
-                    mn = ccj_min(mn, ccj_min(ccj_P_lean(ly, i, j, l, 0, 1, 0, 2), ccj_P_lean(ly, i, j, l, 0, 1, 1, 2)));   // two "lanes"
+                    for (int wid = 0; wid < 2; ++wid)
+                        for (int lane = 0; lane < 3; ++lane) mn = ccj_min(mn, ccj_P_lean(ly, i, j, l, wid, 2, lane, 3));
                 } else if (lean) {
                     ccj_lean_plain ly;
                     ly.t4 = c.q.t4; ly.st4 = c.q.stride4; ly.tab = leantab.data(); ly.n = n;
-                    mn = ccj_min(mn, ccj_P_lean(ly, i, j, l, 0, 1, 0, 1));
+                    for (int wid = 0; wid < 2; ++wid)
+                        for (int lane = 0; lane < 4; ++lane) mn = ccj_min(mn, ccj_P_lean(ly, i, j, l, wid, 2, lane, 4));
                 } else {
                     for (int d = j + 1; d < l; ++d)
                         for (int k = d + 1; k < l; ++k) mn = ccj_min(mn, ccj_P_term(c, i, l, j, d, k));
