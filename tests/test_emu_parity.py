@@ -90,7 +90,10 @@ def test_cell_functions_under_asan_ubsan(tmp_path, golden_folds, golden_hashes):
     folds += [r for r in golden_folds if r["rc"] != 0 and len(r["seq"]) <= 34][:1]
     assert len(folds) >= 4
     for r in folds:
-        for extra in ([], ["0", "0", "1", "1"], ["0", "4", "1", "1"], ["0", "3", "0", "0"]):
+        # [noGU, ranks, packed 2D records, partner lists, lean]; the last three: ccj_cells4_lean.cuh (ordinary, power-of-two
+        # and other rank counts) -- its premultiplied level bases / 32-bit offsets must stay inside the exactly sized buffers
+        for extra in ([], ["0", "0", "1", "1"], ["0", "4", "1", "1"], ["0", "3", "0", "0"],
+                      ["0", "0", "1", "1", "1"], ["0", "4", "1", "1", "1"], ["0", "3", "1", "1", "1"]):
             args = [str(exe), "fold", str(ROOT / "params" / r["par"]), str(r["dangles"]), r["seq"]] + extra
             p = subprocess.run(args, capture_output=True, text=True)
             assert "Sanitizer" not in p.stderr and "runtime error" not in p.stderr, p.stderr[-2000:]
