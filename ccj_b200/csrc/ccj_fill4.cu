@@ -15,6 +15,8 @@
 // (k_winLR, k_winM).  Kernels, in launch order per level: k_roles (every third level), k_winLR, k_winM, k_final;
 // per span: k_P_tuned, k_2d (ccj_kernels.cu); once per fill: k_prep_lay, k_fill_pmw, k_prep.
 // Checked bit-for-bit against ccj_cell4d (generic version), the reference's tables and the CPU restatement.
+// CCJ_HOST_EMU (tests/emu/ccj_emu_tuned.cpp only): g++ compiles these kernels for the SIMT emulator of tests/emu/simt_emu.hpp;
+// the inline PTX gets plain C++ equivalents and the <<< >>> launchers are left out.  The CUDA build never defines it.
 #include "ccj_kernels.cuh"
 #include "ccj_cells4.cuh"
 
@@ -222,12 +224,16 @@ enum { ROLE_L1 = 0, ROLE_L2, ROLE_R3, ROLE_R4 };
 // streaming read of a gap-table entry: read-only path, and ask L2 to fetch the whole 256-byte chunk -- the
 // neighbouring warps of the block need the adjacent 64-byte runs of the same slab row
 __device__ __forceinline__ int ld16(const int16_t *__restrict__ p, int off) {
+#ifdef CCJ_HOST_EMU
+    return (int)p[off];
+#else
     int v;
     asm("ld.global.nc.L2::256B.s16 %0, [%1];" : "=r"(v) : "l"(p + off));
     return v;
+#endif
 }
 __device__ __forceinline__ int lo16(int w) { return (int)(int16_t)(w & 0xffff); }
-#ifdef HI16_PRMT   // experiment: sign-extend the high half with one PRMT that the three levels of k_roles share
+#if defined(HI16_PRMT) && !defined(CCJ_HOST_EMU)   // experiment: sign-extend the high half with one PRMT that the three levels of k_roles share
 __device__ __forceinline__ int hi16(int w) { int r; asm("prmt.b32 %0, %1, 0, 0xbb32;" : "=r"(r) : "r"(w)); return r; }
 #else
 __device__ __forceinline__ int hi16(int w) { return w >> 16; }
@@ -546,20 +552,45 @@ __global__ void __launch_bounds__(K4_THREADS, ROLES_MINB) k_roles(const ccj_mode
 
 #define WB 8      // window candidates in flight per lane (FENCE8X assumes 8)
 // keep the compiler from sinking the WB loads of a batch to their uses: all of them must be in flight together
+#ifdef CCJ_HOST_EMU
+#define FENCE8X(v) ((void)0)
+#define CCJ_PIN64(p) ((void)0)
+#else
 #define FENCE8X(v) asm volatile("" : "+r"(v[0].x), "+r"(v[1].x), "+r"(v[2].x), "+r"(v[3].x), "+r"(v[4].x), "+r"(v[5].x), "+r"(v[6].x), "+r"(v[7].x))
+#define CCJ_PIN64(p) asm volatile("" : "+l"(p))
+#endif
 #define WGRP 8    // lanes per run: one pass covers 8 quads = 32 cells
 #define WRUNS (K4_THREADS / WGRP)
 
 __device__ __forceinline__ int2 ldq(const int2 *p, int off) {
+#ifdef CCJ_HOST_EMU
+    return p[off];
+#else
     int2 v;
     asm("ld.global.nc.L2::256B.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p + off));
     return v;
+#endif
 }
 __device__ __forceinline__ int pack_sat(int lo, int hi) {
     return (int)((uint32_t)(uint16_t)sat16(lo) | ((uint32_t)(uint16_t)sat16(hi) << 16));
 }
 
 // packed int16x2 arithmetic (VIADDMNMX.S16x2 / VIMNMX.S16x2): two cells per instruction, no unpacking
+#ifdef CCJ_HOST_EMU   // add.s16x2 wraps, min/max.s16x2 are signed, per 16-bit half
+__device__ __forceinline__ int emu_half(int w, int h) { return (int)(int16_t)((unsigned)w >> (16 * h)); }
+__device__ __forceinline__ int emu_pack(int lo, int hi) { return (int)(((unsigned)lo & 0xffffu) | ((unsigned)hi << 16)); }
+__device__ __forceinline__ int emu_add2(int a, int b) {
+    return emu_pack((int)(int16_t)(emu_half(a, 0) + emu_half(b, 0)), (int)(int16_t)(emu_half(a, 1) + emu_half(b, 1)));
+}
+__device__ __forceinline__ int min2(int a, int b) {
+    return emu_pack(std::min(emu_half(a, 0), emu_half(b, 0)), std::min(emu_half(a, 1), emu_half(b, 1)));
+}
+__device__ __forceinline__ int emu_max2(int a, int b) {
+    return emu_pack(std::max(emu_half(a, 0), emu_half(b, 0)), std::max(emu_half(a, 1), emu_half(b, 1)));
+}
+__device__ __forceinline__ int addmin2(int a, int b, int c) { return min2(emu_add2(a, b), c); }
+__device__ __forceinline__ int addmax2(int a, int b, int c) { return emu_max2(emu_add2(a, b), c); }
+#else
 __device__ __forceinline__ int addmin2(int a, int b, int c) {  // min(a+b, c) per half
     int r, s;
     asm("add.s16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
@@ -577,6 +608,7 @@ __device__ __forceinline__ int min2(int a, int b) {
     asm("min.s16x2 %0, %1, %2;" : "=r"(s) : "r"(a), "r"(b));
     return s;
 }
+#endif
 __device__ __forceinline__ int splat16(int e) { return (int)__byte_perm((unsigned)e, 0u, 0x1010); }
 // A window candidate is value + energy with the sum saturated at 32767 ("INF or clamped", see k_final).  In
 // 16 bits:  min(value, 32767 - max(energy,0)) + energy  -- exact, and it cannot wrap upwards.
@@ -634,7 +666,7 @@ __global__ void __launch_bounds__(K4_THREADS, PIPE ? 6 : 12) k_winLR(const ccj_m
     const bool gact = idx < last && pass * (4 * G) < zc;   // the group has cells in this pass
     const int qd = pass * G + gl;                    // this lane's quad of the run
     const int2 *src = reinterpret_cast<const int2 *>(role == 0 ? q.plw : q.prw) + qd;
-    asm volatile("" : "+l"(src));  // per-lane base in a register pair: one IMAD.WIDE per candidate
+    CCJ_PIN64(src);  // per-lane base in a register pair: one IMAD.WIDE per candidate
     const int own = s_T[0] - s_h4[zc];                  // the run's own (not yet written) quads
     int acc0 = WIN_INF2, acc1 = WIN_INF2;
     if (gact && arm > CCJ_TURN + 2) {  // stacking term, x=y=1 (PL(i+1,j-1,k,l) / PR(i,j,k+1,l-1))
@@ -734,9 +766,13 @@ __global__ void __launch_bounds__(K4_THREADS, PIPE ? 6 : 12) k_winLR(const ccj_m
 }
 
 __device__ __forceinline__ int4 ldq4(const int4 *p, int off) {
+#ifdef CCJ_HOST_EMU
+    return p[off];
+#else
     int4 v;
     asm("ld.global.nc.L2::256B.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p + off));
     return v;
+#endif
 }
 
 // every entry of PMW / PMM starts as 32767 ("not a source"): rows are padded and read past their ends
@@ -783,7 +819,7 @@ __global__ void __launch_bounds__(K4_THREADS, PIPE ? 4 : 10) k_winM(const ccj_mo
     const int wtot4 = q.wtot4;
     const int2 *srcv = reinterpret_cast<const int2 *>(q.pmw) + qd;   // values
     const int2 *srcm = reinterpret_cast<const int2 *>(q.pmm) + qd;   // mask halves, same index
-    asm volatile("" : "+l"(srcv));
+    CCJ_PIN64(srcv);
     const int INF = CCJ_INF;
     const int own = t * wtot4 + __ldg(&q.pmlev4[j * n1 + k]) - qlo;   // the row's own (not yet written) quads
     int acc0 = WIN_INF2, acc1 = WIN_INF2;
@@ -1222,6 +1258,7 @@ __global__ void __launch_bounds__(256) k_P_tuned(const ccj_seq *__restrict__ seq
     }
 }
 
+#ifndef CCJ_HOST_EMU   // the launchers below are CUDA only; the emulation harness issues the same grids itself
 // partner lists + e_stP table only (folds that run the generic cell functions over lists: beyond the tuned range, sharded)
 void launch_prep_lists(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cudaStream_t st) {
     if (d.nmax < 2) return;
@@ -1310,5 +1347,6 @@ void launch_P_tuned(const ccj_model *, const ccj_seq *seqs, LaunchDims d, int s,
     const int nj = std::max(1, std::min(s - 2, (148 * 6 + per - 1) / per));
     k_P_tuned<<<dim3(d.nmax - s, nj, d.nseq), 256, 0, st>>>(seqs, s, nj);
 }
+#endif  // CCJ_HOST_EMU
 
 }  // namespace ccj

@@ -1,0 +1,209 @@
+// TEST TOOL (not part of the product): runs the TUNED CUDA kernels of ccj_b200/csrc/ccj_fill4.cu (k_prep_lay, k_fill_pmw,
+// k_prep, k_roles, k_winLR, k_winM, k_final, k_P_tuned) on the host, compiled by g++ for the SIMT emulator of
+// simt_emu.hpp, in the launch order of ccj_abi.cu (ccj_batch_fill_profiled: one stream) and with the launchers' grids.
+// Buffers have exactly the sizes ccj_abi.cu plans (tab_bytes_uncached) and are poisoned before the fill, so the tool is
+// meaningful under AddressSanitizer / UBSan (out-of-bounds, misaligned vector accesses) and ThreadSanitizer (two threads
+// of a block touching the same word without a barrier) -- the stand-in for compute-sanitizer, which is closed on the GPU
+// pool.  The 2D tables (k_2d) and W (k_W) are swept serially with the same cell functions.
+//
+//   ccj_emu_tuned hash <parfile> <dangles> <seq> [noGU] [pipe]   -> same text as `ccj_ref_dump hash` / `ccj_emu hash`
+//   pipe: -1 = the launcher's choice (small waves: software-pipelined window kernels), 0 / 1 = force
+#define CCJ_HOST_EMU 1
+#include "simt_emu.hpp"
+
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+
+#include "../../ccj_b200/csrc/energy_model.hpp"
+#include "../../ccj_b200/csrc/ccj_fill4.cu"
+
+struct Fnv {
+    uint64_t h = 1469598103934665603ULL;
+    void add(uint64_t v) { h ^= v; h *= 1099511628211ULL; }
+};
+static const char *k4dNames[22] = {
+    "PK", "PL", "PR", "PM", "PO", "PfromL", "PfromR", "PfromM", "PfromMprime", "PfromO",
+    "PLmloop00", "PLmloop01", "PLmloop10", "PRmloop00", "PRmloop01", "PRmloop10",
+    "PMmloop00", "PMmloop01", "PMmloop10", "POmloop00", "POmloop01", "POmloop10"};
+static const char *k2dNames[8] = {"V", "Vtype", "WM", "WMv", "WMp", "P", "WBP", "WPP"};
+
+// one exactly sized, poisoned heap block per device buffer (sizes: tab_bytes_uncached of ccj_abi.cu without its
+// 256-byte rounding, so that the sanitizer sees the first byte past what the plan promises)
+template <class T>
+static T *buf(std::vector<std::vector<char>> &keep, size_t bytes, int poison = 0x55) {
+    keep.emplace_back(bytes ? bytes : 1, (char)poison);
+    return reinterpret_cast<T *>(keep.back().data());
+}
+
+int main(int argc, char **argv) {
+    if (argc < 5 || std::string(argv[1]) != "hash") {
+        fprintf(stderr, "usage: ccj_emu_tuned hash <parfile> <dangles> <seq> [noGU] [pipe]\n");
+        return 2;
+    }
+    std::string seq = argv[4], err;
+    const int dangles = atoi(argv[3]);
+    const int noGU = argc > 5 ? atoi(argv[5]) : 0;
+    const int force_pipe = argc > 6 ? atoi(argv[6]) : -1;
+    ccj::RawParams rp;
+    if (!ccj::load_par_file(argv[2], rp, err)) {
+        fprintf(stderr, "%s\n", err.c_str());
+        return 1;
+    }
+    static ccj_model M;
+    ccj::build_model(rp, dangles, noGU, M);
+    const int n = (int)seq.size();
+    if (n < 4 || n > K4_MAXN) {
+        fprintf(stderr, "length outside the tuned range\n");
+        return 2;
+    }
+    std::vector<std::vector<char>> keep;
+    int8_t *S = buf<int8_t>(keep, (size_t)n + 2, 0);
+    for (int i = 1; i <= n; ++i) S[i] = (int8_t)ccj::encode_base(seq[i - 1]);
+    S[n + 1] = S[1];
+    S[0] = S[n];
+    const size_t tri = (size_t)n * (n - 1) / 2 + 1;
+    const int64_t cells = ccj_cells4(n), s2 = ccj_stride2(n);
+    const int64_t wscr_lr = ccj_winlr_level_max(n);
+    const int32_t wtot4 = (int32_t)ccj_pmw_level_quads(n);
+
+    ccj_seq q;
+    memset(&q, 0, sizeof q);
+    q.n = n;
+    q.S = S;
+    q.seq = seq.c_str();
+    q.status = buf<int32_t>(keep, sizeof(int32_t) * CCJ_STATUS_INTS, 0);
+    q.W = buf<int32_t>(keep, sizeof(int32_t) * (size_t)(n + 1), 0);
+    q.pair_out = buf<int32_t>(keep, sizeof(int32_t) * (size_t)(n + 2), 0);
+    q.t4 = buf<int16_t>(keep, (size_t)cells * CCJ_NT4_STORE * sizeof(int16_t) + 16);
+    q.stride4 = cells;
+    q.g1 = buf<int16_t>(keep, (size_t)cells * 6 * sizeof(int16_t) + 64);
+    q.g2 = buf<int16_t>(keep, (size_t)cells * 6 * sizeof(int16_t) + 64);
+    q.g3 = buf<int16_t>(keep, (size_t)cells * 6 * sizeof(int16_t) + 64);
+    q.g4 = buf<int16_t>(keep, (size_t)cells * 8 * sizeof(int16_t) + 64);
+    q.t2 = buf<int32_t>(keep, (size_t)s2 * CCJ_NT2 * sizeof(int32_t));
+    q.stride2 = s2;
+    q.w3 = buf<int32_t>(keep, (size_t)s2 * 4 * sizeof(int32_t));
+    q.estP = buf<int32_t>(keep, (size_t)s2 * sizeof(int32_t));
+    q.inlist = buf<uint32_t>(keep, tri * CCJ_WIN_IN * sizeof(uint32_t));
+    q.outlist = buf<uint32_t>(keep, tri * CCJ_WIN_OUT * 2 * sizeof(uint32_t));
+    q.incnt = buf<int32_t>(keep, tri * sizeof(int32_t));
+    q.outcnt = buf<int32_t>(keep, tri * sizeof(int32_t));
+    q.lay = buf<int32_t>(keep, (size_t)CCJ_LAY_INTS(n) * sizeof(int32_t));
+    q.scratch = buf<int16_t>(keep, (size_t)ccj_level_max(n) * KF * ccj::Q_COUNT * sizeof(int16_t) + 64);
+    q.scratch_stride = ccj_level_max(n);
+    q.plw = buf<int16_t>(keep, (size_t)ccj_winlr_quads(n) * 4 * sizeof(int16_t) + 256);
+    q.prw = buf<int16_t>(keep, (size_t)ccj_winlr_quads(n) * 4 * sizeof(int16_t) + 256);
+    q.pmw = buf<int16_t>(keep, ((size_t)ccj_pmw_level_quads(n) * (size_t)(n > 2 ? n - 2 : 1) + 16) * 8);
+    q.pmm = buf<int16_t>(keep, ((size_t)ccj_pmw_level_quads(n) * (size_t)(n > 2 ? n - 2 : 1) + 16) * 8);
+    q.pkf = buf<int16_t>(keep, (size_t)ccj_pkf_total(n) * sizeof(int16_t) + 64);
+    q.pkg = buf<int16_t>(keep, (size_t)ccj_pkg_total(n) * sizeof(int16_t) + 64);
+    q.wscr = buf<int16_t>(keep, ((size_t)wscr_lr * 4 + (size_t)wtot4 * 8) * sizeof(int16_t) + 64);
+    q.wscr_lr = wscr_lr;
+    q.wtot4 = wtot4;
+    q.pmlev4 = buf<int32_t>(keep, (size_t)(n + 1) * (n + 1) * sizeof(int32_t) + 64);
+    q.plist = buf<int32_t>(keep, (size_t)(n + 1) * (n + 1) * sizeof(int32_t));
+    q.pcum = buf<int32_t>(keep, (size_t)(n + 1) * (n + 2) * sizeof(int32_t));
+    q.pmlist = buf<int32_t>(keep, tri * sizeof(int32_t));
+    q.pmstart = buf<int32_t>(keep, (size_t)(n + 4) * sizeof(int32_t));
+    q.ftype_out = buf<int8_t>(keep, (size_t)n + 2, 0);
+    q.tb_stack = buf<int32_t>(keep, sizeof(int32_t) * 5 * (size_t)(16 * n + 64));
+    q.tb_cap = 16 * n + 64;
+    q.use_lists = 1;
+    const ccj_seq *seqs = &q;
+    const ccj_model *Mp = &M;
+    ccj_cx c;
+    c.M = Mp;
+    c.q = q;
+
+    // k_init (ccj_kernels.cu)
+    for (int64_t x = 0; x < s2; ++x) {
+        q.t2[T2_V * s2 + x] = CCJ_V_UNSET;
+        q.t2[T2_VTYPE * s2 + x] = 'N';
+        for (int t = T2_WM; t < CCJ_NT2; ++t) q.t2[t * s2 + x] = CCJ_INF + 1;
+    }
+    for (int x = 0; x <= n + 1; ++x) {
+        if (x <= n) q.W[x] = 0;
+        q.pair_out[x] = -1;
+        q.ftype_out[x] = 'N';
+    }
+    // launch_prep
+    const int nseq = 1, nm = n;
+    simt::launch(ccj::k_prep_lay, dim3(nseq), dim3(256), Mp, seqs);
+    simt::launch(ccj::k_fill_pmw, dim3(2, nseq), dim3(256), seqs);   // grid-stride loop: any grid covers the buffer
+    simt::launch(ccj::k_prep, dim3(nm - 1, nseq), dim3(128), Mp, seqs);
+
+    ccj_serial par;
+    auto span_step = [&](int sp) {
+        if (sp >= nm) return;
+        if (sp >= 3 && sp <= nm - 1) {   // launch_P_tuned
+            const int per = (nm - sp) * nseq;
+            const int nj = std::max(1, std::min(sp - 2, (148 * 6 + per - 1) / per));
+            simt::launch(ccj::k_P_tuned, dim3(nm - sp, nj, nseq), dim3(256), seqs, sp, nj);
+        }
+        for (int i = 1; i + sp <= n; ++i) ccj_cell2d(c, i, i + sp, par);   // k_2d
+    };
+    const int lead = KF - 2 > 0 ? KF - 2 : 0;
+    for (int sp = 0; sp < lead; ++sp) span_step(sp);
+    for (int t = 0; t < nm; ++t) {
+        span_step(t + lead);
+        const int m = nm - t - 2;
+        if (m < 1) continue;
+        const int bx = (m * (m + 1) / 2 + K4_THREADS - 1) / K4_THREADS;
+        if (t % KF == 0) simt::launch(ccj::k_roles, dim3(bx, t + 1, nseq * 4), dim3(K4_THREADS), Mp, seqs, t);
+        {   // launch_4d_windows
+            const bool pipe = force_pipe < 0 ? (long long)nm * nm * nseq < 120000 : force_pipe != 0;
+            if (!pipe && m >= 32) {
+                const int runs = K4_THREADS / 16, nchunk = (m + runs - 1) / runs, npass = (m + 63) / 64;
+                simt::launch(ccj::k_winLR<false, 16>, dim3(nchunk * npass, t + 1, nseq * 2), dim3(K4_THREADS), Mp, seqs, t, nchunk);
+            } else {
+                const int nchunk = (m + WRUNS - 1) / WRUNS, npass = (m + 4 * WGRP - 1) / (4 * WGRP);
+                const dim3 grid(nchunk * npass, t + 1, nseq * 2);
+                if (pipe) simt::launch(ccj::k_winLR<true, 8>, grid, dim3(K4_THREADS), Mp, seqs, t, nchunk);
+                else simt::launch(ccj::k_winLR<false, 8>, grid, dim3(K4_THREADS), Mp, seqs, t, nchunk);
+            }
+            long long rows = 0;
+            for (int s = CCJ_TURN + 1; s <= nm - 1 - t; ++s) rows += nm - s;
+            if (rows >= 1) {
+                const int cm = std::max(1, std::min(t + 1, nm - 4 - t));
+                const int nq = ((cm + 2) >> 2) + 1;
+                const int nchunk = (int)((rows + WRUNS - 1) / WRUNS), npass = (nq + WGRP - 1) / WGRP;
+                const dim3 grid(nchunk * npass, nseq);
+                if (pipe) simt::launch(ccj::k_winM<true>, grid, dim3(K4_THREADS), Mp, seqs, t, nchunk);
+                else simt::launch(ccj::k_winM<false>, grid, dim3(K4_THREADS), Mp, seqs, t, nchunk);
+            }
+        }
+        simt::launch(ccj::k_final, dim3(bx, t + 1, nseq), dim3(K4_THREADS), Mp, seqs, t, t % KF);
+    }
+    for (int j = CCJ_TURN + 1; j <= n; ++j) q.W[j] = ccj_W_at(c, j, par);
+    if (q.status[5] || q.status[7]) fprintf(stderr, "status: list overflow %d, int16 guard %d\n", q.status[5], q.status[7]);
+
+    printf("n %d\n", n);
+    for (int t = 0; t < 22; ++t) {
+        Fnv f;
+        long finite = 0;
+        int mn = 1 << 30;
+        for (int i = 1; i <= n; ++i)
+            for (int j = i; j <= n; ++j)
+                for (int k = j + 2; k <= n; ++k)
+                    for (int l = k; l <= n; ++l) {
+                        const int v = ccj_get4(c, t, i, j, k, l);
+                        f.add((uint16_t)(int16_t)v);
+                        if (v < 32767) { ++finite; if (v < mn) mn = v; }
+                    }
+        printf("%s %ld %d %016llx\n", k4dNames[t], finite, finite ? mn : 0, (unsigned long long)f.h);
+    }
+    for (int t = 0; t < 8; ++t) {
+        Fnv f;
+        long finite = 0;
+        long long sum = 0;
+        for (int i = 1; i <= n; ++i)
+            for (int j = i; j <= n; ++j) {
+                const int32_t v = ccj_raw2(c, t, i, j);
+                f.add((uint32_t)v);
+                if (v < CCJ_INF / 2) { ++finite; sum += v; }
+            }
+        printf("%s %ld %lld %016llx\n", k2dNames[t], finite, sum, (unsigned long long)f.h);
+    }
+    return 0;
+}
