@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256) k_P(const ccj_model *M, const ccj_seq *se
 
 // the same with ccj_P_lean (ccj_cells4_lean.cuh): warps take delta = k-d, lanes walk d (first factors consecutive in memory)
 __global__ void __launch_bounds__(256) k_P_lean(const ccj_model *M, const ccj_seq *seqs, int s) {
-    extern __shared__ int64_t s_tab[];
+    CCJ_DYN_SHARED(int64_t, s_tab);
     __shared__ int sm[8];
     const ccj_seq &q = seqs[blockIdx.z];
     const int n = q.n;
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(128, 12) k_4d(const ccj_model *M, const ccj_se
 #define K4D_LEAN_MINB 8
 #endif
 __global__ void __launch_bounds__(128, K4D_LEAN_MINB) k_4d_lean(const ccj_model *M, const ccj_seq *seqs, int t, int nmax) {
-    extern __shared__ int64_t s_tab[];   // per-block copy for the block's sequence: Cb(0..n), Tet(0..n)
+    CCJ_DYN_SHARED(int64_t, s_tab);   // per-block copy for the block's sequence: Cb(0..n), Tet(0..n)
     ccj_cx c;
     c.M = M;
     c.q = seqs[blockIdx.z];
@@ -218,6 +218,7 @@ __global__ void k_tb_step(const ccj_model *M, const ccj_seq *seqs, int seq, int 
     if (par.lane() == 0) *out_top = T.top;
 }
 
+#ifndef CCJ_HOST_EMU   // the launchers below are CUDA only; the emulation harness issues the same grids itself
 // ---------------------------------------------------------------------------------------------
 void launch_tb_step(const ccj_model *M, const ccj_seq *seqs, int seq, const int *node, int *out_top, cudaStream_t st) {
     k_tb_step<<<1, 32, 0, st>>>(M, seqs, seq, node[0], node[1], node[2], node[3], node[4], out_top);
@@ -280,5 +281,6 @@ int fill_launch_count(int nmax, bool tuned) {
     }
     return c;
 }
+#endif  // CCJ_HOST_EMU
 
 }  // namespace ccj

@@ -7,6 +7,13 @@
 
 #include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges cost nothing unless a profiler is attached
 
+// dynamic shared memory of a kernel; CCJ_HOST_EMU: the g++ build of the kernels for tests/emu/simt_emu.hpp (test tool only)
+#ifdef CCJ_HOST_EMU
+#define CCJ_DYN_SHARED(T, name) T *name = reinterpret_cast<T *>(simt::dyn_shared())
+#else
+#define CCJ_DYN_SHARED(T, name) extern __shared__ T name[]
+#endif
+
 namespace ccj {
 
 // NVTX range around a phase of the fold (tracing); shows up in Nsight timelines

@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(128, 12) k_4d_shard(const ccj_model *M, const 
 #endif
 template <bool POW2>
 __global__ void __launch_bounds__(128, SHARD_LEAN_MINB) k_4d_shard_lean(const ccj_model *M, const ccj_seq *seqs, int t) {
-    extern __shared__ ccj_lean_lvl s_lvl[];
+    CCJ_DYN_SHARED(ccj_lean_lvl, s_lvl);
     ccj_cx c;
     c.M = M;
     c.q = seqs[0];
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(256) k_P_shard(const ccj_model *M, const ccj_s
 // entries of one row, the second factors a constant stride apart on one level
 template <bool POW2>
 __global__ void __launch_bounds__(256) k_P_shard_lean(const ccj_model *M, const ccj_seq *seqs, int s) {
-    extern __shared__ ccj_lean_lvl s_lvl[];
+    CCJ_DYN_SHARED(ccj_lean_lvl, s_lvl);
     __shared__ int sm[8];
     const ccj_seq &q = seqs[0];
     const int n = q.n, G = q.shard_G;

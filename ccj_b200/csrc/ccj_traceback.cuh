@@ -66,13 +66,20 @@
 enum { TBM_NONE = 0, TBM_BORDER_CASE, TBM_BORDER_CASES, TBM_BODER_CASES, TBM_IMPOSSIBLE_CASE, TBM_IMPOSSIBLE_CASES,
        TBM_IMPOSSBIBLE_CASES };
 
+// CCJ_HOST_EMU (the g++ build for tests/emu/simt_emu.hpp): the three members that store to global memory stay out of
+// line, so that ThreadSanitizer's suppression list can name exactly them (tests/emu/tsan_traceback.supp)
+#ifdef CCJ_HOST_EMU
+#define CCJ_TB_STORE __attribute__((noinline))
+#else
+#define CCJ_TB_STORE
+#endif
 struct ccj_tb {
     const ccj_cx &c;
     int top;   // number of nodes on the stack
     bool stop; // an exit() was reached
     CCJ_HD ccj_tb(const ccj_cx &cx) : c(cx), top(0), stop(false) {}
 
-    CCJ_HD void push(int i, int j, int k, int l, int type) {
+    CCJ_TB_STORE CCJ_HD void push(int i, int j, int k, int l, int type) {
         if (top >= c.q.tb_cap) {
             fail(CCJ_STACK_OVERFLOW, 0);
             return;
@@ -81,7 +88,7 @@ struct ccj_tb {
         s[0] = i; s[1] = j; s[2] = k; s[3] = l; s[4] = type;
     }
     CCJ_HD void push2(int i, int j, int type) { push(i, j, 0, 0, type); }
-    CCJ_HD void fail(int status, int msg) {
+    CCJ_TB_STORE CCJ_HD void fail(int status, int msg) {
         if (!stop) {
             c.q.status[0] = status;
             c.q.status[2] = msg;
@@ -89,7 +96,7 @@ struct ccj_tb {
         stop = true;
     }
     CCJ_HD void die(int prefix, int type) { fail(CCJ_EXIT_FAILURE, prefix * 256 + type); }
-    CCJ_HD void setpair(int x, int y, int type) {
+    CCJ_TB_STORE CCJ_HD void setpair(int x, int y, int type) {
         c.q.pair_out[x] = y; c.q.pair_out[y] = x;
         c.q.ftype_out[x] = (int8_t)type; c.q.ftype_out[y] = (int8_t)type;
     }

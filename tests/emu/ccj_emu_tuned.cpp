@@ -1,13 +1,17 @@
-// TEST TOOL (not part of the product): runs the TUNED CUDA kernels of ccj_b200/csrc/ccj_fill4.cu (k_prep_lay, k_fill_pmw,
-// k_prep, k_roles, k_winLR, k_winM, k_final, k_P_tuned) on the host, compiled by g++ for the SIMT emulator of
-// simt_emu.hpp, in the launch order of ccj_abi.cu (ccj_batch_fill_profiled: one stream) and with the launchers' grids.
+// TEST TOOL (not part of the product): runs the CUDA kernels of ccj_b200/csrc/ccj_fill4.cu (tuned fill: k_prep_lay,
+// k_fill_pmw, k_prep, k_roles, k_winLR, k_winM, k_final, k_P_tuned) and of ccj_b200/csrc/ccj_kernels.cu (k_init, k_2d, k_W,
+// k_traceback; and with path=generic the one-thread-per-cell fill k_P_lean + k_4d_lean, or k_P + k_4d) on the host,
+// compiled by g++ for the SIMT emulator of simt_emu.hpp, in the launch order of ccj_abi.cu (ccj_batch_fill_profiled:
+// one stream) and with the launchers' grids.
 // Buffers have exactly the sizes ccj_abi.cu plans (tab_bytes_uncached) and are poisoned before the fill, so the tool is
 // meaningful under AddressSanitizer / UBSan (out-of-bounds, misaligned vector accesses) and ThreadSanitizer (two threads
 // of a block touching the same word without a barrier) -- the stand-in for compute-sanitizer, which is closed on the GPU
-// pool.  The 2D tables (k_2d) and W (k_W) are swept serially with the same cell functions.
+// pool.
 //
-//   ccj_emu_tuned hash <parfile> <dangles> <seq> [noGU] [pipe]   -> same text as `ccj_ref_dump hash` / `ccj_emu hash`
+//   ccj_emu_tuned hash <parfile> <dangles> <seq> [noGU] [pipe] [path]  -> same text as `ccj_ref_dump hash` / `ccj_emu hash`
+//   ccj_emu_tuned fold <parfile> <dangles> <seq> [noGU] [pipe] [path]  -> stdout / stderr / exit code of the CCJ binary
 //   pipe: -1 = the launcher's choice (small waves: software-pipelined window kernels), 0 / 1 = force
+//   path: tuned (default) | lean (k_P_lean + k_4d_lean) | generic (k_P + k_4d); suffix +2d: k_init / k_2d / k_W as kernels
 #define CCJ_HOST_EMU 1
 #include "simt_emu.hpp"
 
@@ -17,6 +21,8 @@
 
 #include "../../ccj_b200/csrc/energy_model.hpp"
 #include "../../ccj_b200/csrc/ccj_fill4.cu"
+#include "../../ccj_b200/csrc/ccj_kernels.cu"
+#include "../../ccj_b200/csrc/ccj_render.hpp"
 
 struct Fnv {
     uint64_t h = 1469598103934665603ULL;
@@ -37,11 +43,19 @@ static T *buf(std::vector<std::vector<char>> &keep, size_t bytes, int poison = 0
 }
 
 int main(int argc, char **argv) {
-    if (argc < 5 || std::string(argv[1]) != "hash") {
-        fprintf(stderr, "usage: ccj_emu_tuned hash <parfile> <dangles> <seq> [noGU] [pipe]\n");
+    if (argc < 5 || (std::string(argv[1]) != "hash" && std::string(argv[1]) != "fold")) {
+        fprintf(stderr, "usage: ccj_emu_tuned hash|fold <parfile> <dangles> <seq> [noGU] [pipe] [tuned|lean|generic]\n");
         return 2;
     }
-    std::string seq = argv[4], err;
+    std::string mode = argv[1], seq = argv[4], err;
+    std::string path = argc > 7 ? argv[7] : "tuned";
+    // "+2d": k_init, k_2d and k_W run as kernels too (warp collectives per 2D cell: slow here); else the same cell
+    // functions are swept serially, as tests/emu/ccj_emu.cpp does
+    bool kernels2d = false;
+    if (path.size() > 3 && path.substr(path.size() - 3) == "+2d") {
+        kernels2d = true;
+        path = path.substr(0, path.size() - 3);
+    }
     const int dangles = atoi(argv[3]);
     const int noGU = argc > 5 ? atoi(argv[5]) : 0;
     const int force_pipe = argc > 6 ? atoi(argv[6]) : -1;
@@ -116,39 +130,60 @@ int main(int argc, char **argv) {
     c.M = Mp;
     c.q = q;
 
-    // k_init (ccj_kernels.cu)
-    for (int64_t x = 0; x < s2; ++x) {
-        q.t2[T2_V * s2 + x] = CCJ_V_UNSET;
-        q.t2[T2_VTYPE * s2 + x] = 'N';
-        for (int t = T2_WM; t < CCJ_NT2; ++t) q.t2[t * s2 + x] = CCJ_INF + 1;
-    }
-    for (int x = 0; x <= n + 1; ++x) {
-        if (x <= n) q.W[x] = 0;
-        q.pair_out[x] = -1;
-        q.ftype_out[x] = 'N';
-    }
-    // launch_prep
     const int nseq = 1, nm = n;
-    simt::launch(ccj::k_prep_lay, dim3(nseq), dim3(256), Mp, seqs);
-    simt::launch(ccj::k_fill_pmw, dim3(2, nseq), dim3(256), seqs);   // grid-stride loop: any grid covers the buffer
+    const bool tuned = path == "tuned";
+    const size_t lean_smem = 2 * (size_t)(nm + 1) * sizeof(int64_t);
+    // launch_init; launch_prep (tuned) / launch_prep_lists (one thread per cell)
+    ccj_serial serial;
+    if (kernels2d) {
+        simt::launch(ccj::k_init, dim3(2, nseq), dim3(256), Mp, seqs);
+    } else {
+        for (int64_t x = 0; x < s2; ++x) {
+            q.t2[T2_V * s2 + x] = CCJ_V_UNSET;
+            q.t2[T2_VTYPE * s2 + x] = 'N';
+            for (int t = T2_WM; t < CCJ_NT2; ++t) q.t2[t * s2 + x] = CCJ_INF + 1;
+        }
+        for (int x = 0; x <= n + 1; ++x) {
+            if (x <= n) q.W[x] = 0;
+            q.pair_out[x] = -1;
+            q.ftype_out[x] = 'N';
+        }
+        memset(q.status, 0, sizeof(int32_t) * CCJ_STATUS_INTS);
+    }
+    if (tuned) {
+        simt::launch(ccj::k_prep_lay, dim3(nseq), dim3(256), Mp, seqs);
+        simt::launch(ccj::k_fill_pmw, dim3(2, nseq), dim3(256), seqs);   // grid-stride loop: any grid covers the buffer
+    }
     simt::launch(ccj::k_prep, dim3(nm - 1, nseq), dim3(128), Mp, seqs);
 
-    ccj_serial par;
     auto span_step = [&](int sp) {
         if (sp >= nm) return;
-        if (sp >= 3 && sp <= nm - 1) {   // launch_P_tuned
-            const int per = (nm - sp) * nseq;
-            const int nj = std::max(1, std::min(sp - 2, (148 * 6 + per - 1) / per));
-            simt::launch(ccj::k_P_tuned, dim3(nm - sp, nj, nseq), dim3(256), seqs, sp, nj);
+        if (sp >= 3 && sp <= nm - 1) {
+            if (tuned) {   // launch_P_tuned
+                const int per = (nm - sp) * nseq;
+                const int nj = std::max(1, std::min(sp - 2, (148 * 6 + per - 1) / per));
+                simt::launch(ccj::k_P_tuned, dim3(nm - sp, nj, nseq), dim3(256), seqs, sp, nj);
+            } else if (path == "lean") {   // launch_P
+                simt::launch_smem(ccj::k_P_lean, dim3(nm - sp, sp, nseq), dim3(256), lean_smem, Mp, seqs, sp);
+            } else {
+                simt::launch(ccj::k_P, dim3(nm - sp, sp, nseq), dim3(256), Mp, seqs, sp);
+            }
         }
-        for (int i = 1; i + sp <= n; ++i) ccj_cell2d(c, i, i + sp, par);   // k_2d
+        if (kernels2d) simt::launch(ccj::k_2d, dim3((nm - sp + 3) / 4, nseq), dim3(128), Mp, seqs, sp);   // launch_2d
+        else for (int i = 1; i + sp <= n; ++i) ccj_cell2d(c, i, i + sp, serial);
     };
-    const int lead = KF - 2 > 0 ? KF - 2 : 0;
+    const int lead = tuned ? (KF - 2 > 0 ? KF - 2 : 0) : 0;
     for (int sp = 0; sp < lead; ++sp) span_step(sp);
     for (int t = 0; t < nm; ++t) {
         span_step(t + lead);
         const int m = nm - t - 2;
         if (m < 1) continue;
+        if (!tuned) {   // launch_4d
+            const dim3 grid((m * (m + 1) / 2 + 127) / 128, t + 1, nseq);
+            if (path == "lean") simt::launch_smem(ccj::k_4d_lean, grid, dim3(128), lean_smem, Mp, seqs, t, nm);
+            else simt::launch(ccj::k_4d, grid, dim3(128), Mp, seqs, t);
+            continue;
+        }
         const int bx = (m * (m + 1) / 2 + K4_THREADS - 1) / K4_THREADS;
         if (t % KF == 0) simt::launch(ccj::k_roles, dim3(bx, t + 1, nseq * 4), dim3(K4_THREADS), Mp, seqs, t);
         {   // launch_4d_windows
@@ -175,9 +210,14 @@ int main(int argc, char **argv) {
         }
         simt::launch(ccj::k_final, dim3(bx, t + 1, nseq), dim3(K4_THREADS), Mp, seqs, t, t % KF);
     }
-    for (int j = CCJ_TURN + 1; j <= n; ++j) q.W[j] = ccj_W_at(c, j, par);
+    if (kernels2d) simt::launch(ccj::k_W, dim3(nseq), dim3(32), Mp, seqs);   // launch_W
+    else for (int j = CCJ_TURN + 1; j <= n; ++j) q.W[j] = ccj_W_at(c, j, serial);
     if (q.status[5] || q.status[7]) fprintf(stderr, "status: list overflow %d, int16 guard %d\n", q.status[5], q.status[7]);
 
+    if (mode == "fold") {
+        simt::launch(ccj::k_traceback, dim3(nseq), dim3(TB_THREADS), Mp, seqs);   // launch_traceback
+        return ccj::emit_result(seq, n, q.W[n], q.pair_out, q.status, stdout, stderr);
+    }
     printf("n %d\n", n);
     for (int t = 0; t < 22; ++t) {
         Fnv f;

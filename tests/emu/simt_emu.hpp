@@ -14,6 +14,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <thread>
@@ -70,6 +71,9 @@ struct Block {
 };
 
 inline Block *&cur_block() { static Block *b = nullptr; return b; }
+// dynamic shared memory of the running launch (CCJ_DYN_SHARED in ccj_kernels.cuh)
+inline std::vector<long long> &dyn_store() { static std::vector<long long> v; return v; }
+inline void *dyn_shared() { return dyn_store().data(); }
 
 }  // namespace simt
 
@@ -79,11 +83,15 @@ inline dim3 blockDim, gridDim;
 
 inline void __syncthreads() { simt::cur_block()->bar.arrive(); }
 inline simt::Warp &simt_warp() { return simt::cur_block()->warps[threadIdx.x >> 5]; }
-#ifdef SIMT_EMU_DROP_SYNCWARP   // negative control for the race detector: the kernels' __syncwarp() do nothing
-inline void __syncwarp(unsigned = 0xffffffffu) {}
-#else
-inline void __syncwarp(unsigned = 0xffffffffu) { simt_warp().bar.arrive(); }
-#endif
+// SIMT_EMU_DROP_SYNCWARP=1 in the environment: the kernels' __syncwarp() do nothing -- the negative control of the race
+// detector (tests/test_emu_tuned.py)
+inline bool simt_drop_syncwarp() {
+    static const bool drop = [] { const char *e = getenv("SIMT_EMU_DROP_SYNCWARP"); return e && e[0] == '1'; }();
+    return drop;
+}
+inline void __syncwarp(unsigned = 0xffffffffu) {
+    if (!simt_drop_syncwarp()) simt_warp().bar.arrive();
+}
 template <class F>
 inline int simt_collective(int v, F fold, int init) {
     simt::Warp &w = simt_warp();
@@ -123,7 +131,8 @@ namespace simt {
 // The block's threads are created once per launch and walk the blocks together: a full barrier separates two blocks
 // (the __shared__ arrays and the barrier state are per block).
 template <class K, class... A>
-void launch(K kernel, dim3 grid, dim3 block, A... args) {
+void launch_smem(K kernel, dim3 grid, dim3 block, size_t smem_bytes, A... args) {
+    dyn_store().assign(smem_bytes / sizeof(long long) + 2, 0x5555555555555555LL);
     gridDim = grid;
     blockDim = block;
     const int T = (int)block.x, nwarp = (T + 31) / 32;
@@ -169,6 +178,10 @@ void launch(K kernel, dim3 grid, dim3 block, A... args) {
         });
     for (auto &x : th) x.join();
     cur_block() = nullptr;
+}
+template <class K, class... A>
+void launch(K kernel, dim3 grid, dim3 block, A... args) {
+    launch_smem(kernel, grid, block, 0, args...);
 }
 
 }  // namespace simt

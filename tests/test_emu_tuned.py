@@ -1,16 +1,20 @@
-"""CPU: the TUNED CUDA kernels themselves (ccj_b200/csrc/ccj_fill4.cu: k_prep_lay, k_fill_pmw, k_prep, k_roles, k_winLR,
-k_winM, k_final, k_P_tuned) compiled by g++ for a small SIMT emulator (tests/emu/simt_emu.hpp: one OS thread per CUDA
-thread, real barriers, warp collectives) and launched in the product's order with the product's grids
-(tests/emu/ccj_emu_tuned.cpp).  Only the inline PTX has plain C++ stand-ins; the CUDA build of the same file is
-byte-identical with and without those guards.
+"""CPU: the CUDA kernels themselves -- the tuned fill of ccj_b200/csrc/ccj_fill4.cu (k_prep_lay, k_fill_pmw, k_prep, k_roles,
+k_winLR, k_winM, k_final, k_P_tuned) and the kernels of ccj_b200/csrc/ccj_kernels.cu (k_init, k_2d, k_W, k_traceback, the
+one-thread-per-cell fill k_P_lean / k_4d_lean) -- compiled by g++ for a small SIMT emulator (tests/emu/simt_emu.hpp: one
+OS thread per CUDA thread, real barriers, warp collectives) and launched in the product's order with the product's grids
+(tests/emu/ccj_emu_tuned.cpp).  Only the inline PTX has plain C++ stand-ins and the <<< >>> launchers are left out; the
+CUDA build of the same sources is unchanged by those guards.
 
-* every one of the 22 + 8 tables equals the golden vector the unmodified reference wrote (poisoned, exactly sized buffers);
+* every one of the 22 + 8 tables equals the golden vector the unmodified reference wrote (poisoned, exactly sized buffers),
+  folds (with k_traceback, 128 threads) equal the reference's (rc, stdout, stderr);
 * the same under AddressSanitizer + UBSan and under ThreadSanitizer -- compute-sanitizer (memcheck / initcheck /
-  racecheck) is closed on the GPU pool (profiles/r2_compute_sanitizer_closed.log); a build whose __syncwarp() does nothing
-  is the detector's negative control."""
+  racecheck) is closed on the GPU pool (profiles/r2_compute_sanitizer_closed.log); a run whose __syncwarp() does nothing
+  is the detector's negative control.
+The emulator spends its time in futex waits, not on the cores: independent runs go side by side."""
 import os
 import random
 import subprocess
+from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 
 import pytest
@@ -19,6 +23,7 @@ ROOT = Path(__file__).resolve().parent.parent
 CUDA_INC = Path(os.environ.get("CUDA_HOME", "/usr/local/cuda")) / "include"
 SRCS = [ROOT / "tests" / "emu" / "ccj_emu_tuned.cpp", ROOT / "ccj_b200" / "csrc" / "energy_model.cpp",
         ROOT / "ccj_b200" / "csrc" / "embedded_params.cpp"]
+SUPP = ROOT / "tests" / "emu" / "tsan_traceback.supp"
 
 pytestmark = pytest.mark.skipif(not (CUDA_INC / "cuda_runtime.h").exists(), reason="CUDA toolkit headers not found")
 
@@ -35,66 +40,100 @@ def _build(out: Path, flags):
 
 
 @pytest.fixture(scope="module")
-def tuned_bin():
-    return _build(ROOT / "build" / "ccj_emu_tuned", ["-O2"])
+def bins():
+    """plain, ASan + UBSan and TSan builds of the harness, compiled side by side"""
+    want = {"plain": (ROOT / "build" / "ccj_emu_tuned", ["-O2"]),
+            "asan": (ROOT / "build" / "ccj_emu_tuned_asan", ["-O1", "-fsanitize=address,undefined", "-fno-sanitize-recover=all"]),
+            "tsan": (ROOT / "build" / "ccj_emu_tuned_tsan", ["-O1", "-g", "-fsanitize=thread"])}
+    with ThreadPoolExecutor(3) as ex:
+        futs = {k: ex.submit(_build, *v) for k, v in want.items()}
+        return {k: f.result() for k, f in futs.items()}
 
 
-def _hash(exe, par, dangles, seq, no_gu=False, pipe=-1, timeout=900):
-    p = subprocess.run([str(exe), "hash", str(ROOT / "params" / par), str(dangles), seq, "1" if no_gu else "0", str(pipe)],
-                       capture_output=True, text=True, timeout=timeout)
+def _run(exe, mode, par, dangles, seq, no_gu=False, pipe=-1, path="tuned", env=None, timeout=900):
+    return subprocess.run([str(exe), mode, str(ROOT / "params" / par), str(dangles), seq, "1" if no_gu else "0", str(pipe), path],
+                          capture_output=True, text=True, timeout=timeout, env=env)
+
+
+def _together(jobs):
+    with ThreadPoolExecutor(len(jobs)) as ex:
+        return [f.result() for f in [ex.submit(_run, *a, **kw) for a, kw in jobs]]
+
+
+def _tables(stdout):
     got = {}
-    for line in p.stdout.splitlines()[1:]:
+    for line in stdout.splitlines()[1:]:
         name, cnt, agg, h = line.split()
         got[name] = [int(cnt), int(agg), h]
-    return p, got
+    return got
 
 
-@pytest.mark.parametrize("n,pipe", [(20, -1), (26, 0), (35, 0)])
-def test_tuned_kernels_on_the_host_match_the_reference(tuned_bin, golden_hashes, n, pipe):
-    """pipe -1: what the launcher picks for one short sequence (software-pipelined window kernels); 0: the plain window
-    kernels of large waves -- at n = 35 with the 16-lane groups on the first levels (runs of >= 32 cells)."""
-    rec = next(r for r in golden_hashes if len(r["seq"]) == n)
-    p, got = _hash(tuned_bin, rec["par"], rec["dangles"], rec["seq"], "--noGU" in rec.get("extra", []), pipe)
-    assert p.returncode == 0 and p.stderr == "", p.stderr[-2000:]
-    assert got == rec["tables"]
+def _small_folds(golden_folds, count):
+    return [r for r in golden_folds if 18 <= len(r["seq"]) <= 23 and not r["extra"]][:count]
 
 
-@pytest.mark.parametrize("par,dangles,no_gu", [("rna_DirksPierce09.par", 2, False), ("rna_Turner04.par", 1, False),
-                                               ("rna_Turner04.par", 0, True)])
-def test_tuned_kernels_on_the_host_other_models(tuned_bin, emu_bin, par, dangles, no_gu):
-    """Other parameter sets / dangle models / --noGU: against the cell-function sweep (tests/emu/ccj_emu.cpp), which the
-    golden vectors and live runs of the reference pin."""
-    rng = random.Random(77 + dangles + len(par))
-    seq = "".join(rng.choice("ACGU") for _ in range(21))
-    p, got = _hash(tuned_bin, par, dangles, seq, no_gu)
-    assert p.returncode == 0 and p.stderr == "", p.stderr[-2000:]
-    q = subprocess.run([str(emu_bin), "hash", str(ROOT / "params" / par), str(dangles), seq, "1" if no_gu else "0"],
-                       capture_output=True, text=True, check=True)
-    assert p.stdout == q.stdout
+def test_kernels_on_the_host_match_the_reference_tables(bins, emu_bin, golden_hashes):
+    """n = 20, the launcher's choice for one short sequence (software-pipelined window kernels), k_init / k_2d / k_W as
+    kernels too; n = 35 with the plain window kernels of large waves, the 16-lane groups on the first levels (runs of
+    >= 32 cells); n = 20 through k_P_lean + k_4d_lean (dynamic shared memory); two other models (DP09; Turner04 -d1
+    --noGU) against the cell-function sweep of tests/emu/ccj_emu.cpp, which the golden vectors pin."""
+    exe = bins["plain"]
+    r20 = next(r for r in golden_hashes if len(r["seq"]) == 20)
+    r35 = next(r for r in golden_hashes if len(r["seq"]) == 35)
+    rng = random.Random(77)
+    others = [("rna_DirksPierce09.par", 2, False, "".join(rng.choice("ACGU") for _ in range(21))),
+              ("rna_Turner04.par", 1, True, "".join(rng.choice("ACGU") for _ in range(21)))]
+    jobs = [((exe, "hash", r20["par"], r20["dangles"], r20["seq"], False, -1, "tuned+2d"), {}),
+            ((exe, "hash", r35["par"], r35["dangles"], r35["seq"], False, 0, "tuned"), {}),
+            ((exe, "hash", r20["par"], r20["dangles"], r20["seq"], False, -1, "lean"), {})]
+    jobs += [((exe, "hash", par, d, seq, gu, -1, "tuned"), {}) for par, d, gu, seq in others]
+    out = _together(jobs)
+    for p in out:
+        assert p.returncode == 0 and p.stderr == "", p.stderr[-2000:]
+    assert _tables(out[0].stdout) == r20["tables"]
+    assert _tables(out[1].stdout) == r35["tables"]
+    assert _tables(out[2].stdout) == r20["tables"]
+    for p, (par, d, gu, seq) in zip(out[3:], others):
+        q = subprocess.run([str(emu_bin), "hash", str(ROOT / "params" / par), str(d), seq, "1" if gu else "0"],
+                           capture_output=True, text=True, check=True)
+        assert p.stdout == q.stdout, (par, d, gu)
 
 
-def test_tuned_kernels_under_asan_ubsan(golden_hashes):
-    exe = _build(ROOT / "build" / "ccj_emu_tuned_asan",
-                 ["-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all"])
-    rec = next(r for r in golden_hashes if len(r["seq"]) == 20)
-    p, got = _hash(exe, rec["par"], rec["dangles"], rec["seq"], False, 0)
-    assert "Sanitizer" not in p.stderr and "runtime error" not in p.stderr, p.stderr[-3000:]
-    assert p.returncode == 0 and got == rec["tables"]
+def test_folds_through_the_emulated_kernels(bins, golden_folds):
+    """Fill + k_traceback (one block of 128 threads, block-wide ordered argmin) + the host rendering."""
+    recs = _small_folds(golden_folds, 3)
+    assert len(recs) == 3
+    paths = ["tuned+2d", "lean", "tuned"]
+    out = _together([((bins["plain"], "fold", r["par"], r["dangles"], r["seq"], False, -1, path), {}) for r, path in zip(recs, paths)])
+    for p, r in zip(out, recs):
+        assert (p.returncode, p.stdout, p.stderr) == (r["rc"], r["stdout"], r["stderr"]), r["seq"]
 
 
-def test_tuned_kernels_under_tsan(golden_hashes):
+def test_kernels_under_asan_ubsan(bins, golden_folds):
+    """Out-of-bounds and misaligned accesses of any kernel against the exactly sized buffers; plain window kernels with the
+    tuned fill, the lean one-thread-per-cell fill, 2D / W / traceback kernels."""
+    r = _small_folds(golden_folds, 1)[0]
+    out = _together([((bins["asan"], "fold", r["par"], r["dangles"], r["seq"], False, 0, "tuned+2d"), {}),
+                     ((bins["asan"], "fold", r["par"], r["dangles"], r["seq"], False, -1, "lean"), {})])
+    for p in out:
+        assert "Sanitizer" not in p.stderr and "runtime error" not in p.stderr, p.stderr[-3000:]
+        assert (p.returncode, p.stdout, p.stderr) == (r["rc"], r["stdout"], r["stderr"])
+
+
+def test_kernels_under_tsan(bins, golden_folds):
     """Threads of a block are OS threads here: a shared-memory (or global-memory) word touched by two of them without a
-    barrier in between is a data race ThreadSanitizer reports."""
-    flags = ["-O1", "-g", "-fsanitize=thread"]
-    exe = _build(ROOT / "build" / "ccj_emu_tuned_tsan", flags)
-    rec = next(r for r in golden_hashes if len(r["seq"]) == 20)
+    barrier in between is a data race ThreadSanitizer reports.  The only suppressed reports are k_traceback's intended
+    identical-value stores (tests/emu/tsan_traceback.supp)."""
+    exe = bins["tsan"]
     probe = subprocess.run([str(exe)], capture_output=True, text=True)
     if "ThreadSanitizer" in probe.stderr and "usage" not in probe.stderr:
         pytest.skip("ThreadSanitizer does not run in this environment: " + probe.stderr[-200:])
-    p, got = _hash(exe, rec["par"], rec["dangles"], rec["seq"], False, -1)
-    assert "ThreadSanitizer" not in p.stderr, p.stderr[-3000:]
-    assert p.returncode == 0 and got == rec["tables"]
-    # negative control: without the kernels' __syncwarp() the window kernels race on their shared-memory tiles
-    neg = _build(ROOT / "build" / "ccj_emu_tuned_tsan_neg", flags + ["-DSIMT_EMU_DROP_SYNCWARP"])
-    p, _ = _hash(neg, rec["par"], rec["dangles"], rec["seq"], False, -1)
-    assert "data race" in p.stderr and "k_win" in p.stderr
+    env = dict(os.environ, TSAN_OPTIONS=f"suppressions={SUPP}")
+    r = _small_folds(golden_folds, 1)[0]
+    # second run: the negative control -- without the kernels' __syncwarp() the window kernels race on their tiles
+    good, bad = _together([((exe, "fold", r["par"], r["dangles"], r["seq"], False, -1, "tuned+2d"), {"env": env}),
+                           ((exe, "hash", r["par"], r["dangles"], r["seq"], False, -1, "tuned"),
+                            {"env": dict(env, SIMT_EMU_DROP_SYNCWARP="1")})])
+    assert "ThreadSanitizer" not in good.stderr, good.stderr[-3000:]
+    assert (good.returncode, good.stdout, good.stderr) == (r["rc"], r["stdout"], r["stderr"])
+    assert "data race" in bad.stderr and "k_win" in bad.stderr
