@@ -109,6 +109,22 @@ def test_folds_through_the_emulated_kernels(bins, golden_folds):
         assert (p.returncode, p.stdout, p.stderr) == (r["rc"], r["stdout"], r["stderr"]), r["seq"]
 
 
+def test_edge_inputs_through_the_emulated_kernels(bins, emu_bin):
+    """The shortest sequences the tuned kernels accept, no pair at all, every base paired: tables and folds against the
+    cell-function sweep (whole levels fit one warp, most thread blocks return early, empty partner lists)."""
+    seqs = ["ACGU", "GGAUC", "UACACUG", "GGGGCCCC", "AAAAAAAAAAAA", "ACCCCGGCCCC", "GCGCGCGCGCGC"]
+    jobs = []
+    for seq in seqs:
+        jobs.append(((bins["plain"], "hash", "rna_Turner04.par", 2, seq, False, -1, "tuned+2d"), {}))
+        jobs.append(((bins["plain"], "fold", "rna_Turner04.par", 2, seq, False, 0, "tuned"), {}))
+    with ThreadPoolExecutor(4) as ex:
+        out = [f.result() for f in [ex.submit(_run, *a, **kw) for a, kw in jobs]]
+    for x, seq in enumerate(seqs):
+        for p, mode in ((out[2 * x], "hash"), (out[2 * x + 1], "fold")):
+            q = subprocess.run([str(emu_bin), mode, str(ROOT / "params" / "rna_Turner04.par"), "2", seq], capture_output=True, text=True)
+            assert (p.returncode, p.stdout, p.stderr) == (q.returncode, q.stdout, q.stderr), (seq, mode)
+
+
 def test_kernels_under_asan_ubsan(bins, golden_folds):
     """Out-of-bounds and misaligned accesses of any kernel against the exactly sized buffers; plain window kernels with the
     tuned fill, the lean one-thread-per-cell fill, 2D / W / traceback kernels."""
