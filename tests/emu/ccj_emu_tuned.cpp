@@ -11,7 +11,9 @@
 //   ccj_emu_tuned hash <parfile> <dangles> <seq> [noGU] [pipe] [path]  -> same text as `ccj_ref_dump hash` / `ccj_emu hash`
 //   ccj_emu_tuned fold <parfile> <dangles> <seq> [noGU] [pipe] [path]  -> stdout / stderr / exit code of the CCJ binary
 //   pipe: -1 = the launcher's choice (small waves: software-pipelined window kernels), 0 / 1 = force
-//   path: tuned (default) | lean (k_P_lean + k_4d_lean) | generic (k_P + k_4d); suffix +2d: k_init / k_2d / k_W as kernels
+//   path: tuned (default) | lean (k_P_lean + k_4d_lean) | generic (k_P + k_4d) | shardG (the row-sharded fold of
+//         ccj_shard.cu for G ranks: k_P_shard_lean + k_4d_shard_lean per rank and level; the ranks share the replicated
+//         region, which is the state the per-level allgather establishes); suffix +2d: k_init / k_2d / k_W as kernels
 #define CCJ_HOST_EMU 1
 #include "simt_emu.hpp"
 
@@ -23,6 +25,9 @@
 #include "../../ccj_b200/csrc/ccj_fill4.cu"
 #include "../../ccj_b200/csrc/ccj_kernels.cu"
 #include "../../ccj_b200/csrc/ccj_render.hpp"
+namespace {
+#include "../../ccj_b200/csrc/ccj_shard_kernels.cuh"   // inside an unnamed namespace, as ccj_shard.cu includes it
+}
 
 struct Fnv {
     uint64_t h = 1469598103934665603ULL;
@@ -40,6 +45,37 @@ template <class T>
 static T *buf(std::vector<std::vector<char>> &keep, size_t bytes, int poison = 0x55) {
     keep.emplace_back(bytes ? bytes : 1, (char)poison);
     return reinterpret_cast<T *>(keep.back().data());
+}
+
+static int print_hashes(const ccj_cx &c, int n) {
+    printf("n %d\n", n);
+    for (int t = 0; t < 22; ++t) {
+        Fnv f;
+        long finite = 0;
+        int mn = 1 << 30;
+        for (int i = 1; i <= n; ++i)
+            for (int j = i; j <= n; ++j)
+                for (int k = j + 2; k <= n; ++k)
+                    for (int l = k; l <= n; ++l) {
+                        const int v = ccj_get4(c, t, i, j, k, l);
+                        f.add((uint16_t)(int16_t)v);
+                        if (v < 32767) { ++finite; if (v < mn) mn = v; }
+                    }
+        printf("%s %ld %d %016llx\n", k4dNames[t], finite, finite ? mn : 0, (unsigned long long)f.h);
+    }
+    for (int t = 0; t < 8; ++t) {
+        Fnv f;
+        long finite = 0;
+        long long sum = 0;
+        for (int i = 1; i <= n; ++i)
+            for (int j = i; j <= n; ++j) {
+                const int32_t v = ccj_raw2(c, t, i, j);
+                f.add((uint32_t)v);
+                if (v < CCJ_INF / 2) { ++finite; sum += v; }
+            }
+        printf("%s %ld %lld %016llx\n", k2dNames[t], finite, sum, (unsigned long long)f.h);
+    }
+    return 0;
 }
 
 int main(int argc, char **argv) {
@@ -131,6 +167,77 @@ int main(int argc, char **argv) {
     c.q = q;
 
     const int nseq = 1, nm = n;
+    if (path.rfind("shard", 0) == 0) {
+        const int G = atoi(path.c_str() + 5);
+        if (G < 1 || G > 16) return 2;
+        std::vector<int64_t> lev(n + 2, 0);
+        for (int t = 0; t <= n; ++t) lev[t + 1] = lev[t] + ccj_shard_level_cells(n, t, G);
+        int16_t *rep = buf<int16_t>(keep, (size_t)lev[n + 1] * CCJ_SHARD_NREP * G * sizeof(int16_t) + 16);
+        std::vector<int16_t *> locptr;
+        for (int r = 0; r < G; ++r) locptr.push_back(buf<int16_t>(keep, (size_t)lev[n + 1] * CCJ_SHARD_NLOC * sizeof(int16_t) + 16));
+        std::vector<ccj_seq> qs(G, q);
+        for (int r = 0; r < G; ++r) {
+            ccj_seq &z = qs[r];
+            z.t4 = nullptr;   // nothing may touch the ordinary layout
+            z.g1 = z.g2 = z.g3 = z.g4 = nullptr;
+            z.lay = nullptr;
+            z.scratch = z.plw = z.prw = z.pmw = z.pmm = z.pkf = z.pkg = z.wscr = nullptr;
+            z.shard_G = G;
+            z.shard_rank = r;
+            z.shard_shift = -1;
+            for (int b = 0; b < 16; ++b)
+                if ((1 << b) == G) z.shard_shift = b;
+            z.shard_lev = lev.data();
+            z.shard_rep = rep;
+            z.shard_loc = locptr.data();
+            ccj_shard_kinds(z.shard_kind);
+            if (!shard_lean_ok(z, lev.data(), n, G)) {
+                fprintf(stderr, "shard_lean_ok refuses this fold\n");
+                return 2;
+            }
+        }
+        c.q = qs[0];
+        ccj_serial serial;
+        for (int64_t x = 0; x < s2; ++x) {
+            q.t2[T2_V * s2 + x] = CCJ_V_UNSET;
+            q.t2[T2_VTYPE * s2 + x] = 'N';
+            for (int t = T2_WM; t < CCJ_NT2; ++t) q.t2[t * s2 + x] = CCJ_INF + 1;
+        }
+        for (int x = 0; x <= n + 1; ++x) {
+            if (x <= n) q.W[x] = 0;
+            q.pair_out[x] = -1;
+            q.ftype_out[x] = 'N';
+        }
+        memset(q.status, 0, sizeof(int32_t) * CCJ_STATUS_INTS);
+        simt::launch(ccj::k_prep, dim3(nm - 1, nseq), dim3(128), Mp, (const ccj_seq *)&qs[0]);   // launch_prep_lists
+        const bool pow2 = qs[0].shard_shift >= 0;
+        for (int sp = 0; sp < nm; ++sp) {   // the loop of ccj_shard_fill
+            const size_t smem = (size_t)(sp + 1) * sizeof(ccj_lean_lvl);
+            if (sp >= 3 && sp <= nm - 1)
+                for (int r = 0; r < G; ++r) {
+                    const int rows = (int)ccj_shard_rows(nm - sp, r, G);
+                    if (rows <= 0) continue;
+                    if (pow2) simt::launch_smem(k_P_shard_lean<true>, dim3(rows, sp), dim3(256), smem, Mp, (const ccj_seq *)&qs[r], sp);
+                    else simt::launch_smem(k_P_shard_lean<false>, dim3(rows, sp), dim3(256), smem, Mp, (const ccj_seq *)&qs[r], sp);
+                }   // every rank's atomicMin lands in the one 2D table: the allreduce(min) of the span-sp diagonal
+            if (kernels2d) simt::launch(ccj::k_2d, dim3((nm - sp + 3) / 4, nseq), dim3(128), Mp, (const ccj_seq *)&qs[0], sp);
+            else for (int i = 1; i + sp <= n; ++i) ccj_cell2d(c, i, i + sp, serial);
+            const int m = nm - sp - 2;
+            for (int r = 0; r < G && m >= 1; ++r) {
+                const int64_t ncell = ccj_shard_slab(m, r, G);
+                if (ncell < 1) continue;
+                const dim3 grid((unsigned)((ncell + 127) / 128), sp + 1);
+                if (pow2) simt::launch_smem(k_4d_shard_lean<true>, grid, dim3(128), smem, Mp, (const ccj_seq *)&qs[r], sp);
+                else simt::launch_smem(k_4d_shard_lean<false>, grid, dim3(128), smem, Mp, (const ccj_seq *)&qs[r], sp);
+            }
+        }
+        for (int j = CCJ_TURN + 1; j <= n; ++j) q.W[j] = ccj_W_at(c, j, serial);
+        if (mode == "fold") {
+            simt::launch(ccj::k_traceback, dim3(nseq), dim3(TB_THREADS), Mp, (const ccj_seq *)&qs[0]);
+            return ccj::emit_result(seq, n, q.W[n], q.pair_out, q.status, stdout, stderr);
+        }
+        return print_hashes(c, n);
+    }
     const bool tuned = path == "tuned";
     const size_t lean_smem = 2 * (size_t)(nm + 1) * sizeof(int64_t);
     // launch_init; launch_prep (tuned) / launch_prep_lists (one thread per cell)
@@ -218,32 +325,5 @@ int main(int argc, char **argv) {
         simt::launch(ccj::k_traceback, dim3(nseq), dim3(TB_THREADS), Mp, seqs);   // launch_traceback
         return ccj::emit_result(seq, n, q.W[n], q.pair_out, q.status, stdout, stderr);
     }
-    printf("n %d\n", n);
-    for (int t = 0; t < 22; ++t) {
-        Fnv f;
-        long finite = 0;
-        int mn = 1 << 30;
-        for (int i = 1; i <= n; ++i)
-            for (int j = i; j <= n; ++j)
-                for (int k = j + 2; k <= n; ++k)
-                    for (int l = k; l <= n; ++l) {
-                        const int v = ccj_get4(c, t, i, j, k, l);
-                        f.add((uint16_t)(int16_t)v);
-                        if (v < 32767) { ++finite; if (v < mn) mn = v; }
-                    }
-        printf("%s %ld %d %016llx\n", k4dNames[t], finite, finite ? mn : 0, (unsigned long long)f.h);
-    }
-    for (int t = 0; t < 8; ++t) {
-        Fnv f;
-        long finite = 0;
-        long long sum = 0;
-        for (int i = 1; i <= n; ++i)
-            for (int j = i; j <= n; ++j) {
-                const int32_t v = ccj_raw2(c, t, i, j);
-                f.add((uint32_t)v);
-                if (v < CCJ_INF / 2) { ++finite; sum += v; }
-            }
-        printf("%s %ld %lld %016llx\n", k2dNames[t], finite, sum, (unsigned long long)f.h);
-    }
-    return 0;
+    return print_hashes(c, n);
 }

@@ -1,6 +1,7 @@
 """CPU: the CUDA kernels themselves -- the tuned fill of ccj_b200/csrc/ccj_fill4.cu (k_prep_lay, k_fill_pmw, k_prep, k_roles,
-k_winLR, k_winM, k_final, k_P_tuned) and the kernels of ccj_b200/csrc/ccj_kernels.cu (k_init, k_2d, k_W, k_traceback, the
-one-thread-per-cell fill k_P_lean / k_4d_lean) -- compiled by g++ for a small SIMT emulator (tests/emu/simt_emu.hpp: one
+k_winLR, k_winM, k_final, k_P_tuned), the kernels of ccj_b200/csrc/ccj_kernels.cu (k_init, k_2d, k_W, k_traceback, the
+one-thread-per-cell fill k_P_lean / k_4d_lean) and those of the row-sharded fold (ccj_shard_kernels.cuh: k_P_shard_lean,
+k_4d_shard_lean for power-of-two and other rank counts) -- compiled by g++ for a small SIMT emulator (tests/emu/simt_emu.hpp: one
 OS thread per CUDA thread, real barriers, warp collectives) and launched in the product's order with the product's grids
 (tests/emu/ccj_emu_tuned.cpp).  Only the inline PTX has plain C++ stand-ins and the <<< >>> launchers are left out; the
 CUDA build of the same sources is unchanged by those guards.
@@ -10,8 +11,10 @@ CUDA build of the same sources is unchanged by those guards.
 * the same under AddressSanitizer + UBSan and under ThreadSanitizer -- compute-sanitizer (memcheck / initcheck /
   racecheck) is closed on the GPU pool (profiles/r2_compute_sanitizer_closed.log); a run whose __syncwarp() does nothing
   is the detector's negative control.
-The emulator spends its time in futex waits, not on the cores: independent runs go side by side."""
+The emulator spends its time in futex wake-ups, not in arithmetic: a run is fastest on two to four cores (128-256 threads
+that meet at barriers migrate less), so independent runs go side by side, each pinned to its own pair of cores."""
 import os
+import queue
 import random
 import subprocess
 from concurrent.futures import ThreadPoolExecutor
@@ -50,13 +53,24 @@ def bins():
         return {k: f.result() for k, f in futs.items()}
 
 
+_CORES = sorted(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else []
+_PAIRS = queue.Queue()
+for _x in range(0, max(len(_CORES) - 1, 1), 2):
+    _PAIRS.put(set(_CORES[_x:_x + 2]) if _CORES else None)
+
+
 def _run(exe, mode, par, dangles, seq, no_gu=False, pipe=-1, path="tuned", env=None, timeout=900):
-    return subprocess.run([str(exe), mode, str(ROOT / "params" / par), str(dangles), seq, "1" if no_gu else "0", str(pipe), path],
-                          capture_output=True, text=True, timeout=timeout, env=env)
+    cores = _PAIRS.get()
+    try:
+        pin = (lambda: os.sched_setaffinity(0, cores)) if cores else None
+        return subprocess.run([str(exe), mode, str(ROOT / "params" / par), str(dangles), seq, "1" if no_gu else "0", str(pipe), path],
+                              capture_output=True, text=True, timeout=timeout, env=env, preexec_fn=pin)
+    finally:
+        _PAIRS.put(cores)
 
 
 def _together(jobs):
-    with ThreadPoolExecutor(len(jobs)) as ex:
+    with ThreadPoolExecutor(max(1, min(len(jobs), _PAIRS.qsize()))) as ex:
         return [f.result() for f in [ex.submit(_run, *a, **kw) for a, kw in jobs]]
 
 
@@ -109,6 +123,20 @@ def test_folds_through_the_emulated_kernels(bins, golden_folds):
         assert (p.returncode, p.stdout, p.stderr) == (r["rc"], r["stdout"], r["stderr"]), r["seq"]
 
 
+def test_sharded_fold_kernels_on_the_host(bins, emu_bin):
+    """k_P_shard_lean + k_4d_shard_lean per rank and level, the ranks sharing the replicated region (the state the per-level
+    allgather establishes): 2 ranks and 3 ranks -- the <false> instantiations (rank counts that are not a power of two)
+    never run in the GPU suite -- against the cell-function sweep, tables and folds."""
+    rng = random.Random(1414)
+    seq = "".join(rng.choice("ACGU") for _ in range(15))
+    jobs = [((bins["plain"], mode, "rna_Turner04.par", 2, seq, False, -1, path), {})
+            for mode, path in (("hash", "shard3"), ("fold", "shard3"), ("hash", "shard2+2d"), ("fold", "shard2"))]
+    out = _together(jobs)
+    for p, (a, kw) in zip(out, jobs):
+        q = subprocess.run([str(emu_bin), a[1], str(ROOT / "params" / "rna_Turner04.par"), "2", seq], capture_output=True, text=True)
+        assert (p.returncode, p.stdout, p.stderr) == (q.returncode, q.stdout, q.stderr), a[1:]
+
+
 def test_edge_inputs_through_the_emulated_kernels(bins, emu_bin):
     """The shortest sequences the tuned kernels accept, no pair at all, every base paired: tables and folds against the
     cell-function sweep (whole levels fit one warp, most thread blocks return early, empty partner lists)."""
@@ -117,8 +145,7 @@ def test_edge_inputs_through_the_emulated_kernels(bins, emu_bin):
     for seq in seqs:
         jobs.append(((bins["plain"], "hash", "rna_Turner04.par", 2, seq, False, -1, "tuned+2d"), {}))
         jobs.append(((bins["plain"], "fold", "rna_Turner04.par", 2, seq, False, 0, "tuned"), {}))
-    with ThreadPoolExecutor(4) as ex:
-        out = [f.result() for f in [ex.submit(_run, *a, **kw) for a, kw in jobs]]
+    out = _together(jobs)
     for x, seq in enumerate(seqs):
         for p, mode in ((out[2 * x], "hash"), (out[2 * x + 1], "fold")):
             q = subprocess.run([str(emu_bin), mode, str(ROOT / "params" / "rna_Turner04.par"), "2", seq], capture_output=True, text=True)
