@@ -47,6 +47,64 @@ static T *buf(std::vector<std::vector<char>> &keep, size_t bytes, int poison = 0
     return reinterpret_cast<T *>(keep.back().data());
 }
 
+// all device buffers of one sequence, exactly sized and poisoned (ccj_abi.cu: ccj_batch_prepare)
+static ccj_seq make_seq(const std::string &seq, std::vector<std::vector<char>> &keep) {
+    const int n = (int)seq.size();
+    int8_t *S = buf<int8_t>(keep, (size_t)n + 2, 0);
+    for (int i = 1; i <= n; ++i) S[i] = (int8_t)ccj::encode_base(seq[i - 1]);
+    S[n + 1] = S[1];
+    S[0] = S[n];
+    const size_t tri = (size_t)n * (n - 1) / 2 + 1;
+    const int64_t cells = ccj_cells4(n), s2 = ccj_stride2(n);
+    const int64_t wscr_lr = ccj_winlr_level_max(n);
+    const int32_t wtot4 = (int32_t)ccj_pmw_level_quads(n);
+
+    ccj_seq q;
+    memset(&q, 0, sizeof q);
+    q.n = n;
+    q.S = S;
+    q.seq = seq.c_str();   // the caller keeps the string alive
+    q.status = buf<int32_t>(keep, sizeof(int32_t) * CCJ_STATUS_INTS, 0);
+    q.W = buf<int32_t>(keep, sizeof(int32_t) * (size_t)(n + 1), 0);
+    q.pair_out = buf<int32_t>(keep, sizeof(int32_t) * (size_t)(n + 2), 0);
+    q.t4 = buf<int16_t>(keep, (size_t)cells * CCJ_NT4_STORE * sizeof(int16_t) + 16);
+    q.stride4 = cells;
+    q.g1 = buf<int16_t>(keep, (size_t)cells * 6 * sizeof(int16_t) + 64);
+    q.g2 = buf<int16_t>(keep, (size_t)cells * 6 * sizeof(int16_t) + 64);
+    q.g3 = buf<int16_t>(keep, (size_t)cells * 6 * sizeof(int16_t) + 64);
+    q.g4 = buf<int16_t>(keep, (size_t)cells * 8 * sizeof(int16_t) + 64);
+    q.t2 = buf<int32_t>(keep, (size_t)s2 * CCJ_NT2 * sizeof(int32_t));
+    q.stride2 = s2;
+    q.w3 = buf<int32_t>(keep, (size_t)s2 * 4 * sizeof(int32_t));
+    q.estP = buf<int32_t>(keep, (size_t)s2 * sizeof(int32_t));
+    q.inlist = buf<uint32_t>(keep, tri * CCJ_WIN_IN * sizeof(uint32_t));
+    q.outlist = buf<uint32_t>(keep, tri * CCJ_WIN_OUT * 2 * sizeof(uint32_t));
+    q.incnt = buf<int32_t>(keep, tri * sizeof(int32_t));
+    q.outcnt = buf<int32_t>(keep, tri * sizeof(int32_t));
+    q.lay = buf<int32_t>(keep, (size_t)CCJ_LAY_INTS(n) * sizeof(int32_t));
+    q.scratch = buf<int16_t>(keep, (size_t)ccj_level_max(n) * KF * ccj::Q_COUNT * sizeof(int16_t) + 64);
+    q.scratch_stride = ccj_level_max(n);
+    q.plw = buf<int16_t>(keep, (size_t)ccj_winlr_quads(n) * 4 * sizeof(int16_t) + 256);
+    q.prw = buf<int16_t>(keep, (size_t)ccj_winlr_quads(n) * 4 * sizeof(int16_t) + 256);
+    q.pmw = buf<int16_t>(keep, ((size_t)ccj_pmw_level_quads(n) * (size_t)(n > 2 ? n - 2 : 1) + 16) * 8);
+    q.pmm = buf<int16_t>(keep, ((size_t)ccj_pmw_level_quads(n) * (size_t)(n > 2 ? n - 2 : 1) + 16) * 8);
+    q.pkf = buf<int16_t>(keep, (size_t)ccj_pkf_total(n) * sizeof(int16_t) + 64);
+    q.pkg = buf<int16_t>(keep, (size_t)ccj_pkg_total(n) * sizeof(int16_t) + 64);
+    q.wscr = buf<int16_t>(keep, ((size_t)wscr_lr * 4 + (size_t)wtot4 * 8) * sizeof(int16_t) + 64);
+    q.wscr_lr = wscr_lr;
+    q.wtot4 = wtot4;
+    q.pmlev4 = buf<int32_t>(keep, (size_t)(n + 1) * (n + 1) * sizeof(int32_t) + 64);
+    q.plist = buf<int32_t>(keep, (size_t)(n + 1) * (n + 1) * sizeof(int32_t));
+    q.pcum = buf<int32_t>(keep, (size_t)(n + 1) * (n + 2) * sizeof(int32_t));
+    q.pmlist = buf<int32_t>(keep, tri * sizeof(int32_t));
+    q.pmstart = buf<int32_t>(keep, (size_t)(n + 4) * sizeof(int32_t));
+    q.ftype_out = buf<int8_t>(keep, (size_t)n + 2, 0);
+    q.tb_stack = buf<int32_t>(keep, sizeof(int32_t) * 5 * (size_t)(16 * n + 64));
+    q.tb_cap = 16 * n + 64;
+    q.use_lists = 1;
+    return q;
+}
+
 static int print_hashes(const ccj_cx &c, int n) {
     printf("n %d\n", n);
     for (int t = 0; t < 22; ++t) {
@@ -102,71 +160,40 @@ int main(int argc, char **argv) {
     }
     static ccj_model M;
     ccj::build_model(rp, dangles, noGU, M);
-    const int n = (int)seq.size();
-    if (n < 4 || n > K4_MAXN) {
-        fprintf(stderr, "length outside the tuned range\n");
+    // several sequences separated by commas = one wave (hash mode, tuned / lean / generic paths): the kernels index the
+    // sequence with blockIdx.z / .y and the grids are sized for the longest one, as ccj_batch_fill launches them
+    std::vector<std::string> seqv;
+    for (size_t a = 0; a <= seq.size();) {
+        const size_t b = seq.find(',', a);
+        seqv.push_back(seq.substr(a, b == std::string::npos ? std::string::npos : b - a));
+        if (b == std::string::npos) break;
+        a = b + 1;
+    }
+    seq = seqv[0];
+    int nm = 0;
+    for (const std::string &x : seqv) {
+        if (x.size() < 4 || x.size() > K4_MAXN) {
+            fprintf(stderr, "length outside the tuned range\n");
+            return 2;
+        }
+        nm = std::max(nm, (int)x.size());
+    }
+    const int n = (int)seq.size(), nseq = (int)seqv.size();
+    if (nseq > 1 && (mode != "hash" || argc <= 7 || std::string(argv[7]).rfind("shard", 0) == 0)) {
+        fprintf(stderr, "a wave of several sequences: hash mode, explicit path tuned / lean / generic\n");
         return 2;
     }
     std::vector<std::vector<char>> keep;
-    int8_t *S = buf<int8_t>(keep, (size_t)n + 2, 0);
-    for (int i = 1; i <= n; ++i) S[i] = (int8_t)ccj::encode_base(seq[i - 1]);
-    S[n + 1] = S[1];
-    S[0] = S[n];
-    const size_t tri = (size_t)n * (n - 1) / 2 + 1;
-    const int64_t cells = ccj_cells4(n), s2 = ccj_stride2(n);
-    const int64_t wscr_lr = ccj_winlr_level_max(n);
-    const int32_t wtot4 = (int32_t)ccj_pmw_level_quads(n);
-
-    ccj_seq q;
-    memset(&q, 0, sizeof q);
-    q.n = n;
-    q.S = S;
-    q.seq = seq.c_str();
-    q.status = buf<int32_t>(keep, sizeof(int32_t) * CCJ_STATUS_INTS, 0);
-    q.W = buf<int32_t>(keep, sizeof(int32_t) * (size_t)(n + 1), 0);
-    q.pair_out = buf<int32_t>(keep, sizeof(int32_t) * (size_t)(n + 2), 0);
-    q.t4 = buf<int16_t>(keep, (size_t)cells * CCJ_NT4_STORE * sizeof(int16_t) + 16);
-    q.stride4 = cells;
-    q.g1 = buf<int16_t>(keep, (size_t)cells * 6 * sizeof(int16_t) + 64);
-    q.g2 = buf<int16_t>(keep, (size_t)cells * 6 * sizeof(int16_t) + 64);
-    q.g3 = buf<int16_t>(keep, (size_t)cells * 6 * sizeof(int16_t) + 64);
-    q.g4 = buf<int16_t>(keep, (size_t)cells * 8 * sizeof(int16_t) + 64);
-    q.t2 = buf<int32_t>(keep, (size_t)s2 * CCJ_NT2 * sizeof(int32_t));
-    q.stride2 = s2;
-    q.w3 = buf<int32_t>(keep, (size_t)s2 * 4 * sizeof(int32_t));
-    q.estP = buf<int32_t>(keep, (size_t)s2 * sizeof(int32_t));
-    q.inlist = buf<uint32_t>(keep, tri * CCJ_WIN_IN * sizeof(uint32_t));
-    q.outlist = buf<uint32_t>(keep, tri * CCJ_WIN_OUT * 2 * sizeof(uint32_t));
-    q.incnt = buf<int32_t>(keep, tri * sizeof(int32_t));
-    q.outcnt = buf<int32_t>(keep, tri * sizeof(int32_t));
-    q.lay = buf<int32_t>(keep, (size_t)CCJ_LAY_INTS(n) * sizeof(int32_t));
-    q.scratch = buf<int16_t>(keep, (size_t)ccj_level_max(n) * KF * ccj::Q_COUNT * sizeof(int16_t) + 64);
-    q.scratch_stride = ccj_level_max(n);
-    q.plw = buf<int16_t>(keep, (size_t)ccj_winlr_quads(n) * 4 * sizeof(int16_t) + 256);
-    q.prw = buf<int16_t>(keep, (size_t)ccj_winlr_quads(n) * 4 * sizeof(int16_t) + 256);
-    q.pmw = buf<int16_t>(keep, ((size_t)ccj_pmw_level_quads(n) * (size_t)(n > 2 ? n - 2 : 1) + 16) * 8);
-    q.pmm = buf<int16_t>(keep, ((size_t)ccj_pmw_level_quads(n) * (size_t)(n > 2 ? n - 2 : 1) + 16) * 8);
-    q.pkf = buf<int16_t>(keep, (size_t)ccj_pkf_total(n) * sizeof(int16_t) + 64);
-    q.pkg = buf<int16_t>(keep, (size_t)ccj_pkg_total(n) * sizeof(int16_t) + 64);
-    q.wscr = buf<int16_t>(keep, ((size_t)wscr_lr * 4 + (size_t)wtot4 * 8) * sizeof(int16_t) + 64);
-    q.wscr_lr = wscr_lr;
-    q.wtot4 = wtot4;
-    q.pmlev4 = buf<int32_t>(keep, (size_t)(n + 1) * (n + 1) * sizeof(int32_t) + 64);
-    q.plist = buf<int32_t>(keep, (size_t)(n + 1) * (n + 1) * sizeof(int32_t));
-    q.pcum = buf<int32_t>(keep, (size_t)(n + 1) * (n + 2) * sizeof(int32_t));
-    q.pmlist = buf<int32_t>(keep, tri * sizeof(int32_t));
-    q.pmstart = buf<int32_t>(keep, (size_t)(n + 4) * sizeof(int32_t));
-    q.ftype_out = buf<int8_t>(keep, (size_t)n + 2, 0);
-    q.tb_stack = buf<int32_t>(keep, sizeof(int32_t) * 5 * (size_t)(16 * n + 64));
-    q.tb_cap = 16 * n + 64;
-    q.use_lists = 1;
-    const ccj_seq *seqs = &q;
+    std::vector<ccj_seq> qv;
+    for (const std::string &x : seqv) qv.push_back(make_seq(x, keep));
+    ccj_seq q = qv[0];
+    const int64_t s2 = ccj_stride2(n);
+    const ccj_seq *seqs = qv.data();
     const ccj_model *Mp = &M;
     ccj_cx c;
     c.M = Mp;
     c.q = q;
 
-    const int nseq = 1, nm = n;
     if (path.rfind("shard", 0) == 0) {
         const int G = atoi(path.c_str() + 5);
         if (G < 1 || G > 16) return 2;
@@ -245,17 +272,20 @@ int main(int argc, char **argv) {
     if (kernels2d) {
         simt::launch(ccj::k_init, dim3(2, nseq), dim3(256), Mp, seqs);
     } else {
-        for (int64_t x = 0; x < s2; ++x) {
-            q.t2[T2_V * s2 + x] = CCJ_V_UNSET;
-            q.t2[T2_VTYPE * s2 + x] = 'N';
-            for (int t = T2_WM; t < CCJ_NT2; ++t) q.t2[t * s2 + x] = CCJ_INF + 1;
+        for (const ccj_seq &z : qv) {
+            const int64_t zs2 = z.stride2;
+            for (int64_t x = 0; x < zs2; ++x) {
+                z.t2[T2_V * zs2 + x] = CCJ_V_UNSET;
+                z.t2[T2_VTYPE * zs2 + x] = 'N';
+                for (int t = T2_WM; t < CCJ_NT2; ++t) z.t2[t * zs2 + x] = CCJ_INF + 1;
+            }
+            for (int x = 0; x <= z.n + 1; ++x) {
+                if (x <= z.n) z.W[x] = 0;
+                z.pair_out[x] = -1;
+                z.ftype_out[x] = 'N';
+            }
+            memset(z.status, 0, sizeof(int32_t) * CCJ_STATUS_INTS);
         }
-        for (int x = 0; x <= n + 1; ++x) {
-            if (x <= n) q.W[x] = 0;
-            q.pair_out[x] = -1;
-            q.ftype_out[x] = 'N';
-        }
-        memset(q.status, 0, sizeof(int32_t) * CCJ_STATUS_INTS);
     }
     if (tuned) {
         simt::launch(ccj::k_prep_lay, dim3(nseq), dim3(256), Mp, seqs);
@@ -277,7 +307,12 @@ int main(int argc, char **argv) {
             }
         }
         if (kernels2d) simt::launch(ccj::k_2d, dim3((nm - sp + 3) / 4, nseq), dim3(128), Mp, seqs, sp);   // launch_2d
-        else for (int i = 1; i + sp <= n; ++i) ccj_cell2d(c, i, i + sp, serial);
+        else for (const ccj_seq &z : qv) {
+            ccj_cx cz;
+            cz.M = Mp;
+            cz.q = z;
+            for (int i = 1; i + sp <= z.n; ++i) ccj_cell2d(cz, i, i + sp, serial);
+        }
     };
     const int lead = tuned ? (KF - 2 > 0 ? KF - 2 : 0) : 0;
     for (int sp = 0; sp < lead; ++sp) span_step(sp);
@@ -318,12 +353,26 @@ int main(int argc, char **argv) {
         simt::launch(ccj::k_final, dim3(bx, t + 1, nseq), dim3(K4_THREADS), Mp, seqs, t, t % KF);
     }
     if (kernels2d) simt::launch(ccj::k_W, dim3(nseq), dim3(32), Mp, seqs);   // launch_W
-    else for (int j = CCJ_TURN + 1; j <= n; ++j) q.W[j] = ccj_W_at(c, j, serial);
-    if (q.status[5] || q.status[7]) fprintf(stderr, "status: list overflow %d, int16 guard %d\n", q.status[5], q.status[7]);
+    else for (const ccj_seq &z : qv) {
+        ccj_cx cz;
+        cz.M = Mp;
+        cz.q = z;
+        for (int j = CCJ_TURN + 1; j <= z.n; ++j) z.W[j] = ccj_W_at(cz, j, serial);
+    }
+    for (const ccj_seq &z : qv)
+        if (z.status[5] || z.status[7]) fprintf(stderr, "status: list overflow %d, int16 guard %d\n", z.status[5], z.status[7]);
 
     if (mode == "fold") {
         simt::launch(ccj::k_traceback, dim3(nseq), dim3(TB_THREADS), Mp, seqs);   // launch_traceback
         return ccj::emit_result(seq, n, q.W[n], q.pair_out, q.status, stdout, stderr);
     }
-    return print_hashes(c, n);
+    if (nseq == 1) return print_hashes(c, n);
+    for (int x = 0; x < nseq; ++x) {
+        printf("# sequence %d\n", x);
+        ccj_cx cz;
+        cz.M = Mp;
+        cz.q = qv[x];
+        print_hashes(cz, qv[x].n);
+    }
+    return 0;
 }

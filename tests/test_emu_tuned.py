@@ -123,6 +123,23 @@ def test_folds_through_the_emulated_kernels(bins, golden_folds):
         assert (p.returncode, p.stdout, p.stderr) == (r["rc"], r["stdout"], r["stderr"]), r["seq"]
 
 
+def test_ragged_wave_through_the_emulated_kernels(bins, emu_bin):
+    """One wave of four sequences of different lengths (26, 20, 13 and 4 nt): the kernels pick their sequence with
+    blockIdx.z / .y, the grids are sized for the longest one and the shorter ones drop out level by level -- tuned kernels
+    (pipelined and plain windows) and the lean one-thread-per-cell kernels, every table of every sequence."""
+    seqs = ["UUGUCAGAACGCUGAAGUGG", "UGAGUCCGAGGAG", "GCGCUAUACGCAGCCAAAACCAAUAC", "ACGU"]
+    want = ""
+    for x, seq in enumerate(seqs):
+        q = subprocess.run([str(emu_bin), "hash", str(ROOT / "params" / "rna_Turner04.par"), "2", seq], capture_output=True,
+                           text=True, check=True)
+        want += f"# sequence {x}\n" + q.stdout
+    out = _together([((bins["plain"], "hash", "rna_Turner04.par", 2, ",".join(seqs), False, pipe, path), {})
+                     for path, pipe in (("tuned+2d", -1), ("tuned", 0), ("lean", -1))])
+    for p in out:
+        assert p.returncode == 0 and p.stderr == "", p.stderr[-2000:]
+        assert p.stdout == want
+
+
 def test_sharded_fold_kernels_on_the_host(bins, emu_bin):
     """k_P_shard_lean + k_4d_shard_lean per rank and level, the ranks sharing the replicated region (the state the per-level
     allgather establishes): 2 ranks and 3 ranks -- the <false> instantiations (rank counts that are not a power of two)
