@@ -41,8 +41,15 @@ static const char *k2dNames[8] = {"V", "Vtype", "WM", "WMv", "WMp", "P", "WBP", 
 
 // one exactly sized, poisoned heap block per device buffer (sizes: tab_bytes_uncached of ccj_abi.cu without its
 // 256-byte rounding, so that the sanitizer sees the first byte past what the plan promises)
+// CCJ_EMU_POISON=<byte, hex>: what uninitialised device memory holds (default 55: 0x5555 = 21845 per int16; 80 makes every
+// stale entry -32640, which would win any minimum it leaked into; 7f a large finite energy)
+static int poison_byte() {
+    static const int v = [] { const char *e = getenv("CCJ_EMU_POISON"); return e ? (int)strtol(e, nullptr, 16) & 0xff : 0x55; }();
+    return v;
+}
 template <class T>
-static T *buf(std::vector<std::vector<char>> &keep, size_t bytes, int poison = 0x55) {
+static T *buf(std::vector<std::vector<char>> &keep, size_t bytes, int poison = -1) {
+    if (poison < 0) poison = poison_byte();
     keep.emplace_back(bytes ? bytes : 1, (char)poison);
     return reinterpret_cast<T *>(keep.back().data());
 }

@@ -123,6 +123,32 @@ def test_folds_through_the_emulated_kernels(bins, golden_folds):
         assert (p.returncode, p.stdout, p.stderr) == (r["rc"], r["stdout"], r["stderr"]), r["seq"]
 
 
+@pytest.mark.skipif(os.environ.get("CCJ_EMU_LONG") != "1", reason="4 minutes; set CCJ_EMU_LONG=1 (last run: profiles/r2_emu_tuned_h60.log)")
+def test_baseline_config_1_through_the_emulated_kernels(bins, golden_hashes, golden_folds):
+    """BASELINE config 1, the designed 60-nt H-type pseudoknot: every table and the fold (-29.07 kcal/mol, crossing
+    brackets) through the emulated tuned kernels."""
+    seq = "AAUAGGCGCAGCAUACACGGUCGAGCUGCGCCAAUAACAAUACGACCGUGAUAAAUAAAA"
+    rec = next(r for r in golden_hashes if r["seq"] == seq and r["par"] == "rna_Turner04.par" and r["dangles"] == 2)
+    fold = next(r for r in golden_folds if r["seq"] == seq and r["par"] == "rna_Turner04.par" and r["dangles"] == 2 and not r["extra"])
+    h, f = _together([((bins["plain"], "hash", rec["par"], 2, seq, False, 0, "tuned+2d"), {"timeout": 3000}),
+                      ((bins["plain"], "fold", rec["par"], 2, seq, False, -1, "tuned"), {"timeout": 3000})])
+    assert _tables(h.stdout) == rec["tables"]
+    assert (f.returncode, f.stdout, f.stderr) == (fold["rc"], fold["stdout"], fold["stderr"])
+
+
+def test_results_do_not_depend_on_uninitialised_memory(bins, golden_hashes):
+    """initcheck by construction: the buffers start as 0x8080 (-32640 per int16: a stale entry would win every minimum it
+    leaked into -- rows of the window copies are padded and read past their ends) and as 0x7f7f instead of the default
+    0x5555; all 22 + 8 tables still equal the golden vector."""
+    rec = next(r for r in golden_hashes if len(r["seq"]) == 20)
+    jobs = [((bins["plain"], "hash", rec["par"], rec["dangles"], rec["seq"], False, pipe, path),
+             {"env": dict(os.environ, CCJ_EMU_POISON=poison)})
+            for poison, path, pipe in (("80", "tuned", -1), ("80", "tuned", 0), ("80", "lean", -1), ("7f", "tuned", 0))]
+    for p in _together(jobs):
+        assert p.returncode == 0 and p.stderr == "", p.stderr[-2000:]
+        assert _tables(p.stdout) == rec["tables"]
+
+
 def test_ragged_wave_through_the_emulated_kernels(bins, emu_bin):
     """One wave of four sequences of different lengths (26, 20, 13 and 4 nt): the kernels pick their sequence with
     blockIdx.z / .y, the grids are sized for the longest one and the shorter ones drop out level by level -- tuned kernels
