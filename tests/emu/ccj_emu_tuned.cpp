@@ -10,6 +10,12 @@
 //
 //   ccj_emu_tuned hash <parfile> <dangles> <seq> [noGU] [pipe] [path]  -> same text as `ccj_ref_dump hash` / `ccj_emu hash`
 //   ccj_emu_tuned fold <parfile> <dangles> <seq> [noGU] [pipe] [path]  -> stdout / stderr / exit code of the CCJ binary
+//   order=<issue|side|main|prio:ABC|rnd:SEED> as 8th argument (tuned path only, needs -DCCJ_ENQUEUE_FILL_INC=<file>): the launch
+//         sequence is then NOT restated here -- the text of enqueue_fill() of ccj_abi.cu (extracted by the test into that
+//         file) runs against mock streams / events, which turns its launches into a dependency graph (stream order +
+//         event record -> wait edges), and the kernels are executed in a legal order of that graph: as issued, side
+//         streams (windows, P + 2D) as far ahead as the events allow, main stream first, or random.  Every legal order must
+//         give the same tables: a missing dependency of the three-stream graph shows up as a wrong table here.
 //   pipe: -1 = the launcher's choice (small waves: software-pipelined window kernels), 0 / 1 = force
 //   path: tuned (default) | lean (k_P_lean + k_4d_lean) | generic (k_P + k_4d) | shardG (the row-sharded fold of
 //         ccj_shard.cu for G ranks: k_P_shard_lean + k_4d_shard_lean per rank and level; the ranks share the replicated
@@ -143,6 +149,184 @@ static int print_hashes(const ccj_cx &c, int n) {
     return 0;
 }
 
+
+#ifdef CCJ_ENQUEUE_FILL_INC
+// ---- enqueue_fill() of ccj_abi.cu against mock streams and events -------------------------------------------------------
+#include <functional>
+#include <random>
+struct Task {
+    int stream;
+    std::string name;
+    std::vector<int> deps;
+    std::function<void()> run;
+};
+static std::vector<Task> g_tasks;
+static int g_last[4] = {-1, -1, -1, -1};          // last task of each stream
+static std::vector<int> g_pending[4];             // event waits since the stream's last launch
+static std::vector<int> g_event_task;             // event id -> task the record captured (-1: nothing before it)
+static bool g_kernels2d = false;
+static int g_force_pipe = -1;
+static std::vector<ccj_seq> *g_qv = nullptr;
+static int sid(cudaStream_t s) { return (int)(uintptr_t)s; }          // mock handles: small integers
+static int eid(cudaEvent_t e) { return (int)(uintptr_t)e - 1; }
+extern "C" cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) {
+    g_event_task.push_back(-2);
+    *e = (cudaEvent_t)(uintptr_t)g_event_task.size();
+    return cudaSuccess;
+}
+extern "C" cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s) {
+    g_event_task[eid(e)] = g_last[sid(s)];
+    return cudaSuccess;
+}
+extern "C" cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned) {
+    // CCJ_EMU_DROP_WAIT=k: the k-th wait of the sequence is ignored -- the negative control of this checker
+    static const int drop = [] { const char *x = getenv("CCJ_EMU_DROP_WAIT"); return x ? atoi(x) : -1; }();
+    static int nwait = 0;
+    if (nwait++ == drop) {
+        fprintf(stderr, "dropped wait %d: stream %d on the event recorded after task %d (%s)\n", drop, sid(s), g_event_task[eid(e)],
+                g_event_task[eid(e)] >= 0 ? g_tasks[g_event_task[eid(e)]].name.c_str() : "-");
+        return cudaSuccess;
+    }
+    if (g_event_task[eid(e)] == -2) {
+        fprintf(stderr, "wait on an event that was never recorded\n");
+        exit(3);
+    }
+    if (g_event_task[eid(e)] >= 0) g_pending[sid(s)].push_back(g_event_task[eid(e)]);
+    return cudaSuccess;
+}
+extern "C" cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+static void add_task(cudaStream_t st, const std::string &name, std::function<void()> run) {
+    Task t;
+    t.stream = sid(st);
+    t.name = name;
+    if (g_last[t.stream] >= 0) t.deps.push_back(g_last[t.stream]);
+    for (int d : g_pending[t.stream]) t.deps.push_back(d);
+    g_pending[t.stream].clear();
+    t.run = std::move(run);
+    g_tasks.push_back(std::move(t));
+    g_last[g_tasks.back().stream] = (int)g_tasks.size() - 1;
+}
+struct ccj_ctx {   // the members enqueue_fill touches
+    const ccj_model *d_model;
+    const ccj_seq *d_seqs;
+    cudaStream_t stream, s_win, s_2d;
+    std::vector<cudaEvent_t> dep;
+};
+static bool use_tuned(int) { return true; }
+static bool generic_scan() { return false; }
+namespace ccj {   // the launchers of ccj_kernels.cu / ccj_fill4.cu (left out under CCJ_HOST_EMU): same grids, as graph nodes
+void launch_init(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cudaStream_t st) {
+    add_task(st, "init", [=] { simt::launch(k_init, dim3(2, d.nseq), dim3(256), M, seqs); });
+}
+void launch_prep(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cudaStream_t st) {
+    add_task(st, "prep", [=] {
+        simt::launch(k_prep_lay, dim3(d.nseq), dim3(256), M, seqs);
+        simt::launch(k_fill_pmw, dim3(2, d.nseq), dim3(256), seqs);
+        simt::launch(k_prep, dim3(d.nmax - 1, d.nseq), dim3(128), M, seqs);
+    });
+}
+void launch_prep_lists(const ccj_model *, const ccj_seq *, LaunchDims, cudaStream_t) {}
+void launch_P(const ccj_model *, const ccj_seq *, LaunchDims, int, cudaStream_t) {}
+void launch_4d(const ccj_model *, const ccj_seq *, LaunchDims, int, cudaStream_t) {}
+void launch_P_tuned(const ccj_model *, const ccj_seq *seqs, LaunchDims d, int s, cudaStream_t st) {
+    if (s < 3 || s > d.nmax - 1) return;
+    const int per = (d.nmax - s) * d.nseq;
+    const int nj = std::max(1, std::min(s - 2, (148 * 6 + per - 1) / per));
+    add_task(st, "P" + std::to_string(s), [=] { simt::launch(k_P_tuned, dim3(d.nmax - s, nj, d.nseq), dim3(256), seqs, s, nj); });
+}
+void launch_2d(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int s, cudaStream_t st) {
+    if (d.nmax - s < 1) return;
+    add_task(st, "2d" + std::to_string(s), [=] {
+        if (g_kernels2d) {
+            simt::launch(k_2d, dim3((d.nmax - s + 3) / 4, d.nseq), dim3(128), M, seqs, s);
+            return;
+        }
+        ccj_serial serial;
+        for (const ccj_seq &z : *g_qv) {
+            ccj_cx cz;
+            cz.M = M;
+            cz.q = z;
+            for (int i = 1; i + s <= z.n; ++i) ccj_cell2d(cz, i, i + s, serial);
+        }
+    });
+}
+void launch_4d_roles(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st) {
+    const int m = d.nmax - t - 2;
+    if (t % KF != 0 || m < 1) return;
+    const int bx = (m * (m + 1) / 2 + K4_THREADS - 1) / K4_THREADS;
+    add_task(st, "roles" + std::to_string(t), [=] { simt::launch(k_roles, dim3(bx, t + 1, d.nseq * 4), dim3(K4_THREADS), M, seqs, t); });
+}
+void launch_4d_windows(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st) {
+    const int nm = d.nmax, m = nm - t - 2, nseq = d.nseq;
+    if (m < 1) return;
+    add_task(st, "win" + std::to_string(t), [=] {
+        const bool pipe = g_force_pipe < 0 ? (long long)nm * nm * nseq < 120000 : g_force_pipe != 0;
+        if (!pipe && m >= 32) {
+            const int runs = K4_THREADS / 16, nchunk = (m + runs - 1) / runs, npass = (m + 63) / 64;
+            simt::launch(k_winLR<false, 16>, dim3(nchunk * npass, t + 1, nseq * 2), dim3(K4_THREADS), M, seqs, t, nchunk);
+        } else {
+            const int nchunk = (m + WRUNS - 1) / WRUNS, npass = (m + 4 * WGRP - 1) / (4 * WGRP);
+            const dim3 grid(nchunk * npass, t + 1, nseq * 2);
+            if (pipe) simt::launch(k_winLR<true, 8>, grid, dim3(K4_THREADS), M, seqs, t, nchunk);
+            else simt::launch(k_winLR<false, 8>, grid, dim3(K4_THREADS), M, seqs, t, nchunk);
+        }
+        long long rows = 0;
+        for (int s = CCJ_TURN + 1; s <= nm - 1 - t; ++s) rows += nm - s;
+        if (rows < 1) return;
+        const int cm = std::max(1, std::min(t + 1, nm - 4 - t));
+        const int nq = ((cm + 2) >> 2) + 1;
+        const int nchunk = (int)((rows + WRUNS - 1) / WRUNS), npass = (nq + WGRP - 1) / WGRP;
+        if (pipe) simt::launch(k_winM<true>, dim3(nchunk * npass, nseq), dim3(K4_THREADS), M, seqs, t, nchunk);
+        else simt::launch(k_winM<false>, dim3(nchunk * npass, nseq), dim3(K4_THREADS), M, seqs, t, nchunk);
+    });
+}
+void launch_4d_final(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, int t, cudaStream_t st) {
+    const int m = d.nmax - t - 2;
+    if (m < 1) return;
+    const int bx = (m * (m + 1) / 2 + K4_THREADS - 1) / K4_THREADS;
+    add_task(st, "final" + std::to_string(t), [=] { simt::launch(k_final, dim3(bx, t + 1, d.nseq), dim3(K4_THREADS), M, seqs, t, t % KF); });
+}
+void launch_W(const ccj_model *M, const ccj_seq *seqs, LaunchDims d, cudaStream_t st) {
+    add_task(st, "W", [=] { simt::launch(k_W, dim3(d.nseq), dim3(32), M, seqs); });
+}
+int fill4_fused_levels() { return KF; }
+}  // namespace ccj
+#define CU(x) x
+#define CCJ_STR2(x) #x
+#define CCJ_STR(x) CCJ_STR2(x)
+#include CCJ_STR(CCJ_ENQUEUE_FILL_INC)   // cudaError_t enqueue_fill(ccj_ctx *ctx, ccj::LaunchDims d), verbatim from ccj_abi.cu
+
+// runs the graph in a legal order: prio[stream] decides among the ready tasks (lower first), or a seeded random pick
+static int run_graph(const std::string &order) {
+    const size_t N = g_tasks.size();
+    std::vector<char> done(N, 0);
+    std::mt19937 rng(order.rfind("rnd:", 0) == 0 ? (unsigned)atoi(order.c_str() + 4) : 0u);
+    int prio[4] = {0, 0, 0, 0};   // streams: 1 main, 2 windows, 3 P + 2D
+    if (order == "side") { prio[3] = 0; prio[2] = 1; prio[1] = 2; }
+    else if (order == "main") { prio[1] = 0; prio[2] = 1; prio[3] = 2; }
+    else if (order.rfind("prio:", 0) == 0 && order.size() == 8)   // prio:ABC -- stream A before B before C whenever ready
+        for (int x = 0; x < 3; ++x) prio[(order[5 + x] - '0') & 3] = x;
+    for (size_t ran = 0; ran < N; ++ran) {
+        std::vector<int> ready;
+        for (size_t x = 0; x < N; ++x) {
+            if (done[x]) continue;
+            bool ok = true;
+            for (int d : g_tasks[x].deps) ok = ok && done[d];
+            if (ok) ready.push_back((int)x);
+        }
+        if (ready.empty()) { fprintf(stderr, "dependency cycle\n"); return 3; }
+        int pick = ready[0];
+        if (order.rfind("rnd:", 0) == 0) pick = ready[rng() % ready.size()];
+        else if (order != "issue")   // side / main / prio:ABC
+            for (int x : ready)
+                if (prio[g_tasks[x].stream] < prio[g_tasks[pick].stream]) pick = x;
+        g_tasks[pick].run();
+        done[pick] = 1;
+    }
+    return 0;
+}
+#endif  // CCJ_ENQUEUE_FILL_INC
+
 int main(int argc, char **argv) {
     if (argc < 5 || (std::string(argv[1]) != "hash" && std::string(argv[1]) != "fold")) {
         fprintf(stderr, "usage: ccj_emu_tuned hash|fold <parfile> <dangles> <seq> [noGU] [pipe] [tuned|lean|generic]\n");
@@ -201,6 +385,42 @@ int main(int argc, char **argv) {
     c.M = Mp;
     c.q = q;
 
+    const std::string order = argc > 8 ? argv[8] : "";
+    if (!order.empty()) {
+#ifdef CCJ_ENQUEUE_FILL_INC
+        if (path != "tuned" || mode != "hash") return 2;
+        g_kernels2d = kernels2d;
+        g_force_pipe = force_pipe;
+        g_qv = &qv;
+        ccj_ctx ctx;
+        ctx.d_model = Mp;
+        ctx.d_seqs = seqs;
+        ctx.stream = (cudaStream_t)(uintptr_t)1;
+        ctx.s_win = (cudaStream_t)(uintptr_t)2;
+        ctx.s_2d = (cudaStream_t)(uintptr_t)3;
+        ccj::LaunchDims d;
+        d.nseq = nseq;
+        d.nmax = nm;
+        if (enqueue_fill(&ctx, d) != cudaSuccess) return 3;
+        size_t cross = 0;
+        for (const Task &t : g_tasks)
+            for (int dd : t.deps) cross += g_tasks[dd].stream != t.stream;
+        fprintf(stderr, "graph: %zu launches, %zu cross-stream dependencies, order %s\n", g_tasks.size(), cross, order.c_str());
+        if (run_graph(order.substr(order.rfind('=') == std::string::npos ? 0 : order.rfind('=') + 1))) return 3;
+        if (nseq == 1) return print_hashes(c, n);
+        for (int x = 0; x < nseq; ++x) {
+            printf("# sequence %d\n", x);
+            ccj_cx cz;
+            cz.M = Mp;
+            cz.q = qv[x];
+            print_hashes(cz, qv[x].n);
+        }
+        return 0;
+#else
+        fprintf(stderr, "built without CCJ_ENQUEUE_FILL_INC\n");
+        return 2;
+#endif
+    }
     if (path.rfind("shard", 0) == 0) {
         const int G = atoi(path.c_str() + 5);
         if (G < 1 || G > 16) return 2;

@@ -42,13 +42,26 @@ def _build(out: Path, flags):
     return out
 
 
+def _extract_enqueue_fill() -> Path:
+    """the text of enqueue_fill() (with its two helper macros) exactly as ccj_abi.cu has it"""
+    src = (ROOT / "ccj_b200" / "csrc" / "ccj_abi.cu").read_text()
+    a, b = src.index("#define EQ(call)"), src.index("#undef EQL") + len("#undef EQL\n")
+    assert "cudaError_t enqueue_fill(ccj_ctx *ctx, ccj::LaunchDims d)" in src[a:b]
+    out = ROOT / "build" / "enqueue_fill.inc"
+    out.parent.mkdir(exist_ok=True)
+    if not out.exists() or out.read_text() != src[a:b]:
+        out.write_text(src[a:b])
+    return out
+
+
 @pytest.fixture(scope="module")
 def bins():
-    """plain, ASan + UBSan and TSan builds of the harness, compiled side by side"""
+    """plain, ASan + UBSan and TSan builds of the harness and the one that compiles enqueue_fill(), side by side"""
     want = {"plain": (ROOT / "build" / "ccj_emu_tuned", ["-O2"]),
+            "graph": (ROOT / "build" / "ccj_emu_graph", ["-O2", f"-DCCJ_ENQUEUE_FILL_INC={_extract_enqueue_fill()}"]),
             "asan": (ROOT / "build" / "ccj_emu_tuned_asan", ["-O1", "-fsanitize=address,undefined", "-fno-sanitize-recover=all"]),
             "tsan": (ROOT / "build" / "ccj_emu_tuned_tsan", ["-O1", "-g", "-fsanitize=thread"])}
-    with ThreadPoolExecutor(3) as ex:
+    with ThreadPoolExecutor(4) as ex:
         futs = {k: ex.submit(_build, *v) for k, v in want.items()}
         return {k: f.result() for k, f in futs.items()}
 
@@ -59,12 +72,12 @@ for _x in range(0, max(len(_CORES) - 1, 1), 2):
     _PAIRS.put(set(_CORES[_x:_x + 2]) if _CORES else None)
 
 
-def _run(exe, mode, par, dangles, seq, no_gu=False, pipe=-1, path="tuned", env=None, timeout=900):
+def _run(exe, mode, par, dangles, seq, no_gu=False, pipe=-1, path="tuned", env=None, timeout=900, order=None):
     cores = _PAIRS.get()
     try:
         pin = (lambda: os.sched_setaffinity(0, cores)) if cores else None
-        return subprocess.run([str(exe), mode, str(ROOT / "params" / par), str(dangles), seq, "1" if no_gu else "0", str(pipe), path],
-                              capture_output=True, text=True, timeout=timeout, env=env, preexec_fn=pin)
+        return subprocess.run([str(exe), mode, str(ROOT / "params" / par), str(dangles), seq, "1" if no_gu else "0", str(pipe), path]
+                              + ([order] if order else []), capture_output=True, text=True, timeout=timeout, env=env, preexec_fn=pin)
     finally:
         _PAIRS.put(cores)
 
@@ -111,6 +124,36 @@ def test_kernels_on_the_host_match_the_reference_tables(bins, emu_bin, golden_ha
         q = subprocess.run([str(emu_bin), "hash", str(ROOT / "params" / par), str(d), seq, "1" if gu else "0"],
                            capture_output=True, text=True, check=True)
         assert p.stdout == q.stdout, (par, d, gu)
+
+
+def test_launch_graph_of_enqueue_fill_in_every_stream_priority_order(bins, emu_bin, golden_hashes):
+    """The three-stream launch sequence of the tuned fill (main: k_roles / k_final, windows one level ahead, P + 2D tables one
+    span ahead; dependency events between them) is not restated for this test: the text of enqueue_fill() of ccj_abi.cu runs
+    against mock streams and events, its launches become a dependency graph (stream order + record -> wait edges), and the
+    emulated kernels run in a legal order of that graph -- each of the six orders "stream A before B before C whenever
+    ready", which push every side stream as far ahead or behind as the events allow.  Uninitialised memory is 0x8080 so
+    that a value read too early wins its minimum.  Every order must give the reference's tables; as negative control three
+    of the waits are dropped one at a time (windows on k_final two levels back, k_roles on the 2D span, compute_P on
+    k_final three levels back) and some order must then go wrong."""
+    rec = next(r for r in golden_hashes if len(r["seq"]) == 20)
+    env = dict(os.environ, CCJ_EMU_POISON="80")
+    orders = ["prio:123", "prio:132", "prio:213", "prio:231", "prio:312", "prio:321"]
+    out = _together([((bins["graph"], "hash", rec["par"], rec["dangles"], rec["seq"], False, -1, "tuned"), {"env": env, "order": o})
+                     for o in orders])
+    for p, o in zip(out, orders):
+        assert p.returncode == 0 and "cross-stream dependencies" in p.stderr, p.stderr[-2000:]
+        assert _tables(p.stdout) == rec["tables"], o
+    seq = rec["seq"][:14]
+    want = subprocess.run([str(emu_bin), "hash", str(ROOT / "params" / rec["par"]), str(rec["dangles"]), seq], capture_output=True,
+                          text=True, check=True).stdout
+    ok = _run(bins["graph"], "hash", rec["par"], rec["dangles"], seq, False, -1, "tuned", env=env, order="prio:231")
+    assert ok.stdout == want
+    drops = [(6, "prio:231", "final0"), (10, "prio:123", "2d4"), (12, "prio:132", "final2")]
+    out = _together([((bins["graph"], "hash", rec["par"], rec["dangles"], seq, False, -1, "tuned"),
+                      {"env": dict(env, CCJ_EMU_DROP_WAIT=str(k)), "order": o}) for k, o, _ in drops])
+    for p, (k, o, src) in zip(out, drops):
+        assert f"dropped wait {k}:" in p.stderr and f"({src})" in p.stderr, p.stderr[:300]
+        assert p.stdout != want, (k, o)
 
 
 def test_folds_through_the_emulated_kernels(bins, golden_folds):
